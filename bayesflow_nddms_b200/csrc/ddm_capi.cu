@@ -1,0 +1,692 @@
+// ddm_capi.cu -- the C ABI of include/ddm_b200.h over the kernels in ddm_kernels.cu.
+//
+// One ddm_ctx owns a device, a stream, grow-only device arenas and a pool of output
+// buffers (so that a steady-state online-training loop performs no cudaMalloc, even
+// when every batch is handed away through DLPack).  No torch types, no global state
+// except the last-create error string.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/ddm_b200.h"
+#include "../../include/ddm_dlpack.h"
+#include "ddm_kernels.cuh"
+#include "ddm_microbench.cuh"
+
+#define DDM_API extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// ---- pooled device buffers (outputs can outlive the ctx via DLPack) -----------------
+struct BufferPool {
+    std::mutex mu;
+    std::vector<std::pair<void *, size_t>> free_list;
+    std::atomic<int> refs{1};
+    int device = 0;
+    size_t cached_bytes = 0;
+    static constexpr size_t kMaxCachedBuffers = 4;
+
+    void *take(size_t bytes, size_t *cap) {
+        std::lock_guard<std::mutex> g(mu);
+        int best = -1;
+        for (int i = 0; i < (int)free_list.size(); i++)
+            if (free_list[i].second >= bytes && (best < 0 || free_list[i].second < free_list[best].second)) best = i;
+        if (best < 0 || free_list[best].second > 2 * bytes + (1u << 20)) return nullptr;
+        void *p = free_list[best].first;
+        *cap = free_list[best].second;
+        free_list.erase(free_list.begin() + best);
+        return p;
+    }
+    void give(void *p, size_t cap) {
+        void *drop = nullptr;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            free_list.emplace_back(p, cap);
+            if (free_list.size() > kMaxCachedBuffers) {
+                drop = free_list.front().first;
+                free_list.erase(free_list.begin());
+            }
+        }
+        if (drop) {
+            int prev = 0;
+            cudaGetDevice(&prev);
+            cudaSetDevice(device);
+            cudaFree(drop);
+            cudaSetDevice(prev);
+        }
+    }
+    void release() {
+        if (refs.fetch_sub(1) == 1) {
+            int prev = 0;
+            cudaGetDevice(&prev);
+            cudaSetDevice(device);
+            for (auto &b : free_list) cudaFree(b.first);
+            cudaSetDevice(prev);
+            delete this;
+        }
+    }
+};
+
+struct DlpackHolder {
+    DLManagedTensor t;
+    int64_t shape[3];
+    void *buf;
+    size_t cap;
+    BufferPool *pool;
+};
+
+void dlpack_deleter(DLManagedTensor *self) {
+    if (!self) return;
+    auto *h = static_cast<DlpackHolder *>(self->manager_ctx);
+    h->pool->give(h->buf, h->cap);
+    h->pool->release();
+    delete h;
+}
+
+template <typename T>
+struct Arena {  // grow-only device array
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 4 + 64;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        cap = want;
+        return cudaSuccess;
+    }
+    void free_() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+int n_params_of(int model) {
+    switch (model) {
+    case DDM_MODEL_BASIC: return 5;
+    case DDM_MODEL_ALPHA_SCALE: return 8;
+    case DDM_MODEL_TRIALWISE: return 4;
+    case DDM_MODEL_ALPHA:
+    case DDM_MODEL_ALPHA_DC:
+    case DDM_MODEL_ALPHA_SCALE2: return 7;
+    default: return -1;
+    }
+}
+
+int kind_of(int model) {
+    switch (model) {
+    case DDM_MODEL_BASIC: return ddm::KIND_FIXED;
+    case DDM_MODEL_ALPHA_DC: return ddm::KIND_DC;
+    case DDM_MODEL_TRIALWISE: return ddm::KIND_TRIALWISE;
+    default: return ddm::KIND_BOUND;
+    }
+}
+
+}  // namespace
+
+struct ddm_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    BufferPool *pool = nullptr;
+
+    Arena<double> params;
+    Arena<ddm::DsConst> dconst;
+    Arena<int32_t> steps, group;
+    Arena<double> bound, dbg_z, export_buf;
+    Arena<int64_t> dbg_off;
+    Arena<uint32_t> philox_buf;
+    unsigned long long *counters = nullptr;       // device: [0] work counter, [1..] stats
+    unsigned long long *counters_host = nullptr;  // pinned mirror
+
+    // uploaded parameters
+    int model = -1;
+    int64_t n_datasets = 0;
+    int n_params = 0;
+    bool have_params = false;
+
+    // shared-increment mode
+    bool dbg_on = false;
+    size_t dbg_n = 0;
+    int64_t dbg_trials = 0;
+
+    // last run
+    void *out = nullptr;
+    size_t out_cap = 0, out_bytes = 0;
+    bool have_run = false, out64 = true, have_steps = false, stats_pending = false;
+    int64_t run_rows = 0, run_datasets = 0, run_trials = 0;  // rows = trials in total
+    bool run_trialwise = false;
+    ddm_stats stats{};
+
+    // tuning (0 = automatic)
+    int tune_threshold = 0, tune_blocks_per_sm = 0, tune_tile = 0;
+};
+
+namespace {
+
+int fail(ddm_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define DDM_CUDA(ctx, call)                                                                        \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? DDM_ERR_NOMEM : DDM_ERR_CUDA,      \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int ensure_output(ddm_ctx *ctx, size_t bytes) {
+    if (ctx->out && ctx->out_cap >= bytes) return DDM_OK;
+    if (ctx->out) {
+        ctx->pool->give(ctx->out, ctx->out_cap);
+        ctx->out = nullptr;
+        ctx->out_cap = 0;
+    }
+    size_t cap = 0;
+    void *p = ctx->pool->take(bytes, &cap);
+    if (!p) {
+        cap = bytes < 256 ? 256 : bytes;
+        DDM_CUDA(ctx, cudaMalloc(&p, cap));
+    }
+    ctx->out = p;
+    ctx->out_cap = cap;
+    return DDM_OK;
+}
+
+// Shared by ddm_run and ddm_simulate_trialwise.
+int run_common(ddm_ctx *ctx, int model, int64_t n_datasets, int64_t n_trials, double dt, int max_steps,
+               uint64_t seed, uint64_t dataset_offset, uint64_t trial_offset, int precision, int flags,
+               int n_groups) {
+    if (precision != 32 && precision != 64) return fail(ctx, DDM_ERR_INVALID, "precision must be 32 or 64, got %d", precision);
+    if (!(dt > 0.0) || !std::isfinite(dt)) return fail(ctx, DDM_ERR_INVALID, "dt must be positive and finite");
+    if (max_steps < 0) return fail(ctx, DDM_ERR_INVALID, "max_steps must be >= 0");
+    if (n_trials < 0 || n_datasets < 0) return fail(ctx, DDM_ERR_INVALID, "negative shape");
+    const bool trialwise = (model == DDM_MODEL_TRIALWISE);
+    const int64_t rows = trialwise ? n_trials : n_datasets * n_trials;
+    if (n_trials > 0xffffffffLL || n_datasets > 0xffffffffLL) return fail(ctx, DDM_ERR_INVALID, "shape exceeds 2^32");
+    if (dataset_offset + (uint64_t)n_datasets > 0xffffffffULL)
+        return fail(ctx, DDM_ERR_INVALID, "dataset_offset + n_datasets must stay below 2^32 (Philox counter word)");
+    if (trial_offset + (uint64_t)n_trials > 0xffffffffULL)
+        return fail(ctx, DDM_ERR_INVALID, "trial_offset + n_trials must stay below 2^32 (Philox counter word)");
+    if (ctx->dbg_on && ctx->dbg_trials != rows)
+        return fail(ctx, DDM_ERR_INVALID, "shared-increment buffer was set for %lld trials, run has %lld",
+                    (long long)ctx->dbg_trials, (long long)rows);
+
+    const bool out64 = !(flags & DDM_FLAG_OUT_F32);
+    const size_t out_bytes = (size_t)rows * 2 * (out64 ? 8 : 4);
+    int rc = ensure_output(ctx, out_bytes);
+    if (rc) return rc;
+    const bool keep_steps = (flags & DDM_FLAG_KEEP_STEPS) != 0;
+    if (keep_steps) DDM_CUDA(ctx, ctx->steps.reserve((size_t)rows));
+
+    const int kind = kind_of(model);
+    ddm::RunArgs a{};
+    a.dconst = ctx->dconst.p;
+    a.params = ctx->params.p;
+    a.group = ctx->group.p;
+    a.bound_in = ctx->bound.p;
+    a.dbg_z = ctx->dbg_on ? ctx->dbg_z.p : nullptr;
+    a.dbg_off = ctx->dbg_on ? ctx->dbg_off.p : nullptr;
+    a.dbg_n = ctx->dbg_on ? ctx->dbg_n : 0;
+    a.out = ctx->out;
+    a.steps_out = keep_steps ? ctx->steps.p : nullptr;
+    a.work_counter = ctx->counters;
+    a.stats = ctx->counters + 1;
+    a.n_datasets = (uint32_t)n_datasets;
+    a.n_trials = (uint32_t)n_trials;
+    a.n_params = (uint32_t)(trialwise ? 4 : ctx->n_params);
+    a.dataset_offset = (uint32_t)dataset_offset;
+    a.trial_offset = (uint32_t)trial_offset;
+    a.key.k0 = (uint32_t)seed;
+    a.key.k1 = (uint32_t)(seed >> 32);
+    a.max_steps = (uint32_t)max_steps;
+    a.model = model;
+    a.flags = flags;
+    a.dt = dt;
+    a.sqrt_dt = std::sqrt(dt);
+    a.kdt = (float)(-1.3862943611198906188 * dt);
+    (void)n_groups;
+
+    const bool persistent = precision == 32 && !ctx->dbg_on && !trialwise && !(flags & DDM_FLAG_FORCE_GENERIC) &&
+                            (max_steps % 4 == 0);
+    ddm_stats st{};
+    st.n_trials = (uint64_t)rows;
+
+    DDM_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long) * (1 + ddm::STAT_COUNT), ctx->stream));
+    int launches = 0;
+    if (rows > 0) {
+        if (precision == 32 && !trialwise && !ctx->dbg_on) {
+            DDM_CUDA(ctx, ctx->dconst.reserve((size_t)n_datasets));
+            a.dconst = ctx->dconst.p;
+            DDM_CUDA(ctx, ddm::launch_prep(ctx->params.p, ctx->dconst.p, (uint32_t)n_datasets, (uint32_t)ctx->n_params,
+                                           model, dt, ctx->stream));
+            launches++;
+        }
+        DDM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        if (persistent) {
+            const int block = 256;
+            int per_sm = ctx->tune_blocks_per_sm;
+            const int max_per_sm = ddm::persistent_max_blocks_per_sm(kind, out64, block);
+            if (max_per_sm <= 0) return fail(ctx, DDM_ERR_CUDA, "occupancy query failed for the persistent kernel");
+            if (per_sm <= 0 || per_sm > max_per_sm) per_sm = max_per_sm;
+            // tile: trials of one dataset handed out per atomic claim
+            uint32_t tile = ctx->tune_tile > 0 ? (uint32_t)ctx->tune_tile : 64u;
+            if (tile > (uint32_t)n_trials) tile = (uint32_t)n_trials;
+            a.tile = tile;
+            a.tiles_per_dataset = (uint32_t)((n_trials + tile - 1) / tile);
+            a.n_items = (uint64_t)a.tiles_per_dataset * (uint64_t)n_datasets;
+            a.refill_threshold = ctx->tune_threshold > 0 ? ctx->tune_threshold : 8;
+            if (a.refill_threshold > 32) a.refill_threshold = 32;
+            const uint64_t warps_needed = ((uint64_t)rows + 31) / 32;
+            uint64_t grid = (uint64_t)ctx->sm_count * per_sm;
+            const uint64_t blocks_needed = (warps_needed + (block / 32) - 1) / (block / 32);
+            if (grid > blocks_needed) grid = blocks_needed;
+            if (grid < 1) grid = 1;
+            DDM_CUDA(ctx, ddm::launch_persistent(a, kind, out64, (int)grid, block, ctx->stream));
+            st.used_persistent = 1;
+            st.grid = (int)grid;
+            st.block = block;
+            st.refill_threshold = a.refill_threshold;
+            st.tile = (int)tile;
+        } else {
+            DDM_CUDA(ctx, ddm::launch_generic(a, kind, precision == 64, ctx->dbg_on, out64, (uint64_t)rows, ctx->stream));
+            st.grid = (int)(((uint64_t)rows + 127) / 128);
+            st.block = 128;
+        }
+        launches++;
+        DDM_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    }
+    DDM_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, ctx->counters, sizeof(unsigned long long) * (1 + ddm::STAT_COUNT),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    st.kernel_launches = launches;
+    ctx->stats = st;
+    ctx->stats_pending = true;
+    ctx->have_run = true;
+    ctx->out64 = out64;
+    ctx->out_bytes = out_bytes;
+    ctx->have_steps = keep_steps;
+    ctx->run_rows = rows;
+    ctx->run_datasets = n_datasets;
+    ctx->run_trials = n_trials;
+    ctx->run_trialwise = trialwise;
+    return DDM_OK;
+}
+
+int finish_stats(ddm_ctx *ctx) {
+    if (!ctx->stats_pending) return DDM_OK;
+    DDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const unsigned long long *c = ctx->counters_host + 1;
+    ctx->stats.total_steps = c[ddm::STAT_STEPS];
+    ctx->stats.n_timeouts = c[ddm::STAT_TIMEOUTS];
+    ctx->stats.n_upper = c[ddm::STAT_UPPER];
+    ctx->stats.reject_cap_hits = c[ddm::STAT_REJECT_CAP];
+    ctx->stats.debug_overruns = c[ddm::STAT_DBG_OVERRUN];
+    float ms = 0.f;
+    if (ctx->run_rows > 0) DDM_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->stats.kernel_ms = ms;
+    ctx->stats_pending = false;
+    return DDM_OK;
+}
+
+}  // namespace
+
+// ---- lifecycle --------------------------------------------------------------------------
+DDM_API int ddm_version(void) { return DDM_B200_VERSION; }
+
+DDM_API const char *ddm_last_error(const ddm_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+DDM_API int ddm_create(int device, ddm_ctx **out) {
+    if (!out) return fail(nullptr, DDM_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, DDM_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= count) return fail(nullptr, DDM_ERR_INVALID, "device %d out of range [0,%d)", device, count);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return fail(nullptr, DDM_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, DDM_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                    prop.major, prop.minor);
+    ddm_ctx *ctx = new (std::nothrow) ddm_ctx();
+    if (!ctx) return fail(nullptr, DDM_ERR_NOMEM, "out of host memory");
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    DeviceGuard g(device);
+    auto bail = [&](const char *what, cudaError_t err) {
+        int rc = fail(nullptr, DDM_ERR_CUDA, "%s: %s", what, cudaGetErrorString(err));
+        ddm_destroy(ctx);
+        return rc;
+    };
+    ctx->pool = new BufferPool();
+    ctx->pool->device = device;
+    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    ctx->stream = ctx->own_stream;
+    if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaMalloc(&ctx->counters, sizeof(unsigned long long) * (1 + ddm::STAT_COUNT))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMallocHost(&ctx->counters_host, sizeof(unsigned long long) * (1 + ddm::STAT_COUNT))) != cudaSuccess)
+        return bail("cudaMallocHost", e);
+    *out = ctx;
+    return DDM_OK;
+}
+
+DDM_API int ddm_destroy(ddm_ctx *ctx) {
+    if (!ctx) return DDM_OK;
+    {
+        DeviceGuard g(ctx->device);
+        if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+        ctx->params.free_();
+        ctx->dconst.free_();
+        ctx->steps.free_();
+        ctx->group.free_();
+        ctx->bound.free_();
+        ctx->dbg_z.free_();
+        ctx->export_buf.free_();
+        ctx->dbg_off.free_();
+        ctx->philox_buf.free_();
+        if (ctx->counters) cudaFree(ctx->counters);
+        if (ctx->counters_host) cudaFreeHost(ctx->counters_host);
+        if (ctx->out && ctx->pool) ctx->pool->give(ctx->out, ctx->out_cap);
+        if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+        if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+        if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+        if (ctx->pool) ctx->pool->release();
+    }
+    delete ctx;
+    return DDM_OK;
+}
+
+DDM_API int ddm_set_stream(ddm_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return DDM_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    DDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return DDM_OK;
+}
+
+DDM_API int ddm_synchronize(ddm_ctx *ctx) {
+    if (!ctx) return DDM_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    DDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DDM_OK;
+}
+
+DDM_API int ddm_set_tuning(ddm_ctx *ctx, int refill_threshold, int blocks_per_sm, int tile) {
+    if (!ctx) return DDM_ERR_INVALID;
+    if (refill_threshold < 0 || refill_threshold > 32 || blocks_per_sm < 0 || tile < 0)
+        return fail(ctx, DDM_ERR_INVALID, "tuning values out of range");
+    ctx->tune_threshold = refill_threshold;
+    ctx->tune_blocks_per_sm = blocks_per_sm;
+    ctx->tune_tile = tile;
+    return DDM_OK;
+}
+
+// ---- the hot path -----------------------------------------------------------------------
+DDM_API int ddm_upload_params(ddm_ctx *ctx, int model, const double *params, int64_t n_datasets, int n_params) {
+    if (!ctx) return DDM_ERR_INVALID;
+    const int want = n_params_of(model);
+    if (want < 0 || model == DDM_MODEL_TRIALWISE)
+        return fail(ctx, DDM_ERR_INVALID, "model %d is not a dataset-wise model (use ddm_simulate_trialwise for 5)", model);
+    if (n_params != want) return fail(ctx, DDM_ERR_INVALID, "model %d takes %d parameters per dataset, got %d", model, want, n_params);
+    if (n_datasets < 0) return fail(ctx, DDM_ERR_INVALID, "n_datasets < 0");
+    if (n_datasets > 0 && !params) return fail(ctx, DDM_ERR_INVALID, "params is NULL");
+    DeviceGuard g(ctx->device);
+    const size_t n = (size_t)n_datasets * n_params;
+    DDM_CUDA(ctx, ctx->params.reserve(n ? n : 1));
+    if (n) DDM_CUDA(ctx, cudaMemcpyAsync(ctx->params.p, params, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->model = model;
+    ctx->n_datasets = n_datasets;
+    ctx->n_params = n_params;
+    ctx->have_params = true;
+    return DDM_OK;
+}
+
+DDM_API int ddm_run(ddm_ctx *ctx, int64_t n_trials, double dt, int max_steps, uint64_t seed, uint64_t dataset_offset,
+                    int precision, int flags) {
+    if (!ctx) return DDM_ERR_INVALID;
+    if (!ctx->have_params) return fail(ctx, DDM_ERR_STATE, "ddm_run before ddm_upload_params");
+    DeviceGuard g(ctx->device);
+    return run_common(ctx, ctx->model, ctx->n_datasets, n_trials, dt, max_steps, seed, dataset_offset, 0, precision, flags, 0);
+}
+
+DDM_API int ddm_download(ddm_ctx *ctx, void *out_host) {
+    if (!ctx) return DDM_ERR_INVALID;
+    if (!ctx->have_run || !ctx->out) return fail(ctx, DDM_ERR_STATE, "no output to download (run first; DLPack hand-off moves it away)");
+    if (!out_host && ctx->out_bytes) return fail(ctx, DDM_ERR_INVALID, "out_host is NULL");
+    DeviceGuard g(ctx->device);
+    if (ctx->out_bytes) DDM_CUDA(ctx, cudaMemcpyAsync(out_host, ctx->out, ctx->out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    DDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DDM_OK;
+}
+
+DDM_API int ddm_simulate(ddm_ctx *ctx, int model, const double *params, int64_t n_datasets, int n_params,
+                         int64_t n_trials, double dt, int max_steps, uint64_t seed, uint64_t dataset_offset,
+                         int precision, int flags, void *out_host) {
+    int rc = ddm_upload_params(ctx, model, params, n_datasets, n_params);
+    if (rc) return rc;
+    rc = ddm_run(ctx, n_trials, dt, max_steps, seed, dataset_offset, precision, flags);
+    if (rc) return rc;
+    if (out_host) return ddm_download(ctx, out_host);
+    return DDM_OK;
+}
+
+DDM_API int ddm_simulate_trialwise(ddm_ctx *ctx, const int32_t *group, const double *bound, const double *group_params,
+                                   int64_t n, int n_groups, double dt, int max_steps, uint64_t seed,
+                                   uint64_t trial_offset, int precision, int flags, void *out_host) {
+    if (!ctx) return DDM_ERR_INVALID;
+    if (n < 0 || n_groups < 0) return fail(ctx, DDM_ERR_INVALID, "negative shape");
+    if (n > 0 && (!group || !bound || !group_params)) return fail(ctx, DDM_ERR_INVALID, "NULL input");
+    for (int64_t i = 0; i < n; i++) {
+        // imputation_from_stahl_not_scaled.py:124-125 raises ValueError; NaN passes there too (NaN < 0 is False)
+        if (bound[i] < 0) {
+            return fail(ctx, DDM_ERR_NEGATIVE_BOUND, "Trial-level boundary cannot be less than zero (trial %lld: %g)",
+                        (long long)i, bound[i]);
+        }
+        if (group[i] < 0 || group[i] >= n_groups)
+            return fail(ctx, DDM_ERR_INVALID, "group[%lld] = %d outside [0,%d)", (long long)i, group[i], n_groups);
+    }
+    DeviceGuard g(ctx->device);
+    DDM_CUDA(ctx, ctx->group.reserve(n ? (size_t)n : 1));
+    DDM_CUDA(ctx, ctx->bound.reserve(n ? (size_t)n : 1));
+    DDM_CUDA(ctx, ctx->params.reserve(n_groups ? (size_t)n_groups * 4 : 1));
+    ctx->have_params = false;  // the params arena now holds group parameters
+    if (n) {
+        DDM_CUDA(ctx, cudaMemcpyAsync(ctx->group.p, group, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        DDM_CUDA(ctx, cudaMemcpyAsync(ctx->bound.p, bound, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        DDM_CUDA(ctx, cudaMemcpyAsync(ctx->params.p, group_params, (size_t)n_groups * 4 * sizeof(double), cudaMemcpyHostToDevice,
+                                      ctx->stream));
+    }
+    int rc = run_common(ctx, DDM_MODEL_TRIALWISE, 1, n, dt, max_steps, seed, 0, trial_offset, precision, flags, n_groups);
+    if (rc) return rc;
+    if (out_host) return ddm_download(ctx, out_host);
+    return DDM_OK;
+}
+
+DDM_API int ddm_last_steps(ddm_ctx *ctx, int32_t *steps_host) {
+    if (!ctx) return DDM_ERR_INVALID;
+    if (!ctx->have_run || !ctx->have_steps) return fail(ctx, DDM_ERR_STATE, "last run did not keep step counts (DDM_FLAG_KEEP_STEPS)");
+    DeviceGuard g(ctx->device);
+    if (ctx->run_rows)
+        DDM_CUDA(ctx, cudaMemcpyAsync(steps_host, ctx->steps.p, (size_t)ctx->run_rows * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    DDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DDM_OK;
+}
+
+DDM_API int ddm_last_stats(ddm_ctx *ctx, ddm_stats *out) {
+    if (!ctx || !out) return DDM_ERR_INVALID;
+    if (!ctx->have_run) return fail(ctx, DDM_ERR_STATE, "no run yet");
+    DeviceGuard g(ctx->device);
+    int rc = finish_stats(ctx);
+    if (rc) return rc;
+    *out = ctx->stats;
+    return DDM_OK;
+}
+
+DDM_API int ddm_last_output_device_ptr(ddm_ctx *ctx, void **ptr, size_t *bytes) {
+    if (!ctx || !ptr) return DDM_ERR_INVALID;
+    if (!ctx->have_run || !ctx->out) return fail(ctx, DDM_ERR_STATE, "no output resident");
+    *ptr = ctx->out;
+    if (bytes) *bytes = ctx->out_bytes;
+    return DDM_OK;
+}
+
+DDM_API int ddm_last_output_dlpack(ddm_ctx *ctx, struct DLManagedTensor **out) {
+    if (!ctx || !out) return DDM_ERR_INVALID;
+    if (!ctx->have_run || !ctx->out) return fail(ctx, DDM_ERR_STATE, "no output resident (already handed off?)");
+    DeviceGuard g(ctx->device);
+    DDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    auto *h = new (std::nothrow) DlpackHolder();
+    if (!h) return fail(ctx, DDM_ERR_NOMEM, "out of host memory");
+    h->buf = ctx->out;
+    h->cap = ctx->out_cap;
+    h->pool = ctx->pool;
+    ctx->pool->refs.fetch_add(1);
+    DLTensor &t = h->t.dl_tensor;
+    t.data = ctx->out;
+    t.device.device_type = kDLCUDA;
+    t.device.device_id = ctx->device;
+    t.dtype.code = kDLFloat;
+    t.dtype.bits = ctx->out64 ? 64 : 32;
+    t.dtype.lanes = 1;
+    if (ctx->run_trialwise) {
+        t.ndim = 2;
+        h->shape[0] = ctx->run_rows;
+        h->shape[1] = 2;
+    } else {
+        t.ndim = 3;
+        h->shape[0] = ctx->run_datasets;
+        h->shape[1] = ctx->run_trials;
+        h->shape[2] = 2;
+    }
+    t.shape = h->shape;
+    t.strides = nullptr;
+    t.byte_offset = 0;
+    h->t.manager_ctx = h;
+    h->t.deleter = dlpack_deleter;
+    ctx->out = nullptr;  // ownership moved to the consumer
+    ctx->out_cap = 0;
+    *out = &h->t;
+    return DDM_OK;
+}
+
+// ---- parity hooks -------------------------------------------------------------------------
+DDM_API int ddm_set_normals_debug(ddm_ctx *ctx, const double *z, size_t n, const int64_t *offsets, int64_t n_trials) {
+    if (!ctx) return DDM_ERR_INVALID;
+    if (!z) {
+        ctx->dbg_on = false;
+        return DDM_OK;
+    }
+    if (!offsets || n_trials < 0) return fail(ctx, DDM_ERR_INVALID, "offsets required");
+    for (int64_t i = 0; i < n_trials; i++)
+        if (offsets[i] < 0 || (size_t)offsets[i] > n) return fail(ctx, DDM_ERR_INVALID, "offsets[%lld] outside the buffer", (long long)i);
+    DeviceGuard g(ctx->device);
+    DDM_CUDA(ctx, ctx->dbg_z.reserve(n ? n : 1));
+    DDM_CUDA(ctx, ctx->dbg_off.reserve(n_trials ? (size_t)n_trials : 1));
+    if (n) DDM_CUDA(ctx, cudaMemcpyAsync(ctx->dbg_z.p, z, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (n_trials)
+        DDM_CUDA(ctx, cudaMemcpyAsync(ctx->dbg_off.p, offsets, (size_t)n_trials * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    DDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->dbg_on = true;
+    ctx->dbg_n = n;
+    ctx->dbg_trials = n_trials;
+    return DDM_OK;
+}
+
+DDM_API int ddm_export_normals(ddm_ctx *ctx, uint64_t seed, uint32_t dataset, uint32_t trial, uint32_t stream,
+                               uint32_t first, uint32_t count, int precision, double *out_host) {
+    if (!ctx) return DDM_ERR_INVALID;
+    if (precision != 32 && precision != 64) return fail(ctx, DDM_ERR_INVALID, "precision must be 32 or 64");
+    if (stream > 1) return fail(ctx, DDM_ERR_INVALID, "stream must be 0 (step) or 1 (aux)");
+    if (count == 0) return DDM_OK;
+    if (!out_host) return fail(ctx, DDM_ERR_INVALID, "out_host is NULL");
+    DeviceGuard g(ctx->device);
+    DDM_CUDA(ctx, ctx->export_buf.reserve(count));
+    ddm::PhiloxKey key{(uint32_t)seed, (uint32_t)(seed >> 32)};
+    DDM_CUDA(ctx, ddm::launch_export_normals(key, dataset, trial, stream, first, count, precision == 64, ctx->export_buf.p, ctx->stream));
+    DDM_CUDA(ctx, cudaMemcpyAsync(out_host, ctx->export_buf.p, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    DDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DDM_OK;
+}
+
+DDM_API int ddm_philox4x32(ddm_ctx *ctx, const uint32_t *ctr4, const uint32_t *key2, uint32_t *out4, int64_t n_blocks) {
+    if (!ctx) return DDM_ERR_INVALID;
+    if (n_blocks < 0) return fail(ctx, DDM_ERR_INVALID, "n_blocks < 0");
+    if (n_blocks == 0) return DDM_OK;
+    if (!ctr4 || !key2 || !out4) return fail(ctx, DDM_ERR_INVALID, "NULL argument");
+    DeviceGuard g(ctx->device);
+    const size_t n = (size_t)n_blocks;
+    DDM_CUDA(ctx, ctx->philox_buf.reserve(n * 10));
+    uint32_t *d_ctr = ctx->philox_buf.p, *d_key = d_ctr + 4 * n, *d_out = d_key + 2 * n;
+    DDM_CUDA(ctx, cudaMemcpyAsync(d_ctr, ctr4, n * 16, cudaMemcpyHostToDevice, ctx->stream));
+    DDM_CUDA(ctx, cudaMemcpyAsync(d_key, key2, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    DDM_CUDA(ctx, ddm::launch_philox_blocks(d_ctr, d_key, d_out, n_blocks, ctx->stream));
+    DDM_CUDA(ctx, cudaMemcpyAsync(out4, d_out, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    DDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DDM_OK;
+}
+
+// ---- measurement ------------------------------------------------------------------------------
+DDM_API int ddm_microbench(ddm_ctx *ctx, int which, int iters, double *inst_per_s, double *sm_hz) {
+    if (!ctx) return DDM_ERR_INVALID;
+    if (which < 0 || which >= DDM_MB_COUNT) return fail(ctx, DDM_ERR_INVALID, "unknown micro-benchmark %d", which);
+    if (iters <= 0) iters = 4096;
+    DeviceGuard g(ctx->device);
+    double ips = 0, hz = 0;
+    cudaError_t e = ddm::run_microbench(which, iters, ctx->sm_count, ctx->stream, &ips, &hz);
+    if (e != cudaSuccess) return fail(ctx, DDM_ERR_CUDA, "microbench %d: %s", which, cudaGetErrorString(e));
+    if (inst_per_s) *inst_per_s = ips;
+    if (sm_hz) *sm_hz = hz;
+    return DDM_OK;
+}
+
+DDM_API int ddm_host_alloc(size_t bytes, void **ptr) {
+    if (!ptr) return DDM_ERR_INVALID;
+    *ptr = nullptr;
+    cudaError_t e = cudaMallocHost(ptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaMallocHost: ") + cudaGetErrorString(e);
+        return e == cudaErrorMemoryAllocation ? DDM_ERR_NOMEM : DDM_ERR_CUDA;
+    }
+    return DDM_OK;
+}
+
+DDM_API int ddm_host_free(void *ptr) {
+    if (!ptr) return DDM_OK;
+    return cudaFreeHost(ptr) == cudaSuccess ? DDM_OK : DDM_ERR_CUDA;
+}

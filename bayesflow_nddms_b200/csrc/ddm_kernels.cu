@@ -1,0 +1,451 @@
+// ddm_kernels.cu -- hand-written sm_100a kernels of the DDM trial simulator.
+//
+//   prep_kernel        raw fp64 parameters -> per-dataset fp32 constants
+//   persistent_kernel  production path: one lane per trial, persistent warps that
+//                      refill finished lanes from a global work counter
+//   generic_kernel     one thread per trial, naive scheduling: fp64 validation mode,
+//                      shared-increment (debug buffer) mode, the trialwise (Stahl)
+//                      variant, and the bit-exact cross-check of the persistent kernel
+//   export / philox    parity hooks
+//
+// Replaces (reference, all Python/numba): basic_ddm_dc.py:85-125,
+// single_trial_alpha_not_scaled.py:107-155, :926-974, :1237-1285, :1471-1519,
+// :1710-1722, imputation_from_stahl_not_scaled.py:120-148, :205-213.
+#include "ddm_kernels.cuh"
+
+namespace ddm {
+
+// --------------------------------------------------------------------------------
+// prep: one thread per dataset
+// --------------------------------------------------------------------------------
+__global__ void prep_kernel(const double *__restrict__ params, DsConst *__restrict__ dconst,
+                            uint32_t n_datasets, uint32_t n_params, int model, double dt) {
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n_datasets) return;
+    const double *p = params + (size_t)d * n_params;
+    DsConst c;
+#pragma unroll
+    for (int i = 0; i < 8; i++) c.v[i] = 0.f;
+    const double neg2ln2 = -1.3862943611198906188;
+    if (model == 0) {  // [drift, boundary, beta, tau, dc]
+        c.v[0] = (float)(p[0] * dt);
+        c.v[1] = (float)(p[1] * (p[2] - 0.5));
+        c.v[2] = (float)(0.5 * p[1]);
+        c.v[3] = (float)(neg2ln2 * dt * p[4] * p[4]);
+    } else if (model == 2) {  // alt: [drift, alpha, beta, ter, std_dc, mu_dc, sigma1]
+        c.v[0] = (float)(p[0] * dt);
+        c.v[1] = (float)(p[1] * (p[2] - 0.5));
+        c.v[2] = (float)(0.5 * p[1]);
+        c.v[3] = (float)p[5];
+        c.v[4] = (float)p[4];
+        c.v[5] = (float)p[6];
+    } else {  // alpha / scale / scale2: [drift, mu_alpha, beta, ter, std_alpha, dc, sigma1(, gamma)]
+        c.v[0] = (float)(p[0] * dt);
+        c.v[1] = (float)(p[2] - 0.5);
+        c.v[2] = (float)p[1];
+        c.v[3] = (float)p[4];
+        c.v[4] = (float)(neg2ln2 * dt * p[5] * p[5]);
+        c.v[5] = (float)p[6];
+        c.v[6] = (model == 3) ? (float)p[7] : (model == 4 ? 2.f : 1.f);
+    }
+    dconst[d] = c;
+}
+
+// --------------------------------------------------------------------------------
+// output store
+// --------------------------------------------------------------------------------
+template <bool OUT64>
+__device__ __forceinline__ void store_pair(void *out, uint64_t idx, double o0, double o1) {
+    if (OUT64) {
+        reinterpret_cast<double2 *>(out)[idx] = make_double2(o0, o1);
+    } else {
+        reinterpret_cast<float2 *>(out)[idx] = make_float2((float)o0, (float)o1);
+    }
+}
+
+// --------------------------------------------------------------------------------
+// persistent kernel
+// --------------------------------------------------------------------------------
+// Work item = (dataset, tile of <= `tile` consecutive trials).  A warp claims items
+// with one atomicAdd each and hands the tile's trials to lanes that need one.  All
+// lanes then advance in lock-step, four Euler steps per Philox block; lanes whose
+// trial has crossed are frozen by predication.  When at least `refill_threshold`
+// lanes are frozen the warp takes the (divergent, so deliberately batched) finish +
+// refill path.  Philox counters are (step block, trial, dataset): results do not
+// depend on which lane / warp / SM / GPU ran a trial.
+template <int KIND, bool OUT64>
+__global__ void __launch_bounds__(256) persistent_kernel(const RunArgs a) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    // warp-uniform tile cursor
+    uint32_t cur = 0, end = 0, tile_ds = 0;
+    bool more = true;
+    DsConst tile_c;
+#pragma unroll
+    for (int i = 0; i < 8; i++) tile_c.v[i] = 0.f;
+
+    // per-lane trial
+    TrialF32 t;
+    t.x = 0.f; t.h = 0.f; t.c0 = 0.f; t.k = 0.f; t.ext = 0.f;
+    float x = 0.f;
+    uint32_t n = 0, trial = 0, ds = 0;
+    bool p = false;    // stepping
+    bool has = false;  // holds a trial (stepping, or finished and waiting to be emitted)
+
+    unsigned long long acc_steps = 0;
+    uint32_t acc_timeouts = 0, acc_upper = 0, acc_cap = 0;
+
+    const int thr = a.refill_threshold;
+
+    for (;;) {
+        const unsigned idle = __ballot_sync(FULL_MASK, !p);
+        if (__popc(idle) >= thr) {
+            // ---- finish: emit every frozen trial -----------------------------------
+            if (has && !p) {
+                const int choice = (x >= t.h) ? 1 : ((x <= -t.h) ? -1 : 0);
+                const double tau = a.params[(size_t)ds * a.n_params + 3];
+                double o0, o1;
+                trial_outputs(a.model, a.flags, choice, n, a.dt, tau, (double)t.ext, o0, o1);
+                if (a.flags & 16) o1 = (double)__fadd_rn(x, t.h);
+                const uint64_t idx = (uint64_t)ds * a.n_trials + trial;
+                store_pair<OUT64>(a.out, idx, o0, o1);
+                if (a.steps_out) a.steps_out[idx] = (int32_t)n;
+                acc_steps += n;
+                acc_timeouts += (choice == 0);
+                acc_upper += (choice > 0);
+                has = false;
+            }
+            // ---- refill: hand out trials of the current tile, claiming tiles as needed
+            for (;;) {
+                const unsigned empty = __ballot_sync(FULL_MASK, !has);
+                if (empty == 0u) break;
+                if (cur == end) {
+                    if (!more) break;
+                    unsigned long long w = 0;
+                    if (lane == 0) w = atomicAdd(a.work_counter, 1ull);
+                    w = __shfl_sync(FULL_MASK, w, 0);
+                    if (w >= a.n_items) { more = false; break; }
+                    tile_ds = (uint32_t)(w / a.tiles_per_dataset);
+                    const uint32_t ti = (uint32_t)(w - (unsigned long long)tile_ds * a.tiles_per_dataset);
+                    cur = ti * a.tile;
+                    end = min(cur + a.tile, a.n_trials);
+                    const float4 *src = reinterpret_cast<const float4 *>(a.dconst + tile_ds);
+                    const float4 c0 = __ldg(src), c1 = __ldg(src + 1);
+                    tile_c.v[0] = c0.x; tile_c.v[1] = c0.y; tile_c.v[2] = c0.z; tile_c.v[3] = c0.w;
+                    tile_c.v[4] = c1.x; tile_c.v[5] = c1.y; tile_c.v[6] = c1.z; tile_c.v[7] = c1.w;
+                }
+                const uint32_t rank = __popc(empty & lt_mask);
+                const uint32_t avail = end - cur;
+                if (!has && rank < avail) {
+                    ds = tile_ds;
+                    trial = cur + rank;
+                    trial_setup_f32<KIND>(tile_c, trial + a.trial_offset, ds + a.dataset_offset, a.key, a.kdt, t,
+                                          acc_cap);
+                    x = t.x;
+                    n = 0;
+                    has = true;
+                    p = (fabsf(x) < t.h) && (a.max_steps > 0u);
+                }
+                cur += min((uint32_t)__popc(empty), avail);
+            }
+            if (!__any_sync(FULL_MASK, has)) break;
+        }
+        // ---- four Euler steps for every lane ----------------------------------------
+        step_block_f32(trial + a.trial_offset, ds + a.dataset_offset, a.key, t, x, n, p);
+        p = p && (n < a.max_steps);
+    }
+
+    // ---- per-warp statistics --------------------------------------------------------
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc_steps += __shfl_xor_sync(FULL_MASK, acc_steps, o);
+        acc_timeouts += __shfl_xor_sync(FULL_MASK, acc_timeouts, o);
+        acc_upper += __shfl_xor_sync(FULL_MASK, acc_upper, o);
+        acc_cap += __shfl_xor_sync(FULL_MASK, acc_cap, o);
+    }
+    if (lane == 0) {
+        atomicAdd(a.stats + STAT_STEPS, acc_steps);
+        atomicAdd(a.stats + STAT_TIMEOUTS, (unsigned long long)acc_timeouts);
+        atomicAdd(a.stats + STAT_UPPER, (unsigned long long)acc_upper);
+        if (acc_cap) atomicAdd(a.stats + STAT_REJECT_CAP, (unsigned long long)acc_cap);
+    }
+}
+
+// --------------------------------------------------------------------------------
+// generic kernel: one thread per trial
+// --------------------------------------------------------------------------------
+struct NormalStreamBuf {
+    const double *z, *end;
+    bool overrun;
+    __device__ __forceinline__ double next() {
+        if (z >= end) { overrun = true; return 0.0; }
+        return *z++;
+    }
+};
+
+template <typename Real, int KIND, bool BUFFER, bool OUT64>
+__global__ void __launch_bounds__(128) generic_kernel(const RunArgs a, uint64_t total) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = g < total;
+    unsigned long long acc_steps = 0;
+    uint32_t tout = 0, upper = 0, cap = 0;
+
+    if (active) {
+        uint32_t ds, trial;
+        if (KIND == KIND_TRIALWISE) {
+            ds = 0;
+            trial = (uint32_t)g;
+        } else {
+            ds = (uint32_t)(g / a.n_trials);
+            trial = (uint32_t)(g - (uint64_t)ds * a.n_trials);
+        }
+        const uint32_t ds_g = ds + a.dataset_offset, trial_g = trial + a.trial_offset;
+        const double *prm = (KIND == KIND_TRIALWISE) ? a.params + (size_t)a.group[g] * 4
+                                                     : a.params + (size_t)ds * a.n_params;
+        const double tau = (KIND == KIND_TRIALWISE) ? prm[2] : prm[3];
+        uint32_t n = 0;
+        int choice = 0;
+        double ext = 0.0, final_ev = 0.0;
+
+        if (sizeof(Real) == 4 && !BUFFER && KIND != KIND_TRIALWISE) {
+            // ---- fp32 / Philox: the persistent kernel's arithmetic, naive scheduling ----
+            const DsConst dc = a.dconst[ds];
+            TrialF32 t;
+            trial_setup_f32<(KIND == KIND_TRIALWISE ? KIND_FIXED : KIND)>(dc, trial_g, ds_g, a.key, a.kdt, t, cap);
+            float x = t.x;
+            bool p = (fabsf(x) < t.h) && (a.max_steps > 0u);
+            if ((a.max_steps & 3u) == 0u) {
+                while (p) {
+                    step_block_f32(trial_g, ds_g, a.key, t, x, n, p);
+                    p = p && (n < a.max_steps);
+                }
+            } else {
+                // max_steps not a multiple of the Philox block: step one normal at a time
+                float sA = 0, cA = 0, snA = 0, sB = 0, cB = 0, snB = 0;
+                while (p) {
+                    if ((n & 3u) == 0u) {
+                        uint32_t w[4];
+                        philox4x32<10>(n >> 2, trial_g, ds_g, STREAM_STEP, a.key.k0, a.key.k1, w);
+                        box_muller_scaled(w[0], w[1], t.k, sA, cA, snA);
+                        box_muller_scaled(w[2], w[3], t.k, sB, cB, snB);
+                    }
+                    const uint32_t j = n & 3u;
+                    const float s = (j < 2) ? sA : sB;
+                    const float tr = (j == 0) ? cA : (j == 1 ? snA : (j == 2 ? cB : snB));
+                    x = __fmaf_rn(s, tr, __fadd_rn(x, t.c0));
+                    n++;
+                    p = (fabsf(x) < t.h) && (n < a.max_steps);
+                }
+            }
+            choice = (x >= t.h) ? 1 : ((x <= -t.h) ? -1 : 0);
+            ext = (double)t.ext;
+            final_ev = (double)__fadd_rn(x, t.h);
+        } else {
+            // ---- reference arithmetic in Real (fp64: the reference's exact operation order;
+            //      fp32: the same formulas rounded to float), normals from Philox or a buffer ----
+            NormalStreamBuf buf{BUFFER ? a.dbg_z + a.dbg_off[g] : nullptr, BUFFER ? a.dbg_z + a.dbg_n : nullptr, false};
+            double zc[4];
+            uint32_t zblk = 0xffffffffu;
+            auto philox_normal = [&](uint32_t stream, uint32_t idx) -> double {
+                const uint32_t blk = (idx >> 2) | (stream << 31);  // cache tag
+                if (blk != zblk) {
+                    if (sizeof(Real) == 8) {
+                        philox_normals4_f64(idx >> 2, trial_g, ds_g, stream, a.key, zc);
+                    } else {
+                        float zf[4];
+                        philox_normals4_f32(idx >> 2, trial_g, ds_g, stream, a.key, zf);
+                        zc[0] = zf[0]; zc[1] = zf[1]; zc[2] = zf[2]; zc[3] = zf[3];
+                    }
+                    zblk = blk;
+                }
+                return zc[idx & 3u];
+            };
+            Real drift, beta, bound, dcoef, sigma1 = 0, gain = 1, latent = 0;
+            if (KIND == KIND_TRIALWISE) {
+                drift = (Real)prm[0]; beta = (Real)prm[1]; dcoef = (Real)prm[3];
+                bound = (Real)a.bound_in[g];
+                latent = bound;
+            } else if (KIND == KIND_FIXED) {
+                drift = (Real)prm[0]; bound = (Real)prm[1]; beta = (Real)prm[2]; dcoef = (Real)prm[4];
+            } else {
+                drift = (Real)prm[0]; beta = (Real)prm[2]; sigma1 = (Real)prm[6];
+                const Real mu = (KIND == KIND_BOUND) ? (Real)prm[1] : (Real)prm[5];
+                const Real sd = (Real)prm[4];
+                uint32_t i = 0;
+                for (;;) {
+                    const Real z = (Real)(BUFFER ? buf.next() : philox_normal(STREAM_AUX, 1u + i));
+                    latent = mu + sd * z;  // separate mul and add: see -fmad=false in build
+                    i++;
+                    if (latent > (Real)0) break;
+                    if (i >= 4u * REJECT_CAP_BLOCKS) { cap++; latent = (Real)1e-30; break; }
+                }
+                if (KIND == KIND_BOUND) {
+                    bound = latent; dcoef = (Real)prm[5];
+                    gain = (a.model == 3) ? (Real)prm[7] : ((a.model == 4) ? (Real)2 : (Real)1);
+                } else {
+                    bound = (Real)prm[1]; dcoef = latent; gain = (Real)1;
+                }
+            }
+            const Real dt = (Real)a.dt, sqrt_dt = (Real)a.sqrt_dt;
+            Real ev = bound * beta;
+            while ((ev > (Real)0) && (ev < bound) && (n < a.max_steps)) {
+                const Real z = (Real)(BUFFER ? buf.next() : philox_normal(STREAM_STEP, n));
+                const Real t1 = drift * dt;
+                const Real t2 = sqrt_dt * dcoef;
+                const Real t3 = t2 * z;
+                ev = ev + (t1 + t3);
+                n++;
+            }
+            choice = (ev >= bound) ? 1 : ((ev <= (Real)0) ? -1 : 0);
+            final_ev = (double)ev;
+            if (KIND == KIND_TRIALWISE) {
+                ext = (double)bound;
+            } else if (KIND != KIND_FIXED) {
+                const Real z = (Real)(BUFFER ? buf.next() : philox_normal(STREAM_AUX, 0u));
+                const Real e = gain * latent + sigma1 * z;
+                ext = (double)e;
+            }
+            if (BUFFER && buf.overrun) atomicAdd(a.stats + STAT_DBG_OVERRUN, 1ull);
+        }
+        double o0, o1;
+        trial_outputs(a.model == 5 ? 1 : a.model, a.flags, choice, n, a.dt, tau, ext, o0, o1);
+        if (a.flags & 16) o1 = final_ev;
+        store_pair<OUT64>(a.out, g, o0, o1);
+        if (a.steps_out) a.steps_out[g] = (int32_t)n;
+        acc_steps = n;
+        tout = (choice == 0);
+        upper = (choice > 0);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc_steps += __shfl_xor_sync(FULL_MASK, acc_steps, o);
+        tout += __shfl_xor_sync(FULL_MASK, tout, o);
+        upper += __shfl_xor_sync(FULL_MASK, upper, o);
+        cap += __shfl_xor_sync(FULL_MASK, cap, o);
+    }
+    if ((threadIdx.x & 31u) == 0u) {
+        atomicAdd(a.stats + STAT_STEPS, acc_steps);
+        if (tout) atomicAdd(a.stats + STAT_TIMEOUTS, (unsigned long long)tout);
+        if (upper) atomicAdd(a.stats + STAT_UPPER, (unsigned long long)upper);
+        if (cap) atomicAdd(a.stats + STAT_REJECT_CAP, (unsigned long long)cap);
+    }
+}
+
+// --------------------------------------------------------------------------------
+// parity hooks
+// --------------------------------------------------------------------------------
+__global__ void export_normals_kernel(PhiloxKey key, uint32_t dataset, uint32_t trial, uint32_t stream,
+                                      uint32_t first, uint32_t count, int f64, double *out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t idx = first + i;
+    if (f64) {
+        double z[4];
+        philox_normals4_f64(idx >> 2, trial, dataset, stream, key, z);
+        out[i] = z[idx & 3u];
+    } else {
+        float z[4];
+        philox_normals4_f32(idx >> 2, trial, dataset, stream, key, z);
+        out[i] = (double)z[idx & 3u];
+    }
+}
+
+__global__ void philox_blocks_kernel(const uint32_t *ctr, const uint32_t *key, uint32_t *out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t o[4];
+    philox4x32<10>(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], key[2 * i], key[2 * i + 1], o);
+    out[4 * i] = o[0]; out[4 * i + 1] = o[1]; out[4 * i + 2] = o[2]; out[4 * i + 3] = o[3];
+}
+
+// --------------------------------------------------------------------------------
+// launchers
+// --------------------------------------------------------------------------------
+cudaError_t launch_prep(const double *params, DsConst *dconst, uint32_t n_datasets, uint32_t n_params,
+                        int model, double dt, cudaStream_t s) {
+    const int block = 128;
+    const unsigned grid = (n_datasets + block - 1) / block;
+    prep_kernel<<<grid, block, 0, s>>>(params, dconst, n_datasets, n_params, model, dt);
+    return cudaGetLastError();
+}
+
+template <int KIND>
+static cudaError_t launch_persistent_kind(const RunArgs &a, bool out64, int grid, int block, cudaStream_t s) {
+    if (out64) persistent_kernel<KIND, true><<<grid, block, 0, s>>>(a);
+    else persistent_kernel<KIND, false><<<grid, block, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_persistent(const RunArgs &a, int kind, bool out64, int grid, int block, cudaStream_t s) {
+    switch (kind) {
+    case KIND_FIXED: return launch_persistent_kind<KIND_FIXED>(a, out64, grid, block, s);
+    case KIND_BOUND: return launch_persistent_kind<KIND_BOUND>(a, out64, grid, block, s);
+    case KIND_DC: return launch_persistent_kind<KIND_DC>(a, out64, grid, block, s);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+int persistent_max_blocks_per_sm(int kind, bool out64, int block) {
+    int nb = 0;
+    cudaError_t e = cudaErrorInvalidValue;
+#define DDM_OCC(K, O) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, persistent_kernel<K, O>, block, 0)
+    if (kind == KIND_FIXED) { if (out64) DDM_OCC(KIND_FIXED, true); else DDM_OCC(KIND_FIXED, false); }
+    else if (kind == KIND_BOUND) { if (out64) DDM_OCC(KIND_BOUND, true); else DDM_OCC(KIND_BOUND, false); }
+    else if (kind == KIND_DC) { if (out64) DDM_OCC(KIND_DC, true); else DDM_OCC(KIND_DC, false); }
+#undef DDM_OCC
+    return (e == cudaSuccess) ? nb : -1;
+}
+
+template <typename Real, int KIND, bool BUFFER>
+static cudaError_t launch_generic_3(const RunArgs &a, bool out64, uint64_t total, cudaStream_t s) {
+    const int block = 128;
+    const unsigned grid = (unsigned)((total + block - 1) / block);
+    if (grid == 0) return cudaSuccess;
+    if (out64) generic_kernel<Real, KIND, BUFFER, true><<<grid, block, 0, s>>>(a, total);
+    else generic_kernel<Real, KIND, BUFFER, false><<<grid, block, 0, s>>>(a, total);
+    return cudaGetLastError();
+}
+
+template <typename Real, int KIND>
+static cudaError_t launch_generic_2(const RunArgs &a, bool buffer_src, bool out64, uint64_t total, cudaStream_t s) {
+    return buffer_src ? launch_generic_3<Real, KIND, true>(a, out64, total, s)
+                      : launch_generic_3<Real, KIND, false>(a, out64, total, s);
+}
+
+template <typename Real>
+static cudaError_t launch_generic_1(const RunArgs &a, int kind, bool buffer_src, bool out64, uint64_t total,
+                                    cudaStream_t s) {
+    switch (kind) {
+    case KIND_FIXED: return launch_generic_2<Real, KIND_FIXED>(a, buffer_src, out64, total, s);
+    case KIND_BOUND: return launch_generic_2<Real, KIND_BOUND>(a, buffer_src, out64, total, s);
+    case KIND_DC: return launch_generic_2<Real, KIND_DC>(a, buffer_src, out64, total, s);
+    case KIND_TRIALWISE: return launch_generic_2<Real, KIND_TRIALWISE>(a, buffer_src, out64, total, s);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_generic(const RunArgs &a, int kind, bool f64, bool buffer_src, bool out64,
+                           uint64_t total_trials, cudaStream_t s) {
+    return f64 ? launch_generic_1<double>(a, kind, buffer_src, out64, total_trials, s)
+               : launch_generic_1<float>(a, kind, buffer_src, out64, total_trials, s);
+}
+
+cudaError_t launch_export_normals(PhiloxKey key, uint32_t dataset, uint32_t trial, uint32_t stream,
+                                  uint32_t first, uint32_t count, bool f64, double *out_dev, cudaStream_t s) {
+    if (count == 0) return cudaSuccess;
+    const int block = 128;
+    export_normals_kernel<<<(count + block - 1) / block, block, 0, s>>>(key, dataset, trial, stream, first,
+                                                                         count, f64 ? 1 : 0, out_dev);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_philox_blocks(const uint32_t *ctr, const uint32_t *key, uint32_t *out, int64_t n,
+                                 cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    const int block = 128;
+    philox_blocks_kernel<<<(unsigned)((n + block - 1) / block), block, 0, s>>>(ctr, key, out, n);
+    return cudaGetLastError();
+}
+
+}  // namespace ddm

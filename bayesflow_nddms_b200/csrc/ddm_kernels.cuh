@@ -1,0 +1,160 @@
+// ddm_kernels.cuh -- shared device-side definitions of the DDM simulator kernels.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "ddm_rng.cuh"
+
+namespace ddm {
+
+// Kernel families.  The model enum of include/ddm_b200.h maps onto these.
+enum Kind : int {
+    KIND_FIXED = 0,     // basic_ddm_dc: all trial constants are per-dataset
+    KIND_BOUND = 1,     // per-trial boundary redraw (single_trial_alpha*, _scale, _scale2)
+    KIND_DC = 2,        // per-trial diffusion coefficient redraw (_alt)
+    KIND_TRIALWISE = 3  // per-trial supplied boundary + gathered group params (Stahl)
+};
+
+// Per-dataset constants in fp32, prepared once per upload by prep_kernel (fp64 math,
+// rounded once).  v[] meaning per kind:
+//   FIXED: c0=drift*dt, x0=bound*(beta-.5), h=bound/2, k=-2ln2*dt*dc^2
+//   BOUND: c0, brel=beta-.5, bmu, bsd | k, ext_sd, ext_gain
+//   DC:    c0, x0, h, mu_dc | std_dc, ext_sd
+struct __align__(16) DsConst {
+    float v[8];
+};
+
+constexpr int REJECT_CAP_BLOCKS = 1024;  // 4096 candidates before giving up on a redraw loop
+
+struct RunArgs {
+    // inputs
+    const DsConst *dconst;   // [n_datasets]
+    const double *params;    // raw fp64 parameters [n_datasets * n_params] (group params for trialwise)
+    const int32_t *group;    // trialwise: [n_trials]
+    const double *bound_in;  // trialwise: [n_trials]
+    const double *dbg_z;     // shared-increment mode
+    const int64_t *dbg_off;
+    uint64_t dbg_n;          // normals in dbg_z (reads past the end return 0 and are counted)
+    // outputs
+    void *out;               // float2 / double2 per trial
+    int32_t *steps_out;      // optional
+    unsigned long long *work_counter;
+    unsigned long long *stats;  // see StatSlot
+    // shape
+    uint64_t n_items;        // persistent: number of (dataset, tile) work items
+    uint32_t n_datasets, n_trials, n_params;
+    uint32_t tiles_per_dataset, tile;
+    uint32_t dataset_offset;  // global index of dataset 0 (Philox counter word 2)
+    uint32_t trial_offset;
+    PhiloxKey key;
+    uint32_t max_steps;
+    int model;               // ddm_model
+    int flags;
+    int refill_threshold;
+    double dt, sqrt_dt;
+    float kdt;               // -2 ln2 * dt
+};
+
+constexpr unsigned FULL_MASK = 0xffffffffu;
+
+enum StatSlot { STAT_STEPS = 0, STAT_TIMEOUTS = 1, STAT_UPPER = 2, STAT_REJECT_CAP = 3, STAT_DBG_OVERRUN = 4, STAT_COUNT = 5 };
+
+// ---- fp32 trial state shared by the persistent and the generic kernels ------------
+struct TrialF32 {
+    float x;    // evidence - bound/2 (centred state: one |x| < h compare per step)
+    float h;    // bound/2
+    float c0;   // drift*dt
+    float k;    // -2 ln2 * (sqrt(dt)*dc)^2, folded into the Box-Muller radius
+    float ext;  // second output column (ext-data / boundary), decided at setup
+};
+
+template <int KIND>
+__device__ __forceinline__ void trial_setup_f32(const DsConst &dc, uint32_t trial, uint32_t ds_global,
+                                                PhiloxKey key, float kdt, TrialF32 &t, uint32_t &cap_hits) {
+    t.c0 = dc.v[0];
+    if (KIND == KIND_FIXED) {
+        t.x = dc.v[1];
+        t.h = dc.v[2];
+        t.k = dc.v[3];
+        t.ext = 0.f;
+        return;
+    }
+    const float mu = (KIND == KIND_BOUND) ? dc.v[2] : dc.v[3];
+    const float sd = (KIND == KIND_BOUND) ? dc.v[3] : dc.v[4];
+    float z[4];
+    philox_normals4_f32(0u, trial, ds_global, STREAM_AUX, key, z);
+    const float z_ext = z[0];
+    float latent = __fmaf_rn(sd, z[1], mu);
+    if (!(latent > 0.f)) latent = __fmaf_rn(sd, z[2], mu);
+    if (!(latent > 0.f)) latent = __fmaf_rn(sd, z[3], mu);
+    for (uint32_t j = 1; !(latent > 0.f); j++) {
+        if (j >= REJECT_CAP_BLOCKS) {
+            cap_hits++;
+            latent = 1e-30f;
+            break;
+        }
+        philox_normals4_f32(j, trial, ds_global, STREAM_AUX, key, z);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (!(latent > 0.f)) latent = __fmaf_rn(sd, z[i], mu);
+    }
+    if (KIND == KIND_BOUND) {
+        t.h = __fmul_rn(0.5f, latent);
+        t.x = __fmul_rn(latent, dc.v[1]);
+        t.k = dc.v[4];
+        t.ext = __fmaf_rn(dc.v[5], z_ext, __fmul_rn(dc.v[6], latent));
+    } else {  // KIND_DC
+        t.x = dc.v[1];
+        t.h = dc.v[2];
+        t.k = __fmul_rn(kdt, __fmul_rn(latent, latent));
+        t.ext = __fmaf_rn(dc.v[5], z_ext, latent);
+    }
+}
+
+// Four predicated Euler steps from one Philox block.  `p` = "still inside the
+// boundaries"; a lane whose p is false is frozen (x, n keep their crossing values).
+__device__ __forceinline__ void step_block_f32(uint32_t trial, uint32_t ds_global, PhiloxKey key,
+                                               const TrialF32 &t, float &x, uint32_t &n, bool &p) {
+    uint32_t w[4];
+    philox4x32<10>(n >> 2, trial, ds_global, STREAM_STEP, key.k0, key.k1, w);
+    float sA, cA, snA, sB, cB, snB;
+    box_muller_scaled(w[0], w[1], t.k, sA, cA, snA);
+    box_muller_scaled(w[2], w[3], t.k, sB, cB, snB);
+    if (p) { x = __fmaf_rn(sA, cA, __fadd_rn(x, t.c0)); n++; }
+    p = p && (fabsf(x) < t.h);
+    if (p) { x = __fmaf_rn(sA, snA, __fadd_rn(x, t.c0)); n++; }
+    p = p && (fabsf(x) < t.h);
+    if (p) { x = __fmaf_rn(sB, cB, __fadd_rn(x, t.c0)); n++; }
+    p = p && (fabsf(x) < t.h);
+    if (p) { x = __fmaf_rn(sB, snB, __fadd_rn(x, t.c0)); n++; }
+    p = p && (fabsf(x) < t.h);
+}
+
+// Final outputs of a finished fp32 trial, computed in fp64 with the reference's operation
+// order so that, given the same step count, col0 equals the reference's double exactly
+// (basic_ddm_dc.py:103  rt = n_steps*dt + tau;  single_trial_alpha_not_scaled.py:127,133-138).
+__device__ __forceinline__ void trial_outputs(int model, int flags, int choice, uint32_t n, double dt,
+                                              double tau, double ext, double &o0, double &o1) {
+    const double rt = __dmul_rn((double)n, dt);
+    if (model == 0) {  // DDM_MODEL_BASIC
+        o0 = __dadd_rn(rt, tau);
+        o1 = (choice == 0) ? ((flags & 1) ? 1.0 : 0.0) : (double)choice;
+    } else {
+        o0 = (choice > 0) ? __dadd_rn(tau, rt) : (choice < 0 ? __dsub_rn(-tau, rt) : 0.0);
+        o1 = ext;
+    }
+}
+
+// launchers (ddm_kernels.cu)
+cudaError_t launch_prep(const double *params, DsConst *dconst, uint32_t n_datasets, uint32_t n_params,
+                        int model, double dt, cudaStream_t s);
+cudaError_t launch_persistent(const RunArgs &a, int kind, bool out64, int grid, int block, cudaStream_t s);
+cudaError_t launch_generic(const RunArgs &a, int kind, bool f64, bool buffer_src, bool out64,
+                           uint64_t total_trials, cudaStream_t s);
+cudaError_t launch_export_normals(PhiloxKey key, uint32_t dataset, uint32_t trial, uint32_t stream,
+                                  uint32_t first, uint32_t count, bool f64, double *out_dev, cudaStream_t s);
+cudaError_t launch_philox_blocks(const uint32_t *ctr, const uint32_t *key, uint32_t *out, int64_t n,
+                                 cudaStream_t s);
+int persistent_max_blocks_per_sm(int kind, bool out64, int block);
+
+}  // namespace ddm

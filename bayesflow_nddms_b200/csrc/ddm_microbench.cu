@@ -1,0 +1,144 @@
+// ddm_microbench.cu -- measures the per-pipe issue rates the DDM kernel's roofline is quoted
+// against ("measure them on the box with micro-benchmarks before claiming
+// a roofline").  Every kernel runs 8 blocks x 256 threads per SM (64 resident warps, the
+// simulator's own occupancy class) with 8 independent dependency chains per thread.
+#include <cstdint>
+
+#include "../../include/ddm_b200.h"
+#include "ddm_kernels.cuh"
+#include "ddm_microbench.cuh"
+
+namespace ddm {
+
+constexpr int MB_CHAINS = 8;
+constexpr int MB_UNROLL = 4;  // body = MB_CHAINS * MB_UNROLL measured instructions
+
+struct MbOut {
+    unsigned long long *cycles;  // per block
+    uint32_t *sink;
+};
+
+template <int WHICH>
+__global__ void __launch_bounds__(256) microbench_kernel(int iters, uint32_t seed, float fa, float fb, MbOut o) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t xi[MB_CHAINS];
+    float xf[MB_CHAINS];
+    uint64_t xl[MB_CHAINS];
+#pragma unroll
+    for (int c = 0; c < MB_CHAINS; c++) {
+        xi[c] = tid * 2654435761u + seed + c;
+        xf[c] = 1.0f + (float)((tid + c) & 1023) * 9.765625e-4f;
+        xl[c] = ((uint64_t)xi[c] << 32) | (xi[c] ^ 0x9e3779b9u);
+    }
+    const uint32_t ka = seed | 1u, kb = seed * 31u + 7u;
+    uint32_t acc = 0;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < MB_UNROLL; u++) {
+#pragma unroll
+            for (int c = 0; c < MB_CHAINS; c++) {
+                if (WHICH == DDM_MB_FFMA) {
+                    xf[c] = __fmaf_rn(xf[c], fa, fb);
+                } else if (WHICH == DDM_MB_IMAD_WIDE) {
+                    xl[c] = (uint64_t)(uint32_t)xl[c] * (uint64_t)PHILOX_M0 + xl[c];
+                } else if (WHICH == DDM_MB_LOP3) {
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(xi[c]) : "r"(ka), "r"(kb));
+                } else if (WHICH == DDM_MB_IADD3) {
+                    asm volatile("{ .reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2; }" : "+r"(xi[c]) : "r"(ka), "r"(kb));
+                } else if (WHICH == DDM_MB_MUFU_LG2) {
+                    asm volatile("lg2.approx.ftz.f32 %0, %0;" : "+f"(xf[c]));
+                } else if (WHICH == DDM_MB_MUFU_SIN) {
+                    asm volatile("sin.approx.ftz.f32 %0, %0;" : "+f"(xf[c]));
+                } else if (WHICH == DDM_MB_MIX_FMA_ALU) {
+                    if (c & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(xi[c]) : "r"(ka), "r"(kb));
+                    else xf[c] = __fmaf_rn(xf[c], fa, fb);
+                } else if (WHICH == DDM_MB_FSETP) {
+                    asm volatile("{ .reg .pred p; setp.lt.f32 p, %1, %2; @p add.u32 %0, %0, 1; }" : "+r"(xi[c]) : "f"(xf[c]), "f"(fa));
+                }
+            }
+        }
+        if (WHICH == DDM_MB_PHILOX) {
+            uint32_t w[4];
+            philox4x32<10>((uint32_t)it, tid, xi[0], 0u, ka, kb, w);
+            xi[0] ^= w[0] ^ w[1] ^ w[2] ^ w[3];
+        } else if (WHICH == DDM_MB_NORMALS) {
+            // the simulator's own inner block: Philox -> 4 scaled normals -> 4 predicated Euler steps
+            TrialF32 t;
+            t.h = 3.4e38f; t.c0 = fb; t.k = fa; t.x = 0.f; t.ext = 0.f;
+            uint32_t n = (uint32_t)it * 4u;
+            bool p = true;
+            step_block_f32(tid, xi[0], PhiloxKey{ka, kb}, t, xf[0], n, p);
+            acc += n;
+        }
+    }
+    const long long t1 = clock64();
+#pragma unroll
+    for (int c = 0; c < MB_CHAINS; c++) acc ^= xi[c] ^ __float_as_uint(xf[c]) ^ (uint32_t)xl[c] ^ (uint32_t)(xl[c] >> 32);
+    if (acc == 0x12345678u) o.sink[0] = acc;  // keeps the chains alive
+    if (threadIdx.x == 0) o.cycles[blockIdx.x] = (unsigned long long)(t1 - t0);
+}
+
+template <int WHICH>
+static cudaError_t launch_one(int grid, int iters, MbOut o, cudaStream_t s) {
+    microbench_kernel<WHICH><<<grid, 256, 0, s>>>(iters, 12345u, 1.0000001f, 1e-9f, o);
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_which(int which, int grid, int iters, MbOut o, cudaStream_t s) {
+    switch (which) {
+    case DDM_MB_FFMA: return launch_one<DDM_MB_FFMA>(grid, iters, o, s);
+    case DDM_MB_IMAD_WIDE: return launch_one<DDM_MB_IMAD_WIDE>(grid, iters, o, s);
+    case DDM_MB_LOP3: return launch_one<DDM_MB_LOP3>(grid, iters, o, s);
+    case DDM_MB_IADD3: return launch_one<DDM_MB_IADD3>(grid, iters, o, s);
+    case DDM_MB_MUFU_LG2: return launch_one<DDM_MB_MUFU_LG2>(grid, iters, o, s);
+    case DDM_MB_MUFU_SIN: return launch_one<DDM_MB_MUFU_SIN>(grid, iters, o, s);
+    case DDM_MB_MIX_FMA_ALU: return launch_one<DDM_MB_MIX_FMA_ALU>(grid, iters, o, s);
+    case DDM_MB_FSETP: return launch_one<DDM_MB_FSETP>(grid, iters, o, s);
+    case DDM_MB_PHILOX: return launch_one<DDM_MB_PHILOX>(grid, iters, o, s);
+    case DDM_MB_NORMALS: return launch_one<DDM_MB_NORMALS>(grid, iters, o, s);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t run_microbench(int which, int iters, int sm_count, cudaStream_t s, double *inst_per_s, double *sm_hz) {
+    const int grid = sm_count * 8;
+    MbOut o{};
+    cudaError_t e;
+    if ((e = cudaMalloc(&o.cycles, sizeof(unsigned long long) * grid)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&o.sink, sizeof(uint32_t))) != cudaSuccess) { cudaFree(o.cycles); return e; }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    unsigned long long *h = new unsigned long long[grid];
+    double best_s = 1e30, best_cycles = 0;
+    for (int rep = 0; rep < 4 && e == cudaSuccess; rep++) {  // rep 0 warms up
+        cudaEventRecord(e0, s);
+        e = launch_which(which, grid, iters, o, s);
+        cudaEventRecord(e1, s);
+        if (e != cudaSuccess) break;
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if ((e = cudaMemcpy(h, o.cycles, sizeof(unsigned long long) * grid, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+        unsigned long long mx = 0;
+        for (int i = 0; i < grid; i++) mx = h[i] > mx ? h[i] : mx;
+        if (rep > 0 && ms * 1e-3 < best_s) { best_s = ms * 1e-3; best_cycles = (double)mx; }
+    }
+    delete[] h;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(o.cycles);
+    cudaFree(o.sink);
+    if (e != cudaSuccess) return e;
+    const double warps = (double)grid * 256.0 / 32.0;
+    const double per_iter = (which == DDM_MB_PHILOX || which == DDM_MB_NORMALS) ? 1.0
+                          : (which == DDM_MB_MIX_FMA_ALU ? (double)(MB_CHAINS * MB_UNROLL) : (double)(MB_CHAINS * MB_UNROLL));
+    *inst_per_s = warps * (double)iters * per_iter / best_s;
+    // the kernel's longest block spans (almost) the whole launch: cycles / time = SM clock
+    *sm_hz = best_cycles / best_s;
+    return cudaSuccess;
+}
+
+}  // namespace ddm

@@ -1,0 +1,242 @@
+"""Host-side handle on the CUDA trial simulator (one ddm_ctx per instance).
+
+This is the only place that talks to the C ABI.  The model modules
+(basic_ddm_dc, single_trial_alpha_not_scaled, imputation_from_stahl_not_scaled) keep the
+reference's call signatures and delegate here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import _capi
+from .dlpack import DeviceBatch
+
+
+class DDMError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"[ddm status {status}] {message}")
+        self.status = status
+
+
+class DDMSimulator:
+    """Owns a device context.  ``seed`` keys Philox; ``dataset_counter`` is the global
+    index of the next dataset, so successive batches draw from disjoint counter ranges
+    and any batch can be regenerated from (seed, its first dataset index)."""
+
+    def __init__(self, device: int = 0, seed: int = 2023):
+        self._lib = _capi.load()
+        self._ctx = C.c_void_p()
+        rc = self._lib.ddm_create(int(device), C.byref(self._ctx))
+        if rc != _capi.OK:
+            msg = self._lib.ddm_last_error(None)
+            self._ctx = C.c_void_p()
+            raise DDMError(rc, (msg or b"").decode())
+        self.device = int(device)
+        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.dataset_counter = 0
+        self._pinned = {}
+
+    # ---- plumbing ---------------------------------------------------------------------
+    def close(self):
+        ctx, self._ctx = getattr(self, "_ctx", None), C.c_void_p()
+        if ctx:
+            for ptr, _ in self._pinned.values():
+                self._lib.ddm_host_free(ptr)
+            self._pinned = {}
+            self._lib.ddm_destroy(ctx)
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc == _capi.OK:
+            return
+        msg = (self._lib.ddm_last_error(self._ctx) or b"").decode()
+        if rc == _capi.ERR_NEGATIVE_BOUND:
+            # imputation_from_stahl_not_scaled.py:124-125 raises ValueError
+            raise ValueError(msg)
+        if rc == _capi.ERR_INVALID:
+            raise ValueError(msg)
+        raise DDMError(rc, msg)
+
+    def set_tuning(self, refill_threshold: int = 0, blocks_per_sm: int = 0, tile: int = 0):
+        self._check(self._lib.ddm_set_tuning(self._ctx, refill_threshold, blocks_per_sm, tile))
+
+    def set_stream(self, cuda_stream_ptr: int | None):
+        self._check(self._lib.ddm_set_stream(self._ctx, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def synchronize(self):
+        self._check(self._lib.ddm_synchronize(self._ctx))
+
+    def pinned_empty(self, shape, dtype=np.float64, slot: str = "out") -> np.ndarray:
+        """A numpy array over page-locked host memory, reused per slot (full-rate D2H)."""
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+        ptr, cap = self._pinned.get(slot, (None, 0))
+        if cap < nbytes:
+            if ptr:
+                self._lib.ddm_host_free(ptr)
+            p = C.c_void_p()
+            rc = self._lib.ddm_host_alloc(max(nbytes, 1), C.byref(p))
+            if rc != _capi.OK:
+                raise DDMError(rc, "pinned host allocation failed")
+            ptr, cap = p, max(nbytes, 1)
+            self._pinned[slot] = (ptr, cap)
+        buf = (C.c_char * max(nbytes, 1)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
+
+    # ---- the hot path -----------------------------------------------------------------
+    def _next_offset(self, n_datasets: int, dataset_offset):
+        if dataset_offset is None:
+            dataset_offset = self.dataset_counter
+            self.dataset_counter += int(n_datasets)
+        return int(dataset_offset)
+
+    def run(self, model: int, params, n_trials: int, dt: float = 0.01, max_steps: int = 400, *, seed=None,
+            dataset_offset=None, precision: int = 32, flags: int = 0):
+        """Upload (B, P) parameters and launch; results stay on the device."""
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        if params.ndim == 1:
+            params = params[None, :]
+        if params.ndim != 2:
+            raise ValueError("params must be (P,) or (B, P)")
+        B, P = params.shape
+        off = self._next_offset(B, dataset_offset)
+        self._check(self._lib.ddm_upload_params(self._ctx, int(model), params.ctypes.data_as(_capi._dp), B, P))
+        self._check(self._lib.ddm_run(self._ctx, int(n_trials), float(dt), int(max_steps),
+                                      self.seed if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF, off,
+                                      int(precision), int(flags)))
+        return B
+
+    def download(self, shape, f32: bool, out: np.ndarray | None = None) -> np.ndarray:
+        dtype = np.float32 if f32 else np.float64
+        if out is None:
+            out = np.empty(shape, dtype=dtype)
+        elif out.dtype != dtype or out.shape != tuple(shape) or not out.flags.c_contiguous:
+            raise ValueError("out must be C-contiguous with the result's shape and dtype")
+        self._check(self._lib.ddm_download(self._ctx, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def simulate(self, model: int, params, n_trials: int, dt: float = 0.01, max_steps: int = 400, *, seed=None,
+                 dataset_offset=None, precision: int = 32, flags: int = 0, out: np.ndarray | None = None) -> np.ndarray:
+        """B datasets x n_trials -> numpy (B, n_trials, 2), float64 unless FLAG_OUT_F32."""
+        B = self.run(model, params, n_trials, dt, max_steps, seed=seed, dataset_offset=dataset_offset,
+                     precision=precision, flags=flags)
+        return self.download((B, int(n_trials), 2), bool(flags & _capi.FLAG_OUT_F32), out)
+
+    def simulate_device(self, model: int, params, n_trials: int, dt: float = 0.01, max_steps: int = 400, *,
+                        seed=None, dataset_offset=None, precision: int = 32, flags: int = _capi.FLAG_OUT_F32) -> DeviceBatch:
+        """Same, but the batch stays in HBM and is returned as a DLPack producer."""
+        self.run(model, params, n_trials, dt, max_steps, seed=seed, dataset_offset=dataset_offset,
+                 precision=precision, flags=flags)
+        return self.last_output_dlpack()
+
+    def simulate_trialwise(self, group, bound, group_params, dt: float = 0.01, max_steps: int = 400, *, seed=None,
+                           trial_offset: int = 0, precision: int = 32, flags: int = 0, device: bool = False):
+        """Per-trial supplied boundary, parameters gathered by group (Stahl imputation)."""
+        group = np.ascontiguousarray(group, dtype=np.int32).ravel()
+        bound = np.ascontiguousarray(bound, dtype=np.float64).ravel()
+        group_params = np.ascontiguousarray(group_params, dtype=np.float64)
+        if group_params.ndim == 1:
+            group_params = group_params[None, :]
+        if group_params.ndim != 2 or group_params.shape[1] != 4:
+            raise ValueError("group_params must be (G, 4) = (drift, beta, ter, dc)")
+        if group.size != bound.size:
+            raise ValueError("group and bound must have one entry per trial")
+        n = group.size
+        f32 = bool(flags & _capi.FLAG_OUT_F32)
+        out = None if device else np.empty((n, 2), dtype=np.float32 if f32 else np.float64)
+        self._check(self._lib.ddm_simulate_trialwise(
+            self._ctx, group.ctypes.data_as(C.POINTER(C.c_int32)), bound.ctypes.data_as(_capi._dp),
+            group_params.ctypes.data_as(_capi._dp), n, group_params.shape[0], float(dt), int(max_steps),
+            self.seed if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF, int(trial_offset), int(precision),
+            int(flags), None if device else out.ctypes.data_as(C.c_void_p)))
+        return self.last_output_dlpack() if device else out
+
+    # ---- results of the last run --------------------------------------------------------
+    def last_output_dlpack(self) -> DeviceBatch:
+        m = C.POINTER(_capi.DLManagedTensor)()
+        self._check(self._lib.ddm_last_output_dlpack(self._ctx, C.byref(m)))
+        t = m.contents.dl_tensor
+        shape = [t.shape[i] for i in range(t.ndim)]
+        return DeviceBatch(m, shape, t.dtype.bits, t.device.device_id)
+
+    def last_output_device_ptr(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._check(self._lib.ddm_last_output_device_ptr(self._ctx, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def last_steps(self, n: int) -> np.ndarray:
+        out = np.empty(int(n), dtype=np.int32)
+        self._check(self._lib.ddm_last_steps(self._ctx, out.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out
+
+    def last_stats(self) -> dict:
+        st = _capi.Stats()
+        self._check(self._lib.ddm_last_stats(self._ctx, C.byref(st)))
+        return st.as_dict()
+
+    # ---- parity hooks ---------------------------------------------------------------------
+    def set_normals_debug(self, z, offsets):
+        """Shared-increment mode: trial t consumes z[offsets[t]:] in the reference's order."""
+        if z is None:
+            self._check(self._lib.ddm_set_normals_debug(self._ctx, None, 0, None, 0))
+            return
+        z = np.ascontiguousarray(z, dtype=np.float64).ravel()
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64).ravel()
+        self._check(self._lib.ddm_set_normals_debug(self._ctx, z.ctypes.data_as(_capi._dp), z.size,
+                                                    offsets.ctypes.data_as(C.POINTER(C.c_int64)), offsets.size))
+
+    def export_normals(self, dataset: int, trial: int, stream: int, first: int, count: int, *, seed=None,
+                       precision: int = 32) -> np.ndarray:
+        out = np.empty(int(count), dtype=np.float64)
+        self._check(self._lib.ddm_export_normals(self._ctx, self.seed if seed is None else int(seed), int(dataset),
+                                                 int(trial), int(stream), int(first), int(count), int(precision),
+                                                 out.ctypes.data_as(_capi._dp)))
+        return out
+
+    def philox4x32(self, ctr, key) -> np.ndarray:
+        ctr = np.ascontiguousarray(ctr, dtype=np.uint32).reshape(-1, 4)
+        key = np.ascontiguousarray(key, dtype=np.uint32).reshape(-1, 2)
+        if key.shape[0] != ctr.shape[0]:
+            raise ValueError("one key per counter")
+        out = np.empty_like(ctr)
+        u32p = C.POINTER(C.c_uint32)
+        self._check(self._lib.ddm_philox4x32(self._ctx, ctr.ctypes.data_as(u32p), key.ctypes.data_as(u32p),
+                                             out.ctypes.data_as(u32p), ctr.shape[0]))
+        return out
+
+    def microbench(self, which: int, iters: int = 4096):
+        ips, hz = C.c_double(), C.c_double()
+        self._check(self._lib.ddm_microbench(self._ctx, int(which), int(iters), C.byref(ips), C.byref(hz)))
+        return ips.value, hz.value
+
+
+_default = None
+_default_lock = threading.Lock()
+
+
+def default_simulator() -> DDMSimulator:
+    """Process-wide simulator on the current rank's GPU (LOCAL_RANK, else device 0)."""
+    import os
+
+    global _default
+    with _default_lock:
+        if _default is None:
+            _default = DDMSimulator(device=int(os.environ.get("LOCAL_RANK", "0")),
+                                    seed=int(os.environ.get("DDM_SEED", "2023")))
+        return _default
+
+
+def set_default_simulator(sim: DDMSimulator | None):
+    global _default
+    with _default_lock:
+        _default = sim

@@ -1,0 +1,169 @@
+/*
+ * ddm_b200.h -- C ABI of the B200-native drift-diffusion trial simulator.
+ *
+ * Drop-in boundary for the data-parallel hot path of mdnunez/bayesflow_nddms.
+ * The reference has no FFI of its own (it is pure Python + numba); the operator
+ * interface this library sits behind is BayesFlow 1.1's simulation API as the
+ * reference uses it (basic_ddm_dc.py:130-134).  Each entry point below names
+ * the reference callable it replaces.  Python binds these with ctypes
+ * (bayesflow_nddms_b200/_capi.py); INTEGRATION.md shows the stub.
+ *
+ * Conventions: every function returns 0 (DDM_OK) or a negative ddm_status and
+ * never throws or exits; ddm_last_error(ctx) holds the message.  One ctx per
+ * host thread / rank; functions on distinct ctx are concurrency-safe; there is
+ * no global mutable state.  Host pointers are plain C arrays; no torch types.
+ * Device work is enqueued on the ctx stream (ddm_set_stream to borrow one).
+ */
+#ifndef DDM_B200_H
+#define DDM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDM_B200_VERSION 100
+
+typedef struct ddm_ctx ddm_ctx;
+struct DLManagedTensor; /* include/ddm_dlpack.h (DLPack v0.8 ABI) */
+
+/* Simulator variants.  Parameter vectors keep the reference's order. */
+enum ddm_model {
+    /* basic_ddm_dc.py:85-125.  params[5] = drift, boundary, beta, tau, dc.
+       out = (rt = n*dt + tau, choice in {+1,-1, 0|1 on timeout}) */
+    DDM_MODEL_BASIC = 0,
+    /* single_trial_alpha_not_scaled.py:107-155.  params[7] = drift, mu_alpha,
+       beta, ter, std_alpha, dc, sigma1.  out = (signed choicert, extdata1) */
+    DDM_MODEL_ALPHA = 1,
+    /* :926-974 (diffusion_trial_alt): params[7] = drift, alpha, beta, ter,
+       std_dc, mu_dc, sigma1; per-trial dc; extdata1 = N(dc_trial, sigma1) */
+    DDM_MODEL_ALPHA_DC = 2,
+    /* :1237-1285 (_scale): params[8] = M1 + gamma; extdata1 = N(gamma*bound, sigma1) */
+    DDM_MODEL_ALPHA_SCALE = 3,
+    /* :1471-1519 (_scale2): params[7]; extdata1 = N(2*bound, sigma1) */
+    DDM_MODEL_ALPHA_SCALE2 = 4,
+    /* imputation_from_stahl_not_scaled.py:120-148: per-trial supplied boundary,
+       per-group params[4] = drift, beta, ter, dc.  out = (signed choicert, bound) */
+    DDM_MODEL_TRIALWISE = 5
+};
+
+enum ddm_status {
+    DDM_OK = 0,
+    DDM_ERR_INVALID = -1,        /* bad argument */
+    DDM_ERR_CUDA = -2,           /* CUDA runtime error (message in ddm_last_error) */
+    DDM_ERR_NOMEM = -3,
+    DDM_ERR_NEGATIVE_BOUND = -4, /* the reference raises ValueError (imputation...:124-125) */
+    DDM_ERR_STATE = -5           /* call order (e.g. download before run) */
+};
+
+enum ddm_flags {
+    /* basic_ddm_dc.py:110-112 leaves `choice` unbound on a timeout; under numba
+       0.65 the trial then reports choice = 1.  Default here is 0 (the author's
+       stated intent, and what every other variant does); this flag reproduces
+       the numba artefact. */
+    DDM_FLAG_TIMEOUT_CHOICE_ONE = 1,
+    DDM_FLAG_OUT_F32 = 2,      /* outputs are float32 pairs (configurator dtype) instead of float64 */
+    DDM_FLAG_KEEP_STEPS = 4,   /* also record int32 Euler-step counts per trial */
+    DDM_FLAG_FORCE_GENERIC = 8, /* use the one-thread-per-trial kernel (validation) */
+    DDM_FLAG_OUT_STATE = 16     /* validation: column 1 := the trial's final evidence (reference frame) */
+};
+
+typedef struct ddm_stats {
+    uint64_t n_trials;       /* trials simulated by the last run */
+    uint64_t total_steps;    /* Euler steps executed (sum of per-trial n) */
+    uint64_t n_timeouts;     /* trials that hit max_steps */
+    uint64_t n_upper;        /* trials absorbed at the upper boundary */
+    uint64_t reject_cap_hits;/* per-trial redraw loops that hit the iteration cap */
+    double kernel_ms;        /* CUDA-event time of the simulator kernel(s), launching stream */
+    int32_t kernel_launches; /* kernels of this library launched by the last run */
+    int32_t used_persistent; /* 1 if the persistent refill kernel ran, 0 if generic */
+    int32_t grid, block, refill_threshold, tile;
+    uint64_t debug_overruns; /* shared-increment mode: trials that ran past the normals buffer */
+} ddm_stats;
+
+/* ---- lifecycle -------------------------------------------------------- */
+int ddm_version(void);
+int ddm_create(int device, ddm_ctx **out);
+int ddm_destroy(ddm_ctx *ctx);
+const char *ddm_last_error(const ddm_ctx *ctx); /* ctx may be NULL: last create error */
+int ddm_set_stream(ddm_ctx *ctx, void *cuda_stream); /* NULL restores the ctx-owned stream */
+int ddm_synchronize(ddm_ctx *ctx);
+/* tuning knobs; 0 = automatic */
+int ddm_set_tuning(ddm_ctx *ctx, int refill_threshold, int blocks_per_sm, int tile);
+
+/* ---- the hot path ------------------------------------------------------ */
+/* Replaces B calls of simulate_trials(params[b], n_trials)  (basic_ddm_dc.py:114-125,
+ * single_trial_alpha_not_scaled.py:144-155 and the _alt/_scale/_scale2/_fine variants),
+ * i.e. BayesFlow's batch_simulator_fun contract: params (B,P) f64 host ->
+ * out_host (B, n_trials, 2) f64 (or f32 with DDM_FLAG_OUT_F32).  out_host may be
+ * NULL: results stay on the device (ddm_last_output_dlpack / ddm_download).
+ * dt, max_steps: the reference's default kwargs (.01, 400).  Philox key = seed;
+ * counters = (step block, trial, dataset_offset + b, stream), so the result of
+ * dataset b does not depend on how datasets are sharded over GPUs.
+ * precision: 32 (production) or 64 (validation; reference operation order). */
+int ddm_simulate(ddm_ctx *ctx, int model, const double *params, int64_t n_datasets, int n_params,
+                 int64_t n_trials, double dt, int max_steps, uint64_t seed, uint64_t dataset_offset,
+                 int precision, int flags, void *out_host);
+
+/* The same in three steps, for callers that keep inputs/outputs resident. */
+int ddm_upload_params(ddm_ctx *ctx, int model, const double *params, int64_t n_datasets, int n_params);
+int ddm_run(ddm_ctx *ctx, int64_t n_trials, double dt, int max_steps, uint64_t seed,
+            uint64_t dataset_offset, int precision, int flags);
+int ddm_download(ddm_ctx *ctx, void *out_host); /* dtype as chosen by the run's flags */
+
+/* Replaces the per-row loop imputation_from_stahl_not_scaled.py:205-213:
+ * trial i uses bound[i] and group_params[group[i]] = (drift, beta, ter, dc).
+ * out_host (n, 2): col0 signed choicert, col1 the boundary used (>= 0).
+ * Any bound[i] < 0 -> DDM_ERR_NEGATIVE_BOUND, nothing is simulated.  Philox counters
+ * are (step block, trial_offset + i, 0, stream): shard by trial range with trial_offset. */
+int ddm_simulate_trialwise(ddm_ctx *ctx, const int32_t *group, const double *bound,
+                           const double *group_params, int64_t n, int n_groups, double dt,
+                           int max_steps, uint64_t seed, uint64_t trial_offset, int precision,
+                           int flags, void *out_host);
+
+/* Per-trial Euler-step counts of the last run (needs DDM_FLAG_KEEP_STEPS). */
+int ddm_last_steps(ddm_ctx *ctx, int32_t *steps_host);
+int ddm_last_stats(ddm_ctx *ctx, ddm_stats *out);
+
+/* Device hand-off of the last run's output as a DLPack tensor of shape
+ * (n_datasets, n_trials, 2) (or (n, 2) for trialwise), dtype per the run's flags,
+ * on this ctx's device.  Ownership of the buffer moves to the consumer; its
+ * deleter frees it.  The producer stream is synchronised before return. */
+int ddm_last_output_dlpack(ddm_ctx *ctx, struct DLManagedTensor **out);
+/* Raw device pointer of the last output (borrowed; valid until the next run). */
+int ddm_last_output_device_ptr(ddm_ctx *ctx, void **ptr, size_t *bytes);
+
+/* ---- parity / validation hooks ----------------------------------------- */
+/* Shared-increment mode: subsequent runs read standard normals from this buffer
+ * instead of Philox.  Trial t (flat index dataset*n_trials + trial) consumes
+ * z[offsets[t]], z[offsets[t]+1], ... in the reference's order (pre-draws, steps,
+ * ext).  z == NULL switches the mode off.  Forces the generic kernel. */
+int ddm_set_normals_debug(ddm_ctx *ctx, const double *z, size_t n, const int64_t *offsets, int64_t n_trials);
+/* The normals the production (precision 32) or validation (64) kernels use for
+ * counters (dataset, trial, stream), indices first..first+count-1, as doubles. */
+int ddm_export_normals(ddm_ctx *ctx, uint64_t seed, uint32_t dataset, uint32_t trial, uint32_t stream,
+                       uint32_t first, uint32_t count, int precision, double *out_host);
+/* Raw Philox4x32-10 blocks computed on the device (known-answer tests). */
+int ddm_philox4x32(ddm_ctx *ctx, const uint32_t *ctr4, const uint32_t *key2, uint32_t *out4, int64_t n_blocks);
+
+/* ---- measurement -------------------------------------------------------- */
+/* Pipe micro-benchmarks for the issue roofline.  which: see ddm_microbench_id.
+ * Returns warp-instructions (of the measured kind) per second chip-wide in
+ * *inst_per_s and the SM clock seen (cycles/s from clock64 over event time). */
+enum ddm_microbench_id {
+    DDM_MB_FFMA = 0, DDM_MB_IMAD_WIDE = 1, DDM_MB_LOP3 = 2, DDM_MB_IADD3 = 3,
+    DDM_MB_MUFU_LG2 = 4, DDM_MB_MUFU_SIN = 5, DDM_MB_MIX_FMA_ALU = 6, DDM_MB_FSETP = 7,
+    DDM_MB_PHILOX = 8, DDM_MB_NORMALS = 9, DDM_MB_COUNT = 10
+};
+int ddm_microbench(ddm_ctx *ctx, int which, int iters, double *inst_per_s, double *sm_hz);
+
+/* pinned host memory helpers (for callers that want full-rate D2H) */
+int ddm_host_alloc(size_t bytes, void **ptr);
+int ddm_host_free(void *ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDM_B200_H */
