@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the DDM trial simulator hot path (BASELINE.json metric).
+
+A "step" = one pass of the hot path over one batch of synthetic prior draws:
+the throughput-sweep configuration C5: D datasets x 1000 trials of the
+basic dcDDM, broad prior, tau = 0, dt = 1e-3, max_steps = 4000 (mean ~258 Euler steps/trial,
+heavy-tailed).  Default D = 1 000 000 per GPU (1e9 trials per step per GPU), weak scaling:
+every rank simulates its own D datasets at disjoint global dataset indices (disjoint Philox
+counter ranges), no data-path collective.
+
+  value     Euler steps/s, whole job, parameters resident in HBM, output left in HBM
+  e2e       same metric through the reference-facing call
+            basic_ddm_dc.batch_simulate_trials(params_host, n_trials) -> (B, N, 2) float64
+            host array: H2D of the parameters, kernel, D2H of the batch, all inside the timed region
+  roofline  issue-slot roofline of the persistent kernel (not HBM, not tensor: no contraction)
+  cpu_baseline  the CPU oracle port of the reference's numba loop on this box's host cores
+
+`--impl reference` times that CPU implementation alone (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_TRIALS = 1000
+DT = 1e-3
+MAX_STEPS = 4000
+I_STEP = 28  # algorithmic issue slots per Euler step per lane
+MODEL_BASIC = 0
+FLAG_OUT_F32 = 2
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--datasets", type=int, default=1_000_000, help="datasets per GPU per step")
+    ap.add_argument("--e2e-datasets", type=int, default=0, help="datasets per GPU per e2e step (0 = same as --datasets if host memory allows)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 3)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--microbench", action="store_true", help="also measure per-pipe issue rates")
+    return ap.parse_args()
+
+
+def sweep_params(n_datasets: int, seed: int = 2023) -> np.ndarray:
+    from bayesflow_nddms_b200 import priors
+
+    return priors.draw_prior_batch("sweep", n_datasets, np.random.default_rng(seed))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks during the timed region (pynvml; same fields as the nvidia-smi recipe)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.power = [], set(), []
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    self.nv, "nvmlDeviceGetCurrentClocksEventReasons") else self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+                self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self) -> dict:
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "power_w_median": float(np.median(self.power)) if self.power else None, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's loop, all host threads
+# ------------------------------------------------------------------------------------------------
+def cpu_run(n_datasets: int, threads: int, seed: int = 7):
+    from oracle import cpu as orc
+
+    params = sweep_params(n_datasets, seed=seed)
+    t0 = time.perf_counter()
+    _, steps, _ = orc.simulate_batch_mt(MODEL_BASIC, params, N_TRIALS, seed=seed, dt=DT, max_steps=float(MAX_STEPS),
+                                        n_threads=threads, keep_output=True)
+    dt = time.perf_counter() - t0
+    return steps, n_datasets * N_TRIALS, dt
+
+
+def cpu_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_sample_size(threads: int, target_s: float) -> int:
+    """Datasets whose simulation takes about target_s on `threads` threads (calibrated)."""
+    probe = max(threads * 2, 16)
+    cpu_run(probe, threads)  # warm (page-in, thread start)
+    steps, _, dt = cpu_run(probe, threads)
+    rate = probe / max(dt, 1e-6)
+    return int(max(probe, min(rate * target_s, 2_000_000)))
+
+
+def cpu_baseline(target_s: float) -> dict:
+    threads = cpu_threads()
+    n = cpu_sample_size(threads, target_s)
+    steps, trials, dt = cpu_run(n, threads)
+    return {"value": steps / dt, "unit": "steps/s", "trials_per_s": trials / dt, "cores": threads, "kind": "port",
+            "sample": f"{n} datasets x {N_TRIALS} trials of the same prior (C oracle of the numba loop: MT19937+polar normals, "
+                      f"fp64), {threads} pthreads, {dt:.1f} s",
+            "mean_steps_per_trial": steps / trials}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cpu as orc
+
+    orc.build()
+    threads = cpu_threads()
+    per_step_s = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
+    n = cpu_sample_size(threads, per_step_s)
+    for _ in range(args.warmup):
+        cpu_run(n, threads)
+    tot_steps = tot_trials = 0
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        s, t, _ = cpu_run(n, threads, seed=100 + k)
+        tot_steps += s
+        tot_trials += t
+    el = time.perf_counter() - t0
+    val = tot_steps / el
+    line = {
+        "impl": "reference", "metric": "euler_steps_per_sec", "value": val, "unit": "steps/s",
+        "trials_per_s": tot_trials / el, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": workload_config(n, note="bounded sample per step; CPU arm runs on rank 0 only"),
+        "cpu_baseline": {"value": val, "unit": "steps/s", "cores": threads, "kind": "port",
+                         "sample": f"{n} datasets x {N_TRIALS} trials per step, {threads} pthreads"},
+        "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(datasets_per_gpu: int, note: str = "") -> dict:
+    c = {"workload": "C5 throughput sweep: basic dcDDM, broad prior (drift~N(0,2), alpha~TN(1,.5;0,10), beta~Beta(2,2), "
+                     "dc~TN(1,.5;0,10), tau=0)",
+         "datasets_per_gpu": datasets_per_gpu, "trials_per_dataset": N_TRIALS, "dt": DT, "max_steps": MAX_STEPS,
+         "parallelism": "datasets sharded by rank, disjoint Philox counter ranges, no collective"}
+    if note:
+        c["note"] = note
+    return c
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import bayesflow_nddms_b200 as pkg
+    from bayesflow_nddms_b200 import basic_ddm_dc
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    D = args.datasets
+    sim = pkg.DDMSimulator(device=local_rank, seed=2023)
+    stream = torch.cuda.Stream(device=dev)
+    sim.set_stream(stream.cuda_stream)
+    params = sweep_params(D, seed=2023 + rank)
+    ds_base = rank * D
+
+    # ---- device-resident throughput ("value") ----------------------------------------------------
+    lib, ctx = sim._lib, sim._ctx
+    sim._check(lib.ddm_upload_params(ctx, MODEL_BASIC, params.ctypes.data_as(pkg._capi._dp), D, 5))
+
+    def step(k):
+        sim._check(lib.ddm_run(ctx, N_TRIALS, DT, MAX_STEPS, sim.seed, ds_base + 0, 32, FLAG_OUT_F32))
+
+    for k in range(args.warmup):
+        step(k)
+    sim.synchronize()
+    st0 = sim.last_stats()
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms, launches = [], 0
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for k in range(args.steps):
+            step(k)
+        e1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    clk = clocks.stop()
+    elapsed_ms = max_over_ranks(e0.elapsed_time(e1))
+    st = sim.last_stats()  # every step simulates the same trials: per-step counts are identical
+    launches = st["kernel_launches"] * args.steps
+    steps_per_step = sum_over_ranks(float(st["total_steps"]))
+    trials_per_step = float(D) * N_TRIALS * world
+    value = steps_per_step * args.steps / (elapsed_ms * 1e-3)
+    trials_per_s = trials_per_step * args.steps / (elapsed_ms * 1e-3)
+
+    # dominant kernel, timed live with CUDA events on its own stream (events inside ddm_run)
+    for k in range(3):
+        step(k)
+        kernel_ms.append(sim.last_stats()["kernel_ms"])
+    k_ms = float(np.mean(kernel_ms))
+
+    # ---- roofline -----------------------------------------------------------------------------
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    f_hz = (clk.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)) * 1e6
+    issue_peak = sm_count * 4 * f_hz                           # warp-instructions/s: 1 per SMSP per clock
+    ach = st["total_steps"] * I_STEP / 32.0 / (k_ms * 1e-3)    # algorithmic warp-instructions/s of this rank's kernel
+    out_bytes = D * N_TRIALS * 8 + D * 40 + D * 32             # f32 pair out + fp64 params in + fp32 constants
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    roofline = {
+        "bound": "issue", "achieved": ach / 1e12, "peak": issue_peak / 1e12, "unit": "T warp-inst/s",
+        "frac": ach / issue_peak, "traffic": None,
+        "kernel": "ddm::persistent_kernel<KIND_FIXED, f32 out>", "kernel_ms": k_ms,
+        "steps_per_launch": st["total_steps"], "issue_slots_per_step": I_STEP,
+        "peak_how": f"{sm_count} SMs x 4 schedulers x {f_hz / 1e6:.0f} MHz (median SM clock sampled during the timed region)",
+        "steps_per_s_kernel": st["total_steps"] / (k_ms * 1e-3),
+        "hbm": {"algorithmic_bytes_per_launch": out_bytes, "achieved_gbs": out_bytes / (k_ms * 1e-3) / 1e9,
+                "peak_gbs": hbm_peak, "frac": out_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+    }
+    if args.microbench and rank == 0:
+        mb = {}
+        for i, name in enumerate(pkg._capi.MB_NAMES):
+            ips, hz = sim.microbench(i, 2048)
+            mb[name] = {"warp_inst_per_s": ips, "sm_mhz": hz / 1e6, "per_smsp_per_clk": ips / (sm_count * 4 * hz)}
+        roofline["microbench"] = mb
+
+    # ---- end to end through the reference-facing call ------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        import psutil
+
+        De = args.e2e_datasets or D
+        need = De * N_TRIALS * 16
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+        avail = psutil.virtual_memory().available
+        while De > 1000 and need * local_world * 3 > avail:
+            De //= 2
+            need = De * N_TRIALS * 16
+        pe = sweep_params(De, seed=4000 + rank)
+        out_host = sim.pinned_empty((De, N_TRIALS, 2), np.float64)
+        ke = args.e2e_steps or min(args.steps, 3)
+        basic_ddm_dc.batch_simulate_trials(pe, N_TRIALS, sim, dt=DT, max_steps=MAX_STEPS, dataset_offset=ds_base, out=out_host)
+        steps_e2e = float(sim.last_stats()["total_steps"])
+        barrier()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for k in range(ke):
+                basic_ddm_dc.batch_simulate_trials(pe, N_TRIALS, sim, dt=DT, max_steps=MAX_STEPS, dataset_offset=ds_base,
+                                                   out=out_host)
+            e1.record(stream)
+        torch.cuda.synchronize()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        tot = sum_over_ranks(steps_e2e)
+        e2e = {"value": tot * ke / (ms * 1e-3), "unit": "steps/s", "trials_per_s": De * N_TRIALS * world * ke / (ms * 1e-3),
+               "h2d_bytes_per_step": int(pe.nbytes), "d2h_bytes_per_step": int(out_host.nbytes), "steps": ke,
+               "datasets_per_gpu": De, "ms_per_step": ms / ke,
+               "api": "basic_ddm_dc.batch_simulate_trials(params (B,5) f64 host, n_trials) -> (B, n_trials, 2) f64 pinned host array"}
+        launches += sim.last_stats()["kernel_launches"] * ke
+
+    line = {
+        "metric": "euler_steps_per_sec", "value": value, "unit": "steps/s", "trials_per_s": trials_per_s,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(D, note="output 8 GB per step per GPU streams through L2 (>> 126 MB), parameters 40 MB; "
+                                          "no L2 flush needed: the kernel is issue-bound, not memory-bound"),
+        "mean_steps_per_trial": steps_per_step / trials_per_step,
+        "timeout_frac": sum_over_ranks(float(st["n_timeouts"])) / trials_per_step,
+        "kernel": {"grid": st["grid"], "block": st["block"], "refill_threshold": st["refill_threshold"], "tile": st["tile"],
+                   "persistent": bool(st["used_persistent"])},
+        "clocks": clk, "roofline": roofline, "gpu_launches": launches,
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    sim.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,374 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle
+and the committed reference outputs.  Run on a B200 with `pytest -m gpu`."""
+import numpy as np
+import pytest
+
+from conftest import VARIANT_MODEL, variant_kwargs
+
+pytestmark = pytest.mark.gpu
+
+F_TIMEOUT1, F_F32, F_STEPS, F_GENERIC, F_STATE = 1, 2, 4, 8, 16
+
+
+def _offsets(consumed):
+    off = np.zeros(consumed.size, np.int64)
+    off[1:] = np.cumsum(consumed)[:-1]
+    return off
+
+
+# --------------------------------------------------------------------------------------------
+# Philox and the normal map
+# --------------------------------------------------------------------------------------------
+def test_philox_known_answers_on_device(sim, oracle):
+    ctr = np.array([[0, 0, 0, 0], [0xffffffff] * 4, [0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344]], np.uint32)
+    key = np.array([[0, 0], [0xffffffff] * 2, [0xa4093822, 0x299f31d0]], np.uint32)
+    got = sim.philox4x32(ctr, key)
+    want = np.array([[0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8],
+                     [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd],
+                     [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]], np.uint32)
+    assert np.array_equal(got, want)
+    rng = np.random.default_rng(5)
+    ctr = rng.integers(0, 2**32, (257, 4), dtype=np.uint64).astype(np.uint32)
+    key = rng.integers(0, 2**32, (257, 2), dtype=np.uint64).astype(np.uint32)
+    got = sim.philox4x32(ctr, key)
+    want = np.stack([oracle.philox4x32_10(c, k) for c, k in zip(ctr, key)])
+    assert np.array_equal(got, want)
+
+
+def test_exported_normals_match_ideal_map(sim, oracle):
+    seed = 0x1234567890abcdef
+    for stream in (0, 1):
+        ideal = oracle.philox_normals(seed, 11, 77, stream, 3, 2001)
+        z64 = sim.export_normals(11, 77, stream, 3, 2001, seed=seed, precision=64)
+        z32 = sim.export_normals(11, 77, stream, 3, 2001, seed=seed, precision=32)
+        # fp64 map: libdevice log/sincospi vs glibc -- a few ulp
+        assert np.max(np.abs(z64 - ideal)) < 1e-13
+        # fp32 production map: MUFU lg2/sqrt/sin/cos approximations
+        assert np.max(np.abs(z32 - ideal)) < 2e-5
+        assert np.all(z32 == z32.astype(np.float32))  # exported values are the fp32 numbers
+
+
+# --------------------------------------------------------------------------------------------
+# Check #1a: fp64 kernel on shared increments == the reference's own output, bit for bit
+# --------------------------------------------------------------------------------------------
+def test_fp64_shared_increments_reproduce_reference_outputs(sim, oracle, golden):
+    z, meta = golden
+    for name, m in meta.items():
+        if name == "stahl":
+            continue
+        model = VARIANT_MODEL[m["variant"]]
+        kw = variant_kwargs(m["variant"])
+        params, n = z[f"{name}__params"], m["n_trials"]
+        flags = F_TIMEOUT1 if model == 0 else 0
+        o = oracle.simulate_mt(model, params, n, m["seed"], flags=flags, **kw)
+        total = int(o.n_steps.sum()) + 64 * n + 64
+        normals = oracle.mt_normals(m["seed"], total)
+        ob = oracle.simulate_buffer(model, params, n, normals, flags=flags, **kw)
+        sim.set_normals_debug(normals, _offsets(ob.consumed))
+        try:
+            out = sim.simulate(model, params, n, precision=64, flags=flags | F_STEPS, seed=1, dataset_offset=0, **kw)
+            steps = sim.last_steps(n)
+            st = sim.last_stats()
+            ev = sim.simulate(model, params, n, precision=64, flags=flags | F_STATE, seed=1, dataset_offset=0, **kw)
+        finally:
+            sim.set_normals_debug(None, None)
+        ref = z[f"{name}__out"]
+        assert np.array_equal(out[0].view(np.uint64), ref.view(np.uint64)), name
+        assert np.array_equal(steps, o.n_steps), name
+        assert np.array_equal(ev[0, :, 1].view(np.uint64), o.evidence.view(np.uint64)), name
+        assert st["debug_overruns"] == 0 and st["used_persistent"] == 0
+        assert st["total_steps"] == int(o.n_steps.sum())
+        assert st["n_timeouts"] == int((o.choice == 0).sum())
+
+
+def test_fp64_shared_increments_stahl(sim, oracle, golden):
+    z, meta = golden
+    m = meta["stahl"]
+    bounds, p = z["stahl__bounds"], z["stahl__params"]
+    o = oracle.simulate_mt(5, p, m["n_trials"], m["seed"], bound_in=bounds)
+    normals = oracle.mt_normals(m["seed"], int(o.n_steps.sum()) + 64)
+    ob = oracle.simulate_buffer(5, p, m["n_trials"], normals, bound_in=bounds)
+    sim.set_normals_debug(normals, _offsets(ob.consumed))
+    try:
+        out = sim.simulate_trialwise(np.zeros(bounds.size, np.int32), bounds, p[None, :], precision=64)
+    finally:
+        sim.set_normals_debug(None, None)
+    assert np.array_equal(out[:, 0].view(np.uint64), z["stahl__out"].view(np.uint64))
+    assert np.array_equal(out[:, 1], bounds)
+
+
+# --------------------------------------------------------------------------------------------
+# Check #1b: fp32 production kernel vs the reference fp64 loop on the kernel's own exported
+# increments: choices and crossing steps bit-exact except boundary ties, states within 1e-5
+# --------------------------------------------------------------------------------------------
+PROD_CASES = [
+    (0, [3.0, 1.5, 0.5, 0.4, 1.0], dict(dt=0.01, max_steps=400)),
+    (0, [-0.8, 1.1, 0.35, 0.3, 0.7], dict(dt=0.001, max_steps=4000)),
+    (0, [0.05, 4.0, 0.5, 0.3, 0.3], dict(dt=0.01, max_steps=400)),        # mostly timeouts
+    (1, [3.0, 1.5, 0.5, 0.4, 1.0, 1.0, 0.1], dict(dt=0.01, max_steps=400)),
+    (1, [0.5, 0.2, 0.4, 0.3, 2.5, 1.2, 3.0], dict(dt=0.01, max_steps=400)),  # many boundary redraws
+    (2, [-1.0, 1.0, 0.55, 0.2, 2.0, 0.3, 2.0], dict(dt=0.01, max_steps=400)),
+    (3, [3.0, 1.5, 0.5, 0.4, 1.0, 1.0, 0.1, 1.37], dict(dt=0.01, max_steps=400)),
+    (4, [1.0, 1.5, 0.6, 0.4, 0.5, 1.0, 0.1], dict(dt=0.001, max_steps=4000)),
+]
+
+
+@pytest.mark.parametrize("model,params,kw", PROD_CASES)
+def test_fp32_production_vs_reference_loop_on_exported_increments(sim, oracle, model, params, kw):
+    n, seed, ds = 384, 99, 5
+    out = sim.simulate(model, params, n, precision=32, flags=F_STEPS, seed=seed, dataset_offset=ds, **kw)[0]
+    steps = sim.last_steps(n)
+    assert sim.last_stats()["used_persistent"] == 1
+    state = sim.simulate(model, params, n, precision=32, flags=F_STATE, seed=seed, dataset_offset=ds, **kw)[0, :, 1]
+    # per-trial increments, in the reference's consumption order: pre-draws, steps, ext
+    chunks, consumed = [], []
+    for t in range(n):
+        zs = sim.export_normals(ds, t, 0, 0, int(steps[t]) + 8, seed=seed)
+        if model == 0:
+            c = [zs]
+        else:
+            aux = sim.export_normals(ds, t, 1, 0, 4097, seed=seed)
+            mu, sd = (params[5], params[4]) if model == 2 else (params[1], params[4])
+            cand = np.float32(mu) + np.float32(sd) * aux[1:].astype(np.float32)
+            k = int(np.argmax(cand > 0))          # index of the first positive candidate
+            c = [aux[1:k + 2], zs[:int(steps[t])], aux[:1]]
+            zs = None
+        chunks.append(np.concatenate(c))
+        consumed.append(chunks[-1].size)
+    normals = np.concatenate(chunks)
+    off = _offsets(np.array(consumed))
+    ref_steps = np.empty(n, np.int64)
+    ref_choice = np.empty(n, np.int32)
+    ref_ev = np.empty(n)
+    ref_out = np.empty((n, 2))
+    ref_bound = np.empty(n)
+    for t in range(n):  # one oracle call per trial so each starts at its own offset
+        r = oracle.simulate_buffer(model, params, 1, normals[off[t]:off[t] + consumed[t]], **kw)
+        ref_steps[t], ref_choice[t], ref_ev[t], ref_out[t], ref_bound[t] = (
+            r.n_steps[0], r.choice[0], r.evidence[0], r.sim_data[0], r.bound[0])
+    same = (steps == ref_steps)
+    # documented boundary ties: fp32 rounding flips a strict comparison only when the fp64
+    # path passes within rounding distance of a boundary
+    assert same.mean() >= 0.98, f"{(~same).sum()} of {n} crossing steps differ"
+    rt_col = out[:, 0]
+    if model == 0:
+        gpu_choice = out[:, 1].astype(np.int32)
+    else:
+        gpu_choice = np.sign(rt_col).astype(np.int32)
+    assert np.array_equal(gpu_choice[same], ref_choice[same])
+    # identical step count => identical reported RT bits (fp64 output arithmetic of the reference)
+    assert np.array_equal(rt_col[same].view(np.uint64), ref_out[same, 0].view(np.uint64))
+    scale = np.maximum(ref_bound, 1e-3)
+    assert np.max(np.abs(state[same] - ref_ev[same]) / scale[same]) < 1e-5
+    if model != 0:
+        assert np.max(np.abs(out[same, 1] - ref_out[same, 1])) < 1e-5 * (1 + np.max(np.abs(ref_out[:, 1])))
+
+
+# --------------------------------------------------------------------------------------------
+# Scheduling cannot change results
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("model", [0, 1, 2, 3, 4])
+def test_persistent_equals_generic_bitwise(sim, model):
+    rng = np.random.default_rng(model)
+    from bayesflow_nddms_b200 import priors
+
+    name = ["basic", "alpha", "alpha_dc", "alpha_scale", "alpha_scale2"][model]
+    params = priors.draw_prior_batch(name, 37, rng)
+    for kw in (dict(dt=0.01, max_steps=400), dict(dt=0.001, max_steps=4000)):
+        a = sim.simulate(model, params, 211, precision=32, flags=F_STEPS, seed=3, dataset_offset=10, **kw)
+        sa, st = sim.last_steps(37 * 211), sim.last_stats()
+        assert st["used_persistent"] == 1
+        b = sim.simulate(model, params, 211, precision=32, flags=F_STEPS | F_GENERIC, seed=3, dataset_offset=10, **kw)
+        sb, st2 = sim.last_steps(37 * 211), sim.last_stats()
+        assert st2["used_persistent"] == 0
+        assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+        assert np.array_equal(sa, sb)
+        for k in ("total_steps", "n_timeouts", "n_upper", "reject_cap_hits"):
+            assert st[k] == st2[k]
+        assert st["total_steps"] == int(sa.sum())
+
+
+def test_results_independent_of_tuning_and_sharding(sim):
+    from bayesflow_nddms_b200 import priors
+
+    params = priors.draw_prior_batch("basic", 64, np.random.default_rng(1))
+    base = sim.simulate(0, params, 500, seed=11, dataset_offset=1000)
+    try:
+        for thr, bps, tile in [(1, 1, 7), (32, 2, 500), (16, 0, 32), (4, 3, 1)]:
+            sim.set_tuning(thr, bps, tile)
+            again = sim.simulate(0, params, 500, seed=11, dataset_offset=1000)
+            assert np.array_equal(base, again), (thr, bps, tile)
+    finally:
+        sim.set_tuning(0, 0, 0)
+    # two "ranks": the global dataset index keys the stream, not the launch
+    lo = sim.simulate(0, params[:40], 500, seed=11, dataset_offset=1000)
+    hi = sim.simulate(0, params[40:], 500, seed=11, dataset_offset=1040)
+    assert np.array_equal(base, np.concatenate([lo, hi]))
+    other = sim.simulate(0, params, 500, seed=12, dataset_offset=1000)
+    assert not np.array_equal(base, other)
+
+
+def test_dc_scaling_is_exact_in_fp32(sim):
+    """simulations/Basic_DDM_simulations.py:164-209: (boundary, drift, dc) and (2b, 2d, 2dc) have the
+    same choice-RT law; scaling by 2 is exact in binary floating point, so with the same
+    Philox stream the trials are identical."""
+    a = sim.simulate(0, [1.5, 1.2, 0.5, 0.35, 1.0], 4000, seed=8, dataset_offset=0)
+    b = sim.simulate(0, [3.0, 2.4, 0.5, 0.35, 2.0], 4000, seed=8, dataset_offset=0)
+    assert np.array_equal(a, b)
+
+
+# --------------------------------------------------------------------------------------------
+# fp64 validation mode on the Philox stream vs the oracle on the same (ideal) stream
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("model,params,kw", PROD_CASES[:6])
+def test_fp64_philox_mode_vs_oracle(sim, oracle, model, params, kw):
+    n = 500
+    out = sim.simulate(model, params, n, precision=64, flags=F_STEPS, seed=42, dataset_offset=3, **kw)[0]
+    steps = sim.last_steps(n)
+    o = oracle.simulate_philox(model, params, n, 42, dataset=3, **kw)
+    same = steps == o.n_steps
+    assert same.mean() >= 0.998          # libdevice vs glibc transcendental ulps can flip a tie
+    assert np.array_equal(out[same, 0].view(np.uint64), o.sim_data[same, 0].view(np.uint64))
+    assert np.allclose(out[same, 1], o.sim_data[same, 1], rtol=0, atol=1e-12)
+
+
+# --------------------------------------------------------------------------------------------
+# Edge cases
+# --------------------------------------------------------------------------------------------
+def test_edge_shapes(sim):
+    p = np.array([[1.0, 1.2, 0.5, 0.3, 1.0]])
+    assert sim.simulate(0, p, 0).shape == (1, 0, 2)
+    assert sim.simulate(0, np.empty((0, 5)), 10).shape == (0, 10, 2)
+    one = sim.simulate(0, p, 1)
+    assert one.shape == (1, 1, 2) and one[0, 0, 0] >= 0.3
+    # max_steps = 0: no step is taken, every trial is a timeout at rt = tau
+    z = sim.simulate(0, p, 33, max_steps=0)
+    assert np.all(z[0, :, 0] == 0.3) and np.all(z[0, :, 1] == 0)
+    # max_steps not a multiple of the Philox block (generic kernel) keeps the same stream
+    a = sim.simulate(0, p, 300, max_steps=400, seed=5, dataset_offset=0, flags=F_STEPS)
+    sa = sim.last_steps(300)
+    b = sim.simulate(0, p, 300, max_steps=399, seed=5, dataset_offset=0, flags=F_STEPS)
+    sb = sim.last_steps(300)
+    assert sim.last_stats()["used_persistent"] == 0
+    assert np.array_equal(np.minimum(sa, 399), sb)
+    keep = sa < 399
+    assert np.array_equal(a[0, keep], b[0, keep])
+    # start point on / outside a boundary: zero steps (beta = 1 -> evidence >= boundary)
+    c = sim.simulate(0, [[1.0, 1.2, 1.0, 0.3, 1.0]], 5)
+    assert np.all(c[0, :, 0] == 0.3) and np.all(c[0, :, 1] == 1)
+    d = sim.simulate(0, [[1.0, 1.2, 0.0, 0.3, 1.0]], 5)
+    assert np.all(d[0, :, 0] == 0.3) and np.all(d[0, :, 1] == -1)
+
+
+def test_timeout_flag_and_float32_output(sim):
+    p = [0.05, 4.0, 0.5, 0.3, 0.3]
+    a = sim.simulate(0, p, 256, seed=2, dataset_offset=0)
+    b = sim.simulate(0, p, 256, seed=2, dataset_offset=0, flags=F_TIMEOUT1)
+    to = a[0, :, 1] == 0
+    assert to.sum() > 20
+    assert np.all(b[0, to, 1] == 1) and np.array_equal(a[0, ~to], b[0, ~to])
+    assert np.all(a[0, to, 0] == 400 * 0.01 + 0.3)
+    f = sim.simulate(0, p, 256, seed=2, dataset_offset=0, flags=F_F32)
+    assert f.dtype == np.float32 and np.array_equal(f, a.astype(np.float32))
+
+
+def test_argument_errors(sim):
+    with pytest.raises(ValueError):
+        sim.simulate(0, np.ones((2, 7)), 10)            # wrong parameter count
+    with pytest.raises(ValueError):
+        sim.simulate(9, np.ones((2, 5)), 10)            # unknown model
+    with pytest.raises(ValueError):
+        sim.simulate(0, np.ones((2, 5)), 10, dt=0.0)
+    with pytest.raises(ValueError):
+        sim.simulate(0, np.ones((2, 5)), 10, precision=16)
+    with pytest.raises(ValueError, match="cannot be less than zero"):
+        sim.simulate_trialwise([0, 0], [1.0, -0.5], [[3.0, 0.5, 0.4, 1.0]])
+    with pytest.raises(ValueError):
+        sim.simulate_trialwise([0, 1], [1.0, 0.5], [[3.0, 0.5, 0.4, 1.0]])  # group out of range
+    # the context survives errors
+    assert sim.simulate(0, np.ones((1, 5)), 4).shape == (1, 4, 2)
+
+
+def test_trialwise_ragged_groups(sim, oracle):
+    from bayesflow_nddms_b200 import imputation_from_stahl_not_scaled as stahl
+
+    subj, pe = stahl.synthetic_stahl_like()
+    assert subj.size == 19374 and np.unique(subj).size == 89
+    data, part_ids, part_index = stahl.impute_dataset(subj, pe, simulator=sim, seed=77)
+    assert data.shape == (19374, 2) and data.dtype == np.float64
+    alpha_like, alphas = stahl.boundaries_from_pe(pe)
+    assert np.array_equal(data[:, 1], alpha_like)
+    assert (alphas == 0).sum() > 0
+    # bound == 0 -> +ter, zero steps
+    pp = stahl.draw_participant_params(89, np.random.default_rng(2024))
+    cr = stahl.impute_choicert(part_index, alphas, pp, simulator=sim, seed=77)
+    z = alphas == 0
+    assert np.array_equal(cr[z], pp[part_index[z], 2])
+    # same trials through the oracle on the ideal Philox stream (fp64 mode)
+    cr64 = sim.simulate_trialwise(part_index, alphas, pp, seed=77, precision=64)[:, 0]
+    pick = np.random.default_rng(0).choice(19374, 300, replace=False)
+    for i in pick:
+        o = oracle.simulate_philox(5, pp[part_index[i]], 1, 77, dataset=0, trial_offset=int(i), bound_in=[alphas[i]])
+        assert abs(o.sim_data[0, 0] - cr64[i]) < 1e-12 or abs(abs(o.sim_data[0, 0]) - abs(cr64[i])) <= 0.0100001
+    sizes = [b['sim_data'].shape[1] for b in stahl.participant_batches(data, part_index, 89)]
+    assert sum(sizes) == 19374 and min(sizes) >= 13
+
+
+def test_dlpack_handoff_to_torch(sim):
+    import torch
+
+    from bayesflow_nddms_b200 import basic_ddm_dc as m
+
+    params = m.batch_draw_prior(64)
+    host = m.batch_simulate_trials(params, 500, sim, seed=4, dataset_offset=0)
+    dev = m.batch_simulate_trials_device(params, 500, sim, seed=4, dataset_offset=0)
+    assert dev.shape == (64, 500, 2) and dev.dtype_bits == 32
+    t = torch.from_dlpack(dev)
+    assert t.is_cuda and t.dtype == torch.float32 and tuple(t.shape) == (64, 500, 2)
+    assert np.array_equal(t.cpu().numpy(), host.astype(np.float32))
+    with pytest.raises(RuntimeError):
+        dev.__dlpack__()                       # one-shot
+    # the consumer owns the buffer: a second batch must not alias it
+    dev2 = m.batch_simulate_trials_device(params, 500, sim, seed=5, dataset_offset=0)
+    t2 = torch.from_dlpack(dev2)
+    assert t2.data_ptr() != t.data_ptr()
+    assert np.array_equal(t.cpu().numpy(), host.astype(np.float32))
+    del t, t2
+    # configurators: numpy and device-resident agree
+    d = m.generative_model(32, sim)
+    c = m.configurator(d)
+    assert c['summary_conditions'].dtype == np.float32 and c['direct_conditions'].shape == (32, 1)
+    dd = m.generative_model(32, sim, device=True)
+    cd = m.device_configurator(dd)
+    assert cd['summary_conditions'].is_cuda and cd['parameters'].shape == (32, 5)
+    assert torch.allclose(cd['direct_conditions'].cpu(), torch.full((32, 1), float(np.log(dd['sim_non_batchable_context']))))
+
+
+def test_reference_signatures(sim):
+    from bayesflow_nddms_b200 import basic_ddm_dc as m0
+    from bayesflow_nddms_b200 import single_trial_alpha_not_scaled as m1
+    from bayesflow_nddms_b200 import set_default_simulator
+
+    set_default_simulator(sim)
+    try:
+        p = m0.draw_prior()
+        assert p.shape == (5,) and p.dtype == np.float64
+        out = m0.simulate_trials(p, 300)
+        assert out.shape == (300, 2) and out.dtype == np.float64
+        assert set(np.unique(out[:, 1])) <= {-1.0, 0.0, 1.0}
+        rt, choice = m0.diffusion_trial(3.0, 1.5, 0.5, 0.4, 1.0)
+        assert rt >= 0.4 and choice in (-1, 0, 1)
+        p1 = m1.draw_prior()
+        assert p1.shape == (7,)
+        for fn, pp in ((m1.simulate_trials, p1), (m1.simulate_trials_alt, m1.draw_prior_alt()),
+                       (m1.simulate_trials_scale, m1.draw_prior_scale()), (m1.simulate_trials_scale2, p1),
+                       (m1.simulate_trials_fine, p1)):
+            o = fn(pp, 123)
+            assert o.shape == (123, 2) and np.all(np.isfinite(o))
+        cr, ext = m1.diffusion_trial(3.0, 1.5, 0.5, 0.4, 1.0, 1.0, 0.1)
+        assert np.isfinite(cr) and np.isfinite(ext)
+        # successive calls advance the dataset counter: fresh streams
+        a, b = m0.simulate_trials(p, 50), m0.simulate_trials(p, 50)
+        assert not np.array_equal(a, b)
+    finally:
+        set_default_simulator(None)

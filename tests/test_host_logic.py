@@ -1,0 +1,178 @@
+"""Host-side logic that needs no GPU: priors, configurator, sharding, Stahl preprocessing,
+and the world_size-2 gather path on the gloo backend."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+from scipy import stats
+
+from conftest import ROOT
+
+
+# ---- priors: same distributions as the reference (basic_ddm_dc.py:62-80 etc.) -----------------
+def test_prior_shapes_and_order():
+    from bayesflow_nddms_b200 import basic_ddm_dc as m0
+    from bayesflow_nddms_b200 import priors
+    from bayesflow_nddms_b200 import single_trial_alpha_not_scaled as m1
+
+    assert m0.draw_prior().shape == (5,) and m0.num_params == 5
+    assert m1.draw_prior().shape == (7,) and m1.draw_prior_alt().shape == (7,) and m1.draw_prior_scale().shape == (8,)
+    for name, cols in priors.PARAM_NAMES.items():
+        assert priors.draw_prior_batch(name, 9, np.random.default_rng(0)).shape == (9, len(cols))
+    n = [m0.prior_N() for _ in range(300)]
+    assert min(n) >= 60 and max(n) <= 300
+
+
+def test_prior_marginals_match_reference_distributions():
+    from bayesflow_nddms_b200 import priors
+
+    rng = np.random.default_rng(123)
+    p = priors.draw_prior_batch("alpha_scale", 40000, rng)
+    tn = lambda m, s, lo, hi: stats.truncnorm((lo - m) / s, (hi - m) / s, loc=m, scale=s)  # noqa: E731
+    targets = [stats.norm(0, 2), tn(1, .5, 0, 10), stats.beta(2, 2), tn(.5, .25, 0, 1.5), tn(1, .5, 0, 3), tn(1, .5, 0, 10),
+               stats.uniform(0, 5), stats.uniform(0, 2)]
+    for j, d in enumerate(targets):
+        assert stats.kstest(p[:, j], d.cdf).pvalue > 1e-3, j
+    s = priors.draw_prior_batch("stahl", 40000, rng)
+    for j, d in enumerate([stats.norm(3, 1), stats.beta(25, 25), tn(.4, .1, 0, 1.5), tn(1, .25, 0, 10)]):
+        assert stats.kstest(s[:, j], d.cdf).pvalue > 1e-3, j
+    sw = priors.draw_prior_batch("sweep", 100, rng)
+    assert np.all(sw[:, 3] == 0)
+    x = priors.truncnorm_better(mean=1.0, sd=0.5, low=0.0, upp=10)
+    assert x.shape == (1,) and 0 <= x[0] <= 10
+
+
+def test_reference_prior_agrees_when_available():
+    """In the build container the verbatim reference prior can be exec'd: compare marginals."""
+    from oracle import ref_loader as rl
+
+    if not rl.available():
+        pytest.skip("reference tree not present (GPU box)")
+    from bayesflow_nddms_b200 import priors
+
+    ns = rl.load("basic_prior")
+    ref = np.stack([ns["draw_prior"]() for _ in range(1500)])
+    mine = priors.draw_prior_batch("basic", 20000, np.random.default_rng(5))
+    for j in range(5):
+        assert stats.ks_2samp(ref[:, j], mine[:, j]).pvalue > 1e-3, j
+
+
+# ---- configurator ---------------------------------------------------------------------------------
+def test_configurator_contract():
+    from bayesflow_nddms_b200 import single_trial_alpha_not_scaled as m1
+
+    d = {'sim_data': np.random.default_rng(0).normal(size=(4, 77, 2)), 'sim_non_batchable_context': 77,
+         'prior_draws': np.ones((4, 7))}
+    c = m1.configurator(d)
+    assert c['summary_conditions'].dtype == np.float32 and c['summary_conditions'].shape == (4, 77, 2)
+    assert c['direct_conditions'].shape == (4, 1) and np.allclose(c['direct_conditions'], np.log(77))
+    assert c['parameters'].dtype == np.float32
+    d['prior_draws'] = None                  # single_trial_alpha_not_scaled.py:189
+    assert 'parameters' not in m1.configurator(d)
+
+
+def test_device_configurator_on_cpu_tensor():
+    import torch
+
+    from bayesflow_nddms_b200 import basic_ddm_dc as m0
+
+    d = {'sim_data': torch.ones(3, 10, 2, dtype=torch.float64), 'sim_non_batchable_context': 10, 'prior_draws': np.zeros((3, 5))}
+    c = m0.device_configurator(d)
+    assert c['summary_conditions'].dtype == torch.float32 and c['direct_conditions'].shape == (3, 1)
+    assert abs(float(c['direct_conditions'][0, 0]) - np.log(10)) < 1e-6
+
+
+# ---- Stahl preprocessing (imputation_from_stahl_not_scaled.py:82-105) ---------------------------------
+def test_stahl_boundaries():
+    from bayesflow_nddms_b200 import imputation_from_stahl_not_scaled as st
+
+    subj, pe = st.synthetic_stahl_like()
+    like, alphas = st.boundaries_from_pe(pe)
+    z = (pe - pe.mean()) / pe.std()
+    assert np.array_equal(like, (z + 3) / 3)
+    assert np.array_equal(alphas, np.maximum((z + 3) / 3, 0) * ((z + 3) / 3 >= 0))
+    assert alphas.min() == 0 and like.min() < 0
+    counts = np.unique(subj, return_counts=True)[1]
+    assert counts.size == 89 and counts.min() >= 13 and counts.sum() == 19374
+
+
+def test_stahl_csv_when_available():
+    from bayesflow_nddms_b200 import imputation_from_stahl_not_scaled as st
+
+    path = "/root/reference/stahl_data/base_data.csv"
+    if not os.path.exists(path):
+        pytest.skip("reference data not present (GPU box)")
+    subj, pe = st.load_stahl_csv(path)
+    assert subj.size == 19374 and np.unique(subj).size == 89
+    like, alphas = st.boundaries_from_pe(pe)
+    assert alphas.min() >= 0 and abs(like.mean() - 1.0) < 1e-9
+
+
+# ---- sharding -----------------------------------------------------------------------------------------
+def test_shard_range_partitions():
+    from bayesflow_nddms_b200.distributed import shard_range
+
+    for n in (0, 1, 7, 64, 1000, 1_000_001):
+        for w in (1, 2, 3, 8):
+            r = [shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+            sizes = [hi - lo for lo, hi in r]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, n_total, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+
+    from bayesflow_nddms_b200 import distributed as D
+    from oracle import cpu as orc
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    params = np.tile(np.array([[1.0, 1.2, 0.5, 0.3, 1.0]]), (n_total, 1))
+    params[:, 0] = np.linspace(-2, 2, n_total)
+
+    def fake_simulate(p, n_trials, dataset_offset=0):
+        # stand-in for the CUDA call with the same keying: the global dataset index picks the stream
+        return np.stack([orc.simulate_philox(0, p[i], n_trials, 99, dataset=dataset_offset + i).sim_data
+                         for i in range(p.shape[0])]) if p.shape[0] else np.empty((0, n_trials, 2))
+
+    full, (lo, hi) = D.simulate_sharded(fake_simulate, params, 20, gather=True)
+    local, _ = D.simulate_sharded(fake_simulate, params, 20, gather=False)
+    q.put((rank, lo, hi, full, local))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [8, 7])
+def test_sharded_simulation_with_gloo_gather_world2(n_total, oracle):
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, n_total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    params = np.tile(np.array([[1.0, 1.2, 0.5, 0.3, 1.0]]), (n_total, 1))
+    params[:, 0] = np.linspace(-2, 2, n_total)
+    single = np.stack([oracle.simulate_philox(0, params[i], 20, 99, dataset=i).sim_data for i in range(n_total)])
+    (r0, lo0, hi0, full0, loc0), (r1, lo1, hi1, full1, loc1) = res
+    assert (lo0, hi1) == (0, n_total) and hi0 == lo1
+    assert np.array_equal(full0, single) and np.array_equal(full1, single)   # independent of world size
+    assert np.array_equal(np.concatenate([loc0, loc1]), single)
