@@ -24,11 +24,16 @@ import numpy as np
 
 def prob_lower(v: float, a: float, w: float) -> float:
     """P(absorb at 0) for unit-diffusion Wiener process started at a*w."""
-    if abs(v) < 1e-12:
+    if abs(v * a) < 1e-10:
         return 1.0 - w
-    e1 = np.exp(-2.0 * v * a * w)
-    e2 = np.exp(-2.0 * v * a)
-    return float((e1 - e2) / (1.0 - e2))
+    if v > 0:
+        e1 = np.exp(-2.0 * v * a * w)
+        e2 = np.exp(-2.0 * v * a)
+        return float((e1 - e2) / (1.0 - e2))
+    # v < 0: same expression multiplied through by exp(2va) so every exponent is negative
+    e1 = np.exp(2.0 * v * a * (1.0 - w))
+    e2 = np.exp(2.0 * v * a)
+    return float((e1 - 1.0) / (e2 - 1.0))
 
 
 def _f1_small(u, w, kmax=12):

@@ -1,0 +1,8 @@
+# ncu evidence for the persistent kernel: launch list + one full capture (1 GPU, small case)
+set -x
+mkdir -p gpurun_out
+CMD="python bench.py --steps 2 --warmup 3 --datasets 20000 --no-cpu-baseline --no-e2e"
+$CMD > gpurun_out/ncu_plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:persistent_kernel -s 3 -c 1 -f -o gpurun_out/prof_persistent $CMD > gpurun_out/ncu_full.log 2>&1
+tail -3 gpurun_out/ncu_plain.log; tail -5 gpurun_out/ncu_full.log; ls -la gpurun_out
