@@ -270,8 +270,7 @@ int run_common(ddm_ctx *ctx, int model, int64_t n_datasets, int64_t n_trials, do
     a.n_params = (uint32_t)(trialwise ? 4 : ctx->n_params);
     a.dataset_offset = (uint32_t)dataset_offset;
     a.trial_offset = (uint32_t)trial_offset;
-    a.key.k0 = (uint32_t)seed;
-    a.key.k1 = (uint32_t)(seed >> 32);
+    a.key = ddm::make_philox_key((uint32_t)seed, (uint32_t)(seed >> 32));
     a.max_steps = (uint32_t)max_steps;
     a.model = model;
     a.flags = flags;
@@ -280,8 +279,7 @@ int run_common(ddm_ctx *ctx, int model, int64_t n_datasets, int64_t n_trials, do
     a.kdt = (float)(-1.3862943611198906188 * dt);
     (void)n_groups;
 
-    const bool persistent = precision == 32 && !ctx->dbg_on && !trialwise && !(flags & DDM_FLAG_FORCE_GENERIC) &&
-                            (max_steps % 4 == 0);
+    const bool persistent = precision == 32 && !ctx->dbg_on && !trialwise && !(flags & DDM_FLAG_FORCE_GENERIC);
     ddm_stats st{};
     st.n_trials = (uint64_t)rows;
 
@@ -308,7 +306,7 @@ int run_common(ddm_ctx *ctx, int model, int64_t n_datasets, int64_t n_trials, do
             a.tile = tile;
             a.tiles_per_dataset = (uint32_t)((n_trials + tile - 1) / tile);
             a.n_items = (uint64_t)a.tiles_per_dataset * (uint64_t)n_datasets;
-            a.refill_threshold = ctx->tune_threshold > 0 ? ctx->tune_threshold : 8;
+            a.refill_threshold = ctx->tune_threshold > 0 ? ctx->tune_threshold : 4;
             if (a.refill_threshold > 32) a.refill_threshold = 32;
             const uint64_t warps_needed = ((uint64_t)rows + 31) / 32;
             uint64_t grid = (uint64_t)ctx->sm_count * per_sm;
@@ -637,7 +635,7 @@ DDM_API int ddm_export_normals(ddm_ctx *ctx, uint64_t seed, uint32_t dataset, ui
     if (!out_host) return fail(ctx, DDM_ERR_INVALID, "out_host is NULL");
     DeviceGuard g(ctx->device);
     DDM_CUDA(ctx, ctx->export_buf.reserve(count));
-    ddm::PhiloxKey key{(uint32_t)seed, (uint32_t)(seed >> 32)};
+    const ddm::PhiloxKey key = ddm::make_philox_key((uint32_t)seed, (uint32_t)(seed >> 32));
     DDM_CUDA(ctx, ddm::launch_export_normals(key, dataset, trial, stream, first, count, precision == 64, ctx->export_buf.p, ctx->stream));
     DDM_CUDA(ctx, cudaMemcpyAsync(out_host, ctx->export_buf.p, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     DDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -68,7 +68,7 @@ __device__ __forceinline__ void store_pair(void *out, uint64_t idx, double o0, d
 // --------------------------------------------------------------------------------
 // Work item = (dataset, tile of <= `tile` consecutive trials).  A warp claims items
 // with one atomicAdd each and hands the tile's trials to lanes that need one.  All
-// lanes then advance in lock-step, four Euler steps per Philox block; lanes whose
+// lanes then advance in lock-step, six Euler steps per Philox block; lanes whose
 // trial has crossed are frozen by predication.  When at least `refill_threshold`
 // lanes are frozen the warp takes the (divergent, so deliberately batched) finish +
 // refill path.  Philox counters are (step block, trial, dataset): results do not
@@ -89,71 +89,82 @@ __global__ void __launch_bounds__(256) persistent_kernel(const RunArgs a) {
     TrialF32 t;
     t.x = 0.f; t.h = 0.f; t.c0 = 0.f; t.k = 0.f; t.ext = 0.f;
     float x = 0.f;
-    uint32_t n = 0, trial = 0, ds = 0;
-    bool p = false;    // stepping
+    uint32_t n = 0, blk = 0, trial = 0, ds = 0;
+    uint32_t p = 0;    // 1 = stepping
     bool has = false;  // holds a trial (stepping, or finished and waiting to be emitted)
 
     unsigned long long acc_steps = 0;
     uint32_t acc_timeouts = 0, acc_upper = 0, acc_cap = 0;
 
     const int thr = a.refill_threshold;
+    // a trial's last block is partial when max_steps is not a multiple of 6: n > tail_from
+    const bool partial_tail = (a.max_steps % NORMALS_PER_BLOCK) != 0u;
+    const int tail_from = (int)a.max_steps - NORMALS_PER_BLOCK;
 
     for (;;) {
-        const unsigned idle = __ballot_sync(FULL_MASK, !p);
-        if (__popc(idle) >= thr) {
-            // ---- finish: emit every frozen trial -----------------------------------
-            if (has && !p) {
-                const int choice = (x >= t.h) ? 1 : ((x <= -t.h) ? -1 : 0);
-                const double tau = a.params[(size_t)ds * a.n_params + 3];
-                double o0, o1;
-                trial_outputs(a.model, a.flags, choice, n, a.dt, tau, (double)t.ext, o0, o1);
-                if (a.flags & 16) o1 = (double)__fadd_rn(x, t.h);
-                const uint64_t idx = (uint64_t)ds * a.n_trials + trial;
-                store_pair<OUT64>(a.out, idx, o0, o1);
-                if (a.steps_out) a.steps_out[idx] = (int32_t)n;
-                acc_steps += n;
-                acc_timeouts += (choice == 0);
-                acc_upper += (choice > 0);
-                has = false;
-            }
-            // ---- refill: hand out trials of the current tile, claiming tiles as needed
-            for (;;) {
-                const unsigned empty = __ballot_sync(FULL_MASK, !has);
-                if (empty == 0u) break;
-                if (cur == end) {
-                    if (!more) break;
-                    unsigned long long w = 0;
-                    if (lane == 0) w = atomicAdd(a.work_counter, 1ull);
-                    w = __shfl_sync(FULL_MASK, w, 0);
-                    if (w >= a.n_items) { more = false; break; }
-                    tile_ds = (uint32_t)(w / a.tiles_per_dataset);
-                    const uint32_t ti = (uint32_t)(w - (unsigned long long)tile_ds * a.tiles_per_dataset);
-                    cur = ti * a.tile;
-                    end = min(cur + a.tile, a.n_trials);
-                    const float4 *src = reinterpret_cast<const float4 *>(a.dconst + tile_ds);
-                    const float4 c0 = __ldg(src), c1 = __ldg(src + 1);
-                    tile_c.v[0] = c0.x; tile_c.v[1] = c0.y; tile_c.v[2] = c0.z; tile_c.v[3] = c0.w;
-                    tile_c.v[4] = c1.x; tile_c.v[5] = c1.y; tile_c.v[6] = c1.z; tile_c.v[7] = c1.w;
-                }
-                const uint32_t rank = __popc(empty & lt_mask);
-                const uint32_t avail = end - cur;
-                if (!has && rank < avail) {
-                    ds = tile_ds;
-                    trial = cur + rank;
-                    trial_setup_f32<KIND>(tile_c, trial + a.trial_offset, ds + a.dataset_offset, a.key, a.kdt, t,
-                                          acc_cap);
-                    x = t.x;
-                    n = 0;
-                    has = true;
-                    p = (fabsf(x) < t.h) && (a.max_steps > 0u);
-                }
-                cur += min((uint32_t)__popc(empty), avail);
-            }
-            if (!__any_sync(FULL_MASK, has)) break;
+        // ---- finish: emit every frozen trial ---------------------------------------
+        if (has && p == 0u) {
+            const int choice = (x >= t.h) ? 1 : ((x <= -t.h) ? -1 : 0);
+            const double tau = a.params[(size_t)ds * a.n_params + 3];
+            double o0, o1;
+            trial_outputs(a.model, a.flags, choice, n, a.dt, tau, (double)t.ext, o0, o1);
+            if (a.flags & 16) o1 = (double)__fadd_rn(x, t.h);
+            const uint64_t idx = (uint64_t)ds * a.n_trials + trial;
+            store_pair<OUT64>(a.out, idx, o0, o1);
+            if (a.steps_out) a.steps_out[idx] = (int32_t)n;
+            acc_steps += n;
+            acc_timeouts += (choice == 0);
+            acc_upper += (choice > 0);
+            has = false;
         }
-        // ---- four Euler steps for every lane ----------------------------------------
-        step_block_f32(trial + a.trial_offset, ds + a.dataset_offset, a.key, t, x, n, p);
-        p = p && (n < a.max_steps);
+        // ---- refill: hand out trials of the current tile, claiming tiles as needed ---
+        for (;;) {
+            const unsigned empty = __ballot_sync(FULL_MASK, !has);
+            if (empty == 0u) break;
+            if (cur == end) {
+                if (!more) break;
+                unsigned long long w = 0;
+                if (lane == 0) w = atomicAdd(a.work_counter, 1ull);
+                w = __shfl_sync(FULL_MASK, w, 0);
+                if (w >= a.n_items) { more = false; break; }
+                tile_ds = (uint32_t)(w / a.tiles_per_dataset);
+                const uint32_t ti = (uint32_t)(w - (unsigned long long)tile_ds * a.tiles_per_dataset);
+                cur = ti * a.tile;
+                end = min(cur + a.tile, a.n_trials);
+                const float4 *src = reinterpret_cast<const float4 *>(a.dconst + tile_ds);
+                const float4 c0 = __ldg(src), c1 = __ldg(src + 1);
+                tile_c.v[0] = c0.x; tile_c.v[1] = c0.y; tile_c.v[2] = c0.z; tile_c.v[3] = c0.w;
+                tile_c.v[4] = c1.x; tile_c.v[5] = c1.y; tile_c.v[6] = c1.z; tile_c.v[7] = c1.w;
+            }
+            const uint32_t rank = __popc(empty & lt_mask);
+            const uint32_t avail = end - cur;
+            if (!has && rank < avail) {
+                ds = tile_ds;
+                trial = cur + rank;
+                trial_setup_f32<KIND>(tile_c, trial + a.trial_offset, ds + a.dataset_offset, a.key, a.kdt, t, acc_cap);
+                x = t.x;
+                n = 0;
+                blk = 0;
+                has = true;
+                p = ((fabsf(x) < t.h) && (a.max_steps > 0u)) ? 1u : 0u;
+            }
+            cur += min((uint32_t)__popc(empty), avail);
+        }
+        if (!__any_sync(FULL_MASK, has)) break;
+        // once the work has run out there is nothing to refill with: run the warp's last trials to the end
+        const int thr_now = (more || cur != end) ? thr : 32;
+
+        // ---- step: tight, branch-free inner loop (round keys and constants stay in uniform registers)
+        unsigned idle;
+        do {
+            if (partial_tail && __any_sync(FULL_MASK, p != 0u && (int)n > tail_from))
+                step_block_f32<true>(blk, trial + a.trial_offset, ds + a.dataset_offset, a.key, t, x, n, p, a.max_steps);
+            else
+                step_block_f32<false>(blk, trial + a.trial_offset, ds + a.dataset_offset, a.key, t, x, n, p, a.max_steps);
+            blk++;
+            if (!partial_tail) p = (n < a.max_steps) ? p : 0u;
+            idle = __ballot_sync(FULL_MASK, p == 0u);
+        } while (__popc(idle) < thr_now);
     }
 
     // ---- per-warp statistics --------------------------------------------------------
@@ -214,30 +225,9 @@ __global__ void __launch_bounds__(128) generic_kernel(const RunArgs a, uint64_t 
             TrialF32 t;
             trial_setup_f32<(KIND == KIND_TRIALWISE ? KIND_FIXED : KIND)>(dc, trial_g, ds_g, a.key, a.kdt, t, cap);
             float x = t.x;
-            bool p = (fabsf(x) < t.h) && (a.max_steps > 0u);
-            if ((a.max_steps & 3u) == 0u) {
-                while (p) {
-                    step_block_f32(trial_g, ds_g, a.key, t, x, n, p);
-                    p = p && (n < a.max_steps);
-                }
-            } else {
-                // max_steps not a multiple of the Philox block: step one normal at a time
-                float sA = 0, cA = 0, snA = 0, sB = 0, cB = 0, snB = 0;
-                while (p) {
-                    if ((n & 3u) == 0u) {
-                        uint32_t w[4];
-                        philox4x32<10>(n >> 2, trial_g, ds_g, STREAM_STEP, a.key.k0, a.key.k1, w);
-                        box_muller_scaled(w[0], w[1], t.k, sA, cA, snA);
-                        box_muller_scaled(w[2], w[3], t.k, sB, cB, snB);
-                    }
-                    const uint32_t j = n & 3u;
-                    const float s = (j < 2) ? sA : sB;
-                    const float tr = (j == 0) ? cA : (j == 1 ? snA : (j == 2 ? cB : snB));
-                    x = __fmaf_rn(s, tr, __fadd_rn(x, t.c0));
-                    n++;
-                    p = (fabsf(x) < t.h) && (n < a.max_steps);
-                }
-            }
+            uint32_t p = ((fabsf(x) < t.h) && (a.max_steps > 0u)) ? 1u : 0u;
+            for (uint32_t blk = 0; p != 0u; blk++)
+                step_block_f32<true>(blk, trial_g, ds_g, a.key, t, x, n, p, a.max_steps);
             choice = (x >= t.h) ? 1 : ((x <= -t.h) ? -1 : 0);
             ext = (double)t.ext;
             final_ev = (double)__fadd_rn(x, t.h);
@@ -245,21 +235,23 @@ __global__ void __launch_bounds__(128) generic_kernel(const RunArgs a, uint64_t 
             // ---- reference arithmetic in Real (fp64: the reference's exact operation order;
             //      fp32: the same formulas rounded to float), normals from Philox or a buffer ----
             NormalStreamBuf buf{BUFFER ? a.dbg_z + a.dbg_off[g] : nullptr, BUFFER ? a.dbg_z + a.dbg_n : nullptr, false};
-            double zc[4];
+            double zc[6];
             uint32_t zblk = 0xffffffffu;
             auto philox_normal = [&](uint32_t stream, uint32_t idx) -> double {
-                const uint32_t blk = (idx >> 2) | (stream << 31);  // cache tag
-                if (blk != zblk) {
+                const uint32_t b = idx / 6u;
+                const uint32_t tag = b | (stream << 31);  // cache tag
+                if (tag != zblk) {
                     if (sizeof(Real) == 8) {
-                        philox_normals4_f64(idx >> 2, trial_g, ds_g, stream, a.key, zc);
+                        philox_normals6_f64(b, trial_g, ds_g, stream, a.key, zc);
                     } else {
-                        float zf[4];
-                        philox_normals4_f32(idx >> 2, trial_g, ds_g, stream, a.key, zf);
-                        zc[0] = zf[0]; zc[1] = zf[1]; zc[2] = zf[2]; zc[3] = zf[3];
+                        float zf[6];
+                        philox_normals6_f32(b, trial_g, ds_g, stream, a.key, zf);
+#pragma unroll
+                        for (int i = 0; i < 6; i++) zc[i] = zf[i];
                     }
-                    zblk = blk;
+                    zblk = tag;
                 }
-                return zc[idx & 3u];
+                return zc[idx - 6u * b];
             };
             Real drift, beta, bound, dcoef, sigma1 = 0, gain = 1, latent = 0;
             if (KIND == KIND_TRIALWISE) {
@@ -278,7 +270,7 @@ __global__ void __launch_bounds__(128) generic_kernel(const RunArgs a, uint64_t 
                     latent = mu + sd * z;  // separate mul and add: see -fmad=false in build
                     i++;
                     if (latent > (Real)0) break;
-                    if (i >= 4u * REJECT_CAP_BLOCKS) { cap++; latent = (Real)1e-30; break; }
+                    if (i >= 6u * REJECT_CAP_BLOCKS - 1u) { cap++; latent = (Real)1e-30; break; }
                 }
                 if (KIND == KIND_BOUND) {
                     bound = latent; dcoef = (Real)prm[5];
@@ -340,14 +332,15 @@ __global__ void export_normals_kernel(PhiloxKey key, uint32_t dataset, uint32_t 
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     const uint32_t idx = first + i;
+    const uint32_t b = idx / 6u, j = idx - 6u * b;
     if (f64) {
-        double z[4];
-        philox_normals4_f64(idx >> 2, trial, dataset, stream, key, z);
-        out[i] = z[idx & 3u];
+        double z[6];
+        philox_normals6_f64(b, trial, dataset, stream, key, z);
+        out[i] = z[j];
     } else {
-        float z[4];
-        philox_normals4_f32(idx >> 2, trial, dataset, stream, key, z);
-        out[i] = (double)z[idx & 3u];
+        float z[6];
+        philox_normals6_f32(b, trial, dataset, stream, key, z);
+        out[i] = (double)z[j];
     }
 }
 

@@ -24,7 +24,7 @@ struct __align__(16) DsConst {
     float v[8];
 };
 
-constexpr int REJECT_CAP_BLOCKS = 1024;  // 4096 candidates before giving up on a redraw loop
+constexpr int REJECT_CAP_BLOCKS = 1024;  // ~6000 candidates before giving up on a redraw loop
 
 struct RunArgs {
     // inputs
@@ -70,7 +70,7 @@ struct TrialF32 {
 
 template <int KIND>
 __device__ __forceinline__ void trial_setup_f32(const DsConst &dc, uint32_t trial, uint32_t ds_global,
-                                                PhiloxKey key, float kdt, TrialF32 &t, uint32_t &cap_hits) {
+                                                const PhiloxKey &key, float kdt, TrialF32 &t, uint32_t &cap_hits) {
     t.c0 = dc.v[0];
     if (KIND == KIND_FIXED) {
         t.x = dc.v[1];
@@ -81,21 +81,22 @@ __device__ __forceinline__ void trial_setup_f32(const DsConst &dc, uint32_t tria
     }
     const float mu = (KIND == KIND_BOUND) ? dc.v[2] : dc.v[3];
     const float sd = (KIND == KIND_BOUND) ? dc.v[3] : dc.v[4];
-    float z[4];
-    philox_normals4_f32(0u, trial, ds_global, STREAM_AUX, key, z);
+    float z[6];
+    philox_normals6_f32(0u, trial, ds_global, STREAM_AUX, key, z);
     const float z_ext = z[0];
     float latent = __fmaf_rn(sd, z[1], mu);
-    if (!(latent > 0.f)) latent = __fmaf_rn(sd, z[2], mu);
-    if (!(latent > 0.f)) latent = __fmaf_rn(sd, z[3], mu);
+#pragma unroll
+    for (int i = 2; i < 6; i++)
+        if (!(latent > 0.f)) latent = __fmaf_rn(sd, z[i], mu);
     for (uint32_t j = 1; !(latent > 0.f); j++) {
         if (j >= REJECT_CAP_BLOCKS) {
             cap_hits++;
             latent = 1e-30f;
             break;
         }
-        philox_normals4_f32(j, trial, ds_global, STREAM_AUX, key, z);
+        philox_normals6_f32(j, trial, ds_global, STREAM_AUX, key, z);
 #pragma unroll
-        for (int i = 0; i < 4; i++)
+        for (int i = 0; i < 6; i++)
             if (!(latent > 0.f)) latent = __fmaf_rn(sd, z[i], mu);
     }
     if (KIND == KIND_BOUND) {
@@ -111,23 +112,56 @@ __device__ __forceinline__ void trial_setup_f32(const DsConst &dc, uint32_t tria
     }
 }
 
-// Four predicated Euler steps from one Philox block.  `p` = "still inside the
-// boundaries"; a lane whose p is false is frozen (x, n keep their crossing values).
-__device__ __forceinline__ void step_block_f32(uint32_t trial, uint32_t ds_global, PhiloxKey key,
-                                               const TrialF32 &t, float &x, uint32_t &n, bool &p) {
-    uint32_t w[4];
-    philox4x32<10>(n >> 2, trial, ds_global, STREAM_STEP, key.k0, key.k1, w);
-    float sA, cA, snA, sB, cB, snB;
-    box_muller_scaled(w[0], w[1], t.k, sA, cA, snA);
-    box_muller_scaled(w[2], w[3], t.k, sB, cB, snB);
-    if (p) { x = __fmaf_rn(sA, cA, __fadd_rn(x, t.c0)); n++; }
-    p = p && (fabsf(x) < t.h);
-    if (p) { x = __fmaf_rn(sA, snA, __fadd_rn(x, t.c0)); n++; }
-    p = p && (fabsf(x) < t.h);
-    if (p) { x = __fmaf_rn(sB, cB, __fadd_rn(x, t.c0)); n++; }
-    p = p && (fabsf(x) < t.h);
-    if (p) { x = __fmaf_rn(sB, snB, __fadd_rn(x, t.c0)); n++; }
-    p = p && (fabsf(x) < t.h);
+// Six predicated Euler steps from one Philox block.  `p` (0/1) = "still inside the boundaries and
+// below max_steps"; a lane whose p is 0 is frozen (x, n keep their crossing values).  Written in
+// PTX so that every step is exactly  FFMA, @p FADD, @p IADD, FSETP.AND  (no branches: the warp
+// executes the block while any lane is alive, so skipping buys nothing).  The increment is formed
+// first, inc = fma(s, trig, c0), then x += inc: the reference's own association ev + (t1 + t3)
+// (basic_ddm_dc.py:98), one rounding at ulp(x) per step, and the x-chain is a single FADD.  (Adding
+// c0 to x first would round the tiny drift term to x's grid the same way every step -- a systematic
+// drift error of up to ulp(x)/2 per step.)  TAIL adds the
+// n < max_steps test per step; the callers use it only for a trial's last, partial block.
+#define DDM_STEP(S, T)                         \
+    "fma.rn.f32 inc, " S ", " T ", %3;\n\t"     \
+    "@q add.rn.f32 %0, %0, inc;\n\t"           \
+    "@q add.u32 %1, %1, 1;\n\t"                \
+    "abs.f32 ax, %0;\n\t"                      \
+    "setp.lt.and.f32 q, ax, %4, q;\n\t"
+#define DDM_STEP_TAIL(S, T) DDM_STEP(S, T) "setp.lt.and.u32 q, %1, %14, q;\n\t"
+
+template <bool TAIL>
+__device__ __forceinline__ void euler6(float &x, uint32_t &n, uint32_t &p, float c0, float h,
+                                       const Normals6Scaled &z, uint32_t max_steps) {
+    if (TAIL) {
+        asm volatile("{\n\t.reg .pred q;\n\t.reg .f32 ax, inc;\n\t"
+                     "setp.ne.u32 q, %2, 0;\n\t"
+                     "setp.lt.and.u32 q, %1, %14, q;\n\t"
+                     DDM_STEP_TAIL("%5", "%6") DDM_STEP_TAIL("%5", "%7") DDM_STEP_TAIL("%8", "%9")
+                     DDM_STEP_TAIL("%8", "%10") DDM_STEP_TAIL("%11", "%12") DDM_STEP_TAIL("%11", "%13")
+                     "selp.u32 %2, 1, 0, q;\n\t}"
+                     : "+f"(x), "+r"(n), "+r"(p)
+                     : "f"(c0), "f"(h), "f"(z.s[0]), "f"(z.c[0]), "f"(z.sn[0]), "f"(z.s[1]), "f"(z.c[1]), "f"(z.sn[1]),
+                       "f"(z.s[2]), "f"(z.c[2]), "f"(z.sn[2]), "r"(max_steps));
+    } else {
+        asm volatile("{\n\t.reg .pred q;\n\t.reg .f32 ax, inc;\n\t"
+                     "setp.ne.u32 q, %2, 0;\n\t"
+                     DDM_STEP("%5", "%6") DDM_STEP("%5", "%7") DDM_STEP("%8", "%9")
+                     DDM_STEP("%8", "%10") DDM_STEP("%11", "%12") DDM_STEP("%11", "%13")
+                     "selp.u32 %2, 1, 0, q;\n\t}"
+                     : "+f"(x), "+r"(n), "+r"(p)
+                     : "f"(c0), "f"(h), "f"(z.s[0]), "f"(z.c[0]), "f"(z.sn[0]), "f"(z.s[1]), "f"(z.c[1]), "f"(z.sn[1]),
+                       "f"(z.s[2]), "f"(z.c[2]), "f"(z.sn[2]), "r"(max_steps));
+    }
+}
+
+// One Philox block of a trial: block index `blk` = n / 6 for a lane that is still stepping.
+template <bool TAIL>
+__device__ __forceinline__ void step_block_f32(uint32_t blk, uint32_t trial, uint32_t ds_global, const PhiloxKey &key,
+                                               const TrialF32 &t, float &x, uint32_t &n, uint32_t &p,
+                                               uint32_t max_steps) {
+    Normals6Scaled z;
+    philox_pairs_scaled(blk, trial, ds_global, STREAM_STEP, key, t.k, z);
+    euler6<TAIL>(x, n, p, t.c0, t.h, z, max_steps);
 }
 
 // Final outputs of a finished fp32 trial, computed in fp64 with the reference's operation

@@ -19,7 +19,8 @@ struct MbOut {
 };
 
 template <int WHICH>
-__global__ void __launch_bounds__(256) microbench_kernel(int iters, uint32_t seed, float fa, float fb, MbOut o) {
+__global__ void __launch_bounds__(256) microbench_kernel(int iters, uint32_t seed, float fa, float fb, MbOut o,
+                                                         const PhiloxKey key) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t xi[MB_CHAINS];
     float xf[MB_CHAINS];
@@ -64,12 +65,11 @@ __global__ void __launch_bounds__(256) microbench_kernel(int iters, uint32_t see
             philox4x32<10>((uint32_t)it, tid, xi[0], 0u, ka, kb, w);
             xi[0] ^= w[0] ^ w[1] ^ w[2] ^ w[3];
         } else if (WHICH == DDM_MB_NORMALS) {
-            // the simulator's own inner block: Philox -> 4 scaled normals -> 4 predicated Euler steps
+            // the simulator's own inner block: Philox -> 6 scaled normals -> 6 predicated Euler steps
             TrialF32 t;
             t.h = 3.4e38f; t.c0 = fb; t.k = fa; t.x = 0.f; t.ext = 0.f;
-            uint32_t n = (uint32_t)it * 4u;
-            bool p = true;
-            step_block_f32(tid, xi[0], PhiloxKey{ka, kb}, t, xf[0], n, p);
+            uint32_t n = (uint32_t)it * 6u, p = 1u;
+            step_block_f32<false>((uint32_t)it, tid, xi[0], key, t, xf[0], n, p, 0xffffffffu);
             acc += n;
         }
     }
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(256) microbench_kernel(int iters, uint32_t see
 
 template <int WHICH>
 static cudaError_t launch_one(int grid, int iters, MbOut o, cudaStream_t s) {
-    microbench_kernel<WHICH><<<grid, 256, 0, s>>>(iters, 12345u, 1.0000001f, 1e-9f, o);
+    microbench_kernel<WHICH><<<grid, 256, 0, s>>>(iters, 12345u, 1.0000001f, 1e-9f, o, make_philox_key(12345u, 678u));
     return cudaGetLastError();
 }
 

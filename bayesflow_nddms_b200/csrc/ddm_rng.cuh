@@ -3,21 +3,29 @@
 // Philox4x32-10 (Salmon et al., SC'11).  key = (seed_lo, seed_hi) is uniform for
 // a launch, so the ten round keys live in uniform registers / the constant bank
 // and a round costs 2 IMAD.WIDE.U32 + 2 LOP3 per lane.
-// counter = (block, trial, dataset, stream):
-//   stream 0 ("step"):  block b yields the normals of Euler steps 4b..4b+3
+// counter = (block, trial, dataset, stream); one block yields SIX normals:
+//   stream 0 ("step"):  block b yields the normals of Euler steps 6b..6b+5
 //   stream 1 ("aux"):   normal 0 = the ext-data normal z_ext (drawn after the
 //                       loop in the reference, single_trial_alpha_not_scaled.py:131),
 //                       normal 1+i = i-th candidate of the redraw-until-positive
 //                       boundary / dc loop (:113-116, :932-935)
 // so step normals sit at fixed counters no matter how many pre-draws a trial needs.
 //
-// u32 -> normal: Box-Muller on 23-bit uniforms built by bit injection (no I2F):
-//   f  = as_float((w & 0x7fffff) | 0x3f800000)            in [1,2)
-//   u  = f - (1 - 2^-24) = (2m+1)/2^24                     in (0,1), exact
-//   t  = f' - 1.5                                          in [-.5,.5) revolutions
+// 128 bits -> three Box-Muller pairs of 21-bit uniforms (126 bits used, none twice).
+// IMAD.WIDE issues at one per 4 clocks per scheduler on B200 (measured, bench.py
+// --microbench), so Philox blocks are the scarce resource; 21-bit fields cost a few
+// LOP3/SHF more than 23-bit ones and buy 6 instead of 4 normals per block.
+//   pair 0: U = w0[2..22]  T = w1[2..22]        (fields already at mantissa position)
+//   pair 1: U = w2[2..22]  T = w3[2..22]
+//   pair 2: U = w0[23..31,0..1] ++ w1[23..31,0]  T = the same bits of w2, w3
+//           (mantissa bits 2..12 = rotl(wa,11), bits 13..22 = rotl(wb,22))
+// u32 field m (21 bits) -> by mantissa injection, no I2F:
+//   f  = as_float(0x3f800000 | m << 2)                 in [1,2)
+//   u  = f - (1 - 2^-22) = (2m+1)/2^22                 in (0,1), exact
+//   t  = f' - 1.5                                      in [-.5,.5) revolutions
 //   z_even = sqrt(-2 ln u) cos(2 pi t),  z_odd = sqrt(-2 ln u) sin(2 pi t)
-// with MUFU lg2 / sqrt / sin / cos.  |z| <= 5.77 (P(|Z|>5.77) = 8e-9).
-// oracle/ddm_oracle.c:orc_philox_normals4 is the fp64 value of the same map.
+// with MUFU lg2 / sqrt / sin / cos.  |z| <= 5.53 (P(|Z|>5.53) = 3e-8).
+// oracle/ddm_oracle.c:orc_philox_normals6 is the fp64 value of the same map.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -32,9 +40,21 @@ constexpr uint32_t PHILOX_W1 = 0xBB67AE85u;
 constexpr uint32_t STREAM_STEP = 0u;
 constexpr uint32_t STREAM_AUX = 1u;
 
+// The launch-uniform key with its ten round keys precomputed on the host: they sit in the
+// kernel-parameter constant bank, so a round's key injection is an operand of the LOP3, not
+// an extra uniform-datapath add per round per block.
 struct PhiloxKey {
-    uint32_t k0, k1;
+    uint32_t rk[20];  // rk[2r] = k0 + r*W0, rk[2r+1] = k1 + r*W1
 };
+
+__host__ __device__ inline PhiloxKey make_philox_key(uint32_t k0, uint32_t k1) {
+    PhiloxKey k;
+    for (int r = 0; r < 10; r++) {
+        k.rk[2 * r] = k0 + (uint32_t)r * 0x9E3779B9u;
+        k.rk[2 * r + 1] = k1 + (uint32_t)r * 0xBB67AE85u;
+    }
+    return k;
+}
 
 template <int ROUNDS = 10>
 __device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
@@ -51,6 +71,22 @@ __device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2
         c2 = n2;
         k0 += PHILOX_W0;  // uniform datapath: key is launch-uniform
         k1 += PHILOX_W1;
+    }
+    o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+}
+
+__device__ __forceinline__ void philox4x32_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              const PhiloxKey &key, uint32_t (&o)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint64_t p0 = (uint64_t)PHILOX_M0 * c0;
+        const uint64_t p1 = (uint64_t)PHILOX_M1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ key.rk[2 * r];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ key.rk[2 * r + 1];
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
     }
     o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
 }
@@ -76,8 +112,23 @@ __device__ __forceinline__ float mufu_cos(float x) {
     return y;
 }
 
-__device__ __forceinline__ float bits_to_unit12(uint32_t w) {
-    return __uint_as_float((w & 0x007fffffu) | 0x3f800000u);  // [1,2)
+constexpr int NORMALS_PER_BLOCK = 6;
+constexpr uint32_t FIELD_MASK = 0x007ffffcu;  // mantissa bits 2..22
+constexpr uint32_t ONE_BITS = 0x3f800000u;
+
+// (x & FIELD_MASK) | ONE_BITS in one LOP3: float in [1,2) on a 2^-21 grid
+__device__ __forceinline__ float field_to_unit12(uint32_t x) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(x), "r"(FIELD_MASK), "r"(ONE_BITS));  // (a & b) | c
+    return __uint_as_float(r);
+}
+
+// the leftover bits of two words as a third field: bits 2..12 from rotl(wa,11), 13..22 from rotl(wb,22)
+__device__ __forceinline__ uint32_t leftover_field(uint32_t wa, uint32_t wb) {
+    const uint32_t ra = __funnelshift_l(wa, wa, 11), rb = __funnelshift_l(wb, wb, 22);
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(r) : "r"(0x00001ffcu), "r"(ra), "r"(rb));  // a ? b : c (bit select)
+    return r;
 }
 
 // One Box-Muller pair with the radius pre-scaled:  s = sqrt(|k * lg2(u)|) where the
@@ -85,41 +136,55 @@ __device__ __forceinline__ float bits_to_unit12(uint32_t w) {
 // x = fma(s, trig, x + c0) with no separate multiply.  k = -2 ln2 gives unit normals.
 // |.| guards MUFU.LG2's absolute error near u -> 1 (a slightly positive lg2 would
 // otherwise make the sqrt argument negative).
-__device__ __forceinline__ void box_muller_scaled(uint32_t wa, uint32_t wb, float k, float &s,
+__device__ __forceinline__ void box_muller_scaled(uint32_t fu, uint32_t ft, float k, float &s,
                                                   float &c, float &sn) {
-    const float u = __fadd_rn(bits_to_unit12(wa), -0.99999994f);  // (2m+1)/2^24, exact
+    const float u = __fadd_rn(field_to_unit12(fu), -0.99999976158142089844f);  // (2m+1)/2^22, exact
     const float l = mufu_lg2(u);
     s = mufu_sqrt(fabsf(__fmul_rn(k, l)));
-    const float a = __fmaf_rn(bits_to_unit12(wb), 6.2831853071795865f, -9.4247779607693797f);  // 2pi*(f-1.5)
+    const float a = __fmaf_rn(field_to_unit12(ft), 6.2831853071795865f, -9.4247779607693797f);  // 2pi*(f-1.5)
     c = mufu_cos(a);
     sn = mufu_sin(a);
 }
 
 constexpr float NEG_2LN2 = -1.3862943611198906f;
 
-// The four unit normals of Philox block (block, trial, dataset, stream), fp32 production map.
-__device__ __forceinline__ void philox_normals4_f32(uint32_t block, uint32_t trial, uint32_t dataset,
-                                                    uint32_t stream, PhiloxKey key, float (&z)[4]) {
+// Radii and trig factors of the three pairs of a Philox block (the simulator's inner block).
+struct Normals6Scaled {
+    float s[3], c[3], sn[3];
+};
+
+__device__ __forceinline__ void philox_pairs_scaled(uint32_t block, uint32_t trial, uint32_t dataset,
+                                                    uint32_t stream, const PhiloxKey &key, float k, Normals6Scaled &o) {
     uint32_t w[4];
-    philox4x32<10>(block, trial, dataset, stream, key.k0, key.k1, w);
-    float s, c, sn;
-    box_muller_scaled(w[0], w[1], NEG_2LN2, s, c, sn);
-    z[0] = __fmul_rn(s, c);
-    z[1] = __fmul_rn(s, sn);
-    box_muller_scaled(w[2], w[3], NEG_2LN2, s, c, sn);
-    z[2] = __fmul_rn(s, c);
-    z[3] = __fmul_rn(s, sn);
+    philox4x32_rk(block, trial, dataset, stream, key, w);
+    box_muller_scaled(w[0], w[1], k, o.s[0], o.c[0], o.sn[0]);
+    box_muller_scaled(w[2], w[3], k, o.s[1], o.c[1], o.sn[1]);
+    box_muller_scaled(leftover_field(w[0], w[1]), leftover_field(w[2], w[3]), k, o.s[2], o.c[2], o.sn[2]);
+}
+
+// The six unit normals of Philox block (block, trial, dataset, stream), fp32 production map.
+__device__ __forceinline__ void philox_normals6_f32(uint32_t block, uint32_t trial, uint32_t dataset,
+                                                    uint32_t stream, const PhiloxKey &key, float (&z)[6]) {
+    Normals6Scaled o;
+    philox_pairs_scaled(block, trial, dataset, stream, key, NEG_2LN2, o);
+#pragma unroll
+    for (int p = 0; p < 3; p++) {
+        z[2 * p] = __fmul_rn(o.s[p], o.c[p]);
+        z[2 * p + 1] = __fmul_rn(o.s[p], o.sn[p]);
+    }
 }
 
 // fp64 validation map: same bits, libdevice log/sincospi in double.
-__device__ __forceinline__ void philox_normals4_f64(uint32_t block, uint32_t trial, uint32_t dataset,
-                                                    uint32_t stream, PhiloxKey key, double (&z)[4]) {
+__device__ __forceinline__ void philox_normals6_f64(uint32_t block, uint32_t trial, uint32_t dataset,
+                                                    uint32_t stream, const PhiloxKey &key, double (&z)[6]) {
     uint32_t w[4];
-    philox4x32<10>(block, trial, dataset, stream, key.k0, key.k1, w);
+    philox4x32_rk(block, trial, dataset, stream, key, w);
+    const uint32_t fu[3] = {w[0], w[2], leftover_field(w[0], w[1])};
+    const uint32_t ft[3] = {w[1], w[3], leftover_field(w[2], w[3])};
 #pragma unroll
-    for (int p = 0; p < 2; p++) {
-        const double u = (2.0 * (double)(w[2 * p] & 0x7fffffu) + 1.0) / 16777216.0;
-        const double t = (double)(w[2 * p + 1] & 0x7fffffu) / 8388608.0 - 0.5;
+    for (int p = 0; p < 3; p++) {
+        const double u = (2.0 * (double)((fu[p] & FIELD_MASK) >> 2) + 1.0) / 4194304.0;
+        const double t = (double)((ft[p] & FIELD_MASK) >> 2) / 2097152.0 - 0.5;
         const double r = sqrt(-2.0 * log(u));
         double sn, c;
         sincospi(2.0 * t, &sn, &c);

@@ -48,8 +48,8 @@ def lib() -> C.CDLL:
         L.orc_mt_normals.argtypes = [C.c_uint32, dp, C.c_size_t]
         L.orc_philox4x32_10.restype = None
         L.orc_philox4x32_10.argtypes = [C.POINTER(C.c_uint32)] * 3
-        L.orc_philox_normals4.restype = None
-        L.orc_philox_normals4.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, dp]
+        L.orc_philox_normals6.restype = None
+        L.orc_philox_normals6.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, dp]
         L.orc_simulate_buffer.restype = C.c_int
         L.orc_simulate_buffer.argtypes = [C.c_int, dp, C.c_int64, dp, C.c_double, C.c_double, C.c_int,
                                           dp, C.c_int64, dp, i64p, i32p, dp, dp, i64p]
@@ -183,12 +183,12 @@ def philox4x32_10(ctr, key) -> np.ndarray:
 def philox_normals(seed, dataset, trial, stream, first, count) -> np.ndarray:
     """fp64-ideal normals first..first+count-1 of one (dataset, trial, stream)."""
     out = np.empty(count, np.float64)
-    z = (C.c_double * 4)()
+    z = (C.c_double * 6)()
     cached = -1
     for i in range(count):
         idx = first + i
-        if idx // 4 != cached:
-            cached = idx // 4
-            lib().orc_philox_normals4(int(seed), cached, int(trial), int(dataset), int(stream), z)
-        out[i] = z[idx % 4]
+        if idx // 6 != cached:
+            cached = idx // 6
+            lib().orc_philox_normals6(int(seed), cached, int(trial), int(dataset), int(stream), z)
+        out[i] = z[idx % 6]
     return out

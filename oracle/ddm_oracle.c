@@ -139,20 +139,33 @@ ORC_EXPORT void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], 
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-/* fp64 "ideal" value of the 4 normals a Philox block encodes.  The CUDA
- * kernels compute the same map in fp32 with MUFU lg2/sqrt/sin/cos:
- *   u = (2*(w & 0x7fffff) + 1) / 2^24  in (0,1),  t = (w' & 0x7fffff)/2^23 - 1/2
+/* fp64 "ideal" value of the 6 normals a Philox block encodes (three Box-Muller pairs of
+ * 21-bit uniforms; field layout documented in bayesflow_nddms_b200/csrc/ddm_rng.cuh).  The
+ * CUDA kernels compute the same map in fp32 with MUFU lg2/sqrt/sin/cos:
+ *   u = (2*m + 1) / 2^22  in (0,1),  t = m' / 2^21 - 1/2
  *   z_even = sqrt(-2 ln u) cos(2 pi t),  z_odd = sqrt(-2 ln u) sin(2 pi t)   */
-ORC_EXPORT void orc_philox_normals4(uint64_t seed, uint32_t block, uint32_t trial,
-                                    uint32_t dataset, uint32_t stream, double z[4]) {
+static inline uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+
+static inline uint32_t field21(uint32_t w) { return (w >> 2) & 0x1fffffu; } /* bits 2..22 */
+
+static inline uint32_t leftover21(uint32_t wa, uint32_t wb) {
+    /* mantissa bits 2..12 <- rotl(wa,11), bits 13..22 <- rotl(wb,22) */
+    uint32_t ra = rotl32(wa, 11), rb = rotl32(wb, 22);
+    return field21((ra & 0x00001ffcu) | (rb & ~0x00001ffcu));
+}
+
+ORC_EXPORT void orc_philox_normals6(uint64_t seed, uint32_t block, uint32_t trial,
+                                    uint32_t dataset, uint32_t stream, double z[6]) {
     uint32_t ctr[4] = {block, trial, dataset, stream};
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     uint32_t w[4];
     orc_philox4x32_10(ctr, key, w);
     const double two_pi = 6.283185307179586476925286766559;
-    for (int p = 0; p < 2; p++) {
-        double u = (2.0 * (double)(w[2 * p] & 0x7fffffu) + 1.0) / 16777216.0;
-        double t = (double)(w[2 * p + 1] & 0x7fffffu) / 8388608.0 - 0.5;
+    uint32_t mu[3] = {field21(w[0]), field21(w[2]), leftover21(w[0], w[1])};
+    uint32_t mt[3] = {field21(w[1]), field21(w[3]), leftover21(w[2], w[3])};
+    for (int p = 0; p < 3; p++) {
+        double u = (2.0 * (double)mu[p] + 1.0) / 4194304.0;
+        double t = (double)mt[p] / 2097152.0 - 0.5;
         double r = sqrt(-2.0 * log(u));
         z[2 * p] = r * cos(two_pi * t);
         z[2 * p + 1] = r * sin(two_pi * t);
@@ -178,7 +191,7 @@ typedef struct {
     uint32_t trial, dataset;
     uint32_t stream;    /* current stream */
     uint32_t next_idx;  /* index of next normal within the stream */
-    double cache[4];
+    double cache[6];
     uint32_t cache_block;
     int cache_valid;
 } orc_src;
@@ -191,13 +204,15 @@ static inline double src_next(orc_src *s) {
     case SRC_MT:
         return orc_mt_gauss(&s->mt);
     default: {
-        uint32_t blk = s->next_idx >> 2;
+        uint32_t blk = s->next_idx / 6u;
         if (!s->cache_valid || s->cache_block != blk) {
-            orc_philox_normals4(s->seed, blk, s->trial, s->dataset, s->stream, s->cache);
+            orc_philox_normals6(s->seed, blk, s->trial, s->dataset, s->stream, s->cache);
             s->cache_block = blk;
             s->cache_valid = 1;
         }
-        return s->cache[s->next_idx++ & 3u];
+        uint32_t j = s->next_idx - 6u * blk;
+        s->next_idx++;
+        return s->cache[j];
     }
     }
 }

@@ -244,15 +244,18 @@ def test_edge_shapes(sim):
     # max_steps = 0: no step is taken, every trial is a timeout at rt = tau
     z = sim.simulate(0, p, 33, max_steps=0)
     assert np.all(z[0, :, 0] == 0.3) and np.all(z[0, :, 1] == 0)
-    # max_steps not a multiple of the Philox block (generic kernel) keeps the same stream
+    # max_steps only truncates: the stream of a trial does not depend on it (multiples of the
+    # 6-normal Philox block and partial last blocks alike)
     a = sim.simulate(0, p, 300, max_steps=400, seed=5, dataset_offset=0, flags=F_STEPS)
     sa = sim.last_steps(300)
-    b = sim.simulate(0, p, 300, max_steps=399, seed=5, dataset_offset=0, flags=F_STEPS)
-    sb = sim.last_steps(300)
-    assert sim.last_stats()["used_persistent"] == 0
-    assert np.array_equal(np.minimum(sa, 399), sb)
-    keep = sa < 399
-    assert np.array_equal(a[0, keep], b[0, keep])
+    for ms in (399, 396, 7, 6, 5, 1):
+        b = sim.simulate(0, p, 300, max_steps=ms, seed=5, dataset_offset=0, flags=F_STEPS)
+        sb = sim.last_steps(300)
+        assert sim.last_stats()["used_persistent"] == 1
+        assert np.array_equal(np.minimum(sa, ms), sb), ms
+        keep = sa < ms
+        assert np.array_equal(a[0, keep], b[0, keep]), ms
+        assert np.all(b[0, ~keep, 1] == 0) or np.all(sa[~keep] == ms)
     # start point on / outside a boundary: zero steps (beta = 1 -> evidence >= boundary)
     c = sim.simulate(0, [[1.0, 1.2, 1.0, 0.3, 1.0]], 5)
     assert np.all(c[0, :, 0] == 0.3) and np.all(c[0, :, 1] == 1)
