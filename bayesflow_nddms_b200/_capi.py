@@ -82,6 +82,7 @@ SIGNATURES = {
     "ddm_set_stream": (C.c_int, [_vp, _vp]),
     "ddm_synchronize": (C.c_int, [_vp]),
     "ddm_set_tuning": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
+    "ddm_set_pipeline": (C.c_int, [_vp, C.c_int64, C.c_int64]),
     "ddm_simulate": (C.c_int, [_vp, C.c_int, _dp, C.c_int64, C.c_int, C.c_int64, C.c_double, C.c_int, C.c_uint64,
                                C.c_uint64, C.c_int, C.c_int, _vp]),
     "ddm_upload_params": (C.c_int, [_vp, C.c_int, _dp, C.c_int64, C.c_int]),

@@ -172,8 +172,17 @@ struct ddm_ctx {
     bool run_trialwise = false;
     ddm_stats stats{};
 
+    bool out_resident = false;  // false after a pipelined host-destined run
+
+    // chunked compute / copy pipeline of ddm_simulate (large host-destined batches)
+    cudaStream_t copy_stream = nullptr;
+    void *pipe_buf[2] = {nullptr, nullptr};
+    size_t pipe_cap[2] = {0, 0};
+    cudaEvent_t pipe_kernel_done[2] = {nullptr, nullptr}, pipe_copy_done[2] = {nullptr, nullptr};
+
     // tuning (0 = automatic)
     int tune_threshold = 0, tune_blocks_per_sm = 0, tune_tile = 0;
+    int64_t tune_pipeline_min_rows = -1, tune_pipeline_chunk_rows = -1;  // < 0: default
 };
 
 namespace {
@@ -226,10 +235,9 @@ int ensure_output(ddm_ctx *ctx, size_t bytes) {
     return DDM_OK;
 }
 
-// Shared by ddm_run and ddm_simulate_trialwise.
-int run_common(ddm_ctx *ctx, int model, int64_t n_datasets, int64_t n_trials, double dt, int max_steps,
-               uint64_t seed, uint64_t dataset_offset, uint64_t trial_offset, int precision, int flags,
-               int n_groups) {
+// Argument checks and the launch-invariant part of RunArgs, shared by every entry point.
+int build_args(ddm_ctx *ctx, int model, int64_t n_datasets, int64_t n_trials, double dt, int max_steps, uint64_t seed,
+               uint64_t dataset_offset, uint64_t trial_offset, int precision, int flags, ddm::RunArgs &a) {
     if (precision != 32 && precision != 64) return fail(ctx, DDM_ERR_INVALID, "precision must be 32 or 64, got %d", precision);
     if (!(dt > 0.0) || !std::isfinite(dt)) return fail(ctx, DDM_ERR_INVALID, "dt must be positive and finite");
     if (max_steps < 0) return fail(ctx, DDM_ERR_INVALID, "max_steps must be >= 0");
@@ -244,16 +252,7 @@ int run_common(ddm_ctx *ctx, int model, int64_t n_datasets, int64_t n_trials, do
     if (ctx->dbg_on && ctx->dbg_trials != rows)
         return fail(ctx, DDM_ERR_INVALID, "shared-increment buffer was set for %lld trials, run has %lld",
                     (long long)ctx->dbg_trials, (long long)rows);
-
-    const bool out64 = !(flags & DDM_FLAG_OUT_F32);
-    const size_t out_bytes = (size_t)rows * 2 * (out64 ? 8 : 4);
-    int rc = ensure_output(ctx, out_bytes);
-    if (rc) return rc;
-    const bool keep_steps = (flags & DDM_FLAG_KEEP_STEPS) != 0;
-    if (keep_steps) DDM_CUDA(ctx, ctx->steps.reserve((size_t)rows));
-
-    const int kind = kind_of(model);
-    ddm::RunArgs a{};
+    a = ddm::RunArgs{};
     a.dconst = ctx->dconst.p;
     a.params = ctx->params.p;
     a.group = ctx->group.p;
@@ -261,8 +260,6 @@ int run_common(ddm_ctx *ctx, int model, int64_t n_datasets, int64_t n_trials, do
     a.dbg_z = ctx->dbg_on ? ctx->dbg_z.p : nullptr;
     a.dbg_off = ctx->dbg_on ? ctx->dbg_off.p : nullptr;
     a.dbg_n = ctx->dbg_on ? ctx->dbg_n : 0;
-    a.out = ctx->out;
-    a.steps_out = keep_steps ? ctx->steps.p : nullptr;
     a.work_counter = ctx->counters;
     a.stats = ctx->counters + 1;
     a.n_datasets = (uint32_t)n_datasets;
@@ -277,59 +274,99 @@ int run_common(ddm_ctx *ctx, int model, int64_t n_datasets, int64_t n_trials, do
     a.dt = dt;
     a.sqrt_dt = std::sqrt(dt);
     a.kdt = (float)(-1.3862943611198906188 * dt);
-    (void)n_groups;
+    return DDM_OK;
+}
 
+bool uses_dconst(const ddm_ctx *ctx, int model, int precision) {
+    return precision == 32 && model != DDM_MODEL_TRIALWISE && !ctx->dbg_on;
+}
+
+// Enqueue the simulator kernel for the datasets described by `a` (pointers already offset to the
+// range) on the ctx stream.  The stats counters accumulate; only the work counter is reset.
+int launch_sim(ddm_ctx *ctx, ddm::RunArgs &a, int precision, ddm_stats &st) {
+    const int model = a.model, flags = a.flags;
+    const bool trialwise = (model == DDM_MODEL_TRIALWISE);
+    const int kind = kind_of(model);
+    const bool out64 = !(flags & DDM_FLAG_OUT_F32);
+    const int64_t n_datasets = a.n_datasets, n_trials = a.n_trials;
+    const int64_t rows = trialwise ? n_trials : n_datasets * n_trials;
+    if (rows == 0) return DDM_OK;
     const bool persistent = precision == 32 && !ctx->dbg_on && !trialwise && !(flags & DDM_FLAG_FORCE_GENERIC);
+    DDM_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
+    if (persistent) {
+        const int block = 256;
+        int per_sm = ctx->tune_blocks_per_sm;
+        const int max_per_sm = ddm::persistent_max_blocks_per_sm(kind, out64, block);
+        if (max_per_sm <= 0) return fail(ctx, DDM_ERR_CUDA, "occupancy query failed for the persistent kernel");
+        if (per_sm <= 0 || per_sm > max_per_sm) per_sm = max_per_sm;
+        // tile: trials of one dataset handed out per atomic claim.  (Whole-dataset claims measured
+        // 15 % slower on the sweep: per-dataset cost varies 400x, so coarse claims unbalance the tail.)
+        uint32_t tile = ctx->tune_tile > 0 ? (uint32_t)ctx->tune_tile : 64u;
+        if (tile > (uint32_t)n_trials) tile = (uint32_t)n_trials;
+        if (tile == 0) tile = 1;
+        while (((uint64_t)n_trials + tile - 1) / tile * (uint64_t)n_datasets > 0xffffffffULL) tile *= 2;  // 32-bit item index
+        a.tile = tile;
+        a.tiles_per_dataset = (uint32_t)((n_trials + tile - 1) / tile);
+        a.n_items = (uint64_t)a.tiles_per_dataset * (uint64_t)n_datasets;
+        a.refill_threshold = ctx->tune_threshold > 0 ? ctx->tune_threshold : 5;
+        if (a.refill_threshold > 32) a.refill_threshold = 32;
+        const uint64_t warps_needed = ((uint64_t)rows + 31) / 32;
+        uint64_t grid = (uint64_t)ctx->sm_count * per_sm;
+        const uint64_t blocks_needed = (warps_needed + (block / 32) - 1) / (block / 32);
+        if (grid > blocks_needed) grid = blocks_needed;
+        if (grid < 1) grid = 1;
+        DDM_CUDA(ctx, ddm::launch_persistent(a, kind, out64, (int)grid, block, ctx->stream));
+        st.used_persistent = 1;
+        st.grid = (int)grid;
+        st.block = block;
+        st.refill_threshold = a.refill_threshold;
+        st.tile = (int)tile;
+    } else {
+        DDM_CUDA(ctx, ddm::launch_generic(a, kind, precision == 64, ctx->dbg_on, out64, (uint64_t)rows, ctx->stream));
+        st.grid = (int)(((uint64_t)rows + 127) / 128);
+        st.block = 128;
+    }
+    st.kernel_launches++;
+    return DDM_OK;
+}
+
+// Shared by ddm_run and ddm_simulate_trialwise: one launch over everything, output resident.
+int run_common(ddm_ctx *ctx, int model, int64_t n_datasets, int64_t n_trials, double dt, int max_steps,
+               uint64_t seed, uint64_t dataset_offset, uint64_t trial_offset, int precision, int flags,
+               int n_groups) {
+    (void)n_groups;
+    ddm::RunArgs a;
+    int rc = build_args(ctx, model, n_datasets, n_trials, dt, max_steps, seed, dataset_offset, trial_offset, precision, flags, a);
+    if (rc) return rc;
+    const bool trialwise = (model == DDM_MODEL_TRIALWISE);
+    const int64_t rows = trialwise ? n_trials : n_datasets * n_trials;
+    const bool out64 = !(flags & DDM_FLAG_OUT_F32);
+    const size_t out_bytes = (size_t)rows * 2 * (out64 ? 8 : 4);
+    rc = ensure_output(ctx, out_bytes);
+    if (rc) return rc;
+    const bool keep_steps = (flags & DDM_FLAG_KEEP_STEPS) != 0;
+    if (keep_steps) DDM_CUDA(ctx, ctx->steps.reserve((size_t)rows));
+    a.out = ctx->out;
+    a.steps_out = keep_steps ? ctx->steps.p : nullptr;
+
     ddm_stats st{};
     st.n_trials = (uint64_t)rows;
-
     DDM_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long) * (1 + ddm::STAT_COUNT), ctx->stream));
-    int launches = 0;
     if (rows > 0) {
-        if (precision == 32 && !trialwise && !ctx->dbg_on) {
+        if (uses_dconst(ctx, model, precision)) {
             DDM_CUDA(ctx, ctx->dconst.reserve((size_t)n_datasets));
             a.dconst = ctx->dconst.p;
             DDM_CUDA(ctx, ddm::launch_prep(ctx->params.p, ctx->dconst.p, (uint32_t)n_datasets, (uint32_t)ctx->n_params,
                                            model, dt, ctx->stream));
-            launches++;
+            st.kernel_launches++;
         }
         DDM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-        if (persistent) {
-            const int block = 256;
-            int per_sm = ctx->tune_blocks_per_sm;
-            const int max_per_sm = ddm::persistent_max_blocks_per_sm(kind, out64, block);
-            if (max_per_sm <= 0) return fail(ctx, DDM_ERR_CUDA, "occupancy query failed for the persistent kernel");
-            if (per_sm <= 0 || per_sm > max_per_sm) per_sm = max_per_sm;
-            // tile: trials of one dataset handed out per atomic claim
-            uint32_t tile = ctx->tune_tile > 0 ? (uint32_t)ctx->tune_tile : 64u;
-            if (tile > (uint32_t)n_trials) tile = (uint32_t)n_trials;
-            a.tile = tile;
-            a.tiles_per_dataset = (uint32_t)((n_trials + tile - 1) / tile);
-            a.n_items = (uint64_t)a.tiles_per_dataset * (uint64_t)n_datasets;
-            a.refill_threshold = ctx->tune_threshold > 0 ? ctx->tune_threshold : 4;
-            if (a.refill_threshold > 32) a.refill_threshold = 32;
-            const uint64_t warps_needed = ((uint64_t)rows + 31) / 32;
-            uint64_t grid = (uint64_t)ctx->sm_count * per_sm;
-            const uint64_t blocks_needed = (warps_needed + (block / 32) - 1) / (block / 32);
-            if (grid > blocks_needed) grid = blocks_needed;
-            if (grid < 1) grid = 1;
-            DDM_CUDA(ctx, ddm::launch_persistent(a, kind, out64, (int)grid, block, ctx->stream));
-            st.used_persistent = 1;
-            st.grid = (int)grid;
-            st.block = block;
-            st.refill_threshold = a.refill_threshold;
-            st.tile = (int)tile;
-        } else {
-            DDM_CUDA(ctx, ddm::launch_generic(a, kind, precision == 64, ctx->dbg_on, out64, (uint64_t)rows, ctx->stream));
-            st.grid = (int)(((uint64_t)rows + 127) / 128);
-            st.block = 128;
-        }
-        launches++;
+        rc = launch_sim(ctx, a, precision, st);
+        if (rc) return rc;
         DDM_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     }
     DDM_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, ctx->counters, sizeof(unsigned long long) * (1 + ddm::STAT_COUNT),
                                   cudaMemcpyDeviceToHost, ctx->stream));
-    st.kernel_launches = launches;
     ctx->stats = st;
     ctx->stats_pending = true;
     ctx->have_run = true;
@@ -340,6 +377,98 @@ int run_common(ddm_ctx *ctx, int model, int64_t n_datasets, int64_t n_trials, do
     ctx->run_datasets = n_datasets;
     ctx->run_trials = n_trials;
     ctx->run_trialwise = trialwise;
+    ctx->out_resident = true;
+    return DDM_OK;
+}
+
+// Large host-destined batches: datasets are simulated in chunks into two device buffers while
+// the previous chunk is copied to the host on a second stream, so the batch costs
+// max(kernel, PCIe) instead of kernel + PCIe and needs 2 chunks of HBM instead of the batch.
+constexpr int64_t kPipelineMinRows = 8ll << 20;     // below this one launch + one copy is as fast
+constexpr int64_t kPipelineChunkRows = 32ll << 20;  // trials per chunk (512 MB of float64 pairs)
+
+int run_pipelined(ddm_ctx *ctx, int64_t n_trials, double dt, int max_steps, uint64_t seed, uint64_t dataset_offset,
+                  int precision, int flags, void *out_host) {
+    const int model = ctx->model;
+    const int64_t n_datasets = ctx->n_datasets;
+    ddm::RunArgs base;
+    int rc = build_args(ctx, model, n_datasets, n_trials, dt, max_steps, seed, dataset_offset, 0, precision, flags, base);
+    if (rc) return rc;
+    const bool out64 = !(flags & DDM_FLAG_OUT_F32);
+    const size_t row_bytes = 2 * (out64 ? 8 : 4);
+    const int64_t chunk_rows = ctx->tune_pipeline_chunk_rows > 0 ? ctx->tune_pipeline_chunk_rows : kPipelineChunkRows;
+    int64_t chunk_ds = chunk_rows / (n_trials > 0 ? n_trials : 1);
+    if (chunk_ds < 1) chunk_ds = 1;
+    const size_t chunk_bytes = (size_t)chunk_ds * (size_t)n_trials * row_bytes;
+    // the resident-output buffer is not used by this path: hand it back so the pool can reuse it
+    if (ctx->out) {
+        ctx->pool->give(ctx->out, ctx->out_cap);
+        ctx->out = nullptr;
+        ctx->out_cap = 0;
+    }
+    for (int b = 0; b < 2; b++) {
+        if (ctx->pipe_buf[b] && ctx->pipe_cap[b] >= chunk_bytes) continue;
+        if (ctx->pipe_buf[b]) cudaFree(ctx->pipe_buf[b]);
+        ctx->pipe_buf[b] = nullptr;
+        ctx->pipe_cap[b] = 0;
+        DDM_CUDA(ctx, cudaMalloc(&ctx->pipe_buf[b], chunk_bytes));
+        ctx->pipe_cap[b] = chunk_bytes;
+    }
+    if (!ctx->copy_stream) {
+        DDM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; b++) {
+            DDM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_kernel_done[b], cudaEventDisableTiming));
+            DDM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_copy_done[b], cudaEventDisableTiming));
+        }
+    }
+    ddm_stats st{};
+    st.n_trials = (uint64_t)(n_datasets * n_trials);
+    DDM_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long) * (1 + ddm::STAT_COUNT), ctx->stream));
+    const bool dconst = uses_dconst(ctx, model, precision);
+    if (dconst) {
+        DDM_CUDA(ctx, ctx->dconst.reserve((size_t)n_datasets));
+        DDM_CUDA(ctx, ddm::launch_prep(ctx->params.p, ctx->dconst.p, (uint32_t)n_datasets, (uint32_t)ctx->n_params, model, dt,
+                                       ctx->stream));
+        st.kernel_launches++;
+    }
+    DDM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    int64_t chunk = 0;
+    for (int64_t lo = 0; lo < n_datasets; lo += chunk_ds, chunk++) {
+        const int b = (int)(chunk & 1);
+        const int64_t cnt = (n_datasets - lo < chunk_ds) ? (n_datasets - lo) : chunk_ds;
+        if (chunk >= 2) DDM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pipe_copy_done[b], 0));  // buffer free again
+        ddm::RunArgs a = base;
+        a.params = ctx->params.p + (size_t)lo * ctx->n_params;
+        a.dconst = dconst ? ctx->dconst.p + lo : nullptr;
+        a.n_datasets = (uint32_t)cnt;
+        a.dataset_offset = (uint32_t)(dataset_offset + (uint64_t)lo);
+        a.out = ctx->pipe_buf[b];
+        a.steps_out = nullptr;
+        rc = launch_sim(ctx, a, precision, st);
+        if (rc) return rc;
+        DDM_CUDA(ctx, cudaEventRecord(ctx->pipe_kernel_done[b], ctx->stream));
+        DDM_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->pipe_kernel_done[b], 0));
+        DDM_CUDA(ctx, cudaMemcpyAsync(static_cast<char *>(out_host) + (size_t)lo * (size_t)n_trials * row_bytes, ctx->pipe_buf[b],
+                                      (size_t)cnt * (size_t)n_trials * row_bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        DDM_CUDA(ctx, cudaEventRecord(ctx->pipe_copy_done[b], ctx->copy_stream));
+    }
+    DDM_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    DDM_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, ctx->counters, sizeof(unsigned long long) * (1 + ddm::STAT_COUNT),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    // the caller's stream sees the copies as done: join the copy stream back, then block
+    for (int b = 0; b < 2 && b < chunk; b++) DDM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pipe_copy_done[b], 0));
+    DDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats = st;
+    ctx->stats_pending = true;
+    ctx->have_run = true;
+    ctx->out64 = out64;
+    ctx->out_bytes = 0;
+    ctx->have_steps = false;
+    ctx->run_rows = n_datasets * n_trials;
+    ctx->run_datasets = n_datasets;
+    ctx->run_trials = n_trials;
+    ctx->run_trialwise = false;
+    ctx->out_resident = false;  // the batch went to the host chunk by chunk
     return DDM_OK;
 }
 
@@ -418,6 +547,12 @@ DDM_API int ddm_destroy(ddm_ctx *ctx) {
         ctx->export_buf.free_();
         ctx->dbg_off.free_();
         ctx->philox_buf.free_();
+        for (int b = 0; b < 2; b++) {
+            if (ctx->pipe_buf[b]) cudaFree(ctx->pipe_buf[b]);
+            if (ctx->pipe_kernel_done[b]) cudaEventDestroy(ctx->pipe_kernel_done[b]);
+            if (ctx->pipe_copy_done[b]) cudaEventDestroy(ctx->pipe_copy_done[b]);
+        }
+        if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
         if (ctx->counters) cudaFree(ctx->counters);
         if (ctx->counters_host) cudaFreeHost(ctx->counters_host);
         if (ctx->out && ctx->pool) ctx->pool->give(ctx->out, ctx->out_cap);
@@ -455,6 +590,13 @@ DDM_API int ddm_set_tuning(ddm_ctx *ctx, int refill_threshold, int blocks_per_sm
     return DDM_OK;
 }
 
+DDM_API int ddm_set_pipeline(ddm_ctx *ctx, int64_t min_rows, int64_t chunk_rows) {
+    if (!ctx) return DDM_ERR_INVALID;
+    ctx->tune_pipeline_min_rows = min_rows;
+    ctx->tune_pipeline_chunk_rows = chunk_rows;
+    return DDM_OK;
+}
+
 // ---- the hot path -----------------------------------------------------------------------
 DDM_API int ddm_upload_params(ddm_ctx *ctx, int model, const double *params, int64_t n_datasets, int n_params) {
     if (!ctx) return DDM_ERR_INVALID;
@@ -485,7 +627,8 @@ DDM_API int ddm_run(ddm_ctx *ctx, int64_t n_trials, double dt, int max_steps, ui
 
 DDM_API int ddm_download(ddm_ctx *ctx, void *out_host) {
     if (!ctx) return DDM_ERR_INVALID;
-    if (!ctx->have_run || !ctx->out) return fail(ctx, DDM_ERR_STATE, "no output to download (run first; DLPack hand-off moves it away)");
+    if (!ctx->have_run || !ctx->out || !ctx->out_resident)
+        return fail(ctx, DDM_ERR_STATE, "no output to download (run first; DLPack hand-off moves it away)");
     if (!out_host && ctx->out_bytes) return fail(ctx, DDM_ERR_INVALID, "out_host is NULL");
     DeviceGuard g(ctx->device);
     if (ctx->out_bytes) DDM_CUDA(ctx, cudaMemcpyAsync(out_host, ctx->out, ctx->out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -498,6 +641,12 @@ DDM_API int ddm_simulate(ddm_ctx *ctx, int model, const double *params, int64_t 
                          int precision, int flags, void *out_host) {
     int rc = ddm_upload_params(ctx, model, params, n_datasets, n_params);
     if (rc) return rc;
+    const int64_t min_rows = ctx->tune_pipeline_min_rows >= 0 ? ctx->tune_pipeline_min_rows : kPipelineMinRows;
+    if (out_host && n_trials > 0 && n_datasets * n_trials >= min_rows && n_datasets >= 2 && !(flags & DDM_FLAG_KEEP_STEPS) &&
+        !ctx->dbg_on) {
+        DeviceGuard g(ctx->device);
+        return run_pipelined(ctx, n_trials, dt, max_steps, seed, dataset_offset, precision, flags, out_host);
+    }
     rc = ddm_run(ctx, n_trials, dt, max_steps, seed, dataset_offset, precision, flags);
     if (rc) return rc;
     if (out_host) return ddm_download(ctx, out_host);
@@ -558,7 +707,7 @@ DDM_API int ddm_last_stats(ddm_ctx *ctx, ddm_stats *out) {
 
 DDM_API int ddm_last_output_device_ptr(ddm_ctx *ctx, void **ptr, size_t *bytes) {
     if (!ctx || !ptr) return DDM_ERR_INVALID;
-    if (!ctx->have_run || !ctx->out) return fail(ctx, DDM_ERR_STATE, "no output resident");
+    if (!ctx->have_run || !ctx->out || !ctx->out_resident) return fail(ctx, DDM_ERR_STATE, "no output resident");
     *ptr = ctx->out;
     if (bytes) *bytes = ctx->out_bytes;
     return DDM_OK;
@@ -566,7 +715,8 @@ DDM_API int ddm_last_output_device_ptr(ddm_ctx *ctx, void **ptr, size_t *bytes) 
 
 DDM_API int ddm_last_output_dlpack(ddm_ctx *ctx, struct DLManagedTensor **out) {
     if (!ctx || !out) return DDM_ERR_INVALID;
-    if (!ctx->have_run || !ctx->out) return fail(ctx, DDM_ERR_STATE, "no output resident (already handed off?)");
+    if (!ctx->have_run || !ctx->out || !ctx->out_resident)
+        return fail(ctx, DDM_ERR_STATE, "no output resident (already handed off, or the last run streamed to the host)");
     DeviceGuard g(ctx->device);
     DDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     auto *h = new (std::nothrow) DlpackHolder();

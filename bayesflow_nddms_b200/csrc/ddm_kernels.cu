@@ -74,7 +74,7 @@ __device__ __forceinline__ void store_pair(void *out, uint64_t idx, double o0, d
 // refill path.  Philox counters are (step block, trial, dataset): results do not
 // depend on which lane / warp / SM / GPU ran a trial.
 template <int KIND, bool OUT64>
-__global__ void __launch_bounds__(256) persistent_kernel(const RunArgs a) {
+__global__ void __launch_bounds__(256, 6) persistent_kernel(const RunArgs a) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
 
@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(256) persistent_kernel(const RunArgs a) {
     // a trial's last block is partial when max_steps is not a multiple of 6: n > tail_from
     const bool partial_tail = (a.max_steps % NORMALS_PER_BLOCK) != 0u;
     const int tail_from = (int)a.max_steps - NORMALS_PER_BLOCK;
+    constexpr bool BASIC = (KIND == KIND_FIXED);
 
     for (;;) {
         // ---- finish: emit every frozen trial ---------------------------------------
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(256) persistent_kernel(const RunArgs a) {
             const int choice = (x >= t.h) ? 1 : ((x <= -t.h) ? -1 : 0);
             const double tau = a.params[(size_t)ds * a.n_params + 3];
             double o0, o1;
-            trial_outputs(a.model, a.flags, choice, n, a.dt, tau, (double)t.ext, o0, o1);
+            trial_outputs<BASIC>(a.flags, choice, n, a.dt, tau, (double)t.ext, o0, o1);
             if (a.flags & 16) o1 = (double)__fadd_rn(x, t.h);
             const uint64_t idx = (uint64_t)ds * a.n_trials + trial;
             store_pair<OUT64>(a.out, idx, o0, o1);
@@ -127,8 +128,13 @@ __global__ void __launch_bounds__(256) persistent_kernel(const RunArgs a) {
                 if (lane == 0) w = atomicAdd(a.work_counter, 1ull);
                 w = __shfl_sync(FULL_MASK, w, 0);
                 if (w >= a.n_items) { more = false; break; }
-                tile_ds = (uint32_t)(w / a.tiles_per_dataset);
-                const uint32_t ti = (uint32_t)(w - (unsigned long long)tile_ds * a.tiles_per_dataset);
+                uint32_t ti = 0;
+                if (a.tiles_per_dataset == 1u) {  // many datasets: a claim is a whole dataset, no division
+                    tile_ds = (uint32_t)w;
+                } else {
+                    tile_ds = (uint32_t)w / a.tiles_per_dataset;  // host keeps n_items < 2^32
+                    ti = (uint32_t)w - tile_ds * a.tiles_per_dataset;
+                }
                 cur = ti * a.tile;
                 end = min(cur + a.tile, a.n_trials);
                 const float4 *src = reinterpret_cast<const float4 *>(a.dconst + tile_ds);
@@ -301,7 +307,7 @@ __global__ void __launch_bounds__(128) generic_kernel(const RunArgs a, uint64_t 
             if (BUFFER && buf.overrun) atomicAdd(a.stats + STAT_DBG_OVERRUN, 1ull);
         }
         double o0, o1;
-        trial_outputs(a.model == 5 ? 1 : a.model, a.flags, choice, n, a.dt, tau, ext, o0, o1);
+        trial_outputs<KIND == KIND_FIXED>(a.flags, choice, n, a.dt, tau, ext, o0, o1);
         if (a.flags & 16) o1 = final_ev;
         store_pair<OUT64>(a.out, g, o0, o1);
         if (a.steps_out) a.steps_out[g] = (int32_t)n;

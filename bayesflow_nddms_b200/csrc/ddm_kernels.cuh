@@ -129,6 +129,9 @@ __device__ __forceinline__ void trial_setup_f32(const DsConst &dc, uint32_t tria
     "setp.lt.and.f32 q, ax, %4, q;\n\t"
 #define DDM_STEP_TAIL(S, T) DDM_STEP(S, T) "setp.lt.and.u32 q, %1, %14, q;\n\t"
 
+// No warp-level primitive in here: the one-thread-per-trial kernel calls this from divergent code.
+// (A float step counter, to move the increments from the ALU pipe to the FMA pipes, measured 4 %
+// slower on B200: the FMA-heavy pipe is as busy as the ALU pipe because of IMAD.WIDE.)
 template <bool TAIL>
 __device__ __forceinline__ void euler6(float &x, uint32_t &n, uint32_t &p, float c0, float h,
                                        const Normals6Scaled &z, uint32_t max_steps) {
@@ -156,9 +159,9 @@ __device__ __forceinline__ void euler6(float &x, uint32_t &n, uint32_t &p, float
 
 // One Philox block of a trial: block index `blk` = n / 6 for a lane that is still stepping.
 template <bool TAIL>
-__device__ __forceinline__ void step_block_f32(uint32_t blk, uint32_t trial, uint32_t ds_global, const PhiloxKey &key,
-                                               const TrialF32 &t, float &x, uint32_t &n, uint32_t &p,
-                                               uint32_t max_steps) {
+__device__ __forceinline__ void step_block_f32(uint32_t blk, uint32_t trial, uint32_t ds_global,
+                                               const PhiloxKey &key, const TrialF32 &t, float &x, uint32_t &n,
+                                               uint32_t &p, uint32_t max_steps) {
     Normals6Scaled z;
     philox_pairs_scaled(blk, trial, ds_global, STREAM_STEP, key, t.k, z);
     euler6<TAIL>(x, n, p, t.c0, t.h, z, max_steps);
@@ -167,10 +170,11 @@ __device__ __forceinline__ void step_block_f32(uint32_t blk, uint32_t trial, uin
 // Final outputs of a finished fp32 trial, computed in fp64 with the reference's operation
 // order so that, given the same step count, col0 equals the reference's double exactly
 // (basic_ddm_dc.py:103  rt = n_steps*dt + tau;  single_trial_alpha_not_scaled.py:127,133-138).
-__device__ __forceinline__ void trial_outputs(int model, int flags, int choice, uint32_t n, double dt,
-                                              double tau, double ext, double &o0, double &o1) {
+template <bool BASIC>
+__device__ __forceinline__ void trial_outputs(int flags, int choice, uint32_t n, double dt, double tau, double ext,
+                                              double &o0, double &o1) {
     const double rt = __dmul_rn((double)n, dt);
-    if (model == 0) {  // DDM_MODEL_BASIC
+    if (BASIC) {  // DDM_MODEL_BASIC
         o0 = __dadd_rn(rt, tau);
         o1 = (choice == 0) ? ((flags & 1) ? 1.0 : 0.0) : (double)choice;
     } else {

@@ -127,10 +127,34 @@ class DDMSimulator:
 
     def simulate(self, model: int, params, n_trials: int, dt: float = 0.01, max_steps: int = 400, *, seed=None,
                  dataset_offset=None, precision: int = 32, flags: int = 0, out: np.ndarray | None = None) -> np.ndarray:
-        """B datasets x n_trials -> numpy (B, n_trials, 2), float64 unless FLAG_OUT_F32."""
-        B = self.run(model, params, n_trials, dt, max_steps, seed=seed, dataset_offset=dataset_offset,
-                     precision=precision, flags=flags)
-        return self.download((B, int(n_trials), 2), bool(flags & _capi.FLAG_OUT_F32), out)
+        """B datasets x n_trials -> numpy (B, n_trials, 2), float64 unless FLAG_OUT_F32.
+
+        One ``ddm_simulate`` call: upload, launch, copy back.  Large batches are streamed to the host
+        chunk by chunk with the PCIe copy of one chunk overlapping the kernel of the next; pass a
+        ``pinned_empty`` array as ``out`` for full-rate asynchronous copies."""
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        if params.ndim == 1:
+            params = params[None, :]
+        if params.ndim != 2:
+            raise ValueError("params must be (P,) or (B, P)")
+        B, P = params.shape
+        shape = (B, int(n_trials), 2)
+        dtype = np.float32 if flags & _capi.FLAG_OUT_F32 else np.float64
+        if out is None:
+            out = np.empty(shape, dtype=dtype)
+        elif out.dtype != dtype or out.shape != shape or not out.flags.c_contiguous:
+            raise ValueError("out must be C-contiguous with the result's shape and dtype")
+        off = self._next_offset(B, dataset_offset)
+        self._check(self._lib.ddm_simulate(self._ctx, int(model), params.ctypes.data_as(_capi._dp), B, P, int(n_trials),
+                                           float(dt), int(max_steps),
+                                           self.seed if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF, off,
+                                           int(precision), int(flags), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def set_pipeline(self, min_rows: int = -1, chunk_rows: int = -1):
+        """Host-destined batches of at least ``min_rows`` trials are streamed in chunks of about
+        ``chunk_rows`` trials (values < 0: defaults)."""
+        self._check(self._lib.ddm_set_pipeline(self._ctx, int(min_rows), int(chunk_rows)))
 
     def simulate_device(self, model: int, params, n_trials: int, dt: float = 0.01, max_steps: int = 400, *,
                         seed=None, dataset_offset=None, precision: int = 32, flags: int = _capi.FLAG_OUT_F32) -> DeviceBatch:

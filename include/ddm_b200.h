@@ -92,6 +92,11 @@ int ddm_set_stream(ddm_ctx *ctx, void *cuda_stream); /* NULL restores the ctx-ow
 int ddm_synchronize(ddm_ctx *ctx);
 /* tuning knobs; 0 = automatic */
 int ddm_set_tuning(ddm_ctx *ctx, int refill_threshold, int blocks_per_sm, int tile);
+/* ddm_simulate with a host destination streams batches of at least min_rows trials to the host in
+ * chunks of about chunk_rows trials, overlapping kernel and PCIe copy (defaults 8 Mi / 32 Mi trials;
+ * values < 0 restore them; a huge min_rows switches the pipeline off).  After such a run the batch
+ * is not resident on the device.  Results do not depend on the chunking. */
+int ddm_set_pipeline(ddm_ctx *ctx, int64_t min_rows, int64_t chunk_rows);
 
 /* ---- the hot path ------------------------------------------------------ */
 /* Replaces B calls of simulate_trials(params[b], n_trials)  (basic_ddm_dc.py:114-125,

@@ -16,6 +16,13 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run on the GPU box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    # a hung kernel must fail the test, not hang the GPU box until the outer limit
+    for item in items:
+        if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+            item.add_marker(pytest.mark.timeout(300, method="thread"))
+
+
 @pytest.fixture(scope="session")
 def golden():
     z = np.load(GOLDEN)
