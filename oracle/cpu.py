@@ -62,6 +62,9 @@ def lib() -> C.CDLL:
         L.orc_simulate_batch_mt.restype = C.c_int
         L.orc_simulate_batch_mt.argtypes = [C.c_int, dp, C.c_int64, C.c_int64, C.c_double, C.c_double,
                                             C.c_int, C.c_uint32, C.c_int, dp, i64p, i64p]
+        L.orc_simulate_evidence.restype = C.c_int
+        L.orc_simulate_evidence.argtypes = [dp, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, dp,
+                                            C.c_int64, C.c_uint64, C.c_uint32, C.c_uint32, dp, i64p, i64p]
         _lib = L
     return _lib
 
@@ -192,3 +195,29 @@ def philox_normals(seed, dataset, trial, stream, first, count) -> np.ndarray:
             lib().orc_philox_normals6(int(seed), cached, int(trial), int(dataset), int(stream), z)
         out[i] = z[idx % 6]
     return out
+
+
+def simulate_evidence(params, n_trials, n_obs=200, mode=1, dt=0.001, max_steps=4000.0, *, normals=None, mt_seed=None,
+                      philox_seed=None, dataset=0, trial_offset=0):
+    """Evidence-path variants (retired_models/basic_ddm_dc_evidence*.py).  params = [drift, boundary, beta,
+    tau, dc, sigma1]; mode 0 raw noisy path, 1 per-trial z-score, 2 dataset-level standardisation.
+    Exactly one normal source: ``normals`` (buffer), ``mt_seed`` or ``philox_seed``.
+    Returns (sim_data (n_trials, 2 + n_obs), n_steps, consumed)."""
+    params = np.ascontiguousarray(params, dtype=np.float64).ravel()
+    if params.size != 6:
+        raise ValueError("evidence model takes 6 parameters")
+    out = np.empty((n_trials, 2 + n_obs), np.float64)
+    ns = np.empty(n_trials, np.int64)
+    cons = np.empty(n_trials, np.int64)
+    if normals is not None:
+        normals = np.ascontiguousarray(normals, dtype=np.float64)
+        kind, seed, nn = 0, 0, normals.size
+    elif mt_seed is not None:
+        kind, seed, nn = 1, int(mt_seed) & 0xFFFFFFFF, 0
+    else:
+        kind, seed, nn = 2, int(philox_seed), 0
+    rc = lib().orc_simulate_evidence(_dp(params), n_trials, int(n_obs), int(mode), dt, float(max_steps), kind,
+                                     _dp(normals), nn, seed, int(dataset), int(trial_offset), _dp(out),
+                                     ns.ctypes.data_as(C.POINTER(C.c_int64)), cons.ctypes.data_as(C.POINTER(C.c_int64)))
+    _check(rc)
+    return out, ns, cons

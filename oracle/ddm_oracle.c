@@ -422,6 +422,96 @@ ORC_EXPORT int orc_simulate_philox(int model, const double *params, int64_t n_tr
 }
 
 /* ------------------------------------------------------------------ */
+/* Evidence-path variants (retired_models/)      */
+/*   basic_ddm_dc_evidence.py:87-151        200 obs, noise sigma1, per-trial z-score  (mode 1)  */
+/*   basic_ddm_dc_evidence2.py:83-150       200 obs, noise sigma1, dataset-level
+ *                                          (x - mean(path_means)) / std(path_means) (mode 2)  */
+/*   basic_ddm_dc_evidence_no_noise2.py:82-147  400 obs, noise .001, per-trial z-score (mode 1) */
+/* p = [drift, boundary, beta, tau, dc, sigma1]; row = (rt, choice, path[n_obs]).              */
+/* Normals per trial, in order: z_step[0..n-1], z_noise[0..n_obs-1].  Means and variances are  */
+/* plain left-to-right sums (numba's array_mean / array_var), std = sqrt(var).                 */
+/* ------------------------------------------------------------------ */
+static double seq_mean(const double *v, int64_t n) {
+    double c = 0.0;
+    for (int64_t i = 0; i < n; i++) c += v[i];
+    return c / (double)n;
+}
+
+static double seq_std(const double *v, int64_t n) {
+    double m = seq_mean(v, n), ssd = 0.0;
+    for (int64_t i = 0; i < n; i++) {
+        double d = v[i] - m;
+        ssd += d * d;
+    }
+    return sqrt(ssd / (double)n);
+}
+
+static void evidence_trial(const double *p, int n_obs, int mode, double dt, double max_steps, orc_src *src,
+                           double *row, int64_t *n_out, double *mean_out) {
+    double drift = p[0], boundary = p[1], beta = p[2], tau = p[3], dc = p[4], sigma1 = p[5];
+    double n_steps = 0.0, evidence = boundary * beta;
+    double *path = row + 2;
+    for (int k = 0; k < n_obs; k++) path[k] = 0.0;
+    src_seek(src, PH_STREAM_STEP, 0);
+    while ((evidence > 0) && (evidence < boundary) && (n_steps < max_steps)) {
+        double z = src_next(src);
+        double t1 = drift * dt;
+        double t2 = sqrt(dt) * dc;
+        double t3 = t2 * z;
+        evidence = evidence + (t1 + t3);
+        if (n_steps < (double)n_obs) path[(int)n_steps] = evidence;
+        n_steps += 1.0;
+    }
+    row[0] = n_steps * dt + tau;
+    for (int k = (int)n_steps; k < n_obs; k++) path[k] = evidence; /* held at the final value */
+    src_seek(src, PH_STREAM_AUX, 0);
+    for (int k = 0; k < n_obs; k++) path[k] = path[k] + (0.0 + sigma1 * src_next(src));
+    if (mode == 1) {
+        double m = seq_mean(path, n_obs), sd = seq_std(path, n_obs);
+        for (int k = 0; k < n_obs; k++) path[k] = (path[k] - m) / sd;
+    } else if (mean_out) {
+        *mean_out = seq_mean(path, n_obs);
+    }
+    row[1] = (evidence >= boundary) ? 1.0 : ((evidence <= 0) ? -1.0 : 0.0);
+    *n_out = (int64_t)n_steps;
+}
+
+/* src_kind: 0 buffer (normals, n_normals), 1 MT19937 (seed), 2 Philox (seed, dataset, trial_offset). */
+ORC_EXPORT int orc_simulate_evidence(const double *params, int64_t n_trials, int n_obs, int mode, double dt,
+                                     double max_steps, int src_kind, const double *normals, int64_t n_normals,
+                                     uint64_t seed, uint32_t dataset, uint32_t trial_offset, double *out,
+                                     int64_t *n_steps, int64_t *consumed) {
+    if (n_obs < 1 || mode < 0 || mode > 2) return -3;
+    orc_src src;
+    memset(&src, 0, sizeof(src));
+    src.kind = src_kind;
+    if (src_kind == SRC_BUFFER) { src.buf = normals; src.len = (size_t)n_normals; }
+    else if (src_kind == SRC_MT) orc_mt_seed(&src.mt, (uint32_t)seed);
+    else { src.seed = seed; src.dataset = dataset; }
+    const int64_t cols = 2 + n_obs;
+    double *means = (mode == 2) ? (double *)malloc(sizeof(double) * (size_t)(n_trials > 0 ? n_trials : 1)) : NULL;
+    for (int64_t i = 0; i < n_trials; i++) {
+        size_t pos0 = src.pos;
+        int64_t n;
+        src.trial = trial_offset + (uint32_t)i;
+        evidence_trial(params, n_obs, mode, dt, max_steps, &src, out + (size_t)i * cols, &n, means ? &means[i] : NULL);
+        if (src.overrun) { free(means); return -1; }
+        if (n_steps) n_steps[i] = n;
+        if (consumed) consumed[i] = (int64_t)(src.pos - pos0);
+    }
+    if (mode == 2 && n_trials > 0) {
+        double m = seq_mean(means, n_trials), sd = seq_std(means, n_trials);
+        for (int64_t i = 0; i < n_trials; i++)
+            for (int k = 0; k < n_obs; k++) {
+                double *v = out + (size_t)i * cols + 2 + k;
+                *v = (*v - m) / sd;
+            }
+    }
+    free(means);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ */
 /* CPU baseline: B datasets x n_trials on `n_threads` host threads, each */
 /* dataset on its own MT19937 stream (seed + dataset), i.e. the          */
 /* reference's numba loop run process-parallel over datasets.  Returns   */
