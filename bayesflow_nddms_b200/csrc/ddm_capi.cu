@@ -147,7 +147,7 @@ struct ddm_ctx {
     Arena<double> params;
     Arena<ddm::DsConst> dconst;
     Arena<int32_t> steps, group;
-    Arena<double> bound, dbg_z, export_buf;
+    Arena<double> bound, dbg_z, export_buf, ev_scratch, ev_means, ev_ds_stats;
     Arena<int64_t> dbg_off;
     Arena<uint32_t> philox_buf;
     unsigned long long *counters = nullptr;       // device: [0] work counter, [1..] stats
@@ -169,6 +169,7 @@ struct ddm_ctx {
     size_t out_cap = 0, out_bytes = 0;
     bool have_run = false, out64 = true, have_steps = false, stats_pending = false;
     int64_t run_rows = 0, run_datasets = 0, run_trials = 0;  // rows = trials in total
+    int64_t run_cols = 2;                                     // values per trial (2 + n_obs for evidence runs)
     bool run_trialwise = false;
     ddm_stats stats{};
 
@@ -377,6 +378,7 @@ int run_common(ddm_ctx *ctx, int model, int64_t n_datasets, int64_t n_trials, do
     ctx->run_datasets = n_datasets;
     ctx->run_trials = n_trials;
     ctx->run_trialwise = trialwise;
+    ctx->run_cols = 2;
     ctx->out_resident = true;
     return DDM_OK;
 }
@@ -468,6 +470,7 @@ int run_pipelined(ddm_ctx *ctx, int64_t n_trials, double dt, int max_steps, uint
     ctx->run_datasets = n_datasets;
     ctx->run_trials = n_trials;
     ctx->run_trialwise = false;
+    ctx->run_cols = 2;
     ctx->out_resident = false;  // the batch went to the host chunk by chunk
     return DDM_OK;
 }
@@ -545,6 +548,9 @@ DDM_API int ddm_destroy(ddm_ctx *ctx) {
         ctx->bound.free_();
         ctx->dbg_z.free_();
         ctx->export_buf.free_();
+        ctx->ev_scratch.free_();
+        ctx->ev_means.free_();
+        ctx->ev_ds_stats.free_();
         ctx->dbg_off.free_();
         ctx->philox_buf.free_();
         for (int b = 0; b < 2; b++) {
@@ -685,6 +691,124 @@ DDM_API int ddm_simulate_trialwise(ddm_ctx *ctx, const int32_t *group, const dou
     return DDM_OK;
 }
 
+// Evidence-path variants: retired_models/basic_ddm_dc_evidence.py:87-151, basic_ddm_dc_evidence2.py:83-150,
+// basic_ddm_dc_evidence_no_noise2.py:82-147.
+DDM_API int ddm_simulate_evidence(ddm_ctx *ctx, const double *params, int64_t n_datasets, int64_t n_trials, int n_obs,
+                                  int standardize, double dt, int max_steps, uint64_t seed, uint64_t dataset_offset,
+                                  int precision, int flags, void *out_host) {
+    if (!ctx) return DDM_ERR_INVALID;
+    if (precision != 32 && precision != 64) return fail(ctx, DDM_ERR_INVALID, "precision must be 32 or 64, got %d", precision);
+    if (!(dt > 0.0) || !std::isfinite(dt)) return fail(ctx, DDM_ERR_INVALID, "dt must be positive and finite");
+    if (max_steps < 0 || n_trials < 0 || n_datasets < 0) return fail(ctx, DDM_ERR_INVALID, "negative argument");
+    if (n_obs < 1 || n_obs > 32 * 6 * 4) return fail(ctx, DDM_ERR_INVALID, "n_obs must be in [1, 768], got %d", n_obs);
+    if (standardize < 0 || standardize > 2) return fail(ctx, DDM_ERR_INVALID, "standardize must be 0, 1 or 2");
+    if (n_trials > 0xffffffffLL || n_datasets > 0xffffffffLL || dataset_offset + (uint64_t)n_datasets > 0xffffffffULL)
+        return fail(ctx, DDM_ERR_INVALID, "shape exceeds the 32-bit Philox counter words");
+    if (n_datasets > 0 && !params) return fail(ctx, DDM_ERR_INVALID, "params is NULL");
+    const int64_t rows = n_datasets * n_trials;
+    if (ctx->dbg_on && precision != 64) return fail(ctx, DDM_ERR_INVALID, "shared-increment mode needs precision 64 for the evidence model");
+    if (ctx->dbg_on && ctx->dbg_trials != rows)
+        return fail(ctx, DDM_ERR_INVALID, "shared-increment buffer was set for %lld trials, run has %lld",
+                    (long long)ctx->dbg_trials, (long long)rows);
+    DeviceGuard g(ctx->device);
+    const size_t np = (size_t)n_datasets * 6;
+    DDM_CUDA(ctx, ctx->params.reserve(np ? np : 1));
+    if (np) DDM_CUDA(ctx, cudaMemcpyAsync(ctx->params.p, params, np * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->have_params = false;  // the params arena now holds evidence parameters
+    const bool out64 = !(flags & DDM_FLAG_OUT_F32);
+    const uint32_t cols = 2u + (uint32_t)n_obs;
+    const size_t total = (size_t)rows * cols;
+    const size_t out_bytes = total * (out64 ? 8 : 4);
+    int rc = ensure_output(ctx, out_bytes);
+    if (rc) return rc;
+
+    ddm::EvidenceArgs a{};
+    a.params = ctx->params.p;
+    a.dbg_z = ctx->dbg_on ? ctx->dbg_z.p : nullptr;
+    a.dbg_off = ctx->dbg_on ? ctx->dbg_off.p : nullptr;
+    a.dbg_n = ctx->dbg_on ? ctx->dbg_n : 0;
+    a.out = ctx->out;
+    a.work_counter = ctx->counters;
+    a.stats = ctx->counters + 1;
+    a.n_datasets = (uint32_t)n_datasets;
+    a.n_trials = (uint32_t)n_trials;
+    a.n_obs = (uint32_t)n_obs;
+    a.tiles_per_dataset = (uint32_t)((n_trials + 31) / 32);
+    a.n_items = (uint64_t)a.tiles_per_dataset * (uint64_t)n_datasets;
+    if (a.n_items > 0xffffffffULL) return fail(ctx, DDM_ERR_INVALID, "too many trial tiles for one launch");
+    a.dataset_offset = (uint32_t)dataset_offset;
+    a.trial_offset = 0;
+    a.max_steps = (uint32_t)max_steps;
+    a.mode = standardize;
+    a.flags = flags;
+    a.key = ddm::make_philox_key((uint32_t)seed, (uint32_t)(seed >> 32));
+    a.dt = dt;
+    a.sqrt_dt = std::sqrt(dt);
+    if (standardize == 2) {
+        DDM_CUDA(ctx, ctx->ev_means.reserve(rows ? (size_t)rows : 1));
+        DDM_CUDA(ctx, ctx->ev_ds_stats.reserve(n_datasets ? (size_t)n_datasets * 2 : 2));
+        a.path_means = ctx->ev_means.p;
+    }
+    ddm_stats st{};
+    st.n_trials = (uint64_t)rows;
+    DDM_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long) * (1 + ddm::STAT_COUNT), ctx->stream));
+    if (rows > 0) {
+        DDM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        if (precision == 32) {
+            const size_t per_warp = ddm::evidence_smem_per_warp(a.n_obs);
+            int wpb = (int)((200u << 10) / per_warp);
+            if (wpb > 4) wpb = 4;
+            if (wpb < 1) return fail(ctx, DDM_ERR_INVALID, "n_obs too large for shared memory");
+            uint64_t grid = (uint64_t)ctx->sm_count * (size_t)((220u << 10) / (per_warp * wpb) > 0 ? (220u << 10) / (per_warp * wpb) : 1);
+            const uint64_t need = (a.n_items + wpb - 1) / wpb;
+            if (grid > need) grid = need;
+            if (grid < 1) grid = 1;
+            DDM_CUDA(ctx, ddm::launch_evidence_warp(a, out64, (int)grid, wpb, ctx->stream));
+            st.kernel_launches++;
+            st.grid = (int)grid;
+            st.block = 32 * wpb;
+            st.used_persistent = 1;
+            if (standardize == 2) {
+                DDM_CUDA(ctx, ddm::launch_evidence_dataset_stats(ctx->ev_means.p, ctx->ev_ds_stats.p, a.n_datasets, a.n_trials, ctx->stream));
+                DDM_CUDA(ctx, ddm::launch_evidence_finalize(ctx->out, out64, ctx->out, out64, ctx->ev_ds_stats.p, total, cols,
+                                                            a.n_trials, true, ctx->stream));
+                st.kernel_launches += 2;
+            }
+        } else {
+            DDM_CUDA(ctx, ctx->ev_scratch.reserve(total));
+            a.scratch = ctx->ev_scratch.p;
+            DDM_CUDA(ctx, ddm::launch_evidence_generic(a, ctx->dbg_on, (uint64_t)rows, ctx->stream));
+            st.kernel_launches++;
+            st.grid = (int)((rows + 127) / 128);
+            st.block = 128;
+            if (standardize == 2) {
+                DDM_CUDA(ctx, ddm::launch_evidence_dataset_stats(ctx->ev_means.p, ctx->ev_ds_stats.p, a.n_datasets, a.n_trials, ctx->stream));
+                st.kernel_launches++;
+            }
+            DDM_CUDA(ctx, ddm::launch_evidence_finalize(ctx->ev_scratch.p, true, ctx->out, out64, ctx->ev_ds_stats.p, total, cols,
+                                                        a.n_trials, standardize == 2, ctx->stream));
+            st.kernel_launches++;
+        }
+        DDM_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    }
+    DDM_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, ctx->counters, sizeof(unsigned long long) * (1 + ddm::STAT_COUNT),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->stats = st;
+    ctx->stats_pending = true;
+    ctx->have_run = true;
+    ctx->out64 = out64;
+    ctx->out_bytes = out_bytes;
+    ctx->have_steps = false;
+    ctx->run_rows = rows;
+    ctx->run_datasets = n_datasets;
+    ctx->run_trials = n_trials;
+    ctx->run_trialwise = false;
+    ctx->run_cols = cols;
+    ctx->out_resident = true;
+    if (out_host) return ddm_download(ctx, out_host);
+    return DDM_OK;
+}
+
 DDM_API int ddm_last_steps(ddm_ctx *ctx, int32_t *steps_host) {
     if (!ctx) return DDM_ERR_INVALID;
     if (!ctx->have_run || !ctx->have_steps) return fail(ctx, DDM_ERR_STATE, "last run did not keep step counts (DDM_FLAG_KEEP_STEPS)");
@@ -740,7 +864,7 @@ DDM_API int ddm_last_output_dlpack(ddm_ctx *ctx, struct DLManagedTensor **out) {
         t.ndim = 3;
         h->shape[0] = ctx->run_datasets;
         h->shape[1] = ctx->run_trials;
-        h->shape[2] = 2;
+        h->shape[2] = ctx->run_cols;
     }
     t.shape = h->shape;
     t.strides = nullptr;

@@ -183,6 +183,34 @@ __device__ __forceinline__ void trial_outputs(int flags, int choice, uint32_t n,
     }
 }
 
+// ---- evidence-path variants (ddm_evidence.cu) -------------------------------------------------------
+struct EvidenceArgs {
+    const double *params;    // [n_datasets * 6]: drift, boundary, beta, tau, dc, sigma1
+    const double *dbg_z;     // shared-increment mode (validation kernel)
+    const int64_t *dbg_off;
+    uint64_t dbg_n;
+    void *out;               // rows of 2 + n_obs values, float64 or float32
+    double *scratch;         // validation path: fp64 rows
+    double *path_means;      // mode 2: per-trial mean of the noisy path [n_datasets * n_trials]
+    unsigned long long *work_counter;
+    unsigned long long *stats;
+    uint64_t n_items;
+    uint32_t n_datasets, n_trials, n_obs, tiles_per_dataset;
+    uint32_t dataset_offset, trial_offset, max_steps;
+    int mode;                // 0 raw noisy path, 1 per-trial z-score, 2 dataset-level standardisation
+    int flags;
+    PhiloxKey key;
+    double dt, sqrt_dt;
+};
+
+size_t evidence_smem_per_warp(uint32_t n_obs);
+cudaError_t launch_evidence_warp(const EvidenceArgs &a, bool out64, int grid, int warps_per_block, cudaStream_t s);
+cudaError_t launch_evidence_generic(const EvidenceArgs &a, bool buffer_src, uint64_t total, cudaStream_t s);
+cudaError_t launch_evidence_dataset_stats(const double *path_means, double *ds_stats, uint32_t n_datasets,
+                                          uint32_t n_trials, cudaStream_t s);
+cudaError_t launch_evidence_finalize(const void *src, bool src64, void *dst, bool dst64, const double *ds_stats,
+                                     uint64_t total, uint32_t cols, uint32_t n_trials, bool standardize, cudaStream_t s);
+
 // launchers (ddm_kernels.cu)
 cudaError_t launch_prep(const double *params, DsConst *dconst, uint32_t n_datasets, uint32_t n_params,
                         int model, double dt, cudaStream_t s);

@@ -185,6 +185,25 @@ class DDMSimulator:
             int(flags), None if device else out.ctypes.data_as(C.c_void_p)))
         return self.last_output_dlpack() if device else out
 
+    def simulate_evidence(self, params, n_trials: int, n_obs: int = 200, standardize: int = 1, dt: float = 0.001,
+                          max_steps: int = 4000, *, seed=None, dataset_offset=None, precision: int = 32, flags: int = 0,
+                          device: bool = False):
+        """Evidence-path variants: (B, 6) parameters -> (B, n_trials, 2 + n_obs): rt, choice, observed path."""
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        if params.ndim == 1:
+            params = params[None, :]
+        if params.ndim != 2 or params.shape[1] != 6:
+            raise ValueError("params must be (6,) or (B, 6) = drift, boundary, beta, tau, dc, sigma1")
+        B = params.shape[0]
+        f32 = bool(flags & _capi.FLAG_OUT_F32)
+        out = None if device else np.empty((B, int(n_trials), 2 + int(n_obs)), dtype=np.float32 if f32 else np.float64)
+        off = self._next_offset(B, dataset_offset)
+        self._check(self._lib.ddm_simulate_evidence(
+            self._ctx, params.ctypes.data_as(_capi._dp), B, int(n_trials), int(n_obs), int(standardize), float(dt),
+            int(max_steps), self.seed if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF, off, int(precision), int(flags),
+            None if device else out.ctypes.data_as(C.c_void_p)))
+        return self.last_output_dlpack() if device else out
+
     # ---- results of the last run --------------------------------------------------------
     def last_output_dlpack(self) -> DeviceBatch:
         m = C.POINTER(_capi.DLManagedTensor)()

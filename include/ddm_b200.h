@@ -128,12 +128,25 @@ int ddm_simulate_trialwise(ddm_ctx *ctx, const int32_t *group, const double *bou
                            int max_steps, uint64_t seed, uint64_t trial_offset, int precision,
                            int flags, void *out_host);
 
+/* Evidence-path variants of the retired model zoo (retired_models/basic_ddm_dc_evidence.py:87-151,
+ * basic_ddm_dc_evidence2.py:83-150, basic_ddm_dc_evidence_no_noise2.py:82-147): B calls of
+ * simulate_trials(params[b], n_trials) -> out_host (B, n_trials, 2 + n_obs): rt, choice, then the
+ * first n_obs evidence values of the path (held at the final evidence after the crossing) plus
+ * N(0, sigma1) noise, standardised.  params (B,6) = drift, boundary, beta, tau, dc, sigma1 (the
+ * no-noise variants pass sigma1 = .001).  n_obs = int(.2/dt) or int(.4/dt) in the reference.
+ * standardize: 0 none, 1 per-trial z-score (evidence, no_noise*), 2 dataset-level
+ * (x - mean(path_means)) / std(path_means) (evidence2).  Noise normals come from the aux Philox
+ * stream of the trial (index k).  Shared-increment mode needs precision 64. */
+int ddm_simulate_evidence(ddm_ctx *ctx, const double *params, int64_t n_datasets, int64_t n_trials, int n_obs,
+                          int standardize, double dt, int max_steps, uint64_t seed, uint64_t dataset_offset,
+                          int precision, int flags, void *out_host);
+
 /* Per-trial Euler-step counts of the last run (needs DDM_FLAG_KEEP_STEPS). */
 int ddm_last_steps(ddm_ctx *ctx, int32_t *steps_host);
 int ddm_last_stats(ddm_ctx *ctx, ddm_stats *out);
 
 /* Device hand-off of the last run's output as a DLPack tensor of shape
- * (n_datasets, n_trials, 2) (or (n, 2) for trialwise), dtype per the run's flags,
+ * (n_datasets, n_trials, 2) ((n, 2) for trialwise, (n_datasets, n_trials, 2 + n_obs) for evidence runs), dtype per the run's flags,
  * on this ctx's device.  Ownership of the buffer moves to the consumer; its
  * deleter frees it.  The producer stream is synchronised before return. */
 int ddm_last_output_dlpack(ddm_ctx *ctx, struct DLManagedTensor **out);
