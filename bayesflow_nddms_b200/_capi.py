@@ -17,8 +17,9 @@ MODEL_ALPHA_DC = 2
 MODEL_ALPHA_SCALE = 3
 MODEL_ALPHA_SCALE2 = 4
 MODEL_TRIALWISE = 5
+MODEL_ETA = 6
 N_PARAMS = {MODEL_BASIC: 5, MODEL_ALPHA: 7, MODEL_ALPHA_DC: 7, MODEL_ALPHA_SCALE: 8, MODEL_ALPHA_SCALE2: 7,
-            MODEL_TRIALWISE: 4}
+            MODEL_TRIALWISE: 4, MODEL_ETA: 6}
 
 # enum ddm_status
 OK = 0

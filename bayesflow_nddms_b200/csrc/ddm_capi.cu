@@ -118,6 +118,7 @@ int n_params_of(int model) {
     case DDM_MODEL_BASIC: return 5;
     case DDM_MODEL_ALPHA_SCALE: return 8;
     case DDM_MODEL_TRIALWISE: return 4;
+    case DDM_MODEL_ETA: return 6;
     case DDM_MODEL_ALPHA:
     case DDM_MODEL_ALPHA_DC:
     case DDM_MODEL_ALPHA_SCALE2: return 7;
@@ -130,6 +131,7 @@ int kind_of(int model) {
     case DDM_MODEL_BASIC: return ddm::KIND_FIXED;
     case DDM_MODEL_ALPHA_DC: return ddm::KIND_DC;
     case DDM_MODEL_TRIALWISE: return ddm::KIND_TRIALWISE;
+    case DDM_MODEL_ETA: return ddm::KIND_DRIFT;
     default: return ddm::KIND_BOUND;
     }
 }

@@ -32,6 +32,12 @@ __global__ void prep_kernel(const double *__restrict__ params, DsConst *__restri
         c.v[1] = (float)(p[1] * (p[2] - 0.5));
         c.v[2] = (float)(0.5 * p[1]);
         c.v[3] = (float)(neg2ln2 * dt * p[4] * p[4]);
+    } else if (model == 6) {  // eta: [mu_drift, alpha, beta, ter, eta, dc]
+        c.v[0] = (float)(p[0] * dt);
+        c.v[1] = (float)(p[1] * (p[2] - 0.5));
+        c.v[2] = (float)(0.5 * p[1]);
+        c.v[3] = (float)(neg2ln2 * dt * p[5] * p[5]);
+        c.v[4] = (float)(p[4] * dt);
     } else if (model == 2) {  // alt: [drift, alpha, beta, ter, std_dc, mu_dc, sigma1]
         c.v[0] = (float)(p[0] * dt);
         c.v[1] = (float)(p[1] * (p[2] - 0.5));
@@ -100,7 +106,7 @@ __global__ void __launch_bounds__(256, 6) persistent_kernel(const RunArgs a) {
     // a trial's last block is partial when max_steps is not a multiple of 6: n > tail_from
     const bool partial_tail = (a.max_steps % NORMALS_PER_BLOCK) != 0u;
     const int tail_from = (int)a.max_steps - NORMALS_PER_BLOCK;
-    constexpr bool BASIC = (KIND == KIND_FIXED);
+    constexpr bool BASIC = (KIND == KIND_FIXED || KIND == KIND_DRIFT);
 
     for (;;) {
         // ---- finish: emit every frozen trial ---------------------------------------
@@ -266,6 +272,10 @@ __global__ void __launch_bounds__(128) generic_kernel(const RunArgs a, uint64_t 
                 latent = bound;
             } else if (KIND == KIND_FIXED) {
                 drift = (Real)prm[0]; bound = (Real)prm[1]; beta = (Real)prm[2]; dcoef = (Real)prm[4];
+            } else if (KIND == KIND_DRIFT) {  // basic_ddm_eta_dc.py:87-88
+                bound = (Real)prm[1]; beta = (Real)prm[2]; dcoef = (Real)prm[5];
+                const Real z = (Real)(BUFFER ? buf.next() : philox_normal(STREAM_AUX, 1u));
+                drift = (Real)prm[0] + (Real)prm[4] * z;
             } else {
                 drift = (Real)prm[0]; beta = (Real)prm[2]; sigma1 = (Real)prm[6];
                 const Real mu = (KIND == KIND_BOUND) ? (Real)prm[1] : (Real)prm[5];
@@ -299,7 +309,7 @@ __global__ void __launch_bounds__(128) generic_kernel(const RunArgs a, uint64_t 
             final_ev = (double)ev;
             if (KIND == KIND_TRIALWISE) {
                 ext = (double)bound;
-            } else if (KIND != KIND_FIXED) {
+            } else if (KIND != KIND_FIXED && KIND != KIND_DRIFT) {
                 const Real z = (Real)(BUFFER ? buf.next() : philox_normal(STREAM_AUX, 0u));
                 const Real e = gain * latent + sigma1 * z;
                 ext = (double)e;
@@ -307,7 +317,7 @@ __global__ void __launch_bounds__(128) generic_kernel(const RunArgs a, uint64_t 
             if (BUFFER && buf.overrun) atomicAdd(a.stats + STAT_DBG_OVERRUN, 1ull);
         }
         double o0, o1;
-        trial_outputs<KIND == KIND_FIXED>(a.flags, choice, n, a.dt, tau, ext, o0, o1);
+        trial_outputs<(KIND == KIND_FIXED || KIND == KIND_DRIFT)>(a.flags, choice, n, a.dt, tau, ext, o0, o1);
         if (a.flags & 16) o1 = final_ev;
         store_pair<OUT64>(a.out, g, o0, o1);
         if (a.steps_out) a.steps_out[g] = (int32_t)n;
@@ -381,6 +391,7 @@ cudaError_t launch_persistent(const RunArgs &a, int kind, bool out64, int grid, 
     case KIND_FIXED: return launch_persistent_kind<KIND_FIXED>(a, out64, grid, block, s);
     case KIND_BOUND: return launch_persistent_kind<KIND_BOUND>(a, out64, grid, block, s);
     case KIND_DC: return launch_persistent_kind<KIND_DC>(a, out64, grid, block, s);
+    case KIND_DRIFT: return launch_persistent_kind<KIND_DRIFT>(a, out64, grid, block, s);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -392,6 +403,7 @@ int persistent_max_blocks_per_sm(int kind, bool out64, int block) {
     if (kind == KIND_FIXED) { if (out64) DDM_OCC(KIND_FIXED, true); else DDM_OCC(KIND_FIXED, false); }
     else if (kind == KIND_BOUND) { if (out64) DDM_OCC(KIND_BOUND, true); else DDM_OCC(KIND_BOUND, false); }
     else if (kind == KIND_DC) { if (out64) DDM_OCC(KIND_DC, true); else DDM_OCC(KIND_DC, false); }
+    else if (kind == KIND_DRIFT) { if (out64) DDM_OCC(KIND_DRIFT, true); else DDM_OCC(KIND_DRIFT, false); }
 #undef DDM_OCC
     return (e == cudaSuccess) ? nb : -1;
 }
@@ -420,6 +432,7 @@ static cudaError_t launch_generic_1(const RunArgs &a, int kind, bool buffer_src,
     case KIND_BOUND: return launch_generic_2<Real, KIND_BOUND>(a, buffer_src, out64, total, s);
     case KIND_DC: return launch_generic_2<Real, KIND_DC>(a, buffer_src, out64, total, s);
     case KIND_TRIALWISE: return launch_generic_2<Real, KIND_TRIALWISE>(a, buffer_src, out64, total, s);
+    case KIND_DRIFT: return launch_generic_2<Real, KIND_DRIFT>(a, buffer_src, out64, total, s);
     default: return cudaErrorInvalidValue;
     }
 }

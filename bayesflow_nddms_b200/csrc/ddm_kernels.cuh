@@ -12,7 +12,8 @@ enum Kind : int {
     KIND_FIXED = 0,     // basic_ddm_dc: all trial constants are per-dataset
     KIND_BOUND = 1,     // per-trial boundary redraw (single_trial_alpha*, _scale, _scale2)
     KIND_DC = 2,        // per-trial diffusion coefficient redraw (_alt)
-    KIND_TRIALWISE = 3  // per-trial supplied boundary + gathered group params (Stahl)
+    KIND_TRIALWISE = 3, // per-trial supplied boundary + gathered group params (Stahl)
+    KIND_DRIFT = 4      // per-trial drift ~ N(mu_drift, eta) (basic_ddm_eta_dc)
 };
 
 // Per-dataset constants in fp32, prepared once per upload by prep_kernel (fp64 math,
@@ -20,6 +21,7 @@ enum Kind : int {
 //   FIXED: c0=drift*dt, x0=bound*(beta-.5), h=bound/2, k=-2ln2*dt*dc^2
 //   BOUND: c0, brel=beta-.5, bmu, bsd | k, ext_sd, ext_gain
 //   DC:    c0, x0, h, mu_dc | std_dc, ext_sd
+//   DRIFT: mu_drift*dt, x0, h, k | eta*dt
 struct __align__(16) DsConst {
     float v[8];
 };
@@ -72,6 +74,16 @@ template <int KIND>
 __device__ __forceinline__ void trial_setup_f32(const DsConst &dc, uint32_t trial, uint32_t ds_global,
                                                 const PhiloxKey &key, float kdt, TrialF32 &t, uint32_t &cap_hits) {
     t.c0 = dc.v[0];
+    if (KIND == KIND_DRIFT) {  // drift_trial = mu_drift + eta*z, one pre-draw (aux normal 1), no rejection
+        float z[6];
+        philox_normals6_f32(0u, trial, ds_global, STREAM_AUX, key, z);
+        t.c0 = __fmaf_rn(dc.v[4], z[1], dc.v[0]);
+        t.x = dc.v[1];
+        t.h = dc.v[2];
+        t.k = dc.v[3];
+        t.ext = 0.f;
+        return;
+    }
     if (KIND == KIND_FIXED) {
         t.x = dc.v[1];
         t.h = dc.v[2];

@@ -22,6 +22,7 @@ PARAM_NAMES = {
     "alpha_scale": ("drift", "mu_alpha", "beta", "ter", "std_alpha", "dc", "sigma1", "gamma"),
     "alpha_scale2": ("drift", "mu_alpha", "beta", "ter", "std_alpha", "dc", "sigma1"),
     "stahl": ("drift", "beta", "ter", "dc"),
+    "eta": ("mu_drift", "alpha", "beta", "ter", "eta", "dc"),
     # throughput sweep C5: the basic prior with tau = 0
     "sweep": ("drift", "alpha", "beta", "ter", "dc"),
 }
@@ -65,6 +66,11 @@ def draw_prior_batch(model: str, batch_size: int, rng) -> np.ndarray:
         cols = (drift, alpha, beta, ter, std, dc, sigma1)
         if model == "alpha_scale":
             cols = cols + (rng.uniform(0.0, 2.0, B),)
+    elif model == "eta":
+        # retired_models/basic_ddm_eta_dc.py:54-75
+        eta = truncnorm_rvs(rng, 1.0, 0.5, 0.0, 3.0, B)
+        dc = truncnorm_rvs(rng, 1.0, 0.5, 0.0, 10.0, B)
+        cols = (drift, alpha, beta, ter, eta, dc)
     elif model == "stahl":
         # imputation_from_stahl_not_scaled.py:165-174
         cols = (rng.normal(3.0, 1.0, B), rng.beta(25.0, 25.0, B), truncnorm_rvs(rng, 0.4, 0.1, 0.0, 1.5, B),

@@ -46,7 +46,10 @@ enum ddm_model {
     DDM_MODEL_ALPHA_SCALE2 = 4,
     /* imputation_from_stahl_not_scaled.py:120-148: per-trial supplied boundary,
        per-group params[4] = drift, beta, ter, dc.  out = (signed choicert, bound) */
-    DDM_MODEL_TRIALWISE = 5
+    DDM_MODEL_TRIALWISE = 5,
+    /* retired_models/basic_ddm_eta_dc.py:80-120: per-trial drift ~ N(mu_drift, eta) (one pre-draw, no
+       rejection).  params[6] = mu_drift, alpha, beta, ter, eta, dc.  out = (rt, choice) as DDM_MODEL_BASIC */
+    DDM_MODEL_ETA = 6
 };
 
 enum ddm_status {

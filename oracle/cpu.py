@@ -20,6 +20,7 @@ MODEL_ALPHA_DC = 2
 MODEL_ALPHA_SCALE = 3
 MODEL_ALPHA_SCALE2 = 4
 MODEL_TRIALWISE = 5
+MODEL_ETA = 6
 
 FLAG_TIMEOUT_CHOICE_ONE = 1
 

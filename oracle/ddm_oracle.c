@@ -13,6 +13,7 @@
  *   SCALE :1237-1272 (ext = N(gamma*bound, sigma1)), SCALE2 :1471-1506 (gamma==2)
  *   FINE  :1710-1722 (M1 called with dt=.001, max_steps=4000)
  *   M2  imputation_from_stahl_not_scaled.py:120-148 (supplied per-trial bound)
+ *   ETA retired_models/basic_ddm_eta_dc.py:80-120 (per-trial drift ~ N(mu_drift, eta))
  *
  * Parity pin: the reference has no golden vectors, so the
  * oracle is pinned against outputs of the reference itself: tests/golden/
@@ -43,7 +44,8 @@ enum {
     ORC_MODEL_ALPHA_DC = 2,
     ORC_MODEL_ALPHA_SCALE = 3,
     ORC_MODEL_ALPHA_SCALE2 = 4,
-    ORC_MODEL_TRIALWISE = 5
+    ORC_MODEL_TRIALWISE = 5,
+    ORC_MODEL_ETA = 6
 };
 /* flags -- must match include/ddm_b200.h */
 enum { ORC_FLAG_TIMEOUT_CHOICE_ONE = 1 };
@@ -274,6 +276,22 @@ static void trial_run(int model, const double *p, double bound_in, double dt,
         o->out1 = (double)choice;
         o->choice = (ev >= p[1]) ? 1 : (ev <= 0 ? -1 : 0);
         o->bound = p[1];
+    } else if (model == ORC_MODEL_ETA) {
+        /* p = [mu_drift, alpha, beta, ter, eta, dc]  retired_models/basic_ddm_eta_dc.py:80-107;
+         * one pre-draw: drift_trial = mu_drift + eta*z (aux normal 1), then the basic loop */
+        src_seek(src, PH_STREAM_AUX, 1);
+        double drift_trial = p[0] + p[4] * src_next(src);
+        src_seek(src, PH_STREAM_STEP, 0);
+        euler_loop(drift_trial, p[1], p[2], p[5], dt, max_steps, src, &ev, &n);
+        double rt = n * dt + p[3];
+        int choice;
+        if (ev >= p[1]) choice = 1;
+        else if (ev <= 0) choice = -1;
+        else choice = (flags & ORC_FLAG_TIMEOUT_CHOICE_ONE) ? 1 : 0; /* same unbound `choice` typo, :110-112 */
+        o->out0 = rt;
+        o->out1 = (double)choice;
+        o->choice = (ev >= p[1]) ? 1 : (ev <= 0 ? -1 : 0);
+        o->bound = p[1];
     } else if (model == ORC_MODEL_TRIALWISE) {
         /* p = [drift, beta, ter, dc]; imputation_from_stahl_not_scaled.py:120-148 */
         double bound = bound_in;
@@ -336,6 +354,7 @@ static int n_params_of(int model) {
     case ORC_MODEL_BASIC: return 5;
     case ORC_MODEL_ALPHA_SCALE: return 8;
     case ORC_MODEL_TRIALWISE: return 4;
+    case ORC_MODEL_ETA: return 6;
     default: return 7;
     }
 }

@@ -28,6 +28,7 @@ RANGES = {
     "alpha_fine": [("single_trial_alpha_not_scaled.py", 107, 155),
                    ("single_trial_alpha_not_scaled.py", 1710, 1722)],
     "stahl": [("imputation_from_stahl_not_scaled.py", 120, 148)],
+    "eta": [("retired_models/basic_ddm_eta_dc.py", 80, 120)],
     "evidence": [("retired_models/basic_ddm_dc_evidence.py", 87, 151)],
     "evidence2": [("retired_models/basic_ddm_dc_evidence2.py", 83, 150)],
     "evidence_no_noise2": [("retired_models/basic_ddm_dc_evidence_no_noise2.py", 82, 147)],
@@ -43,6 +44,7 @@ ENTRY = {
     "alpha_scale2": "simulate_trials_scale2",
     "alpha_fine": "simulate_trials_fine",
     "stahl": "diffusion_trial",
+    "eta": "simulate_trials",
     "evidence": "simulate_trials",
     "evidence2": "simulate_trials",
     "evidence_no_noise2": "simulate_trials",

@@ -49,7 +49,7 @@ def sim():
     s.close()
 
 
-VARIANT_MODEL = {"basic": 0, "alpha": 1, "alpha_dc": 2, "alpha_scale": 3, "alpha_scale2": 4, "alpha_fine": 1, "stahl": 5}
+VARIANT_MODEL = {"basic": 0, "alpha": 1, "alpha_dc": 2, "alpha_scale": 3, "alpha_scale2": 4, "alpha_fine": 1, "stahl": 5, "eta": 6}
 
 
 def variant_kwargs(variant):

@@ -44,6 +44,9 @@ CASES = [
     ("alpha_scale_vector", "alpha_scale", [3.0, 1.5, 0.5, 0.4, 1.0, 1.0, 0.1, 1.37], 300, 12),
     ("alpha_scale2_vector", "alpha_scale2", [3.0, 1.5, 0.5, 0.4, 1.0, 1.0, 0.1], 300, 13),
     ("alpha_fine_vector", "alpha_fine", [3.0, 1.5, 0.5, 0.4, 1.0, 1.0, 0.1], 100, 14),
+    # retired_models/basic_ddm_eta_dc.py: per-trial drift; participant-17 values of alpha_not_scaled.py:83-88
+    ("eta_participant17", "eta", [3.5, 1.2, 0.5, 0.4, 1.0, 1.2], 300, 16),
+    ("eta_timeouts", "eta", [0.0, 3.5, 0.5, 0.3, 0.4, 0.35], 100, 17),
 ]
 
 # imputation_from_stahl_not_scaled.py:120-148 is plain Python on NumPy's global

@@ -90,6 +90,8 @@ MODEL_CASES = [
     (3, [3.0, 1.5, 0.5, 0.4, 1.0, 1.0, 0.1, 1.37], dict(dt=0.01, max_steps=400)),
     (4, [2.0, 1.0, 0.45, 0.4, 0.5, 1.1, 0.7], dict(dt=0.01, max_steps=400)),
     (0, [0.4, 1.3, 0.55, 0.25, 0.9], dict(dt=0.001, max_steps=4000)),
+    (6, [3.5, 1.2, 0.5, 0.4, 1.0, 1.2], dict(dt=0.01, max_steps=400)),
+    (6, [0.0, 1.0, 0.5, 0.3, 2.5, 1.0], dict(dt=0.01, max_steps=400)),
 ]
 
 
@@ -99,7 +101,7 @@ def test_two_sample_against_reference_loop(sim, oracle, model, params, kw):
     n = 60_000
     g = sim.simulate(model, params, n, seed=31, dataset_offset=2, **kw)[0]
     r = oracle.simulate_mt(model, params, n, seed=77, **kw).sim_data
-    if model == 0:
+    if model in (0, 6):
         gs, rs = g[:, 0] * g[:, 1], r[:, 0] * r[:, 1]
     else:
         gs, rs = g[:, 0], r[:, 0]

@@ -59,7 +59,7 @@ def test_fp64_shared_increments_reproduce_reference_outputs(sim, oracle, golden)
         model = VARIANT_MODEL[m["variant"]]
         kw = variant_kwargs(m["variant"])
         params, n = z[f"{name}__params"], m["n_trials"]
-        flags = F_TIMEOUT1 if model == 0 else 0
+        flags = F_TIMEOUT1 if model in (0, 6) else 0
         o = oracle.simulate_mt(model, params, n, m["seed"], flags=flags, **kw)
         total = int(o.n_steps.sum()) + 64 * n + 64
         normals = oracle.mt_normals(m["seed"], total)
@@ -110,6 +110,8 @@ PROD_CASES = [
     (2, [-1.0, 1.0, 0.55, 0.2, 2.0, 0.3, 2.0], dict(dt=0.01, max_steps=400)),
     (3, [3.0, 1.5, 0.5, 0.4, 1.0, 1.0, 0.1, 1.37], dict(dt=0.01, max_steps=400)),
     (4, [1.0, 1.5, 0.6, 0.4, 0.5, 1.0, 0.1], dict(dt=0.001, max_steps=4000)),
+    (6, [3.5, 1.2, 0.5, 0.4, 1.0, 1.2], dict(dt=0.01, max_steps=400)),       # per-trial drift (eta)
+    (6, [-0.5, 1.4, 0.4, 0.3, 2.0, 0.9], dict(dt=0.001, max_steps=4000)),
 ]
 
 
@@ -126,6 +128,8 @@ def test_fp32_production_vs_reference_loop_on_exported_increments(sim, oracle, m
         zs = sim.export_normals(ds, t, 0, 0, int(steps[t]) + 8, seed=seed)
         if model == 0:
             c = [zs]
+        elif model == 6:
+            c = [sim.export_normals(ds, t, 1, 1, 1, seed=seed), zs[:int(steps[t])]]
         else:
             aux = sim.export_normals(ds, t, 1, 0, 4097, seed=seed)
             mu, sd = (params[5], params[4]) if model == 2 else (params[1], params[4])
@@ -151,7 +155,7 @@ def test_fp32_production_vs_reference_loop_on_exported_increments(sim, oracle, m
     # path passes within rounding distance of a boundary
     assert same.mean() >= 0.98, f"{(~same).sum()} of {n} crossing steps differ"
     rt_col = out[:, 0]
-    if model == 0:
+    if model in (0, 6):
         gpu_choice = out[:, 1].astype(np.int32)
     else:
         gpu_choice = np.sign(rt_col).astype(np.int32)
@@ -160,19 +164,19 @@ def test_fp32_production_vs_reference_loop_on_exported_increments(sim, oracle, m
     assert np.array_equal(rt_col[same].view(np.uint64), ref_out[same, 0].view(np.uint64))
     scale = np.maximum(ref_bound, 1e-3)
     assert np.max(np.abs(state[same] - ref_ev[same]) / scale[same]) < 1e-5
-    if model != 0:
+    if model not in (0, 6):
         assert np.max(np.abs(out[same, 1] - ref_out[same, 1])) < 1e-5 * (1 + np.max(np.abs(ref_out[:, 1])))
 
 
 # --------------------------------------------------------------------------------------------
 # Scheduling cannot change results
 # --------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("model", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("model", [0, 1, 2, 3, 4, 6])
 def test_persistent_equals_generic_bitwise(sim, model):
     rng = np.random.default_rng(model)
     from bayesflow_nddms_b200 import priors
 
-    name = ["basic", "alpha", "alpha_dc", "alpha_scale", "alpha_scale2"][model]
+    name = ["basic", "alpha", "alpha_dc", "alpha_scale", "alpha_scale2", None, "eta"][model]
     params = priors.draw_prior_batch(name, 37, rng)
     for kw in (dict(dt=0.01, max_steps=400), dict(dt=0.001, max_steps=4000)):
         a = sim.simulate(model, params, 211, precision=32, flags=F_STEPS, seed=3, dataset_offset=10, **kw)
@@ -252,7 +256,7 @@ def test_dc_scaling_is_exact_in_fp32(sim):
 # --------------------------------------------------------------------------------------------
 # fp64 validation mode on the Philox stream vs the oracle on the same (ideal) stream
 # --------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("model,params,kw", PROD_CASES[:6])
+@pytest.mark.parametrize("model,params,kw", PROD_CASES[:6] + PROD_CASES[8:])
 def test_fp64_philox_mode_vs_oracle(sim, oracle, model, params, kw):
     n = 500
     out = sim.simulate(model, params, n, precision=64, flags=F_STEPS, seed=42, dataset_offset=3, **kw)[0]
