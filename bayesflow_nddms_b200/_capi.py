@@ -21,6 +21,10 @@ MODEL_ETA = 6
 N_PARAMS = {MODEL_BASIC: 5, MODEL_ALPHA: 7, MODEL_ALPHA_DC: 7, MODEL_ALPHA_SCALE: 8, MODEL_ALPHA_SCALE2: 7,
             MODEL_TRIALWISE: 4, MODEL_ETA: 6}
 
+# enum ddm_prior: name -> (id, columns)
+PRIORS = {"basic": (0, 5), "alpha": (1, 7), "alpha_dc": (2, 7), "alpha_scale": (3, 8), "alpha_scale2": (4, 7),
+          "eta": (6, 6), "sweep": (7, 5), "evidence": (8, 6)}
+
 # enum ddm_status
 OK = 0
 ERR_INVALID = -1
@@ -86,6 +90,7 @@ SIGNATURES = {
     "ddm_set_pipeline": (C.c_int, [_vp, C.c_int64, C.c_int64]),
     "ddm_simulate": (C.c_int, [_vp, C.c_int, _dp, C.c_int64, C.c_int, C.c_int64, C.c_double, C.c_int, C.c_uint64,
                                C.c_uint64, C.c_int, C.c_int, _vp]),
+    "ddm_draw_prior": (C.c_int, [_vp, C.c_int, C.c_int64, C.c_uint64, C.c_uint64, _dp]),
     "ddm_upload_params": (C.c_int, [_vp, C.c_int, _dp, C.c_int64, C.c_int]),
     "ddm_run": (C.c_int, [_vp, C.c_int64, C.c_double, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int]),
     "ddm_download": (C.c_int, [_vp, _vp]),

@@ -75,11 +75,20 @@ class ModelAPI:
             int(self.max_steps if max_steps is None else max_steps), precision=precision, flags=f, seed=seed,
             dataset_offset=dataset_offset)
 
-    def generative_model(self, batch_size, draw_batch, prior_N, simulator=None, device=False):
+    def generative_model(self, batch_size, draw_batch, prior_N, simulator=None, device=False, device_prior=False):
         """What ``bf.simulation.GenerativeModel(prior, simulator)(batch_size)`` returns to the
-        reference's configurator: dict with prior_draws, sim_data, sim_non_batchable_context."""
-        prior_draws = draw_batch(batch_size)
+        reference's configurator: dict with prior_draws, sim_data, sim_non_batchable_context.
+        ``device_prior=True`` draws the parameters on the GPU too (``ddm_draw_prior``): prior and
+        simulation are two launches and the parameters never cross PCIe on their way in."""
         n = int(prior_N())
+        if device_prior:
+            sim = self.sim(simulator)
+            prior_draws = sim.draw_prior(self.prior_name, batch_size)
+            f = self.flags | (_capi.FLAG_OUT_F32 if device else 0)
+            sim.run_uploaded(n, self.dt, int(self.max_steps), flags=f)
+            data = sim.last_output_dlpack() if device else sim.download((int(batch_size), n, 2), False)
+            return {'prior_draws': prior_draws, 'sim_data': data, 'sim_non_batchable_context': n}
+        prior_draws = draw_batch(batch_size)
         if device:
             data = self.batch_simulate_trials_device(prior_draws, n, simulator)
         else:

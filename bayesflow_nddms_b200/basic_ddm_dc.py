@@ -61,9 +61,9 @@ def batch_simulate_trials_device(params, n_trials, simulator=None, **kw):
     return _api.batch_simulate_trials_device(params, n_trials, simulator, **kw)
 
 
-def generative_model(batch_size, simulator=None, device=False):
+def generative_model(batch_size, simulator=None, device=False, device_prior=False):
     """Result dict of ``GenerativeModel(prior, simulator)(batch_size)`` (basic_ddm_dc.py:134)."""
-    return _api.generative_model(batch_size, batch_draw_prior, prior_N, simulator, device)
+    return _api.generative_model(batch_size, batch_draw_prior, prior_N, simulator, device, device_prior)
 
 
 def make_bayesflow_generative_model(batched=True):

@@ -55,5 +55,5 @@ def batch_simulate_trials_device(params, n_trials, simulator=None, **kw):
     return _api.batch_simulate_trials_device(params, n_trials, simulator, **kw)
 
 
-def generative_model(batch_size, simulator=None, device=False):
-    return _api.generative_model(batch_size, batch_draw_prior, prior_N, simulator, device)
+def generative_model(batch_size, simulator=None, device=False, device_prior=False):
+    return _api.generative_model(batch_size, batch_draw_prior, prior_N, simulator, device, device_prior)

@@ -625,6 +625,38 @@ DDM_API int ddm_upload_params(ddm_ctx *ctx, int model, const double *params, int
     return DDM_OK;
 }
 
+DDM_API int ddm_draw_prior(ddm_ctx *ctx, int prior, int64_t n_draws, uint64_t seed, uint64_t draw_offset, double *params_host) {
+    if (!ctx) return DDM_ERR_INVALID;
+    int n_params, model;
+    switch (prior) {
+    case DDM_PRIOR_BASIC: case DDM_PRIOR_SWEEP: n_params = 5; model = DDM_MODEL_BASIC; break;
+    case DDM_PRIOR_ALPHA: case DDM_PRIOR_ALPHA_DC: case DDM_PRIOR_ALPHA_SCALE2: n_params = 7; model = prior; break;
+    case DDM_PRIOR_ALPHA_SCALE: n_params = 8; model = prior; break;
+    case DDM_PRIOR_ETA: n_params = 6; model = DDM_MODEL_ETA; break;
+    case DDM_PRIOR_EVIDENCE: n_params = 6; model = -1; break;
+    default: return fail(ctx, DDM_ERR_INVALID, "unknown prior %d", prior);
+    }
+    if (n_draws < 0) return fail(ctx, DDM_ERR_INVALID, "n_draws < 0");
+    DeviceGuard g(ctx->device);
+    const size_t n = (size_t)n_draws * n_params;
+    DDM_CUDA(ctx, ctx->params.reserve(n ? n : 1));
+    const ddm::PhiloxKey key = ddm::make_philox_key((uint32_t)seed, (uint32_t)(seed >> 32));
+    DDM_CUDA(ctx, ddm::launch_prior(ctx->params.p, prior, (uint32_t)n_params, (uint64_t)n_draws, draw_offset, key, ctx->stream));
+    if (model >= 0) {
+        ctx->model = model;
+        ctx->n_datasets = n_draws;
+        ctx->n_params = n_params;
+        ctx->have_params = true;
+    } else {
+        ctx->have_params = false;
+    }
+    if (params_host && n) {
+        DDM_CUDA(ctx, cudaMemcpyAsync(params_host, ctx->params.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        DDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return DDM_OK;
+}
+
 DDM_API int ddm_run(ddm_ctx *ctx, int64_t n_trials, double dt, int max_steps, uint64_t seed, uint64_t dataset_offset,
                     int precision, int flags) {
     if (!ctx) return DDM_ERR_INVALID;

@@ -223,6 +223,10 @@ cudaError_t launch_evidence_dataset_stats(const double *path_means, double *ds_s
 cudaError_t launch_evidence_finalize(const void *src, bool src64, void *dst, bool dst64, const double *ds_stats,
                                      uint64_t total, uint32_t cols, uint32_t n_trials, bool standardize, cudaStream_t s);
 
+// device-side prior sampler (ddm_prior.cu)
+cudaError_t launch_prior(double *params, int prior, uint32_t n_params, uint64_t n_draws, uint64_t draw_offset,
+                         const PhiloxKey &key, cudaStream_t s);
+
 // launchers (ddm_kernels.cu)
 cudaError_t launch_prep(const double *params, DsConst *dconst, uint32_t n_datasets, uint32_t n_params,
                         int model, double dt, cudaStream_t s);

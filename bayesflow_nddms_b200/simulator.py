@@ -100,6 +100,28 @@ class DDMSimulator:
             self.dataset_counter += int(n_datasets)
         return int(dataset_offset)
 
+    def draw_prior(self, prior: str, n_draws: int, *, seed=None, draw_offset=None, to_host: bool = True):
+        """Device-side batched prior (``ddm_draw_prior``): (n_draws, P) float64 in the reference's column
+        order.  The draws stay in the simulator's parameter arena, so ``run_uploaded`` can simulate them
+        without a host round trip; ``to_host=False`` skips the copy and returns None."""
+        pid, cols = _capi.PRIORS[prior]
+        off = self._next_offset(n_draws, draw_offset)
+        out = np.empty((int(n_draws), cols), dtype=np.float64) if to_host else None
+        self._check(self._lib.ddm_draw_prior(self._ctx, pid, int(n_draws),
+                                             self.seed if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF, off,
+                                             out.ctypes.data_as(_capi._dp) if to_host else None))
+        self._prior_offset = off
+        return out
+
+    def run_uploaded(self, n_trials: int, dt: float = 0.01, max_steps: int = 400, *, seed=None, dataset_offset=None,
+                     precision: int = 32, flags: int = 0):
+        """Launch on the parameters already resident on the device (after ``draw_prior``); the datasets
+        are keyed by the same global indices as the draws unless ``dataset_offset`` is given."""
+        off = getattr(self, "_prior_offset", 0) if dataset_offset is None else int(dataset_offset)
+        self._check(self._lib.ddm_run(self._ctx, int(n_trials), float(dt), int(max_steps),
+                                      self.seed if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF, off,
+                                      int(precision), int(flags)))
+
     def run(self, model: int, params, n_trials: int, dt: float = 0.01, max_steps: int = 400, *, seed=None,
             dataset_offset=None, precision: int = 32, flags: int = 0):
         """Upload (B, P) parameters and launch; results stay on the device."""

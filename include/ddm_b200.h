@@ -52,6 +52,19 @@ enum ddm_model {
     DDM_MODEL_ETA = 6
 };
 
+/* Prior families of ddm_draw_prior; the value is the ddm_model whose parameter layout is produced
+ * (7 and 8 have no model id of their own). */
+enum ddm_prior {
+    DDM_PRIOR_BASIC = 0,        /* basic_ddm_dc.py:62-80 -> (drift, alpha, beta, ter, dc) */
+    DDM_PRIOR_ALPHA = 1,        /* single_trial_alpha_not_scaled.py:78-102 -> 7 columns */
+    DDM_PRIOR_ALPHA_DC = 2,     /* :899-923 (draw_prior_alt) -> 7 columns */
+    DDM_PRIOR_ALPHA_SCALE = 3,  /* :1205-1232 (draw_prior_scale) -> 8 columns */
+    DDM_PRIOR_ALPHA_SCALE2 = 4, /* the model's own prior, 7 columns */
+    DDM_PRIOR_ETA = 6,          /* retired_models/basic_ddm_eta_dc.py:54-75 -> 6 columns */
+    DDM_PRIOR_SWEEP = 7,        /* the basic prior with ter = 0 (throughput sweep) */
+    DDM_PRIOR_EVIDENCE = 8      /* retired_models/basic_ddm_dc_evidence.py:61-82 -> 6 columns (…, dc, sigma1) */
+};
+
 enum ddm_status {
     DDM_OK = 0,
     DDM_ERR_INVALID = -1,        /* bad argument */
@@ -114,6 +127,12 @@ int ddm_set_pipeline(ddm_ctx *ctx, int64_t min_rows, int64_t chunk_rows);
 int ddm_simulate(ddm_ctx *ctx, int model, const double *params, int64_t n_datasets, int n_params,
                  int64_t n_trials, double dt, int max_steps, uint64_t seed, uint64_t dataset_offset,
                  int precision, int flags, void *out_host);
+
+/* Replaces B calls of draw_prior() (see enum ddm_prior): one launch writes the (n_draws, P) float64
+ * parameter matrix into the context's parameter arena -- a following ddm_run simulates these draws
+ * with no host round trip -- and, if params_host != NULL, copies it out (BayesFlow's 'prior_draws').
+ * Draw i uses Philox counters keyed by draw_offset + i, so draws are reproducible and shardable. */
+int ddm_draw_prior(ddm_ctx *ctx, int prior, int64_t n_draws, uint64_t seed, uint64_t draw_offset, double *params_host);
 
 /* The same in three steps, for callers that keep inputs/outputs resident. */
 int ddm_upload_params(ddm_ctx *ctx, int model, const double *params, int64_t n_datasets, int n_params);
