@@ -38,17 +38,20 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile the library if missing or older than its sources; return its path."""
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, out_path: str | None = None, defines=()) -> str:
+    """Compile the library if missing or older than its sources; return its path.
+    ``out_path`` / ``defines`` build an experimental variant next to it (A/B measurements)."""
+    if out_path is None and not force and not is_stale():
         return LIB_PATH
-    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    target = out_path or LIB_PATH
+    cmd = ([find_nvcc()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) +
+           ["-o", target] + SOURCES)
     proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
     if verbose:
         print(proc.stderr)
-    return LIB_PATH
+    return target
 
 
 if __name__ == "__main__":

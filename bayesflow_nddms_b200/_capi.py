@@ -113,7 +113,8 @@ SIGNATURES = {
 
 
 def library_path() -> str:
-    return _build.LIB_PATH
+    # DDM_B200_LIB selects an experimental build of the same library (A/B measurements only)
+    return os.environ.get("DDM_B200_LIB") or _build.LIB_PATH
 
 
 def load() -> C.CDLL:

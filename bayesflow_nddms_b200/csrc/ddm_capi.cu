@@ -294,7 +294,8 @@ int launch_sim(ddm_ctx *ctx, ddm::RunArgs &a, int precision, ddm_stats &st) {
     const int64_t n_datasets = a.n_datasets, n_trials = a.n_trials;
     const int64_t rows = trialwise ? n_trials : n_datasets * n_trials;
     if (rows == 0) return DDM_OK;
-    const bool persistent = precision == 32 && !ctx->dbg_on && !trialwise && !(flags & DDM_FLAG_FORCE_GENERIC);
+    // OUT_STATE (validation) needs the state at exactly max_steps for timeouts: the generic kernel stops there
+    const bool persistent = precision == 32 && !ctx->dbg_on && !trialwise && !(flags & (DDM_FLAG_FORCE_GENERIC | DDM_FLAG_OUT_STATE));
     DDM_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
     if (persistent) {
         const int block = 256;

@@ -79,8 +79,11 @@ __device__ __forceinline__ void store_pair(void *out, uint64_t idx, double o0, d
 // lanes are frozen the warp takes the (divergent, so deliberately batched) finish +
 // refill path.  Philox counters are (step block, trial, dataset): results do not
 // depend on which lane / warp / SM / GPU ran a trial.
+#ifndef DDM_PERSISTENT_MIN_BLOCKS
+#define DDM_PERSISTENT_MIN_BLOCKS 6
+#endif
 template <int KIND, bool OUT64>
-__global__ void __launch_bounds__(256, 6) persistent_kernel(const RunArgs a) {
+__global__ void __launch_bounds__(256, DDM_PERSISTENT_MIN_BLOCKS) persistent_kernel(const RunArgs a) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
 
@@ -103,19 +106,19 @@ __global__ void __launch_bounds__(256, 6) persistent_kernel(const RunArgs a) {
     uint32_t acc_timeouts = 0, acc_upper = 0, acc_cap = 0;
 
     const int thr = a.refill_threshold;
-    // a trial's last block is partial when max_steps is not a multiple of 6: n > tail_from
-    const bool partial_tail = (a.max_steps % NORMALS_PER_BLOCK) != 0u;
-    const int tail_from = (int)a.max_steps - NORMALS_PER_BLOCK;
     constexpr bool BASIC = (KIND == KIND_FIXED || KIND == KIND_DRIFT);
 
     for (;;) {
         // ---- finish: emit every frozen trial ---------------------------------------
         if (has && p == 0u) {
-            const int choice = (x >= t.h) ? 1 : ((x <= -t.h) ? -1 : 0);
+            int choice = (x >= t.h) ? 1 : ((x <= -t.h) ? -1 : 0);
+            // Lanes always run whole 6-step blocks.  A trial that was still inside the boundaries
+            // after max_steps steps is a timeout whatever it did in the surplus steps of its last
+            // block (max_steps need not be a multiple of 6).
+            if (n > a.max_steps) { n = a.max_steps; choice = 0; }
             const double tau = a.params[(size_t)ds * a.n_params + 3];
             double o0, o1;
             trial_outputs<BASIC>(a.flags, choice, n, a.dt, tau, (double)t.ext, o0, o1);
-            if (a.flags & 16) o1 = (double)__fadd_rn(x, t.h);
             const uint64_t idx = (uint64_t)ds * a.n_trials + trial;
             store_pair<OUT64>(a.out, idx, o0, o1);
             if (a.steps_out) a.steps_out[idx] = (int32_t)n;
@@ -169,12 +172,9 @@ __global__ void __launch_bounds__(256, 6) persistent_kernel(const RunArgs a) {
         // ---- step: tight, branch-free inner loop (round keys and constants stay in uniform registers)
         unsigned idle;
         do {
-            if (partial_tail && __any_sync(FULL_MASK, p != 0u && (int)n > tail_from))
-                step_block_f32<true>(blk, trial + a.trial_offset, ds + a.dataset_offset, a.key, t, x, n, p, a.max_steps);
-            else
-                step_block_f32<false>(blk, trial + a.trial_offset, ds + a.dataset_offset, a.key, t, x, n, p, a.max_steps);
+            step_block_f32<false>(blk, trial + a.trial_offset, ds + a.dataset_offset, a.key, t, x, n, p, a.max_steps);
             blk++;
-            if (!partial_tail) p = (n < a.max_steps) ? p : 0u;
+            p = (n < a.max_steps) ? p : 0u;
             idle = __ballot_sync(FULL_MASK, p == 0u);
         } while (__popc(idle) < thr_now);
     }

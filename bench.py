@@ -362,6 +362,39 @@ def main():
                       "array; one ddm_simulate call: H2D params, chunked kernels overlapped with the D2H of the previous chunk"}
         launches += sim.last_stats()["kernel_launches"] * ke
 
+    # ---- BASELINE config 2: one online-training batch (64 datasets x 500 trials, dt=.01), latency -------------
+    training_batch = None
+    if rank == 0:
+        try:
+            from bayesflow_nddms_b200 import _capi as capi
+
+            B2, N2, reps = 64, 500, 200
+            for _ in range(10):
+                sim.draw_prior("basic", B2)
+                sim.run_uploaded(N2, 0.01, 400, flags=capi.FLAG_OUT_F32)
+            sim.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                pd = sim.draw_prior("basic", B2)                                  # device prior + (64,5) copy out
+                sim.run_uploaded(N2, 0.01, 400, flags=capi.FLAG_OUT_F32)          # simulate on the resident draws
+                batch = sim.last_output_dlpack()                                  # hand-off (syncs the stream)
+                del batch
+            lat = (time.perf_counter() - t0) / reps
+            training_batch = {"workload": "basic_ddm_dc online-training batch: 64 datasets x 500 trials, dt=.01, max_steps=400",
+                              "path": "ddm_draw_prior -> ddm_run -> ddm_last_output_dlpack (device-resident f32 batch)",
+                              "ms_per_batch": lat * 1e3, "trials_per_s": B2 * N2 / lat, "launches_per_batch": 3}
+            if not args.no_cpu_baseline and world == 1:
+                from oracle import cpu as orc
+
+                pp = sweep_params(B2, seed=5)
+                pp[:, 3] = 0.3
+                t0 = time.perf_counter()
+                for _ in range(5):
+                    orc.simulate_batch_mt(MODEL_BASIC, pp, N2, seed=1, dt=0.01, max_steps=400.0, n_threads=1)
+                training_batch["cpu_port_1thread_ms_per_batch"] = (time.perf_counter() - t0) / 5 * 1e3
+        except Exception as e:  # a secondary figure must not take the headline down
+            training_batch = {"error": repr(e)}
+
     line = {
         "metric": "euler_steps_per_sec", "value": value, "unit": "steps/s", "trials_per_s": trials_per_s,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
@@ -376,6 +409,8 @@ def main():
     }
     if e2e is not None:
         line["e2e"] = e2e
+    if training_batch is not None:
+        line["training_batch"] = training_batch
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
     if rank == 0:
