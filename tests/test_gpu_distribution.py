@@ -166,3 +166,23 @@ def test_full_size_sweep_properties(sim):
     pu = np.array([wfpt.ddm_prob_upper(params[i, 0], *_corrected(params[i], 1e-3), params[i, 4]) for i in sel])
     emp = (out[sel, :, 1] > 0).mean(1)
     assert sel.size > 300 and np.mean(np.abs(pu - emp)) < 0.015 and np.max(np.abs(pu - emp)) < 0.08
+
+
+def test_alpha_not_scaled_data_generation(sim):
+    """alpha_not_scaled.py:52-131 with the GPU generator in place of simulratcliff: the genparam dict,
+    and participant 17 (fixed parameters, drift variability eta = 1) against the reference sampler's
+    own samples (different algorithm, distribution-level parity)."""
+    from bayesflow_nddms_b200 import alpha_not_scaled as m
+
+    g = m.generate_data(test_num=2, simulator=sim, sim_seed=3)
+    assert g['N'] == 10000 and g['rt'].shape == g['acc'].shape == g['y'].shape == g['participant'].shape == (10000,)
+    assert g['extdata'].shape == (100,) and set(np.unique(g['acc'])) <= {0.0, 0.5, 1.0}
+    assert np.array_equal(g['y'], (2 * g['acc'] - 1) * g['rt']) and np.all(g['rt'] >= np.repeat(g['ndt'], 100))
+    assert abs(np.corrcoef(g['extdata'], g['alpha'])[0, 1]) > 0.7           # sigma = .1 vs sd(alpha) = .17
+    assert abs(g['prop_cog_var'] - 0.03 / 0.04) < 1e-12
+    z = np.load(os.path.join(ROOT, "tests", "golden", "simulratcliff_samples.npz"))
+    y = z["participant17_eta__y"]
+    alpha, tau, nu, beta, eta, vs = z["participant17_eta__params"]
+    out = sim.simulate(6, [nu, alpha, beta, tau, eta, vs], 40_000, dt=1e-4, max_steps=200_000, seed=4, dataset_offset=0)[0]
+    assert stats.ks_2samp(out[:, 0] * out[:, 1], y).pvalue > 1e-3
+    assert abs((out[:, 1] > 0).mean() - (y > 0).mean()) < 0.015

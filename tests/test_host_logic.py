@@ -176,3 +176,16 @@ def test_sharded_simulation_with_gloo_gather_world2(n_total, oracle):
     assert (lo0, hi1) == (0, n_total) and hi0 == lo1
     assert np.array_equal(full0, single) and np.array_equal(full1, single)   # independent of world size
     assert np.array_equal(np.concatenate([loc0, loc1]), single)
+
+
+# ---- alpha_not_scaled.py data generation (:52-131): participant parameters are the reference's own ---------
+def test_alpha_not_scaled_participant_parameters_match_reference():
+    from bayesflow_nddms_b200 import alpha_not_scaled as m
+
+    z = np.load(os.path.join(ROOT, "tests", "golden", "alpha_not_scaled_params.npz"))  # lines 54-88 run verbatim
+    g, _ = m.draw_participants(100, 2, 2021)
+    for k in ("ndt", "alpha", "beta", "delta", "varsigma", "deltatrialsd"):
+        assert np.array_equal(g[k], z[k]), k
+    assert g["sigma"] == float(z["sigma"]) and g["var_alpha"] == float(z["var_alpha"])
+    assert (g["ndt"][17], g["alpha"][17], g["delta"][17], g["deltatrialsd"][17]) == (.4, 1.2, 3.5, 1)
+    assert m.draw_participants(100, 4)[0]["sigma"] == .2
