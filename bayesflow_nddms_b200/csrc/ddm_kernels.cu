@@ -170,13 +170,15 @@ __global__ void __launch_bounds__(256, DDM_PERSISTENT_MIN_BLOCKS) persistent_ker
         const int thr_now = (more || cur != end) ? thr : 32;
 
         // ---- step: tight, branch-free inner loop (round keys and constants stay in uniform registers)
-        unsigned idle;
+        unsigned alive = __ballot_sync(FULL_MASK, p != 0u);
+        const int live_min = 32 - thr_now;  // keep stepping while more than this many lanes are alive
         do {
-            step_block_f32<false>(blk, trial + a.trial_offset, ds + a.dataset_offset, a.key, t, x, n, p, a.max_steps);
+            Normals6Scaled z;
+            philox_pairs_scaled(blk, trial + a.trial_offset, ds + a.dataset_offset, STREAM_STEP, a.key, t.k, z);
+            euler6_warp(x, n, alive, t.c0, t.h, z, a.max_steps);
             blk++;
-            p = (n < a.max_steps) ? p : 0u;
-            idle = __ballot_sync(FULL_MASK, p == 0u);
-        } while (__popc(idle) < thr_now);
+        } while (__popc(alive) > live_min);
+        p = (alive >> lane) & 1u;
     }
 
     // ---- per-warp statistics --------------------------------------------------------

@@ -169,6 +169,52 @@ __device__ __forceinline__ void euler6(float &x, uint32_t &n, uint32_t &p, float
     }
 }
 
+// The persistent kernel's form of the same six steps: lane state "still stepping" travels as the
+// warp's ballot `alive` (bit = lane), so the block needs no predicate<->register conversions:
+// LOP3 (alive & lanemask -> predicate), the steps, ISETP (n < max_steps, folded into the predicate),
+// VOTE.  Convergent code only.
+#ifdef DDM_FLOAT_STEP_COUNTER
+#define DDM_STEPW(S, T)                        \
+    "fma.rn.f32 inc, " S ", " T ", %3;\n\t"     \
+    "@q add.rn.f32 %0, %0, inc;\n\t"           \
+    "@q add.rn.f32 nf, nf, 0f3F800000;\n\t"    \
+    "abs.f32 ax, %0;\n\t"                      \
+    "setp.lt.and.f32 q, ax, %4, q;\n\t"
+#else
+#define DDM_STEPW(S, T) DDM_STEP(S, T)
+#endif
+__device__ __forceinline__ void euler6_warp(float &x, uint32_t &n, unsigned &alive, float c0, float h,
+                                            const Normals6Scaled &z, uint32_t max_steps) {
+#ifdef DDM_FLOAT_STEP_COUNTER
+    asm volatile("{\n\t.reg .pred q;\n\t.reg .f32 ax, inc, nf;\n\t.reg .b32 t;\n\t"
+                 "mov.u32 t, %%lanemask_eq;\n\t"
+                 "and.b32 t, t, %2;\n\t"
+                 "setp.ne.u32 q, t, 0;\n\t"
+                 "mov.f32 nf, 0f00000000;\n\t"
+                 DDM_STEPW("%5", "%6") DDM_STEPW("%5", "%7") DDM_STEPW("%8", "%9")
+                 DDM_STEPW("%8", "%10") DDM_STEPW("%11", "%12") DDM_STEPW("%11", "%13")
+                 "cvt.rzi.u32.f32 t, nf;\n\t"
+                 "add.u32 %1, %1, t;\n\t"
+                 "setp.lt.and.u32 q, %1, %14, q;\n\t"
+                 "vote.sync.ballot.b32 %2, q, 0xffffffff;\n\t}"
+                 : "+f"(x), "+r"(n), "+r"(alive)
+                 : "f"(c0), "f"(h), "f"(z.s[0]), "f"(z.c[0]), "f"(z.sn[0]), "f"(z.s[1]), "f"(z.c[1]), "f"(z.sn[1]),
+                   "f"(z.s[2]), "f"(z.c[2]), "f"(z.sn[2]), "r"(max_steps));
+#else
+    asm volatile("{\n\t.reg .pred q;\n\t.reg .f32 ax, inc;\n\t.reg .b32 t;\n\t"
+                 "mov.u32 t, %%lanemask_eq;\n\t"
+                 "and.b32 t, t, %2;\n\t"
+                 "setp.ne.u32 q, t, 0;\n\t"
+                 DDM_STEPW("%5", "%6") DDM_STEPW("%5", "%7") DDM_STEPW("%8", "%9")
+                 DDM_STEPW("%8", "%10") DDM_STEPW("%11", "%12") DDM_STEPW("%11", "%13")
+                 "setp.lt.and.u32 q, %1, %14, q;\n\t"
+                 "vote.sync.ballot.b32 %2, q, 0xffffffff;\n\t}"
+                 : "+f"(x), "+r"(n), "+r"(alive)
+                 : "f"(c0), "f"(h), "f"(z.s[0]), "f"(z.c[0]), "f"(z.sn[0]), "f"(z.s[1]), "f"(z.c[1]), "f"(z.sn[1]),
+                   "f"(z.s[2]), "f"(z.c[2]), "f"(z.sn[2]), "r"(max_steps));
+#endif
+}
+
 // One Philox block of a trial: block index `blk` = n / 6 for a lane that is still stepping.
 template <bool TAIL>
 __device__ __forceinline__ void step_block_f32(uint32_t blk, uint32_t trial, uint32_t ds_global,

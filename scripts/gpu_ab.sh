@@ -3,7 +3,7 @@ set -x
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
 for rep in 1 2; do
-  for lib in bayesflow_nddms_b200/libddm_b200.so build/libddm_minblk5.so build/libddm_minblk4.so; do
+  for lib in bayesflow_nddms_b200/libddm_b200.so $AB_LIBS; do
     echo "== $lib"
     DDM_B200_LIB=$PWD/$lib python scripts/tune.py 4,0,0 5,0,0 6,0,0 2>&1 | tail -4
   done
