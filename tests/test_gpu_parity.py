@@ -411,3 +411,22 @@ def test_reference_signatures(sim):
         assert not np.array_equal(a, b)
     finally:
         set_default_simulator(None)
+
+
+def test_device_replay_feed(sim):
+    import torch
+
+    from bayesflow_nddms_b200 import basic_ddm_dc as m
+    from bayesflow_nddms_b200.replay import DeviceReplayBuffer, replay_iterations
+
+    buf = DeviceReplayBuffer(4)
+    n = 0
+    for batch in replay_iterations(m, 32, 10, buf, simulator=sim):
+        n += 1
+        x, y, c = batch['summary_conditions'], batch['parameters'], batch['direct_conditions']
+        assert x.is_cuda and y.is_cuda and c.is_cuda and x.dtype == torch.float32
+        assert x.shape[0] == 32 and x.shape[2] == 2 and 60 <= x.shape[1] <= 300 and y.shape == (32, 5)
+        assert abs(float(c[0, 0]) - np.log(x.shape[1])) < 1e-5 and torch.isfinite(x).all()
+    assert n == 10 and len(buf) == 4 and buf.stored_total == 10
+    ptrs = {b['summary_conditions'].data_ptr() for b in buf._slots}
+    assert len(ptrs) == 4                                # four live device batches, none aliased

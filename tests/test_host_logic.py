@@ -189,3 +189,19 @@ def test_alpha_not_scaled_participant_parameters_match_reference():
     assert g["sigma"] == float(z["sigma"]) and g["var_alpha"] == float(z["var_alpha"])
     assert (g["ndt"][17], g["alpha"][17], g["delta"][17], g["deltatrialsd"][17]) == (.4, 1.2, 3.5, 1)
     assert m.draw_participants(100, 4)[0]["sigma"] == .2
+
+
+def test_device_replay_buffer_fifo_and_sampling():
+    import torch
+
+    from bayesflow_nddms_b200.replay import DeviceReplayBuffer
+
+    buf = DeviceReplayBuffer(3, rng=np.random.default_rng(0))
+    with pytest.raises(RuntimeError):
+        buf.sample()
+    for i in range(5):
+        buf.store({'summary_conditions': torch.full((2, 4, 2), float(i)), 'parameters': torch.zeros(2, 5)})
+    assert len(buf) == 3 and buf.is_full() and buf.stored_total == 5
+    seen = {float(buf.sample()['summary_conditions'][0, 0, 0]) for _ in range(200)}
+    assert seen == {2.0, 3.0, 4.0}                       # the two oldest batches were overwritten
+    assert buf.nbytes() == 3 * (2 * 4 * 2 + 2 * 5) * 4
