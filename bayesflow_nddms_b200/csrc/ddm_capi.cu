@@ -160,6 +160,7 @@ struct ddm_ctx {
     int64_t n_datasets = 0;
     int n_params = 0;
     bool have_params = false;
+    bool degenerate_noise = false;  // some dataset has dc == 0 (or denormal / non-finite): no unit-scaled state
 
     // shared-increment mode
     bool dbg_on = false;
@@ -276,7 +277,6 @@ int build_args(ddm_ctx *ctx, int model, int64_t n_datasets, int64_t n_trials, do
     a.flags = flags;
     a.dt = dt;
     a.sqrt_dt = std::sqrt(dt);
-    a.kdt = (float)(-1.3862943611198906188 * dt);
     return DDM_OK;
 }
 
@@ -295,7 +295,10 @@ int launch_sim(ddm_ctx *ctx, ddm::RunArgs &a, int precision, ddm_stats &st) {
     const int64_t rows = trialwise ? n_trials : n_datasets * n_trials;
     if (rows == 0) return DDM_OK;
     // OUT_STATE (validation) needs the state at exactly max_steps for timeouts: the generic kernel stops there
-    const bool persistent = precision == 32 && !ctx->dbg_on && !trialwise && !(flags & (DDM_FLAG_FORCE_GENERIC | DDM_FLAG_OUT_STATE));
+    const bool degenerate = ctx->degenerate_noise && !trialwise;
+    if (degenerate) a.flags |= ddm::FLAG_REFERENCE_ARITHMETIC;
+    const bool persistent = precision == 32 && !ctx->dbg_on && !trialwise && !degenerate &&
+                            !(flags & (DDM_FLAG_FORCE_GENERIC | DDM_FLAG_OUT_STATE));
     DDM_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
     if (persistent) {
         const int block = 256;
@@ -619,6 +622,16 @@ DDM_API int ddm_upload_params(ddm_ctx *ctx, int model, const double *params, int
     const size_t n = (size_t)n_datasets * n_params;
     DDM_CUDA(ctx, ctx->params.reserve(n ? n : 1));
     if (n) DDM_CUDA(ctx, cudaMemcpyAsync(ctx->params.p, params, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    // The production kernel measures the state in units of sqrt(dt)*dc*sqrt(2 ln 2); a dataset without
+    // noise (dc == 0; the reference then runs a deterministic drift) has no such unit and goes through
+    // the kernel that keeps the reference's formulas.  (Model 2 draws its per-trial dc > 0 itself.)
+    ctx->degenerate_noise = false;
+    const int dc_col = (model == DDM_MODEL_BASIC) ? 4 : (model == DDM_MODEL_ALPHA_DC ? -1 : 5);
+    if (dc_col >= 0)
+        for (int64_t d = 0; d < n_datasets; d++) {
+            const double dc = params[(size_t)d * n_params + dc_col];
+            if (!(dc > 1e-30) || !std::isfinite(dc)) { ctx->degenerate_noise = true; break; }
+        }
     ctx->model = model;
     ctx->n_datasets = n_datasets;
     ctx->n_params = n_params;
@@ -643,6 +656,7 @@ DDM_API int ddm_draw_prior(ddm_ctx *ctx, int prior, int64_t n_draws, uint64_t se
     DDM_CUDA(ctx, ctx->params.reserve(n ? n : 1));
     const ddm::PhiloxKey key = ddm::make_philox_key((uint32_t)seed, (uint32_t)(seed >> 32));
     DDM_CUDA(ctx, ddm::launch_prior(ctx->params.p, prior, (uint32_t)n_params, (uint64_t)n_draws, draw_offset, key, ctx->stream));
+    ctx->degenerate_noise = false;  // every prior family has dc > 0
     if (model >= 0) {
         ctx->model = model;
         ctx->n_datasets = n_draws;
@@ -745,6 +759,10 @@ DDM_API int ddm_simulate_evidence(ddm_ctx *ctx, const double *params, int64_t n_
     if (ctx->dbg_on && ctx->dbg_trials != rows)
         return fail(ctx, DDM_ERR_INVALID, "shared-increment buffer was set for %lld trials, run has %lld",
                     (long long)ctx->dbg_trials, (long long)rows);
+    for (int64_t d = 0; d < n_datasets && precision == 32; d++) {
+        const double dc = params[(size_t)d * 6 + 4];
+        if (!(dc > 1e-30) || !std::isfinite(dc)) precision = 64;  // no noise unit: the validation kernel keeps the reference's formulas
+    }
     DeviceGuard g(ctx->device);
     const size_t np = (size_t)n_datasets * 6;
     DDM_CUDA(ctx, ctx->params.reserve(np ? np : 1));

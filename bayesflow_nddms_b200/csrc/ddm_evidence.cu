@@ -54,24 +54,25 @@ __global__ void __launch_bounds__(128) evidence_warp_kernel(const EvidenceArgs a
         const double drift = prm[0], boundary = prm[1], beta = prm[2], tau = prm[3], dcoef = prm[4];
         const float sigma1 = (float)prm[5];
         TrialF32 t;
-        t.c0 = (float)(drift * a.dt);
-        t.h = (float)(0.5 * boundary);
-        t.k = (float)(-1.3862943611198906188 * a.dt * dcoef * dcoef);
+        const double U = a.sqrt_dt * dcoef * SQRT_2LN2_D;  // state unit (ddm_rng.cuh: box_muller_lg2)
+        t.c0 = (float)(drift * a.dt / U);
+        t.h = (float)(0.5 * boundary / U);
+        t.u = (float)U;
         t.ext = 0.f;
-        float x = (float)(boundary * (beta - 0.5));
+        float x = (float)(boundary * (beta - 0.5) / U);
         uint32_t n = 0, blk = 0;
         uint32_t p = (valid && (fabsf(x) < t.h) && (a.max_steps > 0u)) ? 1u : 0u;
 
         // ---- phase 1: step and record while any live trial is inside the observation window ----
         while (__any_sync(FULL_MASK, p != 0u && n < a.n_obs)) {
             Normals6Scaled z;
-            philox_pairs_scaled(blk, trial_g, ds_g, STREAM_STEP, a.key, t.k, z);
+            philox_pairs_lg2(blk, trial_g, ds_g, STREAM_STEP, a.key, z);
 #pragma unroll
             for (int i = 0; i < 6; i++) {
                 if (p) {
                     const float inc = __fmaf_rn(z.s[i >> 1], (i & 1) ? z.sn[i >> 1] : z.c[i >> 1], t.c0);
                     x = __fadd_rn(x, inc);
-                    if (n < a.n_obs) path[lane * stride + n] = __fadd_rn(x, t.h);
+                    if (n < a.n_obs) path[lane * stride + n] = __fmul_rn(__fadd_rn(x, t.h), t.u);
                     n++;
                     p = ((fabsf(x) < t.h) && (n < a.max_steps)) ? 1u : 0u;
                 }
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(128) evidence_warp_kernel(const EvidenceArgs a
             blk++;
         }
         __syncwarp();
-        const float ev_final = __fadd_rn(x, t.h);
+        const float ev_final = __fmul_rn(__fadd_rn(x, t.h), t.u);
         const int choice = (x >= t.h) ? 1 : ((x <= -t.h) ? -1 : 0);
         if (valid) {
             acc_steps += n;

@@ -26,33 +26,38 @@ __global__ void prep_kernel(const double *__restrict__ params, DsConst *__restri
     DsConst c;
 #pragma unroll
     for (int i = 0; i < 8; i++) c.v[i] = 0.f;
-    const double neg2ln2 = -1.3862943611198906188;
+    const double unit1 = sqrt(dt) * SQRT_2LN2_D;  // noise scale of one step at dc = 1, in lg2 units
     if (model == 0) {  // [drift, boundary, beta, tau, dc]
-        c.v[0] = (float)(p[0] * dt);
-        c.v[1] = (float)(p[1] * (p[2] - 0.5));
-        c.v[2] = (float)(0.5 * p[1]);
-        c.v[3] = (float)(neg2ln2 * dt * p[4] * p[4]);
+        const double U = unit1 * p[4];
+        c.v[0] = (float)(p[0] * dt / U);
+        c.v[1] = (float)(p[1] * (p[2] - 0.5) / U);
+        c.v[2] = (float)(0.5 * p[1] / U);
+        c.v[3] = (float)U;
     } else if (model == 6) {  // eta: [mu_drift, alpha, beta, ter, eta, dc]
-        c.v[0] = (float)(p[0] * dt);
-        c.v[1] = (float)(p[1] * (p[2] - 0.5));
-        c.v[2] = (float)(0.5 * p[1]);
-        c.v[3] = (float)(neg2ln2 * dt * p[5] * p[5]);
-        c.v[4] = (float)(p[4] * dt);
+        const double U = unit1 * p[5];
+        c.v[0] = (float)(p[0] * dt / U);
+        c.v[1] = (float)(p[1] * (p[2] - 0.5) / U);
+        c.v[2] = (float)(0.5 * p[1] / U);
+        c.v[3] = (float)U;
+        c.v[4] = (float)(p[4] * dt / U);
     } else if (model == 2) {  // alt: [drift, alpha, beta, ter, std_dc, mu_dc, sigma1]
-        c.v[0] = (float)(p[0] * dt);
-        c.v[1] = (float)(p[1] * (p[2] - 0.5));
-        c.v[2] = (float)(0.5 * p[1]);
+        c.v[0] = (float)(p[0] * dt / unit1);
+        c.v[1] = (float)(p[1] * (p[2] - 0.5) / unit1);
+        c.v[2] = (float)(0.5 * p[1] / unit1);
         c.v[3] = (float)p[5];
         c.v[4] = (float)p[4];
         c.v[5] = (float)p[6];
+        c.v[7] = (float)unit1;
     } else {  // alpha / scale / scale2: [drift, mu_alpha, beta, ter, std_alpha, dc, sigma1(, gamma)]
-        c.v[0] = (float)(p[0] * dt);
-        c.v[1] = (float)(p[2] - 0.5);
+        const double U = unit1 * p[5];
+        c.v[0] = (float)(p[0] * dt / U);
+        c.v[1] = (float)((p[2] - 0.5) / U);
         c.v[2] = (float)p[1];
         c.v[3] = (float)p[4];
-        c.v[4] = (float)(neg2ln2 * dt * p[5] * p[5]);
+        c.v[4] = (float)(0.5 / U);
         c.v[5] = (float)p[6];
         c.v[6] = (model == 3) ? (float)p[7] : (model == 4 ? 2.f : 1.f);
+        c.v[7] = (float)U;
     }
     dconst[d] = c;
 }
@@ -96,7 +101,7 @@ __global__ void __launch_bounds__(256, DDM_PERSISTENT_MIN_BLOCKS) persistent_ker
 
     // per-lane trial
     TrialF32 t;
-    t.x = 0.f; t.h = 0.f; t.c0 = 0.f; t.k = 0.f; t.ext = 0.f;
+    t.x = 0.f; t.h = 0.f; t.c0 = 0.f; t.u = 0.f; t.ext = 0.f;
     float x = 0.f;
     uint32_t n = 0, blk = 0, trial = 0, ds = 0;
     uint32_t p = 0;    // 1 = stepping
@@ -156,7 +161,7 @@ __global__ void __launch_bounds__(256, DDM_PERSISTENT_MIN_BLOCKS) persistent_ker
             if (!has && rank < avail) {
                 ds = tile_ds;
                 trial = cur + rank;
-                trial_setup_f32<KIND>(tile_c, trial + a.trial_offset, ds + a.dataset_offset, a.key, a.kdt, t, acc_cap);
+                trial_setup_f32<KIND>(tile_c, trial + a.trial_offset, ds + a.dataset_offset, a.key, t, acc_cap);
                 x = t.x;
                 n = 0;
                 blk = 0;
@@ -174,7 +179,7 @@ __global__ void __launch_bounds__(256, DDM_PERSISTENT_MIN_BLOCKS) persistent_ker
         const int live_min = 32 - thr_now;  // keep stepping while more than this many lanes are alive
         do {
             Normals6Scaled z;
-            philox_pairs_scaled(blk, trial + a.trial_offset, ds + a.dataset_offset, STREAM_STEP, a.key, t.k, z);
+            philox_pairs_lg2(blk, trial + a.trial_offset, ds + a.dataset_offset, STREAM_STEP, a.key, z);
             euler6_warp(x, n, alive, t.c0, t.h, z, a.max_steps);
             blk++;
         } while (__popc(alive) > live_min);
@@ -233,18 +238,18 @@ __global__ void __launch_bounds__(128) generic_kernel(const RunArgs a, uint64_t 
         int choice = 0;
         double ext = 0.0, final_ev = 0.0;
 
-        if (sizeof(Real) == 4 && !BUFFER && KIND != KIND_TRIALWISE) {
+        if (sizeof(Real) == 4 && !BUFFER && KIND != KIND_TRIALWISE && !(a.flags & FLAG_REFERENCE_ARITHMETIC)) {
             // ---- fp32 / Philox: the persistent kernel's arithmetic, naive scheduling ----
             const DsConst dc = a.dconst[ds];
             TrialF32 t;
-            trial_setup_f32<(KIND == KIND_TRIALWISE ? KIND_FIXED : KIND)>(dc, trial_g, ds_g, a.key, a.kdt, t, cap);
+            trial_setup_f32<(KIND == KIND_TRIALWISE ? KIND_FIXED : KIND)>(dc, trial_g, ds_g, a.key, t, cap);
             float x = t.x;
             uint32_t p = ((fabsf(x) < t.h) && (a.max_steps > 0u)) ? 1u : 0u;
             for (uint32_t blk = 0; p != 0u; blk++)
                 step_block_f32<true>(blk, trial_g, ds_g, a.key, t, x, n, p, a.max_steps);
             choice = (x >= t.h) ? 1 : ((x <= -t.h) ? -1 : 0);
             ext = (double)t.ext;
-            final_ev = (double)__fadd_rn(x, t.h);
+            final_ev = (double)__fmul_rn(__fadd_rn(x, t.h), t.u);
         } else {
             // ---- reference arithmetic in Real (fp64: the reference's exact operation order;
             //      fp32: the same formulas rounded to float), normals from Philox or a buffer ----

@@ -17,11 +17,12 @@ enum Kind : int {
 };
 
 // Per-dataset constants in fp32, prepared once per upload by prep_kernel (fp64 math,
-// rounded once).  v[] meaning per kind:
-//   FIXED: c0=drift*dt, x0=bound*(beta-.5), h=bound/2, k=-2ln2*dt*dc^2
-//   BOUND: c0, brel=beta-.5, bmu, bsd | k, ext_sd, ext_gain
-//   DC:    c0, x0, h, mu_dc | std_dc, ext_sd
-//   DRIFT: mu_drift*dt, x0, h, k | eta*dt
+// rounded once).  The simulator state is measured in units of the step's noise scale,
+// U = sqrt(dt)*dc*sqrt(2 ln 2) (see ddm_rng.cuh: box_muller_lg2).  v[] meaning per kind:
+//   FIXED: c0=drift*dt/U, x0=bound*(beta-.5)/U, h=(bound/2)/U, U
+//   BOUND: c0=drift*dt/U, (beta-.5)/U, bmu, bsd | .5/U, ext_sd, ext_gain, U
+//   DC:    drift*dt/U1, bound*(beta-.5)/U1, (bound/2)/U1, mu_dc | std_dc, ext_sd, -, U1   (U1 = U at dc = 1)
+//   DRIFT: mu_drift*dt/U, x0, h, U | eta*dt/U
 struct __align__(16) DsConst {
     float v[8];
 };
@@ -54,25 +55,27 @@ struct RunArgs {
     int flags;
     int refill_threshold;
     double dt, sqrt_dt;
-    float kdt;               // -2 ln2 * dt
 };
 
 constexpr unsigned FULL_MASK = 0xffffffffu;
+// internal run flag (not part of the C ABI): the fp32 generic kernel uses the reference's formulas in
+// float instead of the unit-scaled production arithmetic (a dataset with dc == 0 has no noise unit)
+constexpr int FLAG_REFERENCE_ARITHMETIC = 1 << 30;
 
 enum StatSlot { STAT_STEPS = 0, STAT_TIMEOUTS = 1, STAT_UPPER = 2, STAT_REJECT_CAP = 3, STAT_DBG_OVERRUN = 4, STAT_COUNT = 5 };
 
 // ---- fp32 trial state shared by the persistent and the generic kernels ------------
 struct TrialF32 {
-    float x;    // evidence - bound/2 (centred state: one |x| < h compare per step)
-    float h;    // bound/2
-    float c0;   // drift*dt
-    float k;    // -2 ln2 * (sqrt(dt)*dc)^2, folded into the Box-Muller radius
+    float x;    // (evidence - bound/2) / U  (centred state: one |x| < h compare per step)
+    float h;    // (bound/2) / U
+    float c0;   // drift*dt / U
+    float u;    // U = sqrt(dt)*dc*sqrt(2 ln 2): evidence = (x + h) * U (validation output only)
     float ext;  // second output column (ext-data / boundary), decided at setup
 };
 
 template <int KIND>
 __device__ __forceinline__ void trial_setup_f32(const DsConst &dc, uint32_t trial, uint32_t ds_global,
-                                                const PhiloxKey &key, float kdt, TrialF32 &t, uint32_t &cap_hits) {
+                                                const PhiloxKey &key, TrialF32 &t, uint32_t &cap_hits) {
     t.c0 = dc.v[0];
     if (KIND == KIND_DRIFT) {  // drift_trial = mu_drift + eta*z, one pre-draw (aux normal 1), no rejection
         float z[6];
@@ -80,14 +83,14 @@ __device__ __forceinline__ void trial_setup_f32(const DsConst &dc, uint32_t tria
         t.c0 = __fmaf_rn(dc.v[4], z[1], dc.v[0]);
         t.x = dc.v[1];
         t.h = dc.v[2];
-        t.k = dc.v[3];
+        t.u = dc.v[3];
         t.ext = 0.f;
         return;
     }
     if (KIND == KIND_FIXED) {
         t.x = dc.v[1];
         t.h = dc.v[2];
-        t.k = dc.v[3];
+        t.u = dc.v[3];
         t.ext = 0.f;
         return;
     }
@@ -112,14 +115,16 @@ __device__ __forceinline__ void trial_setup_f32(const DsConst &dc, uint32_t tria
             if (!(latent > 0.f)) latent = __fmaf_rn(sd, z[i], mu);
     }
     if (KIND == KIND_BOUND) {
-        t.h = __fmul_rn(0.5f, latent);
+        t.h = __fmul_rn(dc.v[4], latent);
         t.x = __fmul_rn(latent, dc.v[1]);
-        t.k = dc.v[4];
+        t.u = dc.v[7];
         t.ext = __fmaf_rn(dc.v[5], z_ext, __fmul_rn(dc.v[6], latent));
-    } else {  // KIND_DC
-        t.x = dc.v[1];
-        t.h = dc.v[2];
-        t.k = __fmul_rn(kdt, __fmul_rn(latent, latent));
+    } else {  // KIND_DC: the per-trial diffusion coefficient rescales the whole state
+        const float inv = __frcp_rn(latent);
+        t.c0 = __fmul_rn(dc.v[0], inv);
+        t.x = __fmul_rn(dc.v[1], inv);
+        t.h = __fmul_rn(dc.v[2], inv);
+        t.u = __fmul_rn(dc.v[7], latent);
         t.ext = __fmaf_rn(dc.v[5], z_ext, latent);
     }
 }
@@ -221,7 +226,7 @@ __device__ __forceinline__ void step_block_f32(uint32_t blk, uint32_t trial, uin
                                                const PhiloxKey &key, const TrialF32 &t, float &x, uint32_t &n,
                                                uint32_t &p, uint32_t max_steps) {
     Normals6Scaled z;
-    philox_pairs_scaled(blk, trial, ds_global, STREAM_STEP, key, t.k, z);
+    philox_pairs_lg2(blk, trial, ds_global, STREAM_STEP, key, z);
     euler6<TAIL>(x, n, p, t.c0, t.h, z, max_steps);
 }
 

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) microbench_kernel(int iters, uint32_t see
         } else if (WHICH == DDM_MB_NORMALS) {
             // the simulator's own inner block: Philox -> 6 scaled normals -> 6 predicated Euler steps
             TrialF32 t;
-            t.h = 3.4e38f; t.c0 = fb; t.k = fa; t.x = 0.f; t.ext = 0.f;
+            t.h = 3.4e38f; t.c0 = fb; t.u = fa; t.x = 0.f; t.ext = 0.f;
             uint32_t n = 0u, p = 1u;
             step_block_f32<false>((uint32_t)it, tid, xi[0], key, t, xf[0], n, p, 0xffffffffu);
             acc += n;

@@ -131,46 +131,47 @@ __device__ __forceinline__ uint32_t leftover_field(uint32_t wa, uint32_t wb) {
     return r;
 }
 
-// One Box-Muller pair with the radius pre-scaled:  s = sqrt(|k * lg2(u)|) where the
-// caller folds its noise scale into k = -2 ln2 * (sqrt(dt)*dc)^2, so an Euler step is
-// x = fma(s, trig, x + c0) with no separate multiply.  k = -2 ln2 gives unit normals.
-// |.| guards MUFU.LG2's absolute error near u -> 1 (a slightly positive lg2 would
-// otherwise make the sqrt argument negative).
-__device__ __forceinline__ void box_muller_scaled(uint32_t fu, uint32_t ft, float k, float &s,
-                                                  float &c, float &sn) {
+// One Box-Muller pair in "lg2 units": s = sqrt(|lg2 u|), so the pair (s*c, s*sn) is N(0, 1/(2 ln 2))
+// -- the kernels fold sqrt(2 ln 2) and their own noise scale into the (per-dataset or per-trial)
+// constants of the state instead of multiplying every radius: the simulator state is
+// x = (evidence - bound/2) / (sqrt(dt) * dc * sqrt(2 ln 2)), and an Euler step is
+// x += fma(s, trig, c0) with no scale multiply at all.  |.| is a free operand modifier; it also
+// guards MUFU.LG2's absolute error near u -> 1 (a slightly positive lg2).
+__device__ __forceinline__ void box_muller_lg2(uint32_t fu, uint32_t ft, float &s, float &c, float &sn) {
     const float u = __fadd_rn(field_to_unit12(fu), -0.99999976158142089844f);  // (2m+1)/2^22, exact
-    const float l = mufu_lg2(u);
-    s = mufu_sqrt(fabsf(__fmul_rn(k, l)));
+    s = mufu_sqrt(fabsf(mufu_lg2(u)));
     const float a = __fmaf_rn(field_to_unit12(ft), 6.2831853071795865f, -9.4247779607693797f);  // 2pi*(f-1.5)
     c = mufu_cos(a);
     sn = mufu_sin(a);
 }
 
-constexpr float NEG_2LN2 = -1.3862943611198906f;
+constexpr float SQRT_2LN2 = 1.1774100225154747f;         // unit normal = SQRT_2LN2 * s * trig
+constexpr double SQRT_2LN2_D = 1.17741002251547469101;
 
 // Radii and trig factors of the three pairs of a Philox block (the simulator's inner block).
 struct Normals6Scaled {
     float s[3], c[3], sn[3];
 };
 
-__device__ __forceinline__ void philox_pairs_scaled(uint32_t block, uint32_t trial, uint32_t dataset,
-                                                    uint32_t stream, const PhiloxKey &key, float k, Normals6Scaled &o) {
+__device__ __forceinline__ void philox_pairs_lg2(uint32_t block, uint32_t trial, uint32_t dataset,
+                                                 uint32_t stream, const PhiloxKey &key, Normals6Scaled &o) {
     uint32_t w[4];
     philox4x32_rk(block, trial, dataset, stream, key, w);
-    box_muller_scaled(w[0], w[1], k, o.s[0], o.c[0], o.sn[0]);
-    box_muller_scaled(w[2], w[3], k, o.s[1], o.c[1], o.sn[1]);
-    box_muller_scaled(leftover_field(w[0], w[1]), leftover_field(w[2], w[3]), k, o.s[2], o.c[2], o.sn[2]);
+    box_muller_lg2(w[0], w[1], o.s[0], o.c[0], o.sn[0]);
+    box_muller_lg2(w[2], w[3], o.s[1], o.c[1], o.sn[1]);
+    box_muller_lg2(leftover_field(w[0], w[1]), leftover_field(w[2], w[3]), o.s[2], o.c[2], o.sn[2]);
 }
 
 // The six unit normals of Philox block (block, trial, dataset, stream), fp32 production map.
 __device__ __forceinline__ void philox_normals6_f32(uint32_t block, uint32_t trial, uint32_t dataset,
                                                     uint32_t stream, const PhiloxKey &key, float (&z)[6]) {
     Normals6Scaled o;
-    philox_pairs_scaled(block, trial, dataset, stream, key, NEG_2LN2, o);
+    philox_pairs_lg2(block, trial, dataset, stream, key, o);
 #pragma unroll
     for (int p = 0; p < 3; p++) {
-        z[2 * p] = __fmul_rn(o.s[p], o.c[p]);
-        z[2 * p + 1] = __fmul_rn(o.s[p], o.sn[p]);
+        const float r = __fmul_rn(SQRT_2LN2, o.s[p]);
+        z[2 * p] = __fmul_rn(r, o.c[p]);
+        z[2 * p + 1] = __fmul_rn(r, o.sn[p]);
     }
 }
 

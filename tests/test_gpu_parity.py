@@ -299,6 +299,23 @@ def test_edge_shapes(sim):
     assert np.all(d[0, :, 0] == 0.3) and np.all(d[0, :, 1] == -1)
 
 
+def test_zero_and_negative_diffusion_coefficient(sim, oracle):
+    """dc == 0: the reference runs a deterministic drift to the boundary; dc < 0 mirrors the noise.  The
+    production kernel's state unit does not exist there; the library falls back to the reference formulas."""
+    p = np.array([[2.0, 1.0, 0.5, 0.3, 0.0], [1.0, 1.2, 0.4, 0.2, 1.0], [-1.0, 0.8, 0.5, 0.1, 0.0]])
+    out = sim.simulate(0, p, 40, seed=3, dataset_offset=0)
+    assert sim.last_stats()["used_persistent"] == 0
+    o0 = oracle.simulate_philox(0, p[0], 40, 3, dataset=0)
+    assert np.all(out[0, :, 1] == 1) and np.allclose(out[0, :, 0], o0.sim_data[:, 0], atol=0.0100001)  # 25 steps of .02, up to a rounding tie
+    assert np.all(out[2, :, 1] == -1) and np.all(np.abs(out[2, :, 0] - (0.1 + 40 * 0.01)) < 0.0100001)
+    assert set(np.unique(out[1, :, 1])) <= {-1.0, 1.0}
+    neg = sim.simulate(0, [[1.0, 1.2, 0.4, 0.2, -1.0]], 2000, seed=3, dataset_offset=1)
+    pos = sim.simulate(0, [[1.0, 1.2, 0.4, 0.2, 1.0]], 2000, seed=4, dataset_offset=1)
+    assert abs((neg[0, :, 1] > 0).mean() - (pos[0, :, 1] > 0).mean()) < 0.05
+    ev = sim.simulate_evidence([[2.0, 1.0, 0.5, 0.3, 0.0, 0.1]], 8, 200, 1, seed=1, dataset_offset=0)
+    assert np.all(np.isfinite(ev)) and np.all(ev[0, :, 1] == 1)
+
+
 def test_timeout_flag_and_float32_output(sim):
     p = [0.05, 4.0, 0.5, 0.3, 0.3]
     a = sim.simulate(0, p, 256, seed=2, dataset_offset=0)
