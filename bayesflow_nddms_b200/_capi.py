@@ -41,7 +41,7 @@ FLAG_FORCE_GENERIC = 8
 FLAG_OUT_STATE = 16
 
 MB_NAMES = ["ffma", "imad_wide", "lop3", "iadd3", "mufu_lg2", "mufu_sin", "mix_fma_alu", "fsetp", "philox",
-            "sim_block"]
+            "sim_block", "mix_imadw_lop3", "mix_mufu_lop3", "mix_mufu_imadw", "mix_blocklike"]
 
 
 class Stats(C.Structure):

@@ -55,6 +55,20 @@ __global__ void __launch_bounds__(256) microbench_kernel(int iters, uint32_t see
                 } else if (WHICH == DDM_MB_MIX_FMA_ALU) {
                     if (c & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(xi[c]) : "r"(ka), "r"(kb));
                     else xf[c] = __fmaf_rn(xf[c], fa, fb);
+                } else if (WHICH == DDM_MB_MIX_IMADW_LOP3) {  // 1 : 1, as inside a Philox round
+                    if (c & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(xi[c]) : "r"(ka), "r"(kb));
+                    else xl[c] = (uint64_t)(uint32_t)xl[c] * (uint64_t)PHILOX_M0 + xl[c];
+                } else if (WHICH == DDM_MB_MIX_MUFU_LOP3) {   // 1 : 3
+                    if ((c & 3) == 0) asm volatile("lg2.approx.ftz.f32 %0, %0;" : "+f"(xf[c]));
+                    else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(xi[c]) : "r"(ka), "r"(kb));
+                } else if (WHICH == DDM_MB_MIX_MUFU_IMADW) {  // 1 : 1
+                    if (c & 1) asm volatile("lg2.approx.ftz.f32 %0, %0;" : "+f"(xf[c]));
+                    else xl[c] = (uint64_t)(uint32_t)xl[c] * (uint64_t)PHILOX_M0 + xl[c];
+                } else if (WHICH == DDM_MB_MIX_BLOCKLIKE) {   // per 8: 1 MUFU, 2 IMAD.WIDE, 3 LOP3, 2 FFMA (the simulator block's mix)
+                    if (c == 0) asm volatile("lg2.approx.ftz.f32 %0, %0;" : "+f"(xf[c]));
+                    else if (c == 1 || c == 2) xl[c] = (uint64_t)(uint32_t)xl[c] * (uint64_t)PHILOX_M0 + xl[c];
+                    else if (c <= 5) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(xi[c]) : "r"(ka), "r"(kb));
+                    else xf[c] = __fmaf_rn(xf[c], fa, fb);
                 } else if (WHICH == DDM_MB_FSETP) {
                     asm volatile("{ .reg .pred p; setp.lt.f32 p, %1, %2; @p add.u32 %0, %0, 1; }" : "+r"(xi[c]) : "f"(xf[c]), "f"(fa));
                 }
@@ -98,6 +112,10 @@ static cudaError_t launch_which(int which, int grid, int iters, MbOut o, cudaStr
     case DDM_MB_FSETP: return launch_one<DDM_MB_FSETP>(grid, iters, o, s);
     case DDM_MB_PHILOX: return launch_one<DDM_MB_PHILOX>(grid, iters, o, s);
     case DDM_MB_NORMALS: return launch_one<DDM_MB_NORMALS>(grid, iters, o, s);
+    case DDM_MB_MIX_IMADW_LOP3: return launch_one<DDM_MB_MIX_IMADW_LOP3>(grid, iters, o, s);
+    case DDM_MB_MIX_MUFU_LOP3: return launch_one<DDM_MB_MIX_MUFU_LOP3>(grid, iters, o, s);
+    case DDM_MB_MIX_MUFU_IMADW: return launch_one<DDM_MB_MIX_MUFU_IMADW>(grid, iters, o, s);
+    case DDM_MB_MIX_BLOCKLIKE: return launch_one<DDM_MB_MIX_BLOCKLIKE>(grid, iters, o, s);
     default: return cudaErrorInvalidValue;
     }
 }

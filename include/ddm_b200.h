@@ -195,7 +195,8 @@ int ddm_philox4x32(ddm_ctx *ctx, const uint32_t *ctr4, const uint32_t *key2, uin
 enum ddm_microbench_id {
     DDM_MB_FFMA = 0, DDM_MB_IMAD_WIDE = 1, DDM_MB_LOP3 = 2, DDM_MB_IADD3 = 3,
     DDM_MB_MUFU_LG2 = 4, DDM_MB_MUFU_SIN = 5, DDM_MB_MIX_FMA_ALU = 6, DDM_MB_FSETP = 7,
-    DDM_MB_PHILOX = 8, DDM_MB_NORMALS = 9, DDM_MB_COUNT = 10
+    DDM_MB_PHILOX = 8, DDM_MB_NORMALS = 9, DDM_MB_MIX_IMADW_LOP3 = 10, DDM_MB_MIX_MUFU_LOP3 = 11,
+    DDM_MB_MIX_MUFU_IMADW = 12, DDM_MB_MIX_BLOCKLIKE = 13, DDM_MB_COUNT = 14
 };
 int ddm_microbench(ddm_ctx *ctx, int which, int iters, double *inst_per_s, double *sm_hz);
 
