@@ -447,3 +447,41 @@ def test_device_replay_feed(sim):
     assert n == 10 and len(buf) == 4 and buf.stored_total == 10
     ptrs = {b['summary_conditions'].data_ptr() for b in buf._slots}
     assert len(ptrs) == 4                                # four live device batches, none aliased
+
+
+def test_reference_wiring_through_bayesflow_simulation_api(sim, monkeypatch):
+    """The reference's own wiring (basic_ddm_dc.py:130-134, single_trial_alpha_not_scaled.py:160-164)
+    driven through a stand-in of bf.simulation (BayesFlow is not installed here): both the reference's
+    non-batched mode and BayesFlow's batched mode, then the reference's configurator."""
+    import sys
+
+    import fake_bayesflow
+    from bayesflow_nddms_b200 import basic_ddm_dc as m0
+    from bayesflow_nddms_b200 import set_default_simulator
+    from bayesflow_nddms_b200 import single_trial_alpha_not_scaled as m1
+
+    bf, bfsim = fake_bayesflow.as_module()
+    monkeypatch.setitem(sys.modules, "bayesflow", bf)
+    monkeypatch.setitem(sys.modules, "bayesflow.simulation", bfsim)
+    set_default_simulator(sim)
+    try:
+        for m, P in ((m0, 5), (m1, 7)):
+            # exactly the reference's lines
+            prior = bf.simulation.Prior(prior_fun=m.draw_prior)
+            experimental_context = bf.simulation.ContextGenerator(non_batchable_context_fun=m.prior_N)
+            simulator = bf.simulation.Simulator(simulator_fun=m.simulate_trials, context_generator=experimental_context)
+            generative_model = bf.simulation.GenerativeModel(prior, simulator)
+            d = generative_model(8)
+            n = d['sim_non_batchable_context']
+            assert d['prior_draws'].shape == (8, P) and d['sim_data'].shape == (8, n, 2) and 60 <= n <= 300
+            c = m.configurator(d)
+            assert c['summary_conditions'].shape == (8, n, 2) and c['parameters'].shape == (8, P)
+            # the batched wiring the package offers
+            for batched in (True, False):
+                gm = m.make_bayesflow_generative_model(batched=batched)
+                d = gm(32)
+                n = d['sim_non_batchable_context']
+                assert d['prior_draws'].shape == (32, P) and d['sim_data'].shape == (32, n, 2)
+                assert np.all(np.isfinite(d['sim_data'])) and d['sim_data'].dtype == np.float64
+    finally:
+        set_default_simulator(None)
