@@ -485,3 +485,25 @@ def test_reference_wiring_through_bayesflow_simulation_api(sim, monkeypatch):
                 assert np.all(np.isfinite(d['sim_data'])) and d['sim_data'].dtype == np.float64
     finally:
         set_default_simulator(None)
+
+
+@pytest.mark.parametrize("B,N", [(3, 100_003), (100_003, 3), (1, 1_000_000), (7104 * 3 + 1, 33)])
+def test_odd_shapes_every_trial_written_once(sim, B, N):
+    """Tiles, ragged last tiles and warps that outnumber the work: every trial written exactly once
+    (step counts are positive wherever the start point is inside the boundaries), counters consistent."""
+    rng = np.random.default_rng(B + N)
+    from bayesflow_nddms_b200 import priors
+
+    params = priors.draw_prior_batch("basic", B, rng)
+    out = sim.simulate(0, params, N, seed=21, dataset_offset=5, flags=F_STEPS | F_F32)
+    steps = sim.last_steps(B * N).reshape(B, N)
+    st = sim.last_stats()
+    assert st["n_trials"] == B * N and st["total_steps"] == int(steps.sum(dtype=np.int64))
+    assert steps.min() >= 1 and steps.max() <= 400
+    tau = params[:, 3][:, None]
+    assert np.array_equal(out[..., 0], (steps * 0.01 + tau).astype(np.float32))
+    assert np.all(np.isin(out[..., 1], (-1.0, 0.0, 1.0))) and st["n_timeouts"] == int((out[..., 1] == 0).sum())
+    # a second, differently tiled run of a slice reproduces it
+    lo = min(B - 1, 2)
+    again = sim.simulate(0, params[lo:lo + 1], N, seed=21, dataset_offset=5 + lo, flags=F_F32)
+    assert np.array_equal(again[0], out[lo])
