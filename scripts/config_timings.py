@@ -79,3 +79,19 @@ cpu = (time.perf_counter() - t0) * 97
 add("C4 imputation_from_stahl 19374 trials (preprocess + simulate + DLPack)", g, cpu, 19374, steps)
 
 json.dump(rows, open(os.path.join("gpurun_out", "config_timings.json"), "w"), indent=1)
+
+# evidence-path variant (retired zoo): 256 datasets x 1000 trials, 200 observed samples, float32 rows left on the device
+from bayesflow_nddms_b200 import basic_ddm_dc_evidence as mev  # noqa: E402
+
+Pe = mev.batch_draw_prior(256)
+for mode, name in ((1, "per-trial z-score"), (2, "dataset-level standardisation")):
+    def go():
+        b = sim.simulate_evidence(Pe, 1000, 200, mode, flags=2, device=True)
+        del b
+    g = timeit(go, 10)
+    st = sim.last_stats()
+    rows.append(dict(config=f"evidence 256x1000, n_obs=200, {name}, device-resident f32", gpu_ms=g * 1e3, trials=256000,
+                     euler_steps=st["total_steps"], gpu_trials_per_s=256000 / g, out_gbs=256000 * 202 * 4 / g / 1e9,
+                     kernel_ms=st["kernel_ms"]))
+    print(json.dumps(rows[-1]), flush=True)
+json.dump(rows, open(os.path.join("gpurun_out", "config_timings.json"), "w"), indent=1)
