@@ -149,7 +149,8 @@ struct ddm_ctx {
     Arena<double> params;
     Arena<ddm::DsConst> dconst;
     Arena<int32_t> steps, group;
-    Arena<double> bound, dbg_z, export_buf, ev_scratch, ev_means, ev_ds_stats;
+    Arena<double> bound, dbg_z, export_buf, ev_scratch, ev_means, ev_ds_stats, ev_pairs;
+    Arena<float> ev_path, ev_xfinal;
     Arena<int64_t> dbg_off;
     Arena<uint32_t> philox_buf;
     unsigned long long *counters = nullptr;       // device: [0] work counter, [1..] stats
@@ -557,6 +558,9 @@ DDM_API int ddm_destroy(ddm_ctx *ctx) {
         ctx->ev_scratch.free_();
         ctx->ev_means.free_();
         ctx->ev_ds_stats.free_();
+        ctx->ev_pairs.free_();
+        ctx->ev_path.free_();
+        ctx->ev_xfinal.free_();
         ctx->dbg_off.free_();
         ctx->philox_buf.free_();
         for (int b = 0; b < 2; b++) {
@@ -759,6 +763,9 @@ DDM_API int ddm_simulate_evidence(ddm_ctx *ctx, const double *params, int64_t n_
     if (ctx->dbg_on && ctx->dbg_trials != rows)
         return fail(ctx, DDM_ERR_INVALID, "shared-increment buffer was set for %lld trials, run has %lld",
                     (long long)ctx->dbg_trials, (long long)rows);
+    // the recording kernel holds a trial's final state, which equals the state at max_steps only when the
+    // observation window ends before max_steps (always so in the reference: .2 s or .4 s of 4 s)
+    if (precision == 32 && max_steps < n_obs) precision = 64;
     for (int64_t d = 0; d < n_datasets && precision == 32; d++) {
         const double dc = params[(size_t)d * 6 + 4];
         if (!(dc > 1e-30) || !std::isfinite(dc)) precision = 64;  // no noise unit: the validation kernel keeps the reference's formulas
@@ -808,19 +815,62 @@ DDM_API int ddm_simulate_evidence(ddm_ctx *ctx, const double *params, int64_t n_
     if (rows > 0) {
         DDM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
         if (precision == 32) {
-            const size_t per_warp = ddm::evidence_smem_per_warp(a.n_obs);
-            int wpb = (int)((200u << 10) / per_warp);
-            if (wpb > 4) wpb = 4;
-            if (wpb < 1) return fail(ctx, DDM_ERR_INVALID, "n_obs too large for shared memory");
-            uint64_t grid = (uint64_t)ctx->sm_count * (size_t)((220u << 10) / (per_warp * wpb) > 0 ? (220u << 10) / (per_warp * wpb) : 1);
-            const uint64_t need = (a.n_items + wpb - 1) / wpb;
+            // (1) step + record with the persistent refill kernel (the basic model's lanes and counters)
+            DDM_CUDA(ctx, ctx->dconst.reserve((size_t)n_datasets));
+            DDM_CUDA(ctx, ctx->steps.reserve((size_t)rows));
+            DDM_CUDA(ctx, ctx->ev_pairs.reserve((size_t)rows * 2));
+            DDM_CUDA(ctx, ctx->ev_xfinal.reserve((size_t)rows));
+            DDM_CUDA(ctx, ctx->ev_path.reserve((size_t)rows * a.n_obs));
+            DDM_CUDA(ctx, ddm::launch_prep(ctx->params.p, ctx->dconst.p, (uint32_t)n_datasets, 6u, DDM_MODEL_BASIC, dt, ctx->stream));
+            ddm::RunArgs r{};
+            r.dconst = ctx->dconst.p;
+            r.params = ctx->params.p;
+            r.out = ctx->ev_pairs.p;
+            r.steps_out = ctx->steps.p;
+            r.rec_path = ctx->ev_path.p;
+            r.rec_xfinal = ctx->ev_xfinal.p;
+            r.n_obs = a.n_obs;
+            r.work_counter = ctx->counters;
+            r.stats = ctx->counters + 1;
+            r.n_datasets = a.n_datasets;
+            r.n_trials = a.n_trials;
+            r.n_params = 6;
+            r.dataset_offset = a.dataset_offset;
+            r.trial_offset = 0;
+            r.key = a.key;
+            r.max_steps = a.max_steps;
+            r.model = DDM_MODEL_BASIC;
+            r.flags = 0;
+            r.dt = dt;
+            r.sqrt_dt = a.sqrt_dt;
+            uint32_t tile = ctx->tune_tile > 0 ? (uint32_t)ctx->tune_tile : 64u;
+            if (tile > a.n_trials) tile = a.n_trials;
+            r.tile = tile;
+            r.tiles_per_dataset = (a.n_trials + tile - 1) / tile;
+            r.n_items = (uint64_t)r.tiles_per_dataset * a.n_datasets;
+            if (r.n_items > 0xffffffffULL) return fail(ctx, DDM_ERR_INVALID, "too many trial tiles for one launch");
+            r.refill_threshold = ctx->tune_threshold > 0 ? ctx->tune_threshold : 5;
+            const int block = 256;
+            int per_sm = ddm::persistent_record_max_blocks_per_sm(block);
+            if (per_sm <= 0) return fail(ctx, DDM_ERR_CUDA, "occupancy query failed for the recording kernel");
+            uint64_t grid = (uint64_t)ctx->sm_count * per_sm;
+            const uint64_t need = ((uint64_t)rows + block - 1) / block;
             if (grid > need) grid = need;
             if (grid < 1) grid = 1;
-            DDM_CUDA(ctx, ddm::launch_evidence_warp(a, out64, (int)grid, wpb, ctx->stream));
-            st.kernel_launches++;
+            DDM_CUDA(ctx, ddm::launch_persistent_record(r, (int)grid, block, ctx->stream));
+            // (2) a warp per trial: noise, standardisation, row stores
+            a.rec_path = ctx->ev_path.p;
+            a.rec_xfinal = ctx->ev_xfinal.p;
+            a.steps = ctx->steps.p;
+            a.pairs = reinterpret_cast<const double2 *>(ctx->ev_pairs.p);
+            a.dconst = ctx->dconst.p;
+            DDM_CUDA(ctx, ddm::launch_evidence_post(a, out64, (uint64_t)rows, ctx->sm_count, ctx->stream));
+            st.kernel_launches += 3;
             st.grid = (int)grid;
-            st.block = 32 * wpb;
+            st.block = block;
             st.used_persistent = 1;
+            st.refill_threshold = r.refill_threshold;
+            st.tile = (int)tile;
             if (standardize == 2) {
                 DDM_CUDA(ctx, ddm::launch_evidence_dataset_stats(ctx->ev_means.p, ctx->ev_ds_stats.p, a.n_datasets, a.n_trials, ctx->stream));
                 DDM_CUDA(ctx, ddm::launch_evidence_finalize(ctx->out, out64, ctx->out, out64, ctx->ev_ds_stats.p, total, cols,

@@ -8,12 +8,14 @@
 // params[6] = drift, boundary, beta, tau, dc, sigma1.  path[k] = evidence after Euler step k+1 for
 // k < n, held at the final evidence for k >= n, plus sigma1 * z_noise[k]; then standardised.
 //
-//   evidence_warp_kernel      production (fp32): a warp owns 32 trials; lanes step them in lock-step and
-//                             record the first n_obs evidence values in shared memory ([trial][k], padded
-//                             to an odd stride: conflict-free while recording); the warp then finishes each
-//                             trial co-operatively: noise normals (aux Philox stream, six per lane), mean and
-//                             variance by shuffle reduction, coalesced row stores.  800 B/trial of output make
-//                             this the one DDM kernel where stores matter.
+//   production (fp32)         two kernels.  (1) The persistent refill kernel of ddm_kernels.cu in its RECORD form
+//                             steps the trials (same lanes, same Philox counters as DDM_MODEL_BASIC) and stores the
+//                             first n_obs states of each trial, six per block as three 8-byte stores, plus step
+//                             count, final state and the (rt, choice) pair.  (2) evidence_post_kernel: a warp per
+//                             trial turns the recorded states into the observed path -- evidence units, held at the
+//                             final evidence after the crossing, noise normals from the aux Philox stream (six per
+//                             lane), mean / variance by shuffle reduction -- and writes the row with coalesced
+//                             stores.  800 B/trial of output make this the one DDM path where stores matter.
 //   evidence_generic_kernel   validation (fp64): one thread per trial, the reference's operation order and
 //                             left-to-right sums (numba's array_mean / array_var); shared-increment mode.
 //   dataset_stats / finalize  mode 2's second pass, and the dtype conversion of the validation path.
@@ -21,167 +23,84 @@
 
 namespace ddm {
 
-constexpr int EV_MAX_BLOCKS_PER_LANE = 4;  // n_obs <= 32 * 6 * 4 = 768
 
 // --------------------------------------------------------------------------------------------
-// production: warp per 32 trials
+// production, second kernel: a warp per trial finishes the recorded path
 // --------------------------------------------------------------------------------------------
 template <bool OUT64>
-__global__ void __launch_bounds__(128) evidence_warp_kernel(const EvidenceArgs a) {
-    extern __shared__ float ev_smem[];
+__global__ void __launch_bounds__(256) evidence_post_kernel(const EvidenceArgs a, uint64_t total) {
+    // Per-warp staging row: every global access below is lane-contiguous (k = lane, lane + 32, ...); the
+    // noise normals, which come six per Philox block and per lane, meet the row in shared memory.
+    extern __shared__ float post_smem[];
     const unsigned lane = threadIdx.x & 31u;
-    const unsigned warp = threadIdx.x >> 5;
-    const uint32_t stride = a.n_obs + 1u;  // odd or even, +1 breaks the power-of-two stride
-    float *path = ev_smem + (size_t)warp * 32u * stride;
+    float *s = post_smem + (size_t)(threadIdx.x >> 5) * a.n_obs;
+    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const uint32_t cols = 2u + a.n_obs;
     const uint32_t n_blocks = (a.n_obs + 5u) / 6u;
-
-    unsigned long long acc_steps = 0;
-    uint32_t acc_timeouts = 0, acc_upper = 0;
-
-    for (;;) {
-        unsigned long long w = 0;
-        if (lane == 0) w = atomicAdd(a.work_counter, 1ull);
-        w = __shfl_sync(FULL_MASK, w, 0);
-        if (w >= a.n_items) break;
-        const uint32_t ds = (uint32_t)w / a.tiles_per_dataset;
-        const uint32_t t0 = ((uint32_t)w - ds * a.tiles_per_dataset) * 32u;
-        const uint32_t trial = t0 + lane;
-        const bool valid = trial < a.n_trials;
-        const uint32_t ds_g = ds + a.dataset_offset, trial_g = trial + a.trial_offset;
-
-        const double *prm = a.params + (size_t)ds * 6;
-        const double drift = prm[0], boundary = prm[1], beta = prm[2], tau = prm[3], dcoef = prm[4];
-        const float sigma1 = (float)prm[5];
-        TrialF32 t;
-        const double U = a.sqrt_dt * dcoef * SQRT_2LN2_D;  // state unit (ddm_rng.cuh: box_muller_lg2)
-        t.c0 = (float)(drift * a.dt / U);
-        t.h = (float)(0.5 * boundary / U);
-        t.u = (float)U;
-        t.ext = 0.f;
-        float x = (float)(boundary * (beta - 0.5) / U);
-        uint32_t n = 0, blk = 0;
-        uint32_t p = (valid && (fabsf(x) < t.h) && (a.max_steps > 0u)) ? 1u : 0u;
-
-        // ---- phase 1: step and record while any live trial is inside the observation window ----
-        while (__any_sync(FULL_MASK, p != 0u && n < a.n_obs)) {
-            Normals6Scaled z;
-            philox_pairs_lg2(blk, trial_g, ds_g, STREAM_STEP, a.key, z);
+    const float inv_n = 1.f / (float)a.n_obs;
+    for (uint64_t g = warp0; g < total; g += n_warps) {
+        const uint32_t ds = (uint32_t)(g / a.n_trials);
+        const uint32_t trial = (uint32_t)(g - (uint64_t)ds * a.n_trials);
+        const uint32_t nj = (uint32_t)a.steps[g];
+        const float h = a.dconst[ds].v[2], u = a.dconst[ds].v[3];
+        const float sigma1 = (float)a.params[(size_t)ds * 6 + 5];
+        const float evj = __fmul_rn(__fadd_rn(a.rec_xfinal[g], h), u);
+        const float *row_in = a.rec_path + g * a.n_obs;
+        // 1. recorded states -> evidence units, held at the final evidence after the crossing
+        for (uint32_t k = lane; k < a.n_obs; k += 32u)
+            s[k] = (k < nj) ? __fmul_rn(__fadd_rn(row_in[k], h), u) : evj;
+        __syncwarp();
+        // 2. + sigma1 * z_noise[k]: lane owns Philox blocks lane, lane + 32, ... of the trial's aux stream
+        for (uint32_t b = lane; b < n_blocks; b += 32u) {
+            float z[6];
+            philox_normals6_f32(b, trial + a.trial_offset, ds + a.dataset_offset, STREAM_AUX, a.key, z);
 #pragma unroll
             for (int i = 0; i < 6; i++) {
-                if (p) {
-                    const float inc = __fmaf_rn(z.s[i >> 1], (i & 1) ? z.sn[i >> 1] : z.c[i >> 1], t.c0);
-                    x = __fadd_rn(x, inc);
-                    if (n < a.n_obs) path[lane * stride + n] = __fmul_rn(__fadd_rn(x, t.h), t.u);
-                    n++;
-                    p = ((fabsf(x) < t.h) && (n < a.max_steps)) ? 1u : 0u;
-                }
-            }
-            blk++;
-        }
-        // ---- phase 2: the rest of the trial needs no recording ----
-        while (__any_sync(FULL_MASK, p != 0u)) {
-            step_block_f32<true>(blk, trial_g, ds_g, a.key, t, x, n, p, a.max_steps);
-            blk++;
-        }
-        __syncwarp();
-        const float ev_final = __fmul_rn(__fadd_rn(x, t.h), t.u);
-        const int choice = (x >= t.h) ? 1 : ((x <= -t.h) ? -1 : 0);
-        if (valid) {
-            acc_steps += n;
-            acc_timeouts += (choice == 0);
-            acc_upper += (choice > 0);
-        }
-
-        // ---- phase 3: the warp finishes one trial at a time ----
-        const uint32_t n_valid = min(32u, a.n_trials - t0);
-        for (uint32_t j = 0; j < n_valid; j++) {
-            const uint32_t nj = __shfl_sync(FULL_MASK, n, j);
-            const float evj = __shfl_sync(FULL_MASK, ev_final, j);
-            const int chj = __shfl_sync(FULL_MASK, choice, j);
-            const uint32_t trial_j = t0 + j + a.trial_offset;
-            float vals[EV_MAX_BLOCKS_PER_LANE * 6];
-            float sum = 0.f;
-#pragma unroll
-            for (int bi = 0; bi < EV_MAX_BLOCKS_PER_LANE; bi++) {
-                const uint32_t b = lane + 32u * bi;
-                if (b < n_blocks) {
-                    float z[6];
-                    philox_normals6_f32(b, trial_j, ds_g, STREAM_AUX, a.key, z);
-#pragma unroll
-                    for (int i = 0; i < 6; i++) {
-                        const uint32_t k = 6u * b + i;
-                        float v = 0.f;
-                        if (k < a.n_obs) {
-                            const float base = (k < nj) ? path[j * stride + k] : evj;
-                            v = __fmaf_rn(sigma1, z[i], base);
-                            sum += v;
-                        }
-                        vals[bi * 6 + i] = v;
-                    }
-                }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL_MASK, sum, o);
-            const float mean = sum / (float)a.n_obs;
-            float scale = 1.f, shift = 0.f;
-            if (a.mode == 1) {
-                float ssd = 0.f;
-#pragma unroll
-                for (int bi = 0; bi < EV_MAX_BLOCKS_PER_LANE; bi++) {
-                    const uint32_t b = lane + 32u * bi;
-#pragma unroll
-                    for (int i = 0; i < 6; i++)
-                        if (b < n_blocks && 6u * b + i < a.n_obs) {
-                            const float d = vals[bi * 6 + i] - mean;
-                            ssd = __fmaf_rn(d, d, ssd);
-                        }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) ssd += __shfl_xor_sync(FULL_MASK, ssd, o);
-                scale = 1.f / sqrtf(ssd / (float)a.n_obs);
-                shift = mean;
-            }
-            const uint64_t row = ((uint64_t)ds * a.n_trials + t0 + j) * cols;
-            if (lane == 0) {
-                const double rt = __dadd_rn(__dmul_rn((double)nj, a.dt), tau);
-                if (OUT64) {
-                    double *o = reinterpret_cast<double *>(a.out) + row;
-                    o[0] = rt;
-                    o[1] = (double)chj;
-                } else {
-                    float *o = reinterpret_cast<float *>(a.out) + row;
-                    o[0] = (float)rt;
-                    o[1] = (float)chj;
-                }
-                if (a.mode == 2) a.path_means[(uint64_t)ds * a.n_trials + t0 + j] = (double)mean;
-            }
-#pragma unroll
-            for (int bi = 0; bi < EV_MAX_BLOCKS_PER_LANE; bi++) {
-                const uint32_t b = lane + 32u * bi;
-#pragma unroll
-                for (int i = 0; i < 6; i++) {
-                    const uint32_t k = 6u * b + i;
-                    if (b < n_blocks && k < a.n_obs) {
-                        const float v = (vals[bi * 6 + i] - shift) * scale;
-                        if (OUT64) reinterpret_cast<double *>(a.out)[row + 2 + k] = (double)v;
-                        else reinterpret_cast<float *>(a.out)[row + 2 + k] = v;
-                    }
-                }
+                const uint32_t k = 6u * b + i;
+                if (k < a.n_obs) s[k] = __fmaf_rn(sigma1, z[i], s[k]);
             }
         }
         __syncwarp();
-    }
+        // 3. mean (and variance) over the row
+        float sum = 0.f;
+        for (uint32_t k = lane; k < a.n_obs; k += 32u) sum += s[k];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        acc_steps += __shfl_xor_sync(FULL_MASK, acc_steps, o);
-        acc_timeouts += __shfl_xor_sync(FULL_MASK, acc_timeouts, o);
-        acc_upper += __shfl_xor_sync(FULL_MASK, acc_upper, o);
-    }
-    if (lane == 0) {
-        atomicAdd(a.stats + STAT_STEPS, acc_steps);
-        atomicAdd(a.stats + STAT_TIMEOUTS, (unsigned long long)acc_timeouts);
-        atomicAdd(a.stats + STAT_UPPER, (unsigned long long)acc_upper);
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL_MASK, sum, o);
+        const float mean = sum * inv_n;
+        float scale = 1.f, shift = 0.f;
+        if (a.mode == 1) {
+            float ssd = 0.f;
+            for (uint32_t k = lane; k < a.n_obs; k += 32u) {
+                const float d = s[k] - mean;
+                ssd = __fmaf_rn(d, d, ssd);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ssd += __shfl_xor_sync(FULL_MASK, ssd, o);
+            scale = 1.f / sqrtf(ssd * inv_n);
+            shift = mean;
+        }
+        // 4. the row
+        const uint64_t row = g * cols;
+        if (lane == 0) {
+            const double2 pr = a.pairs[g];  // (rt, choice) from the stepping kernel, reference fp64 arithmetic
+            if (OUT64) {
+                double *o = reinterpret_cast<double *>(a.out) + row;
+                o[0] = pr.x;
+                o[1] = pr.y;
+            } else {
+                float *o = reinterpret_cast<float *>(a.out) + row;
+                o[0] = (float)pr.x;
+                o[1] = (float)pr.y;
+            }
+            if (a.mode == 2) a.path_means[g] = (double)mean;
+        }
+        for (uint32_t k = lane; k < a.n_obs; k += 32u) {
+            const float v = (s[k] - shift) * scale;
+            if (OUT64) reinterpret_cast<double *>(a.out)[row + 2 + k] = (double)v;
+            else reinterpret_cast<float *>(a.out)[row + 2 + k] = v;
+        }
+        __syncwarp();
     }
 }
 
@@ -306,18 +225,14 @@ __global__ void evidence_finalize_kernel(const Src *__restrict__ src, Dst *__res
 // --------------------------------------------------------------------------------------------
 // launchers
 // --------------------------------------------------------------------------------------------
-size_t evidence_smem_per_warp(uint32_t n_obs) { return (size_t)32 * (n_obs + 1) * sizeof(float); }
-
-cudaError_t launch_evidence_warp(const EvidenceArgs &a, bool out64, int grid, int warps_per_block, cudaStream_t s) {
-    const size_t smem = evidence_smem_per_warp(a.n_obs) * warps_per_block;
-    cudaError_t e;
-    if (out64) {
-        if ((e = cudaFuncSetAttribute(evidence_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        evidence_warp_kernel<true><<<grid, 32 * warps_per_block, smem, s>>>(a);
-    } else {
-        if ((e = cudaFuncSetAttribute(evidence_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        evidence_warp_kernel<false><<<grid, 32 * warps_per_block, smem, s>>>(a);
-    }
+cudaError_t launch_evidence_post(const EvidenceArgs &a, bool out64, uint64_t total, int sm_count, cudaStream_t s) {
+    if (total == 0) return cudaSuccess;
+    uint64_t grid = (total + 7) / 8;  // 8 warps per block, one trial per warp per pass
+    const uint64_t cap = (uint64_t)sm_count * 8 * 4;
+    if (grid > cap) grid = cap;
+    const size_t smem = (size_t)8 * a.n_obs * sizeof(float);
+    if (out64) evidence_post_kernel<true><<<(unsigned)grid, 256, smem, s>>>(a, total);
+    else evidence_post_kernel<false><<<(unsigned)grid, 256, smem, s>>>(a, total);
     return cudaGetLastError();
 }
 

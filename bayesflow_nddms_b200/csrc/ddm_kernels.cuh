@@ -41,6 +41,9 @@ struct RunArgs {
     // outputs
     void *out;               // float2 / double2 per trial
     int32_t *steps_out;      // optional
+    float *rec_path;         // evidence models: [trial][n_obs] centred, unit-scaled state after each step
+    float *rec_xfinal;       // evidence models: final state per trial
+    uint32_t n_obs;
     unsigned long long *work_counter;
     unsigned long long *stats;  // see StatSlot
     // shape
@@ -138,12 +141,13 @@ __device__ __forceinline__ void trial_setup_f32(const DsConst &dc, uint32_t tria
 // c0 to x first would round the tiny drift term to x's grid the same way every step -- a systematic
 // drift error of up to ulp(x)/2 per step.)  TAIL adds the
 // n < max_steps test per step; the callers use it only for a trial's last, partial block.
-#define DDM_STEP(S, T)                         \
-    "fma.rn.f32 inc, " S ", " T ", %3;\n\t"     \
+#define DDM_STEP_G(S, T, C0, H)                \
+    "fma.rn.f32 inc, " S ", " T ", " C0 ";\n\t" \
     "@q add.rn.f32 %0, %0, inc;\n\t"           \
     "@q add.u32 %1, %1, 1;\n\t"                \
     "abs.f32 ax, %0;\n\t"                      \
-    "setp.lt.and.f32 q, ax, %4, q;\n\t"
+    "setp.lt.and.f32 q, ax, " H ", q;\n\t"
+#define DDM_STEP(S, T) DDM_STEP_G(S, T, "%3", "%4")
 #define DDM_STEP_TAIL(S, T) DDM_STEP(S, T) "setp.lt.and.u32 q, %1, %14, q;\n\t"
 
 // No warp-level primitive in here: the one-thread-per-trial kernel calls this from divergent code.
@@ -178,46 +182,38 @@ __device__ __forceinline__ void euler6(float &x, uint32_t &n, uint32_t &p, float
 // warp's ballot `alive` (bit = lane), so the block needs no predicate<->register conversions:
 // LOP3 (alive & lanemask -> predicate), the steps, ISETP (n < max_steps, folded into the predicate),
 // VOTE.  Convergent code only.
-#ifdef DDM_FLOAT_STEP_COUNTER
-#define DDM_STEPW(S, T)                        \
-    "fma.rn.f32 inc, " S ", " T ", %3;\n\t"     \
-    "@q add.rn.f32 %0, %0, inc;\n\t"           \
-    "@q add.rn.f32 nf, nf, 0f3F800000;\n\t"    \
-    "abs.f32 ax, %0;\n\t"                      \
-    "setp.lt.and.f32 q, ax, %4, q;\n\t"
-#else
-#define DDM_STEPW(S, T) DDM_STEP(S, T)
-#endif
 __device__ __forceinline__ void euler6_warp(float &x, uint32_t &n, unsigned &alive, float c0, float h,
                                             const Normals6Scaled &z, uint32_t max_steps) {
-#ifdef DDM_FLOAT_STEP_COUNTER
-    asm volatile("{\n\t.reg .pred q;\n\t.reg .f32 ax, inc, nf;\n\t.reg .b32 t;\n\t"
-                 "mov.u32 t, %%lanemask_eq;\n\t"
-                 "and.b32 t, t, %2;\n\t"
-                 "setp.ne.u32 q, t, 0;\n\t"
-                 "mov.f32 nf, 0f00000000;\n\t"
-                 DDM_STEPW("%5", "%6") DDM_STEPW("%5", "%7") DDM_STEPW("%8", "%9")
-                 DDM_STEPW("%8", "%10") DDM_STEPW("%11", "%12") DDM_STEPW("%11", "%13")
-                 "cvt.rzi.u32.f32 t, nf;\n\t"
-                 "add.u32 %1, %1, t;\n\t"
-                 "setp.lt.and.u32 q, %1, %14, q;\n\t"
-                 "vote.sync.ballot.b32 %2, q, 0xffffffff;\n\t}"
-                 : "+f"(x), "+r"(n), "+r"(alive)
-                 : "f"(c0), "f"(h), "f"(z.s[0]), "f"(z.c[0]), "f"(z.sn[0]), "f"(z.s[1]), "f"(z.c[1]), "f"(z.sn[1]),
-                   "f"(z.s[2]), "f"(z.c[2]), "f"(z.sn[2]), "r"(max_steps));
-#else
     asm volatile("{\n\t.reg .pred q;\n\t.reg .f32 ax, inc;\n\t.reg .b32 t;\n\t"
                  "mov.u32 t, %%lanemask_eq;\n\t"
                  "and.b32 t, t, %2;\n\t"
                  "setp.ne.u32 q, t, 0;\n\t"
-                 DDM_STEPW("%5", "%6") DDM_STEPW("%5", "%7") DDM_STEPW("%8", "%9")
-                 DDM_STEPW("%8", "%10") DDM_STEPW("%11", "%12") DDM_STEPW("%11", "%13")
+                 DDM_STEP("%5", "%6") DDM_STEP("%5", "%7") DDM_STEP("%8", "%9")
+                 DDM_STEP("%8", "%10") DDM_STEP("%11", "%12") DDM_STEP("%11", "%13")
                  "setp.lt.and.u32 q, %1, %14, q;\n\t"
                  "vote.sync.ballot.b32 %2, q, 0xffffffff;\n\t}"
                  : "+f"(x), "+r"(n), "+r"(alive)
                  : "f"(c0), "f"(h), "f"(z.s[0]), "f"(z.c[0]), "f"(z.sn[0]), "f"(z.s[1]), "f"(z.c[1]), "f"(z.sn[1]),
                    "f"(z.s[2]), "f"(z.c[2]), "f"(z.sn[2]), "r"(max_steps));
-#endif
+}
+
+// The same block for the evidence-path models: also hands back the state after each of the six
+// steps (r[k] = x after step k+1; frozen at the crossing value once the lane has stopped), which the
+// caller stores as the observed path.
+#define DDM_STEPR(S, T, R) DDM_STEP_G(S, T, "%9", "%10") "mov.f32 " R ", %0;\n\t"
+__device__ __forceinline__ void euler6_warp_rec(float &x, uint32_t &n, unsigned &alive, float c0, float h,
+                                                const Normals6Scaled &z, uint32_t max_steps, float (&r)[6]) {
+    asm volatile("{\n\t.reg .pred q;\n\t.reg .f32 ax, inc;\n\t.reg .b32 t;\n\t"
+                 "mov.u32 t, %%lanemask_eq;\n\t"
+                 "and.b32 t, t, %2;\n\t"
+                 "setp.ne.u32 q, t, 0;\n\t"
+                 DDM_STEPR("%11", "%12", "%3") DDM_STEPR("%11", "%13", "%4") DDM_STEPR("%14", "%15", "%5")
+                 DDM_STEPR("%14", "%16", "%6") DDM_STEPR("%17", "%18", "%7") DDM_STEPR("%17", "%19", "%8")
+                 "setp.lt.and.u32 q, %1, %20, q;\n\t"
+                 "vote.sync.ballot.b32 %2, q, 0xffffffff;\n\t}"
+                 : "+f"(x), "+r"(n), "+r"(alive), "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5])
+                 : "f"(c0), "f"(h), "f"(z.s[0]), "f"(z.c[0]), "f"(z.sn[0]), "f"(z.s[1]), "f"(z.c[1]), "f"(z.sn[1]),
+                   "f"(z.s[2]), "f"(z.c[2]), "f"(z.sn[2]), "r"(max_steps));
 }
 
 // One Philox block of a trial: block index `blk` = n / 6 for a lane that is still stepping.
@@ -255,6 +251,12 @@ struct EvidenceArgs {
     void *out;               // rows of 2 + n_obs values, float64 or float32
     double *scratch;         // validation path: fp64 rows
     double *path_means;      // mode 2: per-trial mean of the noisy path [n_datasets * n_trials]
+    // production path: products of the stepping kernel (persistent_kernel, RECORD form)
+    const float *rec_path;   // [trial][n_obs] centred, unit-scaled states
+    const float *rec_xfinal; // final state per trial
+    const int32_t *steps;    // Euler steps per trial
+    const double2 *pairs;    // (rt, choice) per trial
+    const DsConst *dconst;   // per-dataset constants (v[2] = h, v[3] = U)
     unsigned long long *work_counter;
     unsigned long long *stats;
     uint64_t n_items;
@@ -266,8 +268,7 @@ struct EvidenceArgs {
     double dt, sqrt_dt;
 };
 
-size_t evidence_smem_per_warp(uint32_t n_obs);
-cudaError_t launch_evidence_warp(const EvidenceArgs &a, bool out64, int grid, int warps_per_block, cudaStream_t s);
+cudaError_t launch_evidence_post(const EvidenceArgs &a, bool out64, uint64_t total, int sm_count, cudaStream_t s);
 cudaError_t launch_evidence_generic(const EvidenceArgs &a, bool buffer_src, uint64_t total, cudaStream_t s);
 cudaError_t launch_evidence_dataset_stats(const double *path_means, double *ds_stats, uint32_t n_datasets,
                                           uint32_t n_trials, cudaStream_t s);
@@ -282,6 +283,7 @@ cudaError_t launch_prior(double *params, int prior, uint32_t n_params, uint64_t 
 cudaError_t launch_prep(const double *params, DsConst *dconst, uint32_t n_datasets, uint32_t n_params,
                         int model, double dt, cudaStream_t s);
 cudaError_t launch_persistent(const RunArgs &a, int kind, bool out64, int grid, int block, cudaStream_t s);
+cudaError_t launch_persistent_record(const RunArgs &a, int grid, int block, cudaStream_t s);  // KIND_FIXED, float64 pairs
 cudaError_t launch_generic(const RunArgs &a, int kind, bool f64, bool buffer_src, bool out64,
                            uint64_t total_trials, cudaStream_t s);
 cudaError_t launch_export_normals(PhiloxKey key, uint32_t dataset, uint32_t trial, uint32_t stream,
@@ -289,5 +291,6 @@ cudaError_t launch_export_normals(PhiloxKey key, uint32_t dataset, uint32_t tria
 cudaError_t launch_philox_blocks(const uint32_t *ctr, const uint32_t *key, uint32_t *out, int64_t n,
                                  cudaStream_t s);
 int persistent_max_blocks_per_sm(int kind, bool out64, int block);
+int persistent_record_max_blocks_per_sm(int block);
 
 }  // namespace ddm

@@ -53,6 +53,7 @@ def test_reference_prior_agrees_when_available():
     from bayesflow_nddms_b200 import priors
 
     ns = rl.load("basic_prior")
+    np.random.seed(12345)  # the reference's truncnorm draws use NumPy's global state: fix it, no flaky KS
     ref = np.stack([ns["draw_prior"]() for _ in range(1500)])
     mine = priors.draw_prior_batch("basic", 20000, np.random.default_rng(5))
     for j in range(5):
