@@ -507,3 +507,68 @@ def test_odd_shapes_every_trial_written_once(sim, B, N):
     lo = min(B - 1, 2)
     again = sim.simulate(0, params[lo:lo + 1], N, seed=21, dataset_offset=5 + lo, flags=F_F32)
     assert np.array_equal(again[0], out[lo])
+
+
+@pytest.mark.parametrize("model,prior", [(0, "basic"), (1, "alpha"), (2, "alpha_dc"), (3, "alpha_scale"), (4, "alpha_scale2"),
+                                         (6, "eta")])
+def test_fp64_shared_increments_on_random_prior_draws(sim, oracle, model, prior):
+    """Breadth: 40 parameter vectors from each model's prior, one launch per model on a shared MT19937
+    increment buffer; every dataset must equal the reference loop bit for bit (fp64, both columns, steps)."""
+    from bayesflow_nddms_b200 import priors
+
+    rng = np.random.default_rng(1000 + model)
+    P = priors.draw_prior_batch(prior, 40, rng)
+    n = 64
+    kw = dict(dt=0.01, max_steps=400) if model % 2 == 0 else dict(dt=0.001, max_steps=4000)
+    normals_all, offs_all, refs, ref_steps = [], [], [], []
+    base = 0
+    for d in range(P.shape[0]):
+        o = oracle.simulate_mt(model, P[d], n, seed=5000 + d, **kw)
+        z = oracle.mt_normals(5000 + d, int(o.n_steps.sum()) + 80 * n + 64)
+        ob = oracle.simulate_buffer(model, P[d], n, z, **kw)
+        assert np.array_equal(ob.sim_data, o.sim_data)
+        used = int(ob.consumed.sum())
+        off = np.zeros(n, np.int64)
+        off[1:] = np.cumsum(ob.consumed)[:-1]
+        normals_all.append(z[:used])
+        offs_all.append(off + base)
+        base += used
+        refs.append(o.sim_data)
+        ref_steps.append(o.n_steps)
+    sim.set_normals_debug(np.concatenate(normals_all), np.concatenate(offs_all))
+    try:
+        out = sim.simulate(model, P, n, precision=64, flags=F_STEPS, seed=1, dataset_offset=0, **kw)
+        steps = sim.last_steps(P.shape[0] * n).reshape(P.shape[0], n)
+        st = sim.last_stats()
+    finally:
+        sim.set_normals_debug(None, None)
+    ref = np.stack(refs)
+    assert np.array_equal(out.view(np.uint64), ref.view(np.uint64))
+    assert np.array_equal(steps, np.stack(ref_steps)) and st["debug_overruns"] == 0
+
+
+def test_full_size_run_is_reproducible_and_counter_keyed(sim):
+    """Size-independent properties at 2e7 trials: two runs agree in every counter and in a checksum of the
+    output; a different seed or dataset offset changes it; the f64 and f32 outputs describe the same trials."""
+    from bayesflow_nddms_b200 import priors
+
+    B, N = 20_000, 1000
+    params = priors.draw_prior_batch("sweep", B, np.random.default_rng(3))
+
+    def run(seed, off):
+        out = sim.simulate(0, params, N, seed=seed, dataset_offset=off, dt=1e-3, max_steps=4000, flags=F_F32)
+        st = sim.last_stats()
+        chk = (float(out[..., 0].sum(dtype=np.float64)), float(out[..., 1].sum(dtype=np.float64)))
+        return st, chk
+
+    a, ca = run(5, 0)
+    b, cb = run(5, 0)
+    for k in ("total_steps", "n_timeouts", "n_upper", "n_trials"):
+        assert a[k] == b[k]
+    assert ca == cb
+    c, cc = run(6, 0)
+    d, cd = run(5, B)
+    assert cc != ca and cd != ca and c["total_steps"] != a["total_steps"] and d["total_steps"] != a["total_steps"]
+    # RT checksum equals dt * total_steps (tau = 0 in the sweep prior) up to float32 row rounding
+    assert abs(ca[0] - 1e-3 * a["total_steps"]) < 1e-6 * a["total_steps"]
+    assert abs(ca[1] - (2 * a["n_upper"] + a["n_timeouts"] - B * N)) < 0.5
