@@ -48,7 +48,11 @@ class DDMSimulator:
             self._pinned = {}
             self._lib.ddm_destroy(ctx)
 
-    __del__ = close
+    def __del__(self):
+        try:  # the interpreter may already be tearing the library down
+            self.close()
+        except Exception:
+            pass
 
     def __enter__(self):
         return self
