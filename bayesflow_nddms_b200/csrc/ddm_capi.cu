@@ -192,6 +192,17 @@ struct ddm_ctx {
 
 namespace {
 
+// Refill threshold: the emit + refill pass (~60 issue slots) is worth taking once `thr` lanes idle.  With lanes
+// finishing at rate r per six-step block the cost per block is ~1.6 (thr - 1) idle-lane slots + 60 r / thr pass
+// slots, minimal near thr = sqrt(37.5 r) = 85 / sqrt(steps per trial).  Under the reference's priors a trial
+// takes ~0.27 / dt steps (28 at dt = .01, 258 at dt = .001), hence 164 sqrt(dt).  Measured optima on B200: 5-6 at
+// dt = .001, 12-16 at dt = .01.  (An in-kernel estimate of r was tried: 2 % slower on the sweep.)  Results never
+// depend on the threshold; ddm_set_tuning overrides it.
+int default_refill_threshold(double dt) {
+    const int thr = (int)std::lround(164.0 * std::sqrt(dt));
+    return thr < 2 ? 2 : (thr > 16 ? 16 : thr);
+}
+
 int fail(ddm_ctx *ctx, int code, const char *fmt, ...) {
     char buf[512];
     va_list ap;
@@ -316,7 +327,7 @@ int launch_sim(ddm_ctx *ctx, ddm::RunArgs &a, int precision, ddm_stats &st) {
         a.tile = tile;
         a.tiles_per_dataset = (uint32_t)((n_trials + tile - 1) / tile);
         a.n_items = (uint64_t)a.tiles_per_dataset * (uint64_t)n_datasets;
-        a.refill_threshold = ctx->tune_threshold > 0 ? ctx->tune_threshold : 5;
+        a.refill_threshold = ctx->tune_threshold > 0 ? ctx->tune_threshold : default_refill_threshold(a.dt);
         if (a.refill_threshold > 32) a.refill_threshold = 32;
         const uint64_t warps_needed = ((uint64_t)rows + 31) / 32;
         uint64_t grid = (uint64_t)ctx->sm_count * per_sm;
@@ -849,7 +860,7 @@ DDM_API int ddm_simulate_evidence(ddm_ctx *ctx, const double *params, int64_t n_
             r.tiles_per_dataset = (a.n_trials + tile - 1) / tile;
             r.n_items = (uint64_t)r.tiles_per_dataset * a.n_datasets;
             if (r.n_items > 0xffffffffULL) return fail(ctx, DDM_ERR_INVALID, "too many trial tiles for one launch");
-            r.refill_threshold = ctx->tune_threshold > 0 ? ctx->tune_threshold : 5;
+            r.refill_threshold = ctx->tune_threshold > 0 ? ctx->tune_threshold : default_refill_threshold(dt);
             const int block = 256;
             int per_sm = ddm::persistent_record_max_blocks_per_sm(block);
             if (per_sm <= 0) return fail(ctx, DDM_ERR_CUDA, "occupancy query failed for the recording kernel");
