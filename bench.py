@@ -155,10 +155,24 @@ def cpu_baseline(target_s: float) -> dict:
     if dt < 0.6 * target_s:  # the small calibration probe under-estimates the rate: size the sample again
         n = int(min(n * target_s / max(dt, 1e-3), 4_000_000))
         steps, trials, dt = cpu_run(n, threads)
-    return {"value": steps / dt, "unit": "steps/s", "trials_per_s": trials / dt, "cores": threads, "kind": "port",
-            "sample": f"{n} datasets x {N_TRIALS} trials of the same prior (C oracle of the numba loop: MT19937+polar normals, "
-                      f"fp64), {threads} pthreads, {dt:.1f} s",
-            "mean_steps_per_trial": steps / trials}
+    out = {"value": steps / dt, "unit": "steps/s", "trials_per_s": trials / dt, "cores": threads, "kind": "port",
+           "sample": f"{n} datasets x {N_TRIALS} trials of the same prior (C oracle of the numba loop: MT19937+polar normals, "
+                     f"fp64), {threads} pthreads, {dt:.1f} s",
+           "mean_steps_per_trial": steps / trials}
+    # the same loop under the reference's own engine (numba), one thread as the reference runs it and numba-parallel
+    try:
+        from oracle import numba_loop as nl
+
+        p1 = sweep_params(300, seed=11)
+        s1, t1 = nl.time_numba(p1, N_TRIALS, DT, MAX_STEPS, parallel=False)
+        pn = sweep_params(300 * min(threads, 16), seed=12)
+        sn, tn = nl.time_numba(pn, N_TRIALS, DT, MAX_STEPS, parallel=True)
+        out["numba_restatement"] = {"steps_per_s_1thread": s1 / t1, "steps_per_s_numba_parallel": sn / tn,
+                                    "sample": f"300 datasets x {N_TRIALS} trials on one thread ({t1:.1f} s); "
+                                              f"{pn.shape[0]} datasets numba-parallel ({tn:.1f} s); JIT compile excluded"}
+    except Exception as e:
+        out["numba_restatement"] = {"unavailable": repr(e)[:200]}
+    return out
 
 
 def run_reference_arm(args):
