@@ -326,7 +326,7 @@ def main():
     roofline = {
         "bound": "issue", "achieved": ach / 1e12, "peak": issue_peak / 1e12, "unit": "T warp-inst/s",
         "frac": ach / issue_peak, "frac_at_survey_28_slots": ach / issue_peak * I_STEP_SURVEY / I_STEP, "traffic": None,
-        "traffic_note": "ncu --set full of this kernel on a 2e7-trial launch (profiles/r01_v5_*): dram read 4.0 MB + write "
+        "traffic_note": "ncu --set full of this kernel on a 2e7-trial launch (profiles/r01_v8_*): dram read 4.0 MB + write "
                         "104 MB against 160 MB of algorithmic output (the remainder still in L2 at kernel end)",
         "kernel": "ddm::persistent_kernel<KIND_FIXED, f32 out>", "kernel_ms": k_ms,
         "steps_per_launch": st["total_steps"], "issue_slots_per_step": I_STEP,
