@@ -80,6 +80,20 @@ class DDMSimulator:
     def synchronize(self):
         self._check(self._lib.ddm_synchronize(self._ctx))
 
+    def bind_host_thread_near_gpu(self) -> bool:
+        """Pin the calling thread to the CPUs closest to this simulator's GPU (NVML's ideal affinity), so that
+        pinned staging buffers allocated afterwards are first-touched on the GPU's own NUMA node.  On a
+        multi-GPU box this keeps every rank's PCIe traffic off the inter-socket link.  Returns False where
+        NVML or the container's cpuset does not allow it."""
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(self.device))
+            return True
+        except Exception:
+            return False
+
     def pinned_empty(self, shape, dtype=np.float64, slot: str = "out") -> np.ndarray:
         """A numpy array over page-locked host memory, reused per slot (full-rate D2H)."""
         dtype = np.dtype(dtype)

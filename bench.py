@@ -267,6 +267,7 @@ def main():
 
     D = args.datasets
     sim = pkg.DDMSimulator(device=local_rank, seed=2023)
+    numa_bound = sim.bind_host_thread_near_gpu() if world > 1 else False  # host staging on the GPU's own NUMA node
     stream = torch.cuda.Stream(device=dev)
     sim.set_stream(stream.cuda_stream)
     params = sweep_params(D, seed=2023 + rank)
@@ -373,7 +374,7 @@ def main():
         tot = sum_over_ranks(steps_e2e)
         e2e = {"value": tot * ke / (ms * 1e-3), "unit": "steps/s", "trials_per_s": De * N_TRIALS * world * ke / (ms * 1e-3),
                "h2d_bytes_per_step": int(pe.nbytes), "d2h_bytes_per_step": int(out_host.nbytes), "steps": ke,
-               "datasets_per_gpu": De, "ms_per_step": ms / ke,
+               "datasets_per_gpu": De, "ms_per_step": ms / ke, "host_thread_bound_near_gpu": bool(numa_bound),
                "api": "basic_ddm_dc.batch_simulate_trials(params (B,5) f64 host, n_trials) -> (B, n_trials, 2) f64 pinned host "
                       "array; one ddm_simulate call: H2D params, chunked kernels overlapped with the D2H of the previous chunk"}
         launches += sim.last_stats()["kernel_launches"] * ke
