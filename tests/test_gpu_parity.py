@@ -572,3 +572,32 @@ def test_full_size_run_is_reproducible_and_counter_keyed(sim):
     # RT checksum equals dt * total_steps (tau = 0 in the sweep prior) up to float32 row rounding
     assert abs(ca[0] - 1e-3 * a["total_steps"]) < 1e-6 * a["total_steps"]
     assert abs(ca[1] - (2 * a["n_upper"] + a["n_timeouts"] - B * N)) < 0.5
+
+
+def test_two_contexts_on_two_host_threads(sim):
+    """include/ddm_b200.h: one ctx per host thread, functions on distinct ctx are concurrency-safe (ctypes
+    releases the GIL around the calls).  Two threads with their own contexts reproduce the serial results."""
+    import threading
+
+    import bayesflow_nddms_b200 as pkg
+    from bayesflow_nddms_b200 import priors
+
+    params = priors.draw_prior_batch("alpha", 200, np.random.default_rng(8))
+    want = [sim.simulate(1, params, 300, seed=100 + i, dataset_offset=7) for i in range(2)]
+    got, errs = [None, None], []
+
+    def work(i):
+        try:
+            with pkg.DDMSimulator(device=0, seed=100 + i) as s:
+                for _ in range(5):
+                    got[i] = s.simulate(1, params, 300, dataset_offset=7)
+        except Exception as e:  # surfaced below
+            errs.append(e)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(120)
+    assert not errs, errs
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
