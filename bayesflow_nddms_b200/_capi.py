@@ -39,6 +39,7 @@ FLAG_OUT_F32 = 2
 FLAG_KEEP_STEPS = 4
 FLAG_FORCE_GENERIC = 8
 FLAG_OUT_STATE = 16
+FLAG_F32_NORMALS = 32
 
 MB_NAMES = ["ffma", "imad_wide", "lop3", "iadd3", "mufu_lg2", "mufu_sin", "mix_fma_alu", "fsetp", "philox",
             "sim_block", "mix_imadw_lop3", "mix_mufu_lop3", "mix_mufu_imadw", "mix_blocklike"]

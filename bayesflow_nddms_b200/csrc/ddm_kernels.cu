@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(128) generic_kernel(const RunArgs a, uint64_t 
                 const uint32_t b = idx / 6u;
                 const uint32_t tag = b | (stream << 31);  // cache tag
                 if (tag != zblk) {
-                    if (sizeof(Real) == 8) {
+                    if (sizeof(Real) == 8 && !(a.flags & 32)) {
                         philox_normals6_f64(b, trial_g, ds_g, stream, a.key, zc);
                     } else {
                         float zf[6];

@@ -83,7 +83,9 @@ enum ddm_flags {
     DDM_FLAG_OUT_F32 = 2,      /* outputs are float32 pairs (configurator dtype) instead of float64 */
     DDM_FLAG_KEEP_STEPS = 4,   /* also record int32 Euler-step counts per trial */
     DDM_FLAG_FORCE_GENERIC = 8, /* use the one-thread-per-trial kernel (validation) */
-    DDM_FLAG_OUT_STATE = 16     /* validation: column 1 := the trial's final evidence (reference frame) */
+    DDM_FLAG_OUT_STATE = 16,    /* validation: column 1 := the trial's final evidence (reference frame) */
+    DDM_FLAG_F32_NORMALS = 32   /* validation, precision 64: run the reference's fp64 arithmetic on the fp32 production
+                                   kernels' normals (the "exported increments" of check #1, at scale, on the device) */
 };
 
 typedef struct ddm_stats {

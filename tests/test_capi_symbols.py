@@ -44,7 +44,7 @@ def test_enums_match_header():
                       ("DDM_MODEL_ALPHA_SCALE2", _capi.MODEL_ALPHA_SCALE2), ("DDM_MODEL_TRIALWISE", _capi.MODEL_TRIALWISE),
                       ("DDM_ERR_NEGATIVE_BOUND", _capi.ERR_NEGATIVE_BOUND), ("DDM_FLAG_OUT_F32", _capi.FLAG_OUT_F32),
                       ("DDM_FLAG_KEEP_STEPS", _capi.FLAG_KEEP_STEPS), ("DDM_FLAG_FORCE_GENERIC", _capi.FLAG_FORCE_GENERIC),
-                      ("DDM_FLAG_OUT_STATE", _capi.FLAG_OUT_STATE)):
+                      ("DDM_FLAG_OUT_STATE", _capi.FLAG_OUT_STATE), ("DDM_FLAG_F32_NORMALS", _capi.FLAG_F32_NORMALS)):
         m = re.search(rf"\b{name}\s*=\s*(-?\d+)", src)
         assert m and int(m.group(1)) == val, name
     # ddm_stats layout mirrors the header field order

@@ -601,3 +601,39 @@ def test_two_contexts_on_two_host_threads(sim):
         t.join(120)
     assert not errs, errs
     assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+
+
+@pytest.mark.parametrize("model,prior,kw", [(0, "basic", dict(dt=0.001, max_steps=4000)), (0, "basic", dict(dt=0.01, max_steps=400)),
+                                            (1, "alpha", dict(dt=0.01, max_steps=400)), (2, "alpha_dc", dict(dt=0.01, max_steps=400)),
+                                            (6, "eta", dict(dt=0.001, max_steps=4000))])
+def test_check1_at_scale_fp32_kernel_vs_fp64_reference_arithmetic_on_the_same_increments(sim, model, prior, kw):
+    """Check #1 on 1e6 trials per model: the fp32 production kernel against the reference's fp64 loop
+    (the validation kernel, itself bit-equal to the CPU oracle) consuming the production kernel's own
+    fp32 normals.  Crossing steps and choices must agree except for boundary ties; the tie rate is
+    asserted (and printed) here: it is the documented exception of the parity claim."""
+    from bayesflow_nddms_b200 import priors
+
+    B, N = 1000, 1000
+    P = priors.draw_prior_batch(prior, B, np.random.default_rng(77 + model))
+    a = sim.simulate(model, P, N, seed=13, dataset_offset=0, flags=F_STEPS, **kw)
+    sa = sim.last_steps(B * N)
+    assert sim.last_stats()["used_persistent"] == 1
+    b = sim.simulate(model, P, N, seed=13, dataset_offset=0, precision=64, flags=F_STEPS | 32, **kw)
+    sb = sim.last_steps(B * N)
+    a2, b2 = a.reshape(-1, 2), b.reshape(-1, 2)
+    same = sa == sb
+    tie_rate = 1.0 - same.mean()
+    print(f"model {model} dt={kw['dt']}: {int((~same).sum())} of {B * N} crossing steps differ (tie rate {tie_rate:.2e})")
+    assert tie_rate < 5e-4
+    # where the step count agrees, the reported RT is bit-identical and the choice equal
+    assert np.array_equal(a2[same, 0].view(np.uint64), b2[same, 0].view(np.uint64))
+    if model in (0, 6):
+        assert np.array_equal(a2[same, 1], b2[same, 1])
+    else:
+        # per-trial redraws decide in fp32 vs fp64: a candidate within rounding of 0 may flip (rarer still)
+        ext_same = np.abs(a2[same, 1] - b2[same, 1]) < 1e-4 * (1 + np.abs(b2[same, 1]))
+        assert ext_same.mean() > 1 - 1e-4
+    # a tie changes a trial's crossing step, not the law: the step-count difference has no drift
+    d = (sa.astype(np.int64) - sb.astype(np.int64))[~same]
+    if d.size > 20:
+        assert abs(np.mean(np.sign(d))) < 0.5
