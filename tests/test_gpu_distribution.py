@@ -186,3 +186,24 @@ def test_alpha_not_scaled_data_generation(sim):
     out = sim.simulate(6, [nu, alpha, beta, tau, eta, vs], 40_000, dt=1e-4, max_steps=200_000, seed=4, dataset_offset=0)[0]
     assert stats.ks_2samp(out[:, 0] * out[:, 1], y).pvalue > 1e-3
     assert abs((out[:, 1] > 0).mean() - (y > 0).mean()) < 0.015
+
+
+@pytest.mark.parametrize("params", [[1.0, 1.2, 0.5, 0.3, 1.0], [-0.6, 1.6, 0.35, 0.2, 0.8]])
+def test_ks_against_exact_discrete_chain_at_2e7_trials(sim, params):
+    """Distribution-exactness where it can be tested hardest: 2e7 trials of one constant-parameter DDM
+    against the exact first-passage law of the Euler chain (quadrature error ~1e-6).  The KS critical
+    value at this n is 3.6e-4 in CDF distance; the chi-square over the step bins must be unremarkable too."""
+    n = 20_000_000
+    out = sim.simulate(0, params, n, seed=41, dataset_offset=0, dt=0.01, max_steps=400, flags=F_STEPS | F_F32)[0]
+    steps = sim.last_steps(n).astype(np.int64)
+    signed = out[:, 1].astype(np.int64) * steps
+    counts = np.bincount(signed + 400, minlength=801).astype(np.float64)
+    pu, pl, pt = euler_chain.first_passage_pmf(params[0], params[1], params[2], params[4], 0.01, 400, grid=2000)
+    support, cdf = euler_chain.signed_step_cdf(pu, pl, pt)
+    ecdf = np.cumsum(counts) / n
+    assert np.max(np.abs(ecdf - cdf)) * np.sqrt(n) < KS_01
+    pmf = np.diff(np.concatenate([[0.0], cdf]))
+    big = pmf * n >= 50
+    chi2 = np.sum((counts[big] - n * pmf[big]) ** 2 / (n * pmf[big]))
+    dof = int(big.sum()) - 1
+    assert stats.chi2.sf(chi2, dof) > 1e-4, (chi2, dof)
