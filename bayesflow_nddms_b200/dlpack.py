@@ -62,6 +62,13 @@ class DeviceBatch:
 
         return torch.from_dlpack(self)
 
+    def to_tensorflow(self):
+        """The batch as a TensorFlow tensor on the same GPU, no copy (BayesFlow 1.1 runs on TensorFlow;
+        TensorFlow is not part of this image, so this path is exercised only where it is installed)."""
+        import tensorflow as tf
+
+        return tf.experimental.dlpack.from_dlpack(self.__dlpack__())
+
     def __del__(self):
         m, self._managed = getattr(self, "_managed", None), None
         if m is not None:
