@@ -313,7 +313,7 @@ int launch_sim(ddm_ctx *ctx, ddm::RunArgs &a, int precision, ddm_stats &st) {
                             !(flags & (DDM_FLAG_FORCE_GENERIC | DDM_FLAG_OUT_STATE));
     DDM_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
     if (persistent) {
-        const int block = 256;
+        const int block = ddm::persistent_block_size();
         int per_sm = ctx->tune_blocks_per_sm;
         const int max_per_sm = ddm::persistent_max_blocks_per_sm(kind, out64, block);
         if (max_per_sm <= 0) return fail(ctx, DDM_ERR_CUDA, "occupancy query failed for the persistent kernel");
@@ -861,7 +861,7 @@ DDM_API int ddm_simulate_evidence(ddm_ctx *ctx, const double *params, int64_t n_
             r.n_items = (uint64_t)r.tiles_per_dataset * a.n_datasets;
             if (r.n_items > 0xffffffffULL) return fail(ctx, DDM_ERR_INVALID, "too many trial tiles for one launch");
             r.refill_threshold = ctx->tune_threshold > 0 ? ctx->tune_threshold : default_refill_threshold(dt);
-            const int block = 256;
+            const int block = ddm::persistent_block_size();
             int per_sm = ddm::persistent_record_max_blocks_per_sm(block);
             if (per_sm <= 0) return fail(ctx, DDM_ERR_CUDA, "occupancy query failed for the recording kernel");
             uint64_t grid = (uint64_t)ctx->sm_count * per_sm;

@@ -86,11 +86,15 @@ __device__ __forceinline__ void store_pair(void *out, uint64_t idx, double o0, d
 // depend on which lane / warp / SM / GPU ran a trial.
 constexpr uint32_t REC_RING = 24;  // floats per lane: three 32-byte sectors, a multiple of the 6-step block
 
+#ifndef DDM_PERSISTENT_BLOCK
+#define DDM_PERSISTENT_BLOCK 256  // threads per block (A/B: 128 and 512 measured equal within 0.5 %)
+#endif
 #ifndef DDM_PERSISTENT_MIN_BLOCKS
-#define DDM_PERSISTENT_MIN_BLOCKS 6
+#define DDM_PERSISTENT_MIN_BLOCKS (1536 / DDM_PERSISTENT_BLOCK)
 #endif
 template <int KIND, bool OUT64, bool RECORD = false>
-__global__ void __launch_bounds__(256, RECORD ? 4 : DDM_PERSISTENT_MIN_BLOCKS) persistent_kernel(const RunArgs a) {
+__global__ void __launch_bounds__(DDM_PERSISTENT_BLOCK, RECORD ? (1024 / DDM_PERSISTENT_BLOCK) : DDM_PERSISTENT_MIN_BLOCKS)
+    persistent_kernel(const RunArgs a) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
 
@@ -470,6 +474,8 @@ int persistent_record_max_blocks_per_sm(int block) {
                                                                   record_smem_bytes(block));
     return (e == cudaSuccess) ? nb : -1;
 }
+
+int persistent_block_size() { return DDM_PERSISTENT_BLOCK; }
 
 int persistent_max_blocks_per_sm(int kind, bool out64, int block) {
     int nb = 0;

@@ -292,5 +292,6 @@ cudaError_t launch_philox_blocks(const uint32_t *ctr, const uint32_t *key, uint3
                                  cudaStream_t s);
 int persistent_max_blocks_per_sm(int kind, bool out64, int block);
 int persistent_record_max_blocks_per_sm(int block);
+int persistent_block_size();
 
 }  // namespace ddm
