@@ -18,8 +18,10 @@ MODEL_ALPHA_SCALE = 3
 MODEL_ALPHA_SCALE2 = 4
 MODEL_TRIALWISE = 5
 MODEL_ETA = 6
+MODEL_GENERAL = 7
 N_PARAMS = {MODEL_BASIC: 5, MODEL_ALPHA: 7, MODEL_ALPHA_DC: 7, MODEL_ALPHA_SCALE: 8, MODEL_ALPHA_SCALE2: 7,
-            MODEL_TRIALWISE: 4, MODEL_ETA: 6}
+            MODEL_TRIALWISE: 4, MODEL_ETA: 6, MODEL_GENERAL: 24}
+N_COLS = {MODEL_GENERAL: 3}  # output columns per trial; every other model has 2
 
 # enum ddm_prior: name -> (id, columns)
 PRIORS = {"basic": (0, 5), "alpha": (1, 7), "alpha_dc": (2, 7), "alpha_scale": (3, 8), "alpha_scale2": (4, 7),

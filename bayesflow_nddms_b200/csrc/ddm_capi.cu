@@ -119,6 +119,7 @@ int n_params_of(int model) {
     case DDM_MODEL_ALPHA_SCALE: return 8;
     case DDM_MODEL_TRIALWISE: return 4;
     case DDM_MODEL_ETA: return 6;
+    case DDM_MODEL_GENERAL: return 24;
     case DDM_MODEL_ALPHA:
     case DDM_MODEL_ALPHA_DC:
     case DDM_MODEL_ALPHA_SCALE2: return 7;
@@ -126,12 +127,15 @@ int n_params_of(int model) {
     }
 }
 
+int n_cols_of(int model) { return model == DDM_MODEL_GENERAL ? 3 : 2; }
+
 int kind_of(int model) {
     switch (model) {
     case DDM_MODEL_BASIC: return ddm::KIND_FIXED;
     case DDM_MODEL_ALPHA_DC: return ddm::KIND_DC;
     case DDM_MODEL_TRIALWISE: return ddm::KIND_TRIALWISE;
     case DDM_MODEL_ETA: return ddm::KIND_DRIFT;
+    case DDM_MODEL_GENERAL: return ddm::KIND_GENERAL;
     default: return ddm::KIND_BOUND;
     }
 }
@@ -148,6 +152,7 @@ struct ddm_ctx {
 
     Arena<double> params;
     Arena<ddm::DsConst> dconst;
+    Arena<ddm::GenConst> gconst;
     Arena<int32_t> steps, group;
     Arena<double> bound, dbg_z, export_buf, ev_scratch, ev_means, ev_ds_stats, ev_pairs;
     Arena<float> ev_path, ev_xfinal;
@@ -270,6 +275,7 @@ int build_args(ddm_ctx *ctx, int model, int64_t n_datasets, int64_t n_trials, do
                     (long long)ctx->dbg_trials, (long long)rows);
     a = ddm::RunArgs{};
     a.dconst = ctx->dconst.p;
+    a.gconst = ctx->gconst.p;
     a.params = ctx->params.p;
     a.group = ctx->group.p;
     a.bound_in = ctx->bound.p;
@@ -360,7 +366,8 @@ int run_common(ddm_ctx *ctx, int model, int64_t n_datasets, int64_t n_trials, do
     const bool trialwise = (model == DDM_MODEL_TRIALWISE);
     const int64_t rows = trialwise ? n_trials : n_datasets * n_trials;
     const bool out64 = !(flags & DDM_FLAG_OUT_F32);
-    const size_t out_bytes = (size_t)rows * 2 * (out64 ? 8 : 4);
+    const int cols = n_cols_of(model);
+    const size_t out_bytes = (size_t)rows * cols * (out64 ? 8 : 4);
     rc = ensure_output(ctx, out_bytes);
     if (rc) return rc;
     const bool keep_steps = (flags & DDM_FLAG_KEEP_STEPS) != 0;
@@ -373,10 +380,16 @@ int run_common(ddm_ctx *ctx, int model, int64_t n_datasets, int64_t n_trials, do
     DDM_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long) * (1 + ddm::STAT_COUNT), ctx->stream));
     if (rows > 0) {
         if (uses_dconst(ctx, model, precision)) {
-            DDM_CUDA(ctx, ctx->dconst.reserve((size_t)n_datasets));
-            a.dconst = ctx->dconst.p;
-            DDM_CUDA(ctx, ddm::launch_prep(ctx->params.p, ctx->dconst.p, (uint32_t)n_datasets, (uint32_t)ctx->n_params,
-                                           model, dt, ctx->stream));
+            if (model == DDM_MODEL_GENERAL) {
+                DDM_CUDA(ctx, ctx->gconst.reserve((size_t)n_datasets));
+                a.gconst = ctx->gconst.p;
+                DDM_CUDA(ctx, ddm::launch_prep_general(ctx->params.p, ctx->gconst.p, (uint32_t)n_datasets, dt, ctx->stream));
+            } else {
+                DDM_CUDA(ctx, ctx->dconst.reserve((size_t)n_datasets));
+                a.dconst = ctx->dconst.p;
+                DDM_CUDA(ctx, ddm::launch_prep(ctx->params.p, ctx->dconst.p, (uint32_t)n_datasets, (uint32_t)ctx->n_params,
+                                               model, dt, ctx->stream));
+            }
             st.kernel_launches++;
         }
         DDM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
@@ -396,7 +409,7 @@ int run_common(ddm_ctx *ctx, int model, int64_t n_datasets, int64_t n_trials, do
     ctx->run_datasets = n_datasets;
     ctx->run_trials = n_trials;
     ctx->run_trialwise = trialwise;
-    ctx->run_cols = 2;
+    ctx->run_cols = cols;
     ctx->out_resident = true;
     return DDM_OK;
 }
@@ -415,7 +428,8 @@ int run_pipelined(ddm_ctx *ctx, int64_t n_trials, double dt, int max_steps, uint
     int rc = build_args(ctx, model, n_datasets, n_trials, dt, max_steps, seed, dataset_offset, 0, precision, flags, base);
     if (rc) return rc;
     const bool out64 = !(flags & DDM_FLAG_OUT_F32);
-    const size_t row_bytes = 2 * (out64 ? 8 : 4);
+    const int cols = n_cols_of(model);
+    const size_t row_bytes = (size_t)cols * (out64 ? 8 : 4);
     const int64_t chunk_rows = ctx->tune_pipeline_chunk_rows > 0 ? ctx->tune_pipeline_chunk_rows : kPipelineChunkRows;
     int64_t chunk_ds = chunk_rows / (n_trials > 0 ? n_trials : 1);
     if (chunk_ds < 1) chunk_ds = 1;
@@ -446,9 +460,14 @@ int run_pipelined(ddm_ctx *ctx, int64_t n_trials, double dt, int max_steps, uint
     DDM_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long) * (1 + ddm::STAT_COUNT), ctx->stream));
     const bool dconst = uses_dconst(ctx, model, precision);
     if (dconst) {
-        DDM_CUDA(ctx, ctx->dconst.reserve((size_t)n_datasets));
-        DDM_CUDA(ctx, ddm::launch_prep(ctx->params.p, ctx->dconst.p, (uint32_t)n_datasets, (uint32_t)ctx->n_params, model, dt,
-                                       ctx->stream));
+        if (model == DDM_MODEL_GENERAL) {
+            DDM_CUDA(ctx, ctx->gconst.reserve((size_t)n_datasets));
+            DDM_CUDA(ctx, ddm::launch_prep_general(ctx->params.p, ctx->gconst.p, (uint32_t)n_datasets, dt, ctx->stream));
+        } else {
+            DDM_CUDA(ctx, ctx->dconst.reserve((size_t)n_datasets));
+            DDM_CUDA(ctx, ddm::launch_prep(ctx->params.p, ctx->dconst.p, (uint32_t)n_datasets, (uint32_t)ctx->n_params, model, dt,
+                                           ctx->stream));
+        }
         st.kernel_launches++;
     }
     DDM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
@@ -459,7 +478,8 @@ int run_pipelined(ddm_ctx *ctx, int64_t n_trials, double dt, int max_steps, uint
         if (chunk >= 2) DDM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pipe_copy_done[b], 0));  // buffer free again
         ddm::RunArgs a = base;
         a.params = ctx->params.p + (size_t)lo * ctx->n_params;
-        a.dconst = dconst ? ctx->dconst.p + lo : nullptr;
+        a.dconst = (dconst && model != DDM_MODEL_GENERAL) ? ctx->dconst.p + lo : nullptr;
+        a.gconst = (dconst && model == DDM_MODEL_GENERAL) ? ctx->gconst.p + lo : nullptr;
         a.n_datasets = (uint32_t)cnt;
         a.dataset_offset = (uint32_t)(dataset_offset + (uint64_t)lo);
         a.out = ctx->pipe_buf[b];
@@ -488,7 +508,7 @@ int run_pipelined(ddm_ctx *ctx, int64_t n_trials, double dt, int max_steps, uint
     ctx->run_datasets = n_datasets;
     ctx->run_trials = n_trials;
     ctx->run_trialwise = false;
-    ctx->run_cols = 2;
+    ctx->run_cols = cols;
     ctx->out_resident = false;  // the batch went to the host chunk by chunk
     return DDM_OK;
 }
@@ -561,6 +581,7 @@ DDM_API int ddm_destroy(ddm_ctx *ctx) {
         if (ctx->stream) cudaStreamSynchronize(ctx->stream);
         ctx->params.free_();
         ctx->dconst.free_();
+        ctx->gconst.free_();
         ctx->steps.free_();
         ctx->group.free_();
         ctx->bound.free_();
@@ -641,10 +662,11 @@ DDM_API int ddm_upload_params(ddm_ctx *ctx, int model, const double *params, int
     // noise (dc == 0; the reference then runs a deterministic drift) has no such unit and goes through
     // the kernel that keeps the reference's formulas.  (Model 2 draws its per-trial dc > 0 itself.)
     ctx->degenerate_noise = false;
-    const int dc_col = (model == DDM_MODEL_BASIC) ? 4 : (model == DDM_MODEL_ALPHA_DC ? -1 : 5);
+    const int dc_col = (model == DDM_MODEL_BASIC || model == DDM_MODEL_GENERAL) ? 4 : (model == DDM_MODEL_ALPHA_DC ? -1 : 5);
     if (dc_col >= 0)
         for (int64_t d = 0; d < n_datasets; d++) {
             const double dc = params[(size_t)d * n_params + dc_col];
+            if (model == DDM_MODEL_GENERAL && params[(size_t)d * n_params + 5] != 0.0) continue;  // redrawn until > 0
             if (!(dc > 1e-30) || !std::isfinite(dc)) { ctx->degenerate_noise = true; break; }
         }
     ctx->model = model;

@@ -62,9 +62,56 @@ __global__ void prep_kernel(const double *__restrict__ params, DsConst *__restri
     dconst[d] = c;
 }
 
+__global__ void prep_general_kernel(const double *__restrict__ params, GenConst *__restrict__ gconst, uint32_t n_datasets,
+                                    double dt) {
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n_datasets) return;
+    const double *p = params + (size_t)d * 24;
+    const double unit1 = sqrt(dt) * SQRT_2LN2_D;
+    GenConst c;
+#pragma unroll
+    for (int i = 0; i < 24; i++) c.v[i] = 0.f;
+    c.v[0] = (float)(p[0] * dt / unit1);
+    c.v[1] = (float)(p[1] * dt / unit1);
+    c.v[2] = (float)p[2];
+    c.v[3] = (float)p[3];
+    c.v[4] = (float)p[4];
+    c.v[5] = (float)p[5];
+    c.v[6] = (float)((p[6] - 0.5) / unit1);
+    c.v[7] = (float)(0.5 / unit1);
+    c.v[8] = (float)p[0];
+    c.v[9] = (float)p[1];
+    c.v[10] = (float)unit1;
+    const int n_ext = (int)p[21];
+    for (int ch = 0; ch < 2; ch++) {
+        const double *e = p + 8 + 6 * ch;
+        float *o = c.v + 11 + 5 * ch;
+        if (ch < n_ext) {
+            o[0] = (float)(-e[4] / e[5]);
+            o[1] = (float)(e[0] / e[5]);
+            o[2] = (float)(e[1] / e[5]);
+            o[3] = (float)(e[2] / e[5]);
+            o[4] = (float)(e[3] / e[5]);
+        }
+    }
+    c.v[21] = (float)p[22];
+    gconst[d] = c;
+}
+
 // --------------------------------------------------------------------------------
 // output store
 // --------------------------------------------------------------------------------
+template <bool OUT64>
+__device__ __forceinline__ void store_triple(void *out, uint64_t idx, double o0, double o1, double o2) {
+    if (OUT64) {
+        double *o = reinterpret_cast<double *>(out) + 3 * idx;
+        o[0] = o0; o[1] = o1; o[2] = o2;
+    } else {
+        float *o = reinterpret_cast<float *>(out) + 3 * idx;
+        o[0] = (float)o0; o[1] = (float)o1; o[2] = (float)o2;
+    }
+}
+
 template <bool OUT64>
 __device__ __forceinline__ void store_pair(void *out, uint64_t idx, double o0, double o1) {
     if (OUT64) {
@@ -107,7 +154,7 @@ __global__ void __launch_bounds__(DDM_PERSISTENT_BLOCK, RECORD ? (1024 / DDM_PER
 
     // per-lane trial
     TrialF32 t;
-    t.x = 0.f; t.h = 0.f; t.c0 = 0.f; t.u = 0.f; t.ext = 0.f;
+    t.x = 0.f; t.h = 0.f; t.c0 = 0.f; t.u = 0.f; t.ext = 0.f; t.ext2 = 0.f;
     float x = 0.f;
     uint32_t n = 0, blk = 0, trial = 0, ds = 0;
     uint32_t p = 0;    // 1 = stepping
@@ -135,11 +182,23 @@ __global__ void __launch_bounds__(DDM_PERSISTENT_BLOCK, RECORD ? (1024 / DDM_PER
             // after max_steps steps is a timeout whatever it did in the surplus steps of its last
             // block (max_steps need not be a multiple of 6).
             if (n > a.max_steps) { n = a.max_steps; choice = 0; }
-            const double tau = a.params[(size_t)ds * a.n_params + 3];
+            const double tau = (KIND == KIND_GENERAL) ? 0.0 : a.params[(size_t)ds * a.n_params + 3];
             double o0, o1;
-            trial_outputs<BASIC>(a.flags, choice, n, a.dt, tau, (double)t.ext, o0, o1);
             const uint64_t idx = (uint64_t)ds * a.n_trials + trial;
-            store_pair<OUT64>(a.out, idx, o0, o1);
+            if (KIND == KIND_GENERAL) {
+                const double tau_g = a.params[(size_t)ds * a.n_params + 7];
+                const bool style0 = a.gconst[ds].v[21] == 0.f;
+                if (style0) {
+                    trial_outputs<true>(a.flags, choice, n, a.dt, tau_g, 0.0, o0, o1);
+                    store_triple<OUT64>(a.out, idx, o0, o1, (double)t.ext);
+                } else {
+                    trial_outputs<false>(a.flags, choice, n, a.dt, tau_g, (double)t.ext, o0, o1);
+                    store_triple<OUT64>(a.out, idx, o0, o1, (double)t.ext2);
+                }
+            } else {
+                trial_outputs<BASIC>(a.flags, choice, n, a.dt, tau, (double)t.ext, o0, o1);
+                store_pair<OUT64>(a.out, idx, o0, o1);
+            }
             if (a.steps_out) a.steps_out[idx] = (int32_t)n;
             if (RECORD) {
                 a.rec_xfinal[idx] = x;
@@ -171,7 +230,8 @@ __global__ void __launch_bounds__(DDM_PERSISTENT_BLOCK, RECORD ? (1024 / DDM_PER
                 }
                 cur = ti * a.tile;
                 end = min(cur + a.tile, a.n_trials);
-                const float4 *src = reinterpret_cast<const float4 *>(a.dconst + tile_ds);
+                const float4 *src = reinterpret_cast<const float4 *>((KIND == KIND_GENERAL) ? (const void *)(a.gconst + tile_ds)
+                                                                                            : (const void *)(a.dconst + tile_ds));
                 const float4 c0 = __ldg(src), c1 = __ldg(src + 1);
                 tile_c.v[0] = c0.x; tile_c.v[1] = c0.y; tile_c.v[2] = c0.z; tile_c.v[3] = c0.w;
                 tile_c.v[4] = c1.x; tile_c.v[5] = c1.y; tile_c.v[6] = c1.z; tile_c.v[7] = c1.w;
@@ -181,7 +241,10 @@ __global__ void __launch_bounds__(DDM_PERSISTENT_BLOCK, RECORD ? (1024 / DDM_PER
             if (!has && rank < avail) {
                 ds = tile_ds;
                 trial = cur + rank;
-                trial_setup_f32<KIND>(tile_c, trial + a.trial_offset, ds + a.dataset_offset, a.key, t, acc_cap);
+                if (KIND == KIND_GENERAL)
+                    trial_setup_general(a.gconst[ds], trial + a.trial_offset, ds + a.dataset_offset, a.key, t, acc_cap);
+                else
+                    trial_setup_f32<KIND>(tile_c, trial + a.trial_offset, ds + a.dataset_offset, a.key, t, acc_cap);
                 x = t.x;
                 n = 0;
                 blk = 0;
@@ -406,6 +469,126 @@ __global__ void __launch_bounds__(128) generic_kernel(const RunArgs a, uint64_t 
 }
 
 // --------------------------------------------------------------------------------
+// general (two-latent, two-channel) model, one thread per trial: validation twin of
+// persistent_kernel<KIND_GENERAL>
+// --------------------------------------------------------------------------------
+template <typename Real, bool BUFFER, bool OUT64>
+__global__ void __launch_bounds__(128) general_generic_kernel(const RunArgs a, uint64_t total) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long acc_steps = 0;
+    uint32_t tout = 0, upper = 0, cap = 0;
+    if (g < total) {
+        const uint32_t ds = (uint32_t)(g / a.n_trials);
+        const uint32_t trial = (uint32_t)(g - (uint64_t)ds * a.n_trials);
+        const uint32_t ds_g = ds + a.dataset_offset, trial_g = trial + a.trial_offset;
+        const double *p = a.params + (size_t)ds * 24;
+        uint32_t n = 0;
+        int choice = 0;
+        double e1 = 0.0, e2 = 0.0, final_ev = 0.0;
+        if (sizeof(Real) == 4 && !BUFFER && !(a.flags & FLAG_REFERENCE_ARITHMETIC)) {
+            // the persistent kernel's arithmetic, naive scheduling
+            TrialF32 t;
+            trial_setup_general(a.gconst[ds], trial_g, ds_g, a.key, t, cap);
+            float x = t.x;
+            uint32_t alive = ((fabsf(x) < t.h) && (a.max_steps > 0u)) ? 1u : 0u;
+            for (uint32_t blk = 0; alive != 0u; blk++)
+                step_block_f32<true>(blk, trial_g, ds_g, a.key, t, x, n, alive, a.max_steps);
+            choice = (x >= t.h) ? 1 : ((x <= -t.h) ? -1 : 0);
+            e1 = (double)t.ext;
+            e2 = (double)t.ext2;
+            final_ev = (double)__fmul_rn(__fadd_rn(x, t.h), t.u);
+        } else {
+            // the reference's formulas in Real, operation for operation (fp64: bit-equal to the numba loop)
+            NormalStreamBuf buf{BUFFER ? a.dbg_z + a.dbg_off[g] : nullptr, BUFFER ? a.dbg_z + a.dbg_n : nullptr, false};
+            double zc[6];
+            uint32_t ztag = 0xffffffffu;
+            auto normal = [&](uint32_t stream, uint32_t idx) -> double {
+                if (BUFFER) return buf.next();
+                const uint32_t b = idx / 6u, tag = b | (stream << 31);
+                if (tag != ztag) {
+                    if (sizeof(Real) == 8 && !(a.flags & 32)) {
+                        philox_normals6_f64(b, trial_g, ds_g, stream, a.key, zc);
+                    } else {
+                        float zf[6];
+                        philox_normals6_f32(b, trial_g, ds_g, stream, a.key, zf);
+#pragma unroll
+                        for (int i = 0; i < 6; i++) zc[i] = zf[i];
+                    }
+                    ztag = tag;
+                }
+                return zc[idx - 6u * b];
+            };
+            int ord = (int)p[20];
+            if (ord < 0 || ord > 5) ord = 0;
+            Real lat[3] = {(Real)p[0], (Real)p[2], (Real)p[4]};
+            uint32_t cand[3] = {0u, 0u, 0u};
+            for (int k = 0; k < 3; k++) {
+                // permutations of (drift, boundary, dc): 012 021 102 120 201 210
+                const int which = (k == 0) ? (ord >> 1) : ((k == 1) ? ((0x102021 >> (4 * ord)) & 3) : ((0x010212 >> (4 * ord)) & 3));
+                const Real mu = (Real)p[2 * which], sd = (Real)p[2 * which + 1];
+                if (sd == (Real)0) continue;
+                for (;;) {
+                    const uint32_t idx = (which == 0) ? 2u : (which == 1 ? 4u + 2u * cand[1] : 5u + 2u * cand[2]);
+                    lat[which] = mu + sd * (Real)normal(STREAM_AUX, idx);
+                    cand[which]++;
+                    if (which == 0 || lat[which] > (Real)0) break;
+                    if (cand[which] >= 3u * REJECT_CAP_BLOCKS - 2u) { cap++; lat[which] = (Real)1e-30; break; }
+                }
+            }
+            const Real drift_t = lat[0], bound_t = lat[1], dc_t = lat[2];
+            const Real dt = (Real)a.dt, sqrt_dt = (Real)a.sqrt_dt, beta = (Real)p[6];
+            Real ev = bound_t * beta;
+            while ((ev > (Real)0) && (ev < bound_t) && (n < a.max_steps)) {
+                const Real z = (Real)normal(STREAM_STEP, n);
+                const Real t1 = drift_t * dt;
+                const Real t2 = sqrt_dt * dc_t;
+                const Real t3 = t2 * z;
+                ev = ev + (t1 + t3);
+                n++;
+            }
+            choice = (ev >= bound_t) ? 1 : ((ev <= (Real)0) ? -1 : 0);
+            final_ev = (double)ev;
+            const int n_ext = (int)p[21];
+            Real ext[2] = {(Real)0, (Real)0};
+            for (int c = 0; c < 2 && c < n_ext; c++) {
+                const double *e = p + 8 + 6 * c;
+                const Real loc = ((Real)e[0] * drift_t + (Real)e[1] * bound_t) + (Real)e[2] * dc_t;
+                const Real temp = loc + (Real)e[3] * (Real)normal(STREAM_AUX, (uint32_t)c);
+                ext[c] = (temp - (Real)e[4]) / (Real)e[5];
+            }
+            e1 = (double)ext[0];
+            e2 = (double)ext[1];
+            if (BUFFER && buf.overrun) atomicAdd(a.stats + STAT_DBG_OVERRUN, 1ull);
+        }
+        double o0, o1;
+        if ((int)p[22] == 0) {
+            trial_outputs<true>(a.flags, choice, n, a.dt, p[7], 0.0, o0, o1);
+            store_triple<OUT64>(a.out, g, o0, o1, (a.flags & 16) ? final_ev : e1);
+        } else {
+            trial_outputs<false>(a.flags, choice, n, a.dt, p[7], e1, o0, o1);
+            store_triple<OUT64>(a.out, g, o0, o1, (a.flags & 16) ? final_ev : e2);
+        }
+        if (a.steps_out) a.steps_out[g] = (int32_t)n;
+        acc_steps = n;
+        tout = (choice == 0);
+        upper = (choice > 0);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc_steps += __shfl_xor_sync(FULL_MASK, acc_steps, o);
+        tout += __shfl_xor_sync(FULL_MASK, tout, o);
+        upper += __shfl_xor_sync(FULL_MASK, upper, o);
+        cap += __shfl_xor_sync(FULL_MASK, cap, o);
+    }
+    if ((threadIdx.x & 31u) == 0u) {
+        atomicAdd(a.stats + STAT_STEPS, acc_steps);
+        if (tout) atomicAdd(a.stats + STAT_TIMEOUTS, (unsigned long long)tout);
+        if (upper) atomicAdd(a.stats + STAT_UPPER, (unsigned long long)upper);
+        if (cap) atomicAdd(a.stats + STAT_REJECT_CAP, (unsigned long long)cap);
+    }
+}
+
+// --------------------------------------------------------------------------------
 // parity hooks
 // --------------------------------------------------------------------------------
 __global__ void export_normals_kernel(PhiloxKey key, uint32_t dataset, uint32_t trial, uint32_t stream,
@@ -457,6 +640,7 @@ cudaError_t launch_persistent(const RunArgs &a, int kind, bool out64, int grid, 
     case KIND_BOUND: return launch_persistent_kind<KIND_BOUND>(a, out64, grid, block, s);
     case KIND_DC: return launch_persistent_kind<KIND_DC>(a, out64, grid, block, s);
     case KIND_DRIFT: return launch_persistent_kind<KIND_DRIFT>(a, out64, grid, block, s);
+    case KIND_GENERAL: return launch_persistent_kind<KIND_GENERAL>(a, out64, grid, block, s);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -485,6 +669,7 @@ int persistent_max_blocks_per_sm(int kind, bool out64, int block) {
     else if (kind == KIND_BOUND) { if (out64) DDM_OCC(KIND_BOUND, true); else DDM_OCC(KIND_BOUND, false); }
     else if (kind == KIND_DC) { if (out64) DDM_OCC(KIND_DC, true); else DDM_OCC(KIND_DC, false); }
     else if (kind == KIND_DRIFT) { if (out64) DDM_OCC(KIND_DRIFT, true); else DDM_OCC(KIND_DRIFT, false); }
+    else if (kind == KIND_GENERAL) { if (out64) DDM_OCC(KIND_GENERAL, true); else DDM_OCC(KIND_GENERAL, false); }
 #undef DDM_OCC
     return (e == cudaSuccess) ? nb : -1;
 }
@@ -518,8 +703,31 @@ static cudaError_t launch_generic_1(const RunArgs &a, int kind, bool buffer_src,
     }
 }
 
+template <typename Real>
+static cudaError_t launch_general_generic(const RunArgs &a, bool buffer_src, bool out64, uint64_t total, cudaStream_t s) {
+    const unsigned grid = (unsigned)((total + 127) / 128);
+    if (grid == 0) return cudaSuccess;
+    if (buffer_src) {
+        if (out64) general_generic_kernel<Real, true, true><<<grid, 128, 0, s>>>(a, total);
+        else general_generic_kernel<Real, true, false><<<grid, 128, 0, s>>>(a, total);
+    } else {
+        if (out64) general_generic_kernel<Real, false, true><<<grid, 128, 0, s>>>(a, total);
+        else general_generic_kernel<Real, false, false><<<grid, 128, 0, s>>>(a, total);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_prep_general(const double *params, GenConst *gconst, uint32_t n_datasets, double dt, cudaStream_t s) {
+    if (n_datasets == 0) return cudaSuccess;
+    prep_general_kernel<<<(n_datasets + 127) / 128, 128, 0, s>>>(params, gconst, n_datasets, dt);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_generic(const RunArgs &a, int kind, bool f64, bool buffer_src, bool out64,
                            uint64_t total_trials, cudaStream_t s) {
+    if (kind == KIND_GENERAL)
+        return f64 ? launch_general_generic<double>(a, buffer_src, out64, total_trials, s)
+                   : launch_general_generic<float>(a, buffer_src, out64, total_trials, s);
     return f64 ? launch_generic_1<double>(a, kind, buffer_src, out64, total_trials, s)
                : launch_generic_1<float>(a, kind, buffer_src, out64, total_trials, s);
 }

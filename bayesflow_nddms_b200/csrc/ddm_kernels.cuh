@@ -13,7 +13,8 @@ enum Kind : int {
     KIND_BOUND = 1,     // per-trial boundary redraw (single_trial_alpha*, _scale, _scale2)
     KIND_DC = 2,        // per-trial diffusion coefficient redraw (_alt)
     KIND_TRIALWISE = 3, // per-trial supplied boundary + gathered group params (Stahl)
-    KIND_DRIFT = 4      // per-trial drift ~ N(mu_drift, eta) (basic_ddm_eta_dc)
+    KIND_DRIFT = 4,     // per-trial drift ~ N(mu_drift, eta) (basic_ddm_eta_dc)
+    KIND_GENERAL = 5    // per-trial drift, boundary and dc + two external channels, three output columns
 };
 
 // Per-dataset constants in fp32, prepared once per upload by prep_kernel (fp64 math,
@@ -27,11 +28,22 @@ struct __align__(16) DsConst {
     float v[8];
 };
 
+// KIND_GENERAL: per-dataset constants (fp64 math in prep_general_kernel, rounded once).  unit1 = sqrt(dt)*sqrt(2 ln 2)
+// is the state unit at dc = 1; the per-trial unit is unit1 * dc_t.
+//   0 drift_mu*dt/unit1  1 drift_sd*dt/unit1  2 bound_mu  3 bound_sd  4 dc_mu  5 dc_sd  6 (beta-.5)/unit1  7 .5/unit1
+//   8 drift_mu  9 drift_sd  10 unit1
+//   11..15 channel 1: A = -shift/scale, coefficients of drift_t, bound_t, dc_t over scale, sigma/scale
+//   16..20 channel 2 likewise   21 output style
+struct __align__(16) GenConst {
+    float v[24];
+};
+
 constexpr int REJECT_CAP_BLOCKS = 1024;  // ~6000 candidates before giving up on a redraw loop
 
 struct RunArgs {
     // inputs
     const DsConst *dconst;   // [n_datasets]
+    const GenConst *gconst;  // [n_datasets], KIND_GENERAL only
     const double *params;    // raw fp64 parameters [n_datasets * n_params] (group params for trialwise)
     const int32_t *group;    // trialwise: [n_trials]
     const double *bound_in;  // trialwise: [n_trials]
@@ -74,6 +86,7 @@ struct TrialF32 {
     float c0;   // drift*dt / U
     float u;    // U = sqrt(dt)*dc*sqrt(2 ln 2): evidence = (x + h) * U (validation output only)
     float ext;  // second output column (ext-data / boundary), decided at setup
+    float ext2; // third output column (KIND_GENERAL)
 };
 
 template <int KIND>
@@ -130,6 +143,41 @@ __device__ __forceinline__ void trial_setup_f32(const DsConst &dc, uint32_t tria
         t.u = __fmul_rn(dc.v[7], latent);
         t.ext = __fmaf_rn(dc.v[5], z_ext, latent);
     }
+}
+
+// KIND_GENERAL: aux stream normal 0 = z_ext1, 1 = z_ext2, 2 = z_drift, boundary candidate i = 4 + 2i,
+// dc candidate i = 5 + 2i (so block 0 carries the first candidate of each redraw loop).
+__device__ __forceinline__ void trial_setup_general(const GenConst &g, uint32_t trial, uint32_t ds_global,
+                                                    const PhiloxKey &key, TrialF32 &t, uint32_t &cap_hits) {
+    float z[6];
+    philox_normals6_f32(0u, trial, ds_global, STREAM_AUX, key, z);
+    const float z1 = z[0], z2 = z[1], zd = z[2];
+    const bool bound_fixed = g.v[3] == 0.f, dc_fixed = g.v[5] == 0.f;
+    float bound_t = bound_fixed ? g.v[2] : __fmaf_rn(g.v[3], z[4], g.v[2]);
+    float dc_t = dc_fixed ? g.v[4] : __fmaf_rn(g.v[5], z[5], g.v[4]);
+    bool need_b = !bound_fixed && !(bound_t > 0.f), need_c = !dc_fixed && !(dc_t > 0.f);
+    for (uint32_t j = 1; need_b || need_c; j++) {
+        if (j >= REJECT_CAP_BLOCKS) {
+            cap_hits++;
+            if (need_b) bound_t = 1e-30f;
+            if (need_c) dc_t = 1e-30f;
+            break;
+        }
+        philox_normals6_f32(j, trial, ds_global, STREAM_AUX, key, z);
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            if (need_b) { bound_t = __fmaf_rn(g.v[3], z[2 * i], g.v[2]); need_b = !(bound_t > 0.f); }
+            if (need_c) { dc_t = __fmaf_rn(g.v[5], z[2 * i + 1], g.v[4]); need_c = !(dc_t > 0.f); }
+        }
+    }
+    const float inv = __frcp_rn(dc_t);
+    t.c0 = __fmul_rn(__fmaf_rn(g.v[1], zd, g.v[0]), inv);
+    t.x = __fmul_rn(__fmul_rn(bound_t, g.v[6]), inv);
+    t.h = __fmul_rn(__fmul_rn(bound_t, g.v[7]), inv);
+    t.u = __fmul_rn(g.v[10], dc_t);
+    const float drift_t = __fmaf_rn(g.v[9], zd, g.v[8]);
+    t.ext = __fmaf_rn(g.v[15], z1, __fmaf_rn(g.v[14], dc_t, __fmaf_rn(g.v[13], bound_t, __fmaf_rn(g.v[12], drift_t, g.v[11]))));
+    t.ext2 = __fmaf_rn(g.v[20], z2, __fmaf_rn(g.v[19], dc_t, __fmaf_rn(g.v[18], bound_t, __fmaf_rn(g.v[17], drift_t, g.v[16]))));
 }
 
 // Six predicated Euler steps from one Philox block.  `p` (0/1) = "still inside the boundaries and
@@ -284,6 +332,7 @@ cudaError_t launch_prep(const double *params, DsConst *dconst, uint32_t n_datase
                         int model, double dt, cudaStream_t s);
 cudaError_t launch_persistent(const RunArgs &a, int kind, bool out64, int grid, int block, cudaStream_t s);
 cudaError_t launch_persistent_record(const RunArgs &a, int grid, int block, cudaStream_t s);  // KIND_FIXED, float64 pairs
+cudaError_t launch_prep_general(const double *params, GenConst *gconst, uint32_t n_datasets, double dt, cudaStream_t s);
 cudaError_t launch_generic(const RunArgs &a, int kind, bool f64, bool buffer_src, bool out64,
                            uint64_t total_trials, cudaStream_t s);
 cudaError_t launch_export_normals(PhiloxKey key, uint32_t dataset, uint32_t trial, uint32_t stream,

@@ -178,7 +178,7 @@ class DDMSimulator:
         if params.ndim != 2:
             raise ValueError("params must be (P,) or (B, P)")
         B, P = params.shape
-        shape = (B, int(n_trials), 2)
+        shape = (B, int(n_trials), _capi.N_COLS.get(int(model), 2))
         dtype = np.float32 if flags & _capi.FLAG_OUT_F32 else np.float64
         if out is None:
             out = np.empty(shape, dtype=dtype)

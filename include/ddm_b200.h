@@ -49,7 +49,20 @@ enum ddm_model {
     DDM_MODEL_TRIALWISE = 5,
     /* retired_models/basic_ddm_eta_dc.py:80-120: per-trial drift ~ N(mu_drift, eta) (one pre-draw, no
        rejection).  params[6] = mu_drift, alpha, beta, ter, eta, dc.  out = (rt, choice) as DDM_MODEL_BASIC */
-    DDM_MODEL_ETA = 6
+    DDM_MODEL_ETA = 6,
+    /* The retired zoo's two-latent / two-channel simulators in one parametrisation, e.g.
+       retired_models/single_trial_drift_dc5.py:90-154, single_trial_drift_dc4.py:90-146,
+       single_trial_alpha_dc.py:109-176.  params[24] =
+         0 drift_mu 1 drift_sd | 2 bound_mu 3 bound_sd | 4 dc_mu 5 dc_sd | 6 beta 7 tau
+         8..13  channel 1: coefficient of drift_t, bound_t, dc_t; sigma; shift; scale
+                ext = ((c_d*drift_t + c_b*bound_t) + c_dc*dc_t + sigma*z - shift) / scale
+         14..19 channel 2 likewise | 20 order of the pre-draws (index into the permutations of
+         (drift, bound, dc): 0 = d,b,c  1 = d,c,b  2 = b,d,c  3 = b,c,d  4 = c,d,b  5 = c,b,d; it matters
+         only in shared-increment mode) | 21 number of channels | 22 output style | 23 reserved.
+       A latent with sd == 0 is fixed; drift is drawn once; boundary and dc are redrawn until > 0.
+       THREE output columns: style 0 (rt, choice, ext1), style 1 (signed choicert, ext1, ext2).
+       bayesflow_nddms_b200/two_channel.py maps the reference's parameter vectors onto these. */
+    DDM_MODEL_GENERAL = 7
 };
 
 /* Prior families of ddm_draw_prior; the value is the ddm_model whose parameter layout is produced
@@ -120,7 +133,7 @@ int ddm_set_pipeline(ddm_ctx *ctx, int64_t min_rows, int64_t chunk_rows);
 /* Replaces B calls of simulate_trials(params[b], n_trials)  (basic_ddm_dc.py:114-125,
  * single_trial_alpha_not_scaled.py:144-155 and the _alt/_scale/_scale2/_fine variants),
  * i.e. BayesFlow's batch_simulator_fun contract: params (B,P) f64 host ->
- * out_host (B, n_trials, 2) f64 (or f32 with DDM_FLAG_OUT_F32).  out_host may be
+ * out_host (B, n_trials, 2) f64 (or f32 with DDM_FLAG_OUT_F32); (B, n_trials, 3) for DDM_MODEL_GENERAL.  out_host may be
  * NULL: results stay on the device (ddm_last_output_dlpack / ddm_download).
  * dt, max_steps: the reference's default kwargs (.01, 400).  Philox key = seed;
  * counters = (step block, trial, dataset_offset + b, stream), so the result of

@@ -21,6 +21,7 @@ MODEL_ALPHA_SCALE = 3
 MODEL_ALPHA_SCALE2 = 4
 MODEL_TRIALWISE = 5
 MODEL_ETA = 6
+MODEL_GENERAL = 7
 
 FLAG_TIMEOUT_CHOICE_ONE = 1
 
@@ -45,6 +46,8 @@ def lib() -> C.CDLL:
         i32p = C.POINTER(C.c_int32)
         L.orc_n_params.restype = C.c_int
         L.orc_n_params.argtypes = [C.c_int]
+        L.orc_n_cols.restype = C.c_int
+        L.orc_n_cols.argtypes = [C.c_int]
         L.orc_mt_normals.restype = None
         L.orc_mt_normals.argtypes = [C.c_uint32, dp, C.c_size_t]
         L.orc_philox4x32_10.restype = None
@@ -89,6 +92,10 @@ def n_params(model: int) -> int:
     return lib().orc_n_params(model)
 
 
+def n_cols(model: int) -> int:
+    return lib().orc_n_cols(model)
+
+
 def _prep(model, params, n_trials, bound_in):
     params = np.ascontiguousarray(params, dtype=np.float64).ravel()
     if params.size != n_params(model):
@@ -97,7 +104,7 @@ def _prep(model, params, n_trials, bound_in):
         bound_in = np.ascontiguousarray(bound_in, dtype=np.float64).ravel()
         if bound_in.size != n_trials:
             raise ValueError("bound_in must have n_trials entries")
-    out = np.empty((n_trials, 2), np.float64)
+    out = np.empty((n_trials, n_cols(model)), np.float64)
     ns = np.empty(n_trials, np.int64)
     ch = np.empty(n_trials, np.int32)
     ev = np.empty(n_trials, np.float64)
@@ -160,7 +167,7 @@ def simulate_batch_mt(model, params, n_trials, seed=0, dt=0.01, max_steps=400.0,
     B = params.shape[0]
     if params.shape[1] != n_params(model):
         raise ValueError("bad parameter count")
-    out = np.empty((B, n_trials, 2), np.float64) if keep_output else None
+    out = np.empty((B, n_trials, n_cols(model)), np.float64) if keep_output else None
     steps = C.c_int64(0)
     touts = C.c_int64(0)
     rc = lib().orc_simulate_batch_mt(model, _dp(params), B, n_trials, dt, float(max_steps), flags,

@@ -14,6 +14,8 @@
  *   FINE  :1710-1722 (M1 called with dt=.001, max_steps=4000)
  *   M2  imputation_from_stahl_not_scaled.py:120-148 (supplied per-trial bound)
  *   ETA retired_models/basic_ddm_eta_dc.py:80-120 (per-trial drift ~ N(mu_drift, eta))
+ *   GENERAL  the retired zoo's two-latent / two-channel scripts in one parametrisation, e.g.
+ *            retired_models/single_trial_drift_dc5.py:90-155, single_trial_alpha_dc.py:109-175
  *
  * Parity pin: the reference has no golden vectors, so the
  * oracle is pinned against outputs of the reference itself: tests/golden/
@@ -45,7 +47,8 @@ enum {
     ORC_MODEL_ALPHA_SCALE = 3,
     ORC_MODEL_ALPHA_SCALE2 = 4,
     ORC_MODEL_TRIALWISE = 5,
-    ORC_MODEL_ETA = 6
+    ORC_MODEL_ETA = 6,
+    ORC_MODEL_GENERAL = 7
 };
 /* flags -- must match include/ddm_b200.h */
 enum { ORC_FLAG_TIMEOUT_CHOICE_ONE = 1 };
@@ -231,6 +234,7 @@ static inline void src_seek(orc_src *s, uint32_t stream, uint32_t idx) {
 /* ------------------------------------------------------------------ */
 typedef struct {
     double out0, out1;   /* the two columns the reference stacks */
+    double out2;         /* third column (general model: second external channel) */
     double evidence;     /* final evidence */
     double bound;        /* boundary used by this trial */
     int64_t n_steps;
@@ -276,6 +280,55 @@ static void trial_run(int model, const double *p, double bound_in, double dt,
         o->out1 = (double)choice;
         o->choice = (ev >= p[1]) ? 1 : (ev <= 0 ? -1 : 0);
         o->bound = p[1];
+    } else if (model == ORC_MODEL_GENERAL) {
+        /* Canonical parameters (include/ddm_b200.h: DDM_MODEL_GENERAL):
+         *  0 drift_mu 1 drift_sd | 2 bound_mu 3 bound_sd | 4 dc_mu 5 dc_sd | 6 beta 7 tau
+         *  8..13  ext1: coefficient of drift_t, bound_t, dc_t; sigma; shift; scale
+         *  14..19 ext2 likewise | 20 order of the pre-draws | 21 number of ext channels | 22 output style
+         * A latent with sd == 0 is fixed and consumes no normal; drift is drawn once, boundary and dc are
+         * redrawn until positive (single_trial_drift_dc5.py:99-105, single_trial_alpha_dc.py:115-125). */
+        static const int ORDER[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
+        int ord = (int)p[20];
+        if (ord < 0 || ord > 5) ord = 0;
+        double lat[3] = {p[0], p[2], p[4]};
+        uint32_t cand[3] = {0, 0, 0};
+        for (int k = 0; k < 3; k++) {
+            int which = ORDER[ord][k];
+            double mu = p[2 * which], sd = p[2 * which + 1];
+            if (sd == 0.0) continue;
+            for (;;) {
+                /* aux stream: drift z = normal 2; boundary candidate i = 4 + 2i; dc candidate i = 5 + 2i */
+                uint32_t idx = (which == 0) ? 2u : (which == 1 ? 4u + 2u * cand[1] : 5u + 2u * cand[2]);
+                src_seek(src, PH_STREAM_AUX, idx);
+                lat[which] = mu + sd * src_next(src);
+                cand[which]++;
+                if (which == 0 || lat[which] > 0) break;
+            }
+        }
+        double drift_t = lat[0], bound_t = lat[1], dc_t = lat[2];
+        src_seek(src, PH_STREAM_STEP, 0);
+        euler_loop(drift_t, bound_t, p[6], dc_t, dt, max_steps, src, &ev, &n);
+        double rt = n * dt;
+        int n_ext = (int)p[21];
+        double ext[2] = {0.0, 0.0};
+        for (int c = 0; c < 2 && c < n_ext; c++) {
+            const double *e = p + 8 + 6 * c;
+            src_seek(src, PH_STREAM_AUX, (uint32_t)c);
+            double loc = (e[0] * drift_t + e[1] * bound_t) + e[2] * dc_t;
+            double temp = loc + e[3] * src_next(src);
+            ext[c] = (temp - e[4]) / e[5];
+        }
+        o->choice = (ev >= bound_t) ? 1 : (ev <= 0 ? -1 : 0);
+        if ((int)p[22] == 0) { /* (rt, choice, ext1) */
+            o->out0 = rt + p[7];
+            o->out1 = (double)o->choice;
+            o->out2 = ext[0];
+        } else {               /* (signed choicert, ext1, ext2) */
+            o->out0 = (o->choice > 0) ? p[7] + rt : (o->choice < 0 ? -p[7] - rt : 0.0);
+            o->out1 = ext[0];
+            o->out2 = ext[1];
+        }
+        o->bound = bound_t;
     } else if (model == ORC_MODEL_ETA) {
         /* p = [mu_drift, alpha, beta, ter, eta, dc]  retired_models/basic_ddm_eta_dc.py:80-107;
          * one pre-draw: drift_trial = mu_drift + eta*z (aux normal 1), then the basic loop */
@@ -355,16 +408,22 @@ static int n_params_of(int model) {
     case ORC_MODEL_ALPHA_SCALE: return 8;
     case ORC_MODEL_TRIALWISE: return 4;
     case ORC_MODEL_ETA: return 6;
+    case ORC_MODEL_GENERAL: return 24;
     default: return 7;
     }
 }
 
 ORC_EXPORT int orc_n_params(int model) { return n_params_of(model); }
 
-static void store_trial(const orc_trial *t, size_t i, double *out, int64_t *n_steps,
+static int n_cols_of(int model) { return model == ORC_MODEL_GENERAL ? 3 : 2; }
+
+ORC_EXPORT int orc_n_cols(int model) { return n_cols_of(model); }
+
+static void store_trial(const orc_trial *t, size_t i, int ncols, double *out, int64_t *n_steps,
                         int32_t *choice, double *evidence, double *bound, int64_t *consumed) {
-    out[2 * i] = t->out0;
-    out[2 * i + 1] = t->out1;
+    out[ncols * i] = t->out0;
+    out[ncols * i + 1] = t->out1;
+    if (ncols > 2) out[ncols * i + 2] = t->out2;
     if (n_steps) n_steps[i] = t->n_steps;
     if (choice) choice[i] = t->choice;
     if (evidence) evidence[i] = t->evidence;
@@ -391,7 +450,7 @@ ORC_EXPORT int orc_simulate_buffer(int model, const double *params, int64_t n_tr
         if (model == ORC_MODEL_TRIALWISE && b < 0) return -2; /* ValueError in the reference */
         trial_run(model, params, b, dt, max_steps, flags, &src, &t);
         if (src.overrun) return -1;
-        store_trial(&t, (size_t)i, out, n_steps, choice, evidence, bound, consumed);
+        store_trial(&t, (size_t)i, n_cols_of(model), out, n_steps, choice, evidence, bound, consumed);
     }
     return 0;
 }
@@ -411,7 +470,7 @@ ORC_EXPORT int orc_simulate_mt(int model, const double *params, int64_t n_trials
         double b = bound_in ? bound_in[i] : 0.0;
         if (model == ORC_MODEL_TRIALWISE && b < 0) return -2;
         trial_run(model, params, b, dt, max_steps, flags, &src, &t);
-        store_trial(&t, (size_t)i, out, n_steps, choice, evidence, bound, NULL);
+        store_trial(&t, (size_t)i, n_cols_of(model), out, n_steps, choice, evidence, bound, NULL);
     }
     return 0;
 }
@@ -435,7 +494,7 @@ ORC_EXPORT int orc_simulate_philox(int model, const double *params, int64_t n_tr
         if (model == ORC_MODEL_TRIALWISE && b < 0) return -2;
         src.trial = trial_offset + (uint32_t)i;
         trial_run(model, params, b, dt, max_steps, flags, &src, &t);
-        store_trial(&t, (size_t)i, out, n_steps, choice, evidence, bound, NULL);
+        store_trial(&t, (size_t)i, n_cols_of(model), out, n_steps, choice, evidence, bound, NULL);
     }
     return 0;
 }
@@ -553,7 +612,7 @@ static void *bench_worker(void *arg) {
     bench_job *job = (bench_job *)arg;
     int64_t steps = 0, timeouts = 0;
     double *scratch = NULL;
-    if (!job->out) scratch = (double *)malloc(sizeof(double) * 2 * (size_t)job->n_trials);
+    if (!job->out) scratch = (double *)malloc(sizeof(double) * 3 * (size_t)job->n_trials);
     for (;;) {
         pthread_mutex_lock(&job->lock);
         int64_t d = job->next++;
@@ -564,12 +623,14 @@ static void *bench_worker(void *arg) {
         src.kind = SRC_MT;
         orc_mt_seed(&src.mt, job->seed + (uint32_t)d);
         const double *p = job->params + (size_t)d * job->n_params;
-        double *o = job->out ? job->out + (size_t)d * 2 * job->n_trials : scratch;
+        const int nc = n_cols_of(job->model);
+        double *o = job->out ? job->out + (size_t)d * nc * job->n_trials : scratch;
         for (int64_t i = 0; i < job->n_trials; i++) {
             orc_trial t;
             trial_run(job->model, p, 0.0, job->dt, job->max_steps, job->flags, &src, &t);
-            o[2 * i] = t.out0;
-            o[2 * i + 1] = t.out1;
+            o[nc * i] = t.out0;
+            o[nc * i + 1] = t.out1;
+            if (nc > 2) o[nc * i + 2] = t.out2;
             steps += t.n_steps;
             timeouts += (t.choice == 0);
         }

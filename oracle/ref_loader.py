@@ -29,6 +29,9 @@ RANGES = {
                    ("single_trial_alpha_not_scaled.py", 1710, 1722)],
     "stahl": [("imputation_from_stahl_not_scaled.py", 120, 148)],
     "eta": [("retired_models/basic_ddm_eta_dc.py", 80, 120)],
+    "drift_dc5": [("retired_models/single_trial_drift_dc5.py", 90, 154)],
+    "drift_dc4": [("retired_models/single_trial_drift_dc4.py", 90, 146)],
+    "alpha_dc2ch": [("retired_models/single_trial_alpha_dc.py", 109, 176)],
     "evidence": [("retired_models/basic_ddm_dc_evidence.py", 87, 151)],
     "evidence2": [("retired_models/basic_ddm_dc_evidence2.py", 83, 150)],
     "evidence_no_noise2": [("retired_models/basic_ddm_dc_evidence_no_noise2.py", 82, 147)],
@@ -45,6 +48,9 @@ ENTRY = {
     "alpha_fine": "simulate_trials_fine",
     "stahl": "diffusion_trial",
     "eta": "simulate_trials",
+    "drift_dc5": "simulate_trials",
+    "drift_dc4": "simulate_trials",
+    "alpha_dc2ch": "simulate_trials",
     "evidence": "simulate_trials",
     "evidence2": "simulate_trials",
     "evidence_no_noise2": "simulate_trials",
