@@ -5,6 +5,8 @@
       standardised external channels, EEG1 ~ N(drift_t + gamma_dc1*dc_t, sigma1), EEG2 ~ N(gamma_dr2*drift_t + dc_t, sigma2)
   retired_models/single_trial_drift_dc4.py:90-146   the same without the standardisation
   retired_models/single_trial_alpha_dc.py:109-176   per-trial boundary and diffusion coefficient, standardised channels
+  retired_models/single_trial_drift_alpha.py:96-152 per-trial drift and boundary, two raw channels
+  retired_models/single_trial_alpha.py:83-135       per-trial boundary, one standardised channel -> (n_trials, 2)
 
 ``simulate_trials_*(params, n_trials) -> (n_trials, 3) float64``: (signed choicert, eeg1, eeg2).
 Each variant's parameter vector (the reference's order) is mapped to the kernel's canonical 24
@@ -69,6 +71,37 @@ def canonical_alpha_dc(params):
     return c
 
 
+def canonical_drift_alpha(params):
+    """[mu_drift, mu_alpha, beta, tau, eta, dc, var_alpha, gamma_bd1, gamma_dr2, sigma1, sigma2] -> (B, 24)."""
+    p = np.atleast_2d(np.asarray(params, dtype=np.float64))
+    mu_drift, mu_alpha, beta, tau, eta, dc, var_alpha, g_bd1, g_dr2, s1, s2 = p.T
+    c = _canon(p.shape[0])
+    c[:, 0], c[:, 1] = mu_drift, eta
+    c[:, 2], c[:, 3] = mu_alpha, var_alpha
+    c[:, 4] = dc
+    c[:, 6], c[:, 7] = beta, tau
+    c[:, 8], c[:, 9], c[:, 11] = 1.0, g_bd1, s1           # EEG1 = N(1*drift_t + gamma_bd1*bound_t, sigma1)
+    c[:, 14], c[:, 15], c[:, 17] = g_dr2, 1.0, s2         # EEG2 = N(gamma_dr2*drift_t + 1*bound_t, sigma2)
+    c[:, 20], c[:, 21], c[:, 22] = ORDER_DRIFT_BOUND_DC, 2, 1
+    return c
+
+
+def canonical_alpha_standardised(params):
+    """single_trial_alpha.py: [drift, mu_alpha, beta, ter, var_alpha, dc, sigma1] -> (B, 24), one channel."""
+    p = np.atleast_2d(np.asarray(params, dtype=np.float64))
+    drift, mu_alpha, beta, ter, var_alpha, dc, s1 = p.T
+    c = _canon(p.shape[0])
+    c[:, 0] = drift
+    c[:, 2], c[:, 3] = mu_alpha, var_alpha
+    c[:, 4] = dc
+    c[:, 6], c[:, 7] = beta, ter
+    c[:, 9], c[:, 11] = 1.0, s1                            # temp = N(1*bound_t, sigma1)
+    c[:, 12] = 1 * mu_alpha                                # single_trial_alpha.py:112-114
+    c[:, 13] = np.sqrt(var_alpha ** 2 + s1 ** 2)
+    c[:, 20], c[:, 21], c[:, 22] = ORDER_DRIFT_BOUND_DC, 1, 1
+    return c
+
+
 def _simulate(canon, n_trials, single, simulator, dt, max_steps, **kw):
     sim = simulator if simulator is not None else default_simulator()
     out = sim.simulate(_capi.MODEL_GENERAL, canon, int(n_trials), dt, int(max_steps), **kw)
@@ -89,3 +122,14 @@ def simulate_trials_drift_dc4(params, n_trials, simulator=None, dt=.01, max_step
 def simulate_trials_alpha_dc(params, n_trials, simulator=None, dt=.01, max_steps=400., **kw):
     """single_trial_alpha_dc.py:164-176 -> (n_trials, 3)."""
     return _simulate(canonical_alpha_dc(params), n_trials, np.ndim(params) == 1, simulator, dt, max_steps, **kw)
+
+
+def simulate_trials_drift_alpha(params, n_trials, simulator=None, dt=.01, max_steps=400., **kw):
+    """single_trial_drift_alpha.py:140-152 -> (n_trials, 3)."""
+    return _simulate(canonical_drift_alpha(params), n_trials, np.ndim(params) == 1, simulator, dt, max_steps, **kw)
+
+
+def simulate_trials_alpha_standardised(params, n_trials, simulator=None, dt=.01, max_steps=400., **kw):
+    """single_trial_alpha.py:124-135 -> (n_trials, 2): (choicert, standardised extdata1)."""
+    out = _simulate(canonical_alpha_standardised(params), n_trials, np.ndim(params) == 1, simulator, dt, max_steps, **kw)
+    return np.ascontiguousarray(out[..., :2])

@@ -32,6 +32,8 @@ RANGES = {
     "drift_dc5": [("retired_models/single_trial_drift_dc5.py", 90, 154)],
     "drift_dc4": [("retired_models/single_trial_drift_dc4.py", 90, 146)],
     "alpha_dc2ch": [("retired_models/single_trial_alpha_dc.py", 109, 176)],
+    "drift_alpha": [("retired_models/single_trial_drift_alpha.py", 96, 152)],
+    "alpha_std1": [("retired_models/single_trial_alpha.py", 83, 135)],
     "evidence": [("retired_models/basic_ddm_dc_evidence.py", 87, 151)],
     "evidence2": [("retired_models/basic_ddm_dc_evidence2.py", 83, 150)],
     "evidence_no_noise2": [("retired_models/basic_ddm_dc_evidence_no_noise2.py", 82, 147)],
@@ -51,6 +53,8 @@ ENTRY = {
     "drift_dc5": "simulate_trials",
     "drift_dc4": "simulate_trials",
     "alpha_dc2ch": "simulate_trials",
+    "drift_alpha": "simulate_trials",
+    "alpha_std1": "simulate_trials",
     "evidence": "simulate_trials",
     "evidence2": "simulate_trials",
     "evidence_no_noise2": "simulate_trials",

@@ -20,6 +20,8 @@ CASES = [
     ("dc4_typical", "drift_dc4", [1.5, 1.2, 0.5, 0.4, 1.0, 1.0, 0.5, 0.7, -0.4, 0.3, 0.6], 300, 34),
     ("alpha_dc_typical", "alpha_dc2ch", [2.0, 1.3, 0.55, 0.35, 0.4, 1.0, 0.5, 0.6, -0.3, 1.0, 2.0], 300, 35),
     ("alpha_dc_rejections", "alpha_dc2ch", [0.5, 0.3, 0.45, 0.3, 1.5, 0.4, 1.2, 1.1, 0.9, 0.2, 0.2], 300, 36),
+    ("drift_alpha_typical", "drift_alpha", [1.0, 1.3, 0.5, 0.4, 1.0, 1.1, 0.5, 0.6, -0.7, 0.4, 0.8], 300, 37),
+    ("alpha_std1_typical", "alpha_std1", [2.0, 1.2, 0.5, 0.35, 0.6, 1.0, 0.7], 300, 38),
 ]
 
 
@@ -32,8 +34,8 @@ def main():
         out = np.asarray(rl.seeded_call(variant, seed, p, n), dtype=np.float64)
         store[f"{name}__out"] = out
         store[f"{name}__params"] = p
-        store[f"{name}__meta"] = np.array([n, seed, {"drift_dc5": 0, "drift_dc4": 1, "alpha_dc2ch": 2}[variant]], dtype=np.int64)
-        print(f"{name:22s} {variant:12s} shape={out.shape} missing={(out[:, 0] == 0).sum()} eeg sd={out[:, 1].std():.3f},{out[:, 2].std():.3f}")
+        store[f"{name}__meta"] = np.array([n, seed, {"drift_dc5": 0, "drift_dc4": 1, "alpha_dc2ch": 2, "drift_alpha": 3, "alpha_std1": 4}[variant]], dtype=np.int64)
+        print(f"{name:22s} {variant:12s} shape={out.shape} missing={(out[:, 0] == 0).sum()} cols={out.shape[1]} eeg1 sd={out[:, 1].std():.3f}")
     np.savez_compressed(OUT, **store)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 

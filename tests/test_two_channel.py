@@ -16,7 +16,8 @@ F_F32, F_STEPS, F_GENERIC = 2, 4, 8
 def _canon(variant, p):
     from bayesflow_nddms_b200 import two_channel as tc
 
-    return {0: tc.canonical_drift_dc5, 1: lambda q: tc.canonical_drift_dc5(q, standardise=False), 2: tc.canonical_alpha_dc}[variant](p)[0]
+    return {0: tc.canonical_drift_dc5, 1: lambda q: tc.canonical_drift_dc5(q, standardise=False), 2: tc.canonical_alpha_dc,
+            3: tc.canonical_drift_alpha, 4: tc.canonical_alpha_standardised}[variant](p)[0]
 
 
 def _cases():
@@ -30,10 +31,11 @@ def test_oracle_reproduces_reference_two_channel_outputs_bit_exact(oracle):
     n_cases = 0
     for name, canon, n, seed, ref in _cases():
         t = oracle.simulate_mt(7, canon, n, seed)
-        assert t.sim_data.shape == ref.shape == (n, 3), name
-        assert np.array_equal(t.sim_data.view(np.uint64), ref.view(np.uint64)), name
+        got = np.ascontiguousarray(t.sim_data[:, :ref.shape[1]])       # the one-channel script stacks two columns
+        assert got.shape == ref.shape, name
+        assert np.array_equal(got.view(np.uint64), ref.view(np.uint64)), name
         n_cases += 1
-    assert n_cases == 6
+    assert n_cases == 8
 
 
 def test_canonical_mapping_layout():
@@ -61,7 +63,8 @@ def test_gpu_fp64_shared_increments_reproduce_reference(sim, oracle):
         finally:
             sim.set_normals_debug(None, None)
         assert out.shape == (n, 3)
-        assert np.array_equal(out.view(np.uint64), ref.view(np.uint64)), name
+        got = np.ascontiguousarray(out[:, :ref.shape[1]])
+        assert np.array_equal(got.view(np.uint64), ref.view(np.uint64)), name
         assert np.array_equal(steps, o.n_steps) and st["debug_overruns"] == 0
 
 
@@ -124,9 +127,12 @@ def test_gpu_two_channel_module_api(sim):
     from bayesflow_nddms_b200 import two_channel as tc
 
     p = [1.5, 1.2, 0.5, 0.4, 1.0, 1.0, 0.5, 0.7, -0.4, 0.3, 0.6]
-    for fn in (tc.simulate_trials_drift_dc5, tc.simulate_trials_drift_dc4, tc.simulate_trials_alpha_dc):
+    for fn in (tc.simulate_trials_drift_dc5, tc.simulate_trials_drift_dc4, tc.simulate_trials_alpha_dc,
+               tc.simulate_trials_drift_alpha):
         out = fn(p, 200, sim)
         assert out.shape == (200, 3) and out.dtype == np.float64 and np.all(np.isfinite(out))
+    one = tc.simulate_trials_alpha_standardised([2.0, 1.2, 0.5, 0.35, 0.6, 1.0, 0.7], 5000, sim)
+    assert one.shape == (5000, 2) and abs(one[:, 1].std() - 1) < 0.06
     d5 = tc.simulate_trials_drift_dc5(p, 20000, sim, seed=1, dataset_offset=0)
     assert abs(d5[:, 1].std() - 1) < 0.05 and abs(d5[:, 2].std() - 1) < 0.05     # standardised channels
     batch = tc.simulate_trials_alpha_dc(np.tile(p, (7, 1)), 64, sim)
