@@ -13,7 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libddm_b200.so")
 SOURCES = ["ddm_kernels.cu", "ddm_capi.cu", "ddm_microbench.cu", "ddm_evidence.cu", "ddm_prior.cu"]
-HEADERS = ["ddm_kernels.cuh", "ddm_rng.cuh", "ddm_microbench.cuh",
+HOST_SOURCES = ["ddm_wire.cpp"]  # g++ only: host threads of the compact device->host wire format
+HEADERS = ["ddm_kernels.cuh", "ddm_rng.cuh", "ddm_microbench.cuh", "ddm_wire.cuh",
            os.path.join("..", "..", "include", "ddm_b200.h"),
            os.path.join("..", "..", "include", "ddm_dlpack.h")]
 
@@ -34,7 +35,7 @@ def is_stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HOST_SOURCES + HEADERS]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
@@ -44,9 +45,20 @@ def build(force: bool = False, verbose: bool = False, out_path: str | None = Non
     if out_path is None and not force and not is_stale():
         return LIB_PATH
     target = out_path or LIB_PATH
+    objs = []
+    for src in HOST_SOURCES:
+        obj = os.path.join(CSRC, os.path.splitext(src)[0] + ".o")
+        gcc = [os.environ.get("CXX", "g++"), "-O3", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-ffp-contract=off", "-pthread",
+               "-c", src, "-o", obj]
+        proc = subprocess.run(gcc, cwd=CSRC, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError("g++ failed:\n" + " ".join(gcc) + "\n" + proc.stdout + proc.stderr)
+        objs.append(obj)
     cmd = ([find_nvcc()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) +
-           ["-o", target] + SOURCES)
+           ["-o", target] + SOURCES + objs)
     proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    for obj in objs:
+        os.remove(obj)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
     if verbose:

@@ -52,7 +52,8 @@ class Stats(C.Structure):
                 ("n_upper", C.c_uint64), ("reject_cap_hits", C.c_uint64), ("kernel_ms", C.c_double),
                 ("kernel_launches", C.c_int32), ("used_persistent", C.c_int32), ("grid", C.c_int32),
                 ("block", C.c_int32), ("refill_threshold", C.c_int32), ("tile", C.c_int32),
-                ("debug_overruns", C.c_uint64)]
+                ("debug_overruns", C.c_uint64), ("d2h_bytes", C.c_uint64), ("host_decode_threads", C.c_int32),
+                ("reserved_", C.c_int32)]
 
     def as_dict(self) -> dict:
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -91,6 +92,9 @@ SIGNATURES = {
     "ddm_synchronize": (C.c_int, [_vp]),
     "ddm_set_tuning": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
     "ddm_set_pipeline": (C.c_int, [_vp, C.c_int64, C.c_int64]),
+    "ddm_set_host_decode": (C.c_int, [_vp, C.c_int]),
+    "ddm_wire_decode_host": (C.c_int, [C.c_void_p, C.c_void_p, _dp, C.c_int, C.c_int64, C.c_int64, C.c_double, C.c_int,
+                                       C.c_int, C.c_int]),
     "ddm_simulate": (C.c_int, [_vp, C.c_int, _dp, C.c_int64, C.c_int, C.c_int64, C.c_double, C.c_int, C.c_uint64,
                                C.c_uint64, C.c_int, C.c_int, _vp]),
     "ddm_draw_prior": (C.c_int, [_vp, C.c_int, C.c_int64, C.c_uint64, C.c_uint64, _dp]),

@@ -188,7 +188,12 @@ struct ddm_ctx {
     cudaStream_t copy_stream = nullptr;
     void *pipe_buf[2] = {nullptr, nullptr};
     size_t pipe_cap[2] = {0, 0};
-    cudaEvent_t pipe_kernel_done[2] = {nullptr, nullptr}, pipe_copy_done[2] = {nullptr, nullptr};
+    cudaEvent_t pipe_kernel_done[2] = {nullptr, nullptr}, pipe_copy_done[3] = {nullptr, nullptr, nullptr};
+    // compact wire (ddm_wire.cuh): pinned staging for three chunks in flight and the host decode threads
+    void *wire_host[3] = {nullptr, nullptr, nullptr};
+    size_t wire_cap[3] = {0, 0, 0};
+    ddm::HostWorkers *workers = nullptr;
+    int tune_host_decode = 0;  // 0 automatic thread count, > 0 that many threads, < 0 plain 16-byte rows over PCIe
 
     // tuning (0 = automatic)
     int tune_threshold = 0, tune_blocks_per_sm = 0, tune_tile = 0;
@@ -420,8 +425,13 @@ int run_common(ddm_ctx *ctx, int model, int64_t n_datasets, int64_t n_trials, do
 constexpr int64_t kPipelineMinRows = 8ll << 20;     // below this one launch + one copy is as fast
 constexpr int64_t kPipelineChunkRows = 32ll << 20;  // trials per chunk (512 MB of float64 pairs)
 
-int run_pipelined(ddm_ctx *ctx, int64_t n_trials, double dt, int max_steps, uint64_t seed, uint64_t dataset_offset,
-                  int precision, int flags, void *out_host) {
+bool takes_persistent_kernel(const ddm_ctx *ctx, int model, int precision, int flags) {
+    return precision == 32 && !ctx->dbg_on && model != DDM_MODEL_TRIALWISE && !ctx->degenerate_noise &&
+           !(flags & (DDM_FLAG_FORCE_GENERIC | DDM_FLAG_OUT_STATE));
+}
+
+int run_pipelined(ddm_ctx *ctx, const double *params_host, int64_t n_trials, double dt, int max_steps, uint64_t seed,
+                  uint64_t dataset_offset, int precision, int flags, void *out_host) {
     const int model = ctx->model;
     const int64_t n_datasets = ctx->n_datasets;
     ddm::RunArgs base;
@@ -430,10 +440,18 @@ int run_pipelined(ddm_ctx *ctx, int64_t n_trials, double dt, int max_steps, uint
     const bool out64 = !(flags & DDM_FLAG_OUT_F32);
     const int cols = n_cols_of(model);
     const size_t row_bytes = (size_t)cols * (out64 ? 8 : 4);
+    // Compact wire (ddm_wire.cuh): two-column models leave the device as (steps, choice[, fp32 draw]) records and
+    // host threads write the rows, so the PCIe copy moves 4 or 8 bytes per trial instead of 16.
+    const int kind = kind_of(model);
+    const bool basic_cols = (kind == ddm::KIND_FIXED || kind == ddm::KIND_DRIFT);
+    const bool compact = ctx->tune_host_decode >= 0 && cols == 2 && takes_persistent_kernel(ctx, model, precision, flags) &&
+                         (uint32_t)max_steps <= ddm::WIRE_MAX_STEPS;
+    const size_t wire_bytes = compact ? (basic_cols ? 4 : 8) : row_bytes;
     const int64_t chunk_rows = ctx->tune_pipeline_chunk_rows > 0 ? ctx->tune_pipeline_chunk_rows : kPipelineChunkRows;
     int64_t chunk_ds = chunk_rows / (n_trials > 0 ? n_trials : 1);
     if (chunk_ds < 1) chunk_ds = 1;
-    const size_t chunk_bytes = (size_t)chunk_ds * (size_t)n_trials * row_bytes;
+    const size_t chunk_bytes = (size_t)chunk_ds * (size_t)n_trials * wire_bytes;
+    const int64_t n_chunks = (n_datasets + chunk_ds - 1) / chunk_ds;
     // the resident-output buffer is not used by this path: hand it back so the pool can reuse it
     if (ctx->out) {
         ctx->pool->give(ctx->out, ctx->out_cap);
@@ -448,12 +466,28 @@ int run_pipelined(ddm_ctx *ctx, int64_t n_trials, double dt, int max_steps, uint
         DDM_CUDA(ctx, cudaMalloc(&ctx->pipe_buf[b], chunk_bytes));
         ctx->pipe_cap[b] = chunk_bytes;
     }
+    if (compact) {
+        for (int b = 0; b < 3 && b < n_chunks; b++) {
+            if (ctx->wire_host[b] && ctx->wire_cap[b] >= chunk_bytes) continue;
+            if (ctx->wire_host[b]) cudaFreeHost(ctx->wire_host[b]);
+            ctx->wire_host[b] = nullptr;
+            ctx->wire_cap[b] = 0;
+            DDM_CUDA(ctx, cudaHostAlloc(&ctx->wire_host[b], chunk_bytes, cudaHostAllocDefault));
+            ctx->wire_cap[b] = chunk_bytes;
+        }
+        int gpus = 1;
+        if (cudaGetDeviceCount(&gpus) != cudaSuccess) gpus = 1;
+        const int want = ctx->tune_host_decode > 0 ? ctx->tune_host_decode : ddm::host_workers_default_count(gpus);
+        if (ctx->workers && ddm::host_workers_size(ctx->workers) != want) {
+            ddm::host_workers_destroy(ctx->workers);
+            ctx->workers = nullptr;
+        }
+        if (!ctx->workers) ctx->workers = ddm::host_workers_create(want);
+    }
     if (!ctx->copy_stream) {
         DDM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-        for (int b = 0; b < 2; b++) {
-            DDM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_kernel_done[b], cudaEventDisableTiming));
-            DDM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_copy_done[b], cudaEventDisableTiming));
-        }
+        for (int b = 0; b < 2; b++) DDM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_kernel_done[b], cudaEventDisableTiming));
+        for (int b = 0; b < 3; b++) DDM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_copy_done[b], cudaEventDisableTiming));
     }
     ddm_stats st{};
     st.n_trials = (uint64_t)(n_datasets * n_trials);
@@ -471,11 +505,13 @@ int run_pipelined(ddm_ctx *ctx, int64_t n_trials, double dt, int max_steps, uint
         st.kernel_launches++;
     }
     DDM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    int64_t chunk = 0;
-    for (int64_t lo = 0; lo < n_datasets; lo += chunk_ds, chunk++) {
-        const int b = (int)(chunk & 1);
+    // chunk i: device buffer i % 2, copy-done event (and wire staging buffer) i % 3
+    auto enqueue = [&](int64_t i) -> int {
+        const int b = (int)(i & 1), s3 = (int)(i % 3);
+        const int64_t lo = i * chunk_ds;
         const int64_t cnt = (n_datasets - lo < chunk_ds) ? (n_datasets - lo) : chunk_ds;
-        if (chunk >= 2) DDM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pipe_copy_done[b], 0));  // buffer free again
+        // device buffer free again?  (compact: the host has already waited for that copy)
+        if (!compact && i >= 2) DDM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pipe_copy_done[(i - 2) % 3], 0));
         ddm::RunArgs a = base;
         a.params = ctx->params.p + (size_t)lo * ctx->n_params;
         a.dconst = (dconst && model != DDM_MODEL_GENERAL) ? ctx->dconst.p + lo : nullptr;
@@ -484,20 +520,59 @@ int run_pipelined(ddm_ctx *ctx, int64_t n_trials, double dt, int max_steps, uint
         a.dataset_offset = (uint32_t)(dataset_offset + (uint64_t)lo);
         a.out = ctx->pipe_buf[b];
         a.steps_out = nullptr;
-        rc = launch_sim(ctx, a, precision, st);
-        if (rc) return rc;
+        if (compact) a.flags |= ddm::FLAG_WIRE_COMPACT;
+        const int rc2 = launch_sim(ctx, a, precision, st);
+        if (rc2) return rc2;
         DDM_CUDA(ctx, cudaEventRecord(ctx->pipe_kernel_done[b], ctx->stream));
         DDM_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->pipe_kernel_done[b], 0));
-        DDM_CUDA(ctx, cudaMemcpyAsync(static_cast<char *>(out_host) + (size_t)lo * (size_t)n_trials * row_bytes, ctx->pipe_buf[b],
-                                      (size_t)cnt * (size_t)n_trials * row_bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
-        DDM_CUDA(ctx, cudaEventRecord(ctx->pipe_copy_done[b], ctx->copy_stream));
+        void *dst = compact ? ctx->wire_host[s3] : static_cast<void *>(static_cast<char *>(out_host) + (size_t)lo * (size_t)n_trials * row_bytes);
+        DDM_CUDA(ctx, cudaMemcpyAsync(dst, ctx->pipe_buf[b], (size_t)cnt * (size_t)n_trials * wire_bytes, cudaMemcpyDeviceToHost,
+                                      ctx->copy_stream));
+        DDM_CUDA(ctx, cudaEventRecord(ctx->pipe_copy_done[s3], ctx->copy_stream));
+        return DDM_OK;
+    };
+    if (!compact) {
+        for (int64_t i = 0; i < n_chunks; i++) {
+            rc = enqueue(i);
+            if (rc) return rc;
+        }
+    } else {
+        // two chunks stay queued on the GPU while the host threads write the rows of the chunk that has landed
+        for (int64_t i = 0; i < 2 && i < n_chunks; i++) {
+            rc = enqueue(i);
+            if (rc) return rc;
+        }
+        for (int64_t i = 0; i < n_chunks; i++) {
+            DDM_CUDA(ctx, cudaEventSynchronize(ctx->pipe_copy_done[i % 3]));
+            if (i + 2 < n_chunks) {
+                rc = enqueue(i + 2);
+                if (rc) return rc;
+            }
+            const int64_t lo = i * chunk_ds;
+            ddm::WireDecode job;
+            job.wire = ctx->wire_host[i % 3];
+            job.out = static_cast<char *>(out_host) + (size_t)lo * (size_t)n_trials * row_bytes;
+            job.params = params_host + (size_t)lo * ctx->n_params;
+            job.n_params = ctx->n_params;
+            job.tau_col = 3;
+            job.n_datasets = (n_datasets - lo < chunk_ds) ? (n_datasets - lo) : chunk_ds;
+            job.n_trials = n_trials;
+            job.dt = dt;
+            job.basic = basic_cols;
+            job.out64 = out64;
+            job.timeout_choice_one = (flags & DDM_FLAG_TIMEOUT_CHOICE_ONE) != 0;
+            ddm::wire_decode(ctx->workers, job);
+        }
     }
     DDM_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     DDM_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, ctx->counters, sizeof(unsigned long long) * (1 + ddm::STAT_COUNT),
                                   cudaMemcpyDeviceToHost, ctx->stream));
     // the caller's stream sees the copies as done: join the copy stream back, then block
-    for (int b = 0; b < 2 && b < chunk; b++) DDM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pipe_copy_done[b], 0));
+    for (int64_t i = (n_chunks > 3 ? n_chunks - 3 : 0); i < n_chunks; i++)
+        DDM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pipe_copy_done[i % 3], 0));
     DDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    st.d2h_bytes = (uint64_t)n_datasets * (uint64_t)n_trials * wire_bytes;
+    st.host_decode_threads = compact ? ddm::host_workers_size(ctx->workers) : 0;
     ctx->stats = st;
     ctx->stats_pending = true;
     ctx->have_run = true;
@@ -598,8 +673,12 @@ DDM_API int ddm_destroy(ddm_ctx *ctx) {
         for (int b = 0; b < 2; b++) {
             if (ctx->pipe_buf[b]) cudaFree(ctx->pipe_buf[b]);
             if (ctx->pipe_kernel_done[b]) cudaEventDestroy(ctx->pipe_kernel_done[b]);
-            if (ctx->pipe_copy_done[b]) cudaEventDestroy(ctx->pipe_copy_done[b]);
         }
+        for (int b = 0; b < 3; b++) {
+            if (ctx->pipe_copy_done[b]) cudaEventDestroy(ctx->pipe_copy_done[b]);
+            if (ctx->wire_host[b]) cudaFreeHost(ctx->wire_host[b]);
+        }
+        if (ctx->workers) ddm::host_workers_destroy(ctx->workers);
         if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
         if (ctx->counters) cudaFree(ctx->counters);
         if (ctx->counters_host) cudaFreeHost(ctx->counters_host);
@@ -642,6 +721,13 @@ DDM_API int ddm_set_pipeline(ddm_ctx *ctx, int64_t min_rows, int64_t chunk_rows)
     if (!ctx) return DDM_ERR_INVALID;
     ctx->tune_pipeline_min_rows = min_rows;
     ctx->tune_pipeline_chunk_rows = chunk_rows;
+    return DDM_OK;
+}
+
+DDM_API int ddm_set_host_decode(ddm_ctx *ctx, int n_threads) {
+    if (!ctx) return DDM_ERR_INVALID;
+    if (n_threads > 256) return fail(ctx, DDM_ERR_INVALID, "at most 256 host decode threads, got %d", n_threads);
+    ctx->tune_host_decode = n_threads;
     return DDM_OK;
 }
 
@@ -737,7 +823,7 @@ DDM_API int ddm_simulate(ddm_ctx *ctx, int model, const double *params, int64_t 
     if (out_host && n_trials > 0 && n_datasets * n_trials >= min_rows && n_datasets >= 2 && !(flags & DDM_FLAG_KEEP_STEPS) &&
         !ctx->dbg_on) {
         DeviceGuard g(ctx->device);
-        return run_pipelined(ctx, n_trials, dt, max_steps, seed, dataset_offset, precision, flags, out_host);
+        return run_pipelined(ctx, params, n_trials, dt, max_steps, seed, dataset_offset, precision, flags, out_host);
     }
     rc = ddm_run(ctx, n_trials, dt, max_steps, seed, dataset_offset, precision, flags);
     if (rc) return rc;
@@ -1049,6 +1135,28 @@ DDM_API int ddm_export_normals(ddm_ctx *ctx, uint64_t seed, uint32_t dataset, ui
     DDM_CUDA(ctx, ddm::launch_export_normals(key, dataset, trial, stream, first, count, precision == 64, ctx->export_buf.p, ctx->stream));
     DDM_CUDA(ctx, cudaMemcpyAsync(out_host, ctx->export_buf.p, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     DDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DDM_OK;
+}
+
+DDM_API int ddm_wire_decode_host(const void *wire, void *out_host, const double *params, int n_params, int64_t n_datasets,
+                                 int64_t n_trials, double dt, int basic_columns, int flags, int n_threads) {
+    if (n_datasets < 0 || n_trials < 0 || n_params < 4 || n_threads < 1 || n_threads > 256) return DDM_ERR_INVALID;
+    if (n_datasets * n_trials > 0 && (!wire || !out_host || !params)) return DDM_ERR_INVALID;
+    ddm::HostWorkers *w = ddm::host_workers_create(n_threads);
+    ddm::WireDecode job;
+    job.wire = wire;
+    job.out = out_host;
+    job.params = params;
+    job.n_params = n_params;
+    job.tau_col = 3;
+    job.n_datasets = n_datasets;
+    job.n_trials = n_trials;
+    job.dt = dt;
+    job.basic = basic_columns != 0;
+    job.out64 = !(flags & DDM_FLAG_OUT_F32);
+    job.timeout_choice_one = (flags & DDM_FLAG_TIMEOUT_CHOICE_ONE) != 0;
+    ddm::wire_decode(w, job);
+    ddm::host_workers_destroy(w);
     return DDM_OK;
 }
 

@@ -196,8 +196,13 @@ __global__ void __launch_bounds__(DDM_PERSISTENT_BLOCK, RECORD ? (1024 / DDM_PER
                     store_triple<OUT64>(a.out, idx, o0, o1, (double)t.ext2);
                 }
             } else {
-                trial_outputs<BASIC>(a.flags, choice, n, a.dt, tau, (double)t.ext, o0, o1);
-                store_pair<OUT64>(a.out, idx, o0, o1);
+                if (a.flags & FLAG_WIRE_COMPACT) {  // chunked host pipeline: the host writes the rows (ddm_wire.cu)
+                    if (BASIC) reinterpret_cast<int32_t *>(a.out)[idx] = wire_pack(n, choice);
+                    else reinterpret_cast<int2 *>(a.out)[idx] = make_int2(wire_pack(n, choice), __float_as_int(t.ext));
+                } else {
+                    trial_outputs<BASIC>(a.flags, choice, n, a.dt, tau, (double)t.ext, o0, o1);
+                    store_pair<OUT64>(a.out, idx, o0, o1);
+                }
             }
             if (a.steps_out) a.steps_out[idx] = (int32_t)n;
             if (RECORD) {

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include "ddm_rng.cuh"
+#include "ddm_wire.cuh"
 
 namespace ddm {
 
@@ -76,6 +77,8 @@ constexpr unsigned FULL_MASK = 0xffffffffu;
 // internal run flag (not part of the C ABI): the fp32 generic kernel uses the reference's formulas in
 // float instead of the unit-scaled production arithmetic (a dataset with dc == 0 has no noise unit)
 constexpr int FLAG_REFERENCE_ARITHMETIC = 1 << 30;
+// internal: the persistent kernel writes ddm_wire.cuh records (4 or 8 bytes per trial) instead of output rows
+constexpr int FLAG_WIRE_COMPACT = 1 << 29;
 
 enum StatSlot { STAT_STEPS = 0, STAT_TIMEOUTS = 1, STAT_UPPER = 2, STAT_REJECT_CAP = 3, STAT_DBG_OVERRUN = 4, STAT_COUNT = 5 };
 

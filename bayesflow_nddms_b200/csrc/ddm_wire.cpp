@@ -1,0 +1,227 @@
+// Host side of the compact wire format (ddm_wire.cuh), compiled by g++ (no device code): a few threads turn each chunk's (steps, choice[, draw])
+// records into the caller's float64 (or float32) pairs with non-temporal stores while the GPU simulates the
+// next chunk.  No simulation happens here: the Euler loop, the random numbers and the boundary test are the
+// kernel's; this is the output formatting of basic_ddm_dc.py:108-112 applied to the kernel's integers.
+#include "ddm_wire.cuh"
+
+#include <immintrin.h>
+#include <sched.h>
+
+#include <algorithm>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace ddm {
+
+namespace {
+
+struct WirePair {  // the kernel's int2 {code, fp32 bits}
+    int32_t x, y;
+};
+
+const bool g_avx2 = __builtin_cpu_supports("avx2");
+
+struct Segment {  // trials [lo, hi) of the chunk, all of one dataset
+    int64_t lo, hi;
+    double tau;
+};
+
+// Four trials per iteration: int32 codes -> (n*dt + tau, choice) float64 pairs, two 32-byte streaming stores.
+// target("avx2") does not enable FMA: the product and the sum round separately, like the kernel's.
+__attribute__((target("avx2"))) int64_t decode_basic64_avx2(const int32_t *w, double *o, int64_t lo, int64_t hi, double dt,
+                                                            double tau, double timeout_val) {
+    const __m256d vdt = _mm256_set1_pd(dt), vtau = _mm256_set1_pd(tau), vto = _mm256_set1_pd(timeout_val);
+    const __m256d zero = _mm256_setzero_pd();
+    const __m128i three = _mm_set1_epi32(3), one = _mm_set1_epi32(1);
+    int64_t i = lo;
+    for (; i + 4 <= hi; i += 4) {
+        const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(w + i));
+        const __m256d rt = _mm256_add_pd(_mm256_mul_pd(_mm256_cvtepi32_pd(_mm_srli_epi32(c, 2)), vdt), vtau);
+        __m256d ch = _mm256_cvtepi32_pd(_mm_sub_epi32(_mm_and_si128(c, three), one));
+        ch = _mm256_blendv_pd(ch, vto, _mm256_cmp_pd(ch, zero, _CMP_EQ_OQ));
+        const __m256d a = _mm256_unpacklo_pd(rt, ch);  // rt0 ch0 | rt2 ch2
+        const __m256d b = _mm256_unpackhi_pd(rt, ch);  // rt1 ch1 | rt3 ch3
+        _mm256_stream_pd(o + 2 * i, _mm256_permute2f128_pd(a, b, 0x20));
+        _mm256_stream_pd(o + 2 * i + 4, _mm256_permute2f128_pd(a, b, 0x31));
+    }
+    return i;
+}
+
+// (rt, choice) rows, float64.  Same operations as trial_outputs<true> in ddm_kernels.cuh.
+void decode_basic64(const int32_t *w, double *o, const Segment &s, double dt, double timeout_val, bool stream) {
+    const double lut[3] = {-1.0, timeout_val, 1.0};
+    int64_t i = s.lo;
+    if (stream && g_avx2) {
+        for (; i < s.hi && ((reinterpret_cast<uintptr_t>(o + 2 * i) & 31u) != 0u); i++) {  // reach a 32-byte boundary
+            const uint32_t c = (uint32_t)w[i];
+            o[2 * i] = (double)(int32_t)(c >> 2) * dt + s.tau;
+            o[2 * i + 1] = lut[c & 3u];
+        }
+        i = decode_basic64_avx2(w, o, i, s.hi, dt, s.tau, timeout_val);
+    } else if (stream) {
+        const __m128d vdt = _mm_set1_pd(dt), vtau = _mm_set1_pd(s.tau);
+        for (; i + 2 <= s.hi; i += 2) {
+            const uint32_t c0 = (uint32_t)w[i], c1 = (uint32_t)w[i + 1];
+            const __m128i n = _mm_set_epi32(0, 0, (int)(c1 >> 2), (int)(c0 >> 2));
+            const __m128d rt = _mm_add_pd(_mm_mul_pd(_mm_cvtepi32_pd(n), vdt), vtau);
+            const __m128d ch = _mm_set_pd(lut[c1 & 3u], lut[c0 & 3u]);
+            _mm_stream_pd(o + 2 * i, _mm_unpacklo_pd(rt, ch));
+            _mm_stream_pd(o + 2 * i + 2, _mm_unpackhi_pd(rt, ch));
+        }
+    }
+    for (; i < s.hi; i++) {
+        const uint32_t c = (uint32_t)w[i];
+        const double rt = (double)(int32_t)(c >> 2) * dt;
+        o[2 * i] = rt + s.tau;
+        o[2 * i + 1] = lut[c & 3u];
+    }
+}
+
+void decode_basic32(const int32_t *w, float *o, const Segment &s, double dt, double timeout_val) {
+    const float lut[3] = {-1.f, (float)timeout_val, 1.f};
+    for (int64_t i = s.lo; i < s.hi; i++) {
+        const uint32_t c = (uint32_t)w[i];
+        const double rt = (double)(int32_t)(c >> 2) * dt;
+        o[2 * i] = (float)(rt + s.tau);
+        o[2 * i + 1] = lut[c & 3u];
+    }
+}
+
+// (signed rt, external measurement) rows.  Same operations as trial_outputs<false>.
+inline double signed_rt(uint32_t c, double dt, double tau) {
+    const double rt = (double)(int32_t)(c >> 2) * dt;
+    const int choice = (int)(c & 3u) - 1;
+    return choice > 0 ? tau + rt : (choice < 0 ? -tau - rt : 0.0);
+}
+
+void decode_ext64(const WirePair *w, double *o, const Segment &s, double dt, bool stream) {
+    for (int64_t i = s.lo; i < s.hi; i++) {
+        const WirePair r = w[i];
+        float ext;
+        static_assert(sizeof(ext) == sizeof(r.y), "fp32 bits");
+        __builtin_memcpy(&ext, &r.y, sizeof(ext));
+        const double o0 = signed_rt((uint32_t)r.x, dt, s.tau), o1 = (double)ext;
+        if (stream) {
+            _mm_stream_pd(o + 2 * i, _mm_set_pd(o1, o0));
+        } else {
+            o[2 * i] = o0;
+            o[2 * i + 1] = o1;
+        }
+    }
+}
+
+void decode_ext32(const WirePair *w, float *o, const Segment &s, double dt) {
+    for (int64_t i = s.lo; i < s.hi; i++) {
+        const WirePair r = w[i];
+        float ext;
+        __builtin_memcpy(&ext, &r.y, sizeof(ext));
+        o[2 * i] = (float)signed_rt((uint32_t)r.x, dt, s.tau);
+        o[2 * i + 1] = ext;
+    }
+}
+
+void decode_slice(const WireDecode &j, int id, int n_threads) {
+    const int64_t total = j.n_datasets * j.n_trials;
+    if (total == 0) return;
+    // contiguous slices, even boundaries so that the 2-trial vector loop stays aligned to the slice start
+    int64_t per = (total + n_threads - 1) / n_threads;
+    per = (per + 1) & ~int64_t(1);
+    const int64_t lo = std::min<int64_t>(total, per * id), hi = std::min<int64_t>(total, lo + per);
+    if (lo >= hi) return;
+    const bool stream = j.out64 && (reinterpret_cast<uintptr_t>(j.out) & 15u) == 0u;
+    const double timeout_val = j.timeout_choice_one ? 1.0 : 0.0;
+    int64_t ds = lo / j.n_trials;
+    for (int64_t at = lo; at < hi; ds++) {
+        Segment s;
+        s.lo = at;
+        s.hi = std::min<int64_t>(hi, (ds + 1) * j.n_trials);
+        s.tau = j.params[(size_t)ds * j.n_params + j.tau_col];
+        if (j.basic) {
+            if (j.out64) decode_basic64(static_cast<const int32_t *>(j.wire), static_cast<double *>(j.out), s, j.dt, timeout_val, stream);
+            else decode_basic32(static_cast<const int32_t *>(j.wire), static_cast<float *>(j.out), s, j.dt, timeout_val);
+        } else {
+            if (j.out64) decode_ext64(static_cast<const WirePair *>(j.wire), static_cast<double *>(j.out), s, j.dt, stream);
+            else decode_ext32(static_cast<const WirePair *>(j.wire), static_cast<float *>(j.out), s, j.dt);
+        }
+        at = s.hi;
+    }
+    if (stream) _mm_sfence();
+}
+
+}  // namespace
+
+class HostWorkers {
+  public:
+    explicit HostWorkers(int n) : n_(n < 1 ? 1 : n) {
+        for (int id = 1; id < n_; id++) threads_.emplace_back([this, id] { loop(id); });
+    }
+    ~HostWorkers() {
+        {
+            std::lock_guard<std::mutex> l(m_);
+            stop_ = true;
+        }
+        start_.notify_all();
+        for (auto &t : threads_) t.join();
+    }
+    int size() const { return n_; }
+    void run(const WireDecode &job) {
+        {
+            std::lock_guard<std::mutex> l(m_);
+            job_ = &job;
+            pending_ = n_ - 1;
+            generation_++;
+        }
+        start_.notify_all();
+        decode_slice(job, 0, n_);
+        std::unique_lock<std::mutex> l(m_);
+        done_.wait(l, [this] { return pending_ == 0; });
+    }
+
+  private:
+    void loop(int id) {
+        uint64_t seen = 0;
+        for (;;) {
+            const WireDecode *job;
+            {
+                std::unique_lock<std::mutex> l(m_);
+                start_.wait(l, [&] { return stop_ || generation_ != seen; });
+                if (stop_) return;
+                seen = generation_;
+                job = job_;
+            }
+            decode_slice(*job, id, n_);
+            std::lock_guard<std::mutex> l(m_);
+            if (--pending_ == 0) done_.notify_one();
+        }
+    }
+    const int n_;
+    std::vector<std::thread> threads_;
+    std::mutex m_;
+    std::condition_variable start_, done_;
+    const WireDecode *job_ = nullptr;
+    uint64_t generation_ = 0;
+    int pending_ = 0;
+    bool stop_ = false;
+};
+
+HostWorkers *host_workers_create(int n_threads) { return new HostWorkers(n_threads); }
+void host_workers_destroy(HostWorkers *w) { delete w; }
+int host_workers_size(const HostWorkers *w) { return w->size(); }
+
+// The CPUs this process may run on, shared between the GPUs of the box (one process per GPU), at most 16:
+// past that the decode is limited by host memory bandwidth, not by cores.
+int host_workers_default_count(int gpus) {
+    int cpus = 0;
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) cpus = CPU_COUNT(&set);
+    if (cpus <= 0) cpus = (int)std::thread::hardware_concurrency();
+    if (gpus < 1) gpus = 1;
+    const int n = cpus / gpus;
+    return n < 1 ? 1 : (n > 16 ? 16 : n);
+}
+
+void wire_decode(HostWorkers *w, const WireDecode &job) { w->run(job); }
+
+}  // namespace ddm

@@ -196,6 +196,11 @@ class DDMSimulator:
         ``chunk_rows`` trials (values < 0: defaults)."""
         self._check(self._lib.ddm_set_pipeline(self._ctx, int(min_rows), int(chunk_rows)))
 
+    def set_host_decode(self, n_threads: int = 0):
+        """Streamed two-column batches cross PCIe as 4- or 8-byte (steps, choice[, draw]) records that
+        ``n_threads`` host threads expand into the float64 rows (0: automatic, < 0: ship float64 rows)."""
+        self._check(self._lib.ddm_set_host_decode(self._ctx, int(n_threads)))
+
     def simulate_device(self, model: int, params, n_trials: int, dt: float = 0.01, max_steps: int = 400, *,
                         seed=None, dataset_offset=None, precision: int = 32, flags: int = _capi.FLAG_OUT_F32) -> DeviceBatch:
         """Same, but the batch stays in HBM and is returned as a DLPack producer."""

@@ -56,6 +56,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--host-decode", type=int, default=0,
+                    help="e2e leg: host threads expanding the compact PCIe records (0 auto, < 0 float64 rows over PCIe)")
     ap.add_argument("--microbench", action="store_true", help="also measure per-pipe issue rates")
     return ap.parse_args()
 
@@ -358,9 +360,11 @@ def main():
             need = De * N_TRIALS * 16
         pe = sweep_params(De, seed=4000 + rank)
         out_host = sim.pinned_empty((De, N_TRIALS, 2), np.float64)
+        sim.set_host_decode(args.host_decode)
         ke = args.e2e_steps or min(args.steps, 3)
         basic_ddm_dc.batch_simulate_trials(pe, N_TRIALS, sim, dt=DT, max_steps=MAX_STEPS, dataset_offset=ds_base, out=out_host)
-        steps_e2e = float(sim.last_stats()["total_steps"])
+        st_e2e = sim.last_stats()
+        steps_e2e = float(st_e2e["total_steps"])
         barrier()
         with torch.cuda.stream(stream):
             e0.record(stream)
@@ -373,10 +377,14 @@ def main():
         ms = max_over_ranks(e0.elapsed_time(e1))
         tot = sum_over_ranks(steps_e2e)
         e2e = {"value": tot * ke / (ms * 1e-3), "unit": "steps/s", "trials_per_s": De * N_TRIALS * world * ke / (ms * 1e-3),
-               "h2d_bytes_per_step": int(pe.nbytes), "d2h_bytes_per_step": int(out_host.nbytes), "steps": ke,
+               "h2d_bytes_per_step": int(pe.nbytes), "d2h_bytes_per_step": int(st_e2e["d2h_bytes"] or out_host.nbytes),
+               "host_rows_bytes_per_step": int(out_host.nbytes), "host_decode_threads": int(st_e2e["host_decode_threads"]),
+               "steps": ke,
                "datasets_per_gpu": De, "ms_per_step": ms / ke, "host_thread_bound_near_gpu": bool(numa_bound),
                "api": "basic_ddm_dc.batch_simulate_trials(params (B,5) f64 host, n_trials) -> (B, n_trials, 2) f64 pinned host "
-                      "array; one ddm_simulate call: H2D params, chunked kernels overlapped with the D2H of the previous chunk"}
+                      "array; one ddm_simulate call: H2D params, chunked kernels overlapped with the D2H of the previous chunk; "
+                      "trials cross PCIe as 4-byte (steps, choice) records and host threads write the float64 rows "
+                      "(rt = n*dt + ndt, choice) while the next chunk is simulated"}
         launches += sim.last_stats()["kernel_launches"] * ke
 
     # ---- BASELINE config 2: one online-training batch (64 datasets x 500 trials, dt=.01), latency -------------

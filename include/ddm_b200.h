@@ -112,6 +112,9 @@ typedef struct ddm_stats {
     int32_t used_persistent; /* 1 if the persistent refill kernel ran, 0 if generic */
     int32_t grid, block, refill_threshold, tile;
     uint64_t debug_overruns; /* shared-increment mode: trials that ran past the normals buffer */
+    uint64_t d2h_bytes;      /* output bytes the run copied device -> host itself (0: batch left resident) */
+    int32_t host_decode_threads; /* > 0: compact wire records were expanded by that many host threads */
+    int32_t reserved_;
 } ddm_stats;
 
 /* ---- lifecycle -------------------------------------------------------- */
@@ -128,6 +131,12 @@ int ddm_set_tuning(ddm_ctx *ctx, int refill_threshold, int blocks_per_sm, int ti
  * values < 0 restore them; a huge min_rows switches the pipeline off).  After such a run the batch
  * is not resident on the device.  Results do not depend on the chunking. */
 int ddm_set_pipeline(ddm_ctx *ctx, int64_t min_rows, int64_t chunk_rows);
+/* Two-column models cross PCIe in that pipeline as compact records -- (Euler steps, choice) in 4 bytes,
+ * plus the fp32 external measurement for the single-trial-boundary models, instead of 16-byte float64
+ * rows -- and n_threads host threads (0 = automatic: the process's CPUs / GPUs on the box, at most 16)
+ * write the rows of basic_ddm_dc.py:108-112 (rt = n*dt + ndt, choice) into out_host while the next chunk
+ * is simulated.  Same bits as the plain copy; n_threads < 0 switches back to float64 rows over PCIe. */
+int ddm_set_host_decode(ddm_ctx *ctx, int n_threads);
 
 /* ---- the hot path ------------------------------------------------------ */
 /* Replaces B calls of simulate_trials(params[b], n_trials)  (basic_ddm_dc.py:114-125,
@@ -202,6 +211,11 @@ int ddm_export_normals(ddm_ctx *ctx, uint64_t seed, uint32_t dataset, uint32_t t
                        uint32_t first, uint32_t count, int precision, double *out_host);
 /* Raw Philox4x32-10 blocks computed on the device (known-answer tests). */
 int ddm_philox4x32(ddm_ctx *ctx, const uint32_t *ctr4, const uint32_t *key2, uint32_t *out4, int64_t n_blocks);
+/* The host half of ddm_set_host_decode on its own (no GPU needed): expands n_datasets * n_trials wire
+ * records -- int32 (steps << 2 | choice + 1) when basic_columns, else {that, fp32 bits} pairs -- into
+ * (rows, 2) float64 / float32 with n_threads threads.  tau = params[d * n_params + 3]. */
+int ddm_wire_decode_host(const void *wire, void *out_host, const double *params, int n_params, int64_t n_datasets,
+                         int64_t n_trials, double dt, int basic_columns, int flags, int n_threads);
 
 /* ---- measurement -------------------------------------------------------- */
 /* Pipe micro-benchmarks for the issue roofline.  which: see ddm_microbench_id.

@@ -244,6 +244,32 @@ def test_pipelined_host_transfer_equals_single_launch(sim):
     assert sim.last_output_device_ptr()[1] == 301 * 257 * 16
 
 
+@pytest.mark.parametrize("model,prior", [(0, "basic"), (1, "alpha"), (2, "alpha_dc"), (6, "eta")])
+def test_compact_wire_matches_plain_copy(sim, model, prior):
+    """The streamed path ships (steps, choice[, fp32 draw]) records and host threads write the float64 rows
+    (ddm_set_host_decode): bit-identical to the kernel's own float64 rows, for every two-column layout, with
+    timeouts (max_steps not a multiple of 6), both timeout conventions, float32 rows, ragged chunks and
+    odd thread counts."""
+    from bayesflow_nddms_b200 import priors
+
+    params = priors.draw_prior_batch(prior, 203, np.random.default_rng(model))
+    kw = dict(dt=0.01, max_steps=47, seed=11, dataset_offset=5)
+    try:
+        for flags in (0, 1, F_F32):
+            sim.set_pipeline(1 << 60, -1)
+            base = sim.simulate(model, params, 131, flags=flags, **kw)
+            assert (base[..., 0] == 0).any() or model in (0, 6)  # timeouts present (signed-rt layouts mark them 0)
+            sim.set_pipeline(1, 131 * 17)
+            for threads in (-1, 1, 3, 0):
+                sim.set_host_decode(threads)
+                again = sim.simulate(model, params, 131, flags=flags, **kw)
+                assert np.array_equal(base, again), (flags, threads)
+                assert sim.last_stats()["n_timeouts"] > 0
+    finally:
+        sim.set_pipeline(-1, -1)
+        sim.set_host_decode(0)
+
+
 def test_dc_scaling_is_exact_in_fp32(sim):
     """simulations/Basic_DDM_simulations.py:164-209: (boundary, drift, dc) and (2b, 2d, 2dc) have the
     same choice-RT law; scaling by 2 is exact in binary floating point, so with the same

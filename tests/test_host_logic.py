@@ -206,3 +206,49 @@ def test_device_replay_buffer_fifo_and_sampling():
     seen = {float(buf.sample()['summary_conditions'][0, 0, 0]) for _ in range(200)}
     assert seen == {2.0, 3.0, 4.0}                       # the two oldest batches were overwritten
     assert buf.nbytes() == 3 * (2 * 4 * 2 + 2 * 5) * 4
+
+
+@pytest.mark.parametrize("basic", [True, False])
+@pytest.mark.parametrize("f32", [False, True])
+def test_wire_decode_host_formats_rows_like_the_reference(basic, f32):
+    """Host half of the compact device->host format (include/ddm_b200.h: ddm_wire_decode_host): from the
+    kernel's integers it must produce basic_ddm_dc.py:108-112's rt = n*dt + ndt and choice (and the signed-rt /
+    external-measurement rows of single_trial_alpha_not_scaled.py:131-141), whatever the thread count."""
+    import ctypes as C
+
+    from bayesflow_nddms_b200 import _capi
+
+    lib = _capi.load()
+    rng = np.random.default_rng(3)
+    D, T, dt = 37, 101, 0.01
+    params = rng.uniform(0.1, 1.0, (D, 6))
+    n = rng.integers(0, 401, (D, T)).astype(np.uint32)
+    ch = rng.integers(-1, 2, (D, T))
+    code = ((n << 2) | (ch + 1).astype(np.uint32)).astype(np.int32)
+    ext = rng.standard_normal((D, T)).astype(np.float32)
+    if basic:
+        wire = code
+    else:
+        wire = np.stack([code, ext.view(np.int32)], axis=-1).copy()
+    rt = n.astype(np.float64) * dt
+    tau = params[:, 3:4]
+    for flags in (0, 1):
+        if basic:
+            want = np.stack([rt + tau, np.where(ch == 0, float(flags & 1), ch).astype(np.float64)], axis=-1)
+        else:
+            want = np.stack([np.where(ch > 0, tau + rt, np.where(ch < 0, -tau - rt, 0.0)), ext.astype(np.float64)], axis=-1)
+        if f32:
+            want = want.astype(np.float32)
+        for threads in (1, 2, 5):
+            out = np.full((D, T, 2), np.nan, dtype=np.float32 if f32 else np.float64)
+            rc = lib.ddm_wire_decode_host(wire.ctypes.data, out.ctypes.data, params.ctypes.data_as(_capi._dp), 6, D, T, dt,
+                                          int(basic), flags | (_capi.FLAG_OUT_F32 if f32 else 0), threads)
+            assert rc == 0
+            assert np.array_equal(out, want), (flags, threads)
+    # misaligned destination: falls back to ordinary stores
+    if not f32:
+        raw = np.empty(D * T * 2 + 1)
+        out = raw[1:].reshape(D, T, 2)
+        assert lib.ddm_wire_decode_host(wire.ctypes.data, out.ctypes.data, params.ctypes.data_as(_capi._dp), 6, D, T, dt,
+                                        int(basic), 1, 3) == 0
+        assert np.array_equal(out, want)
