@@ -39,9 +39,12 @@ __global__ void __launch_bounds__(256) evidence_post_kernel(const EvidenceArgs a
     const uint32_t cols = 2u + a.n_obs;
     const uint32_t n_blocks = (a.n_obs + 5u) / 6u;
     const float inv_n = 1.f / (float)a.n_obs;
+    // (dataset, trial) of the warp's current row, advanced by the grid stride without a 64-bit division per row
+    uint32_t ds = (uint32_t)(warp0 / a.n_trials);
+    uint32_t trial = (uint32_t)(warp0 - (uint64_t)ds * a.n_trials);
+    const uint32_t stride_ds = (uint32_t)(n_warps / a.n_trials);
+    const uint32_t stride_trial = (uint32_t)(n_warps - (uint64_t)stride_ds * a.n_trials);
     for (uint64_t g = warp0; g < total; g += n_warps) {
-        const uint32_t ds = (uint32_t)(g / a.n_trials);
-        const uint32_t trial = (uint32_t)(g - (uint64_t)ds * a.n_trials);
         const uint32_t nj = (uint32_t)a.steps[g];
         const float h = a.dconst[ds].v[2], u = a.dconst[ds].v[3];
         const float sigma1 = (float)a.params[(size_t)ds * 6 + 5];
@@ -51,20 +54,24 @@ __global__ void __launch_bounds__(256) evidence_post_kernel(const EvidenceArgs a
         for (uint32_t k = lane; k < a.n_obs; k += 32u)
             s[k] = (k < nj) ? __fmul_rn(__fadd_rn(row_in[k], h), u) : evj;
         __syncwarp();
-        // 2. + sigma1 * z_noise[k]: lane owns Philox blocks lane, lane + 32, ... of the trial's aux stream
+        // 2. + sigma1 * z_noise[k]: lane owns Philox blocks lane, lane + 32, ... of the trial's aux stream;
+        //    the row sum is taken on the way
+        float sum = 0.f;
         for (uint32_t b = lane; b < n_blocks; b += 32u) {
             float z[6];
             philox_normals6_f32(b, trial + a.trial_offset, ds + a.dataset_offset, STREAM_AUX, a.key, z);
 #pragma unroll
             for (int i = 0; i < 6; i++) {
                 const uint32_t k = 6u * b + i;
-                if (k < a.n_obs) s[k] = __fmaf_rn(sigma1, z[i], s[k]);
+                if (k < a.n_obs) {
+                    const float v = __fmaf_rn(sigma1, z[i], s[k]);
+                    s[k] = v;
+                    sum += v;
+                }
             }
         }
         __syncwarp();
         // 3. mean (and variance) over the row
-        float sum = 0.f;
-        for (uint32_t k = lane; k < a.n_obs; k += 32u) sum += s[k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL_MASK, sum, o);
         const float mean = sum * inv_n;
@@ -101,6 +108,12 @@ __global__ void __launch_bounds__(256) evidence_post_kernel(const EvidenceArgs a
             else reinterpret_cast<float *>(a.out)[row + 2 + k] = v;
         }
         __syncwarp();
+        ds += stride_ds;
+        trial += stride_trial;
+        if (trial >= a.n_trials) {
+            trial -= a.n_trials;
+            ds++;
+        }
     }
 }
 
