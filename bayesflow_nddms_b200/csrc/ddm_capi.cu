@@ -186,6 +186,9 @@ struct ddm_ctx {
 
     // chunked compute / copy pipeline of ddm_simulate (large host-destined batches)
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t pipe_stream2 = nullptr;           // odd chunks: their kernels fill the SMs the even chunk's tail frees
+    unsigned long long *work_counter2 = nullptr;   // and claim work from their own counter
+    cudaEvent_t pipe_ready = nullptr;
     void *pipe_buf[2] = {nullptr, nullptr};
     size_t pipe_cap[2] = {0, 0};
     cudaEvent_t pipe_kernel_done[2] = {nullptr, nullptr}, pipe_copy_done[3] = {nullptr, nullptr, nullptr};
@@ -309,7 +312,8 @@ bool uses_dconst(const ddm_ctx *ctx, int model, int precision) {
 
 // Enqueue the simulator kernel for the datasets described by `a` (pointers already offset to the
 // range) on the ctx stream.  The stats counters accumulate; only the work counter is reset.
-int launch_sim(ddm_ctx *ctx, ddm::RunArgs &a, int precision, ddm_stats &st) {
+int launch_sim(ddm_ctx *ctx, ddm::RunArgs &a, int precision, ddm_stats &st, cudaStream_t stream = nullptr) {
+    if (!stream) stream = ctx->stream;
     const int model = a.model, flags = a.flags;
     const bool trialwise = (model == DDM_MODEL_TRIALWISE);
     const int kind = kind_of(model);
@@ -322,7 +326,7 @@ int launch_sim(ddm_ctx *ctx, ddm::RunArgs &a, int precision, ddm_stats &st) {
     if (degenerate) a.flags |= ddm::FLAG_REFERENCE_ARITHMETIC;
     const bool persistent = precision == 32 && !ctx->dbg_on && !trialwise && !degenerate &&
                             !(flags & (DDM_FLAG_FORCE_GENERIC | DDM_FLAG_OUT_STATE));
-    DDM_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
+    DDM_CUDA(ctx, cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), stream));
     if (persistent) {
         const int block = ddm::persistent_block_size();
         int per_sm = ctx->tune_blocks_per_sm;
@@ -345,14 +349,14 @@ int launch_sim(ddm_ctx *ctx, ddm::RunArgs &a, int precision, ddm_stats &st) {
         const uint64_t blocks_needed = (warps_needed + (block / 32) - 1) / (block / 32);
         if (grid > blocks_needed) grid = blocks_needed;
         if (grid < 1) grid = 1;
-        DDM_CUDA(ctx, ddm::launch_persistent(a, kind, out64, (int)grid, block, ctx->stream));
+        DDM_CUDA(ctx, ddm::launch_persistent(a, kind, out64, (int)grid, block, stream));
         st.used_persistent = 1;
         st.grid = (int)grid;
         st.block = block;
         st.refill_threshold = a.refill_threshold;
         st.tile = (int)tile;
     } else {
-        DDM_CUDA(ctx, ddm::launch_generic(a, kind, precision == 64, ctx->dbg_on, out64, (uint64_t)rows, ctx->stream));
+        DDM_CUDA(ctx, ddm::launch_generic(a, kind, precision == 64, ctx->dbg_on, out64, (uint64_t)rows, stream));
         st.grid = (int)(((uint64_t)rows + 127) / 128);
         st.block = 128;
     }
@@ -486,6 +490,9 @@ int run_pipelined(ddm_ctx *ctx, const double *params_host, int64_t n_trials, dou
     }
     if (!ctx->copy_stream) {
         DDM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        DDM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->pipe_stream2, cudaStreamNonBlocking));
+        DDM_CUDA(ctx, cudaMalloc(&ctx->work_counter2, sizeof(unsigned long long)));
+        DDM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_ready, cudaEventDisableTiming));
         for (int b = 0; b < 2; b++) DDM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_kernel_done[b], cudaEventDisableTiming));
         for (int b = 0; b < 3; b++) DDM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_copy_done[b], cudaEventDisableTiming));
     }
@@ -505,14 +512,21 @@ int run_pipelined(ddm_ctx *ctx, const double *params_host, int64_t n_trials, dou
         st.kernel_launches++;
     }
     DDM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    // chunk i: device buffer i % 2, copy-done event (and wire staging buffer) i % 3
+    // Even chunks run on the ctx stream, odd chunks on a second one with their own work counter: a chunk's kernel
+    // ends with a tail in which a few warps finish their longest trials (up to max_steps steps, ~0.5 ms at
+    // dt = .001) while most SMs idle, and the next chunk's blocks move in as this one's retire.
+    DDM_CUDA(ctx, cudaEventRecord(ctx->pipe_ready, ctx->stream));
+    DDM_CUDA(ctx, cudaStreamWaitEvent(ctx->pipe_stream2, ctx->pipe_ready, 0));  // parameters and constants are in place
+    // chunk i: device buffer and stream i % 2, copy-done event (and wire staging buffer) i % 3
     auto enqueue = [&](int64_t i) -> int {
         const int b = (int)(i & 1), s3 = (int)(i % 3);
+        cudaStream_t ks = b ? ctx->pipe_stream2 : ctx->stream;
         const int64_t lo = i * chunk_ds;
         const int64_t cnt = (n_datasets - lo < chunk_ds) ? (n_datasets - lo) : chunk_ds;
         // device buffer free again?  (compact: the host has already waited for that copy)
-        if (!compact && i >= 2) DDM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pipe_copy_done[(i - 2) % 3], 0));
+        if (!compact && i >= 2) DDM_CUDA(ctx, cudaStreamWaitEvent(ks, ctx->pipe_copy_done[(i - 2) % 3], 0));
         ddm::RunArgs a = base;
+        if (b) a.work_counter = ctx->work_counter2;
         a.params = ctx->params.p + (size_t)lo * ctx->n_params;
         a.dconst = (dconst && model != DDM_MODEL_GENERAL) ? ctx->dconst.p + lo : nullptr;
         a.gconst = (dconst && model == DDM_MODEL_GENERAL) ? ctx->gconst.p + lo : nullptr;
@@ -521,9 +535,9 @@ int run_pipelined(ddm_ctx *ctx, const double *params_host, int64_t n_trials, dou
         a.out = ctx->pipe_buf[b];
         a.steps_out = nullptr;
         if (compact) a.flags |= ddm::FLAG_WIRE_COMPACT;
-        const int rc2 = launch_sim(ctx, a, precision, st);
+        const int rc2 = launch_sim(ctx, a, precision, st, ks);
         if (rc2) return rc2;
-        DDM_CUDA(ctx, cudaEventRecord(ctx->pipe_kernel_done[b], ctx->stream));
+        DDM_CUDA(ctx, cudaEventRecord(ctx->pipe_kernel_done[b], ks));
         DDM_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->pipe_kernel_done[b], 0));
         void *dst = compact ? ctx->wire_host[s3] : static_cast<void *>(static_cast<char *>(out_host) + (size_t)lo * (size_t)n_trials * row_bytes);
         DDM_CUDA(ctx, cudaMemcpyAsync(dst, ctx->pipe_buf[b], (size_t)cnt * (size_t)n_trials * wire_bytes, cudaMemcpyDeviceToHost,
@@ -564,12 +578,12 @@ int run_pipelined(ddm_ctx *ctx, const double *params_host, int64_t n_trials, dou
             ddm::wire_decode(ctx->workers, job);
         }
     }
+    // the caller's stream sees kernels (both streams) and copies as done: join the copy stream back, then block
+    for (int64_t i = (n_chunks > 3 ? n_chunks - 3 : 0); i < n_chunks; i++)
+        DDM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pipe_copy_done[i % 3], 0));
     DDM_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     DDM_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, ctx->counters, sizeof(unsigned long long) * (1 + ddm::STAT_COUNT),
                                   cudaMemcpyDeviceToHost, ctx->stream));
-    // the caller's stream sees the copies as done: join the copy stream back, then block
-    for (int64_t i = (n_chunks > 3 ? n_chunks - 3 : 0); i < n_chunks; i++)
-        DDM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pipe_copy_done[i % 3], 0));
     DDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     st.d2h_bytes = (uint64_t)n_datasets * (uint64_t)n_trials * wire_bytes;
     st.host_decode_threads = compact ? ddm::host_workers_size(ctx->workers) : 0;
@@ -680,6 +694,9 @@ DDM_API int ddm_destroy(ddm_ctx *ctx) {
         }
         if (ctx->workers) ddm::host_workers_destroy(ctx->workers);
         if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+        if (ctx->pipe_stream2) cudaStreamDestroy(ctx->pipe_stream2);
+        if (ctx->work_counter2) cudaFree(ctx->work_counter2);
+        if (ctx->pipe_ready) cudaEventDestroy(ctx->pipe_ready);
         if (ctx->counters) cudaFree(ctx->counters);
         if (ctx->counters_host) cudaFreeHost(ctx->counters_host);
         if (ctx->out && ctx->pool) ctx->pool->give(ctx->out, ctx->out_cap);
