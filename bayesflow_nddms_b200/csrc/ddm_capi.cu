@@ -142,6 +142,8 @@ int kind_of(int model) {
 
 }  // namespace
 
+constexpr int kRunModelEvidence = 100;  // run_model of ddm_simulate_evidence runs ((rt, choice, path) rows)
+
 struct ddm_ctx {
     int device = 0;
     int sm_count = 0;
@@ -158,6 +160,7 @@ struct ddm_ctx {
     Arena<float> ev_path, ev_xfinal;
     Arena<int64_t> dbg_off;
     Arena<uint32_t> philox_buf;
+    Arena<unsigned long long> hist;
     unsigned long long *counters = nullptr;       // device: [0] work counter, [1..] stats
     unsigned long long *counters_host = nullptr;  // pinned mirror
 
@@ -178,6 +181,7 @@ struct ddm_ctx {
     size_t out_cap = 0, out_bytes = 0;
     bool have_run = false, out64 = true, have_steps = false, stats_pending = false;
     int64_t run_rows = 0, run_datasets = 0, run_trials = 0;  // rows = trials in total
+    int run_model = -1;                                       // ddm_model of the last run (kRunModelEvidence for evidence runs)
     int64_t run_cols = 2;                                     // values per trial (2 + n_obs for evidence runs)
     bool run_trialwise = false;
     ddm_stats stats{};
@@ -419,6 +423,7 @@ int run_common(ddm_ctx *ctx, int model, int64_t n_datasets, int64_t n_trials, do
     ctx->run_trials = n_trials;
     ctx->run_trialwise = trialwise;
     ctx->run_cols = cols;
+    ctx->run_model = model;
     ctx->out_resident = true;
     return DDM_OK;
 }
@@ -598,6 +603,7 @@ int run_pipelined(ddm_ctx *ctx, const double *params_host, int64_t n_trials, dou
     ctx->run_trials = n_trials;
     ctx->run_trialwise = false;
     ctx->run_cols = cols;
+    ctx->run_model = model;
     ctx->out_resident = false;  // the batch went to the host chunk by chunk
     return DDM_OK;
 }
@@ -684,6 +690,7 @@ DDM_API int ddm_destroy(ddm_ctx *ctx) {
         ctx->ev_xfinal.free_();
         ctx->dbg_off.free_();
         ctx->philox_buf.free_();
+        ctx->hist.free_();
         for (int b = 0; b < 2; b++) {
             if (ctx->pipe_buf[b]) cudaFree(ctx->pipe_buf[b]);
             if (ctx->pipe_kernel_done[b]) cudaEventDestroy(ctx->pipe_kernel_done[b]);
@@ -1043,6 +1050,7 @@ DDM_API int ddm_simulate_evidence(ddm_ctx *ctx, const double *params, int64_t n_
     ctx->run_trials = n_trials;
     ctx->run_trialwise = false;
     ctx->run_cols = cols;
+    ctx->run_model = kRunModelEvidence;
     ctx->out_resident = true;
     if (out_host) return ddm_download(ctx, out_host);
     return DDM_OK;
@@ -1065,6 +1073,23 @@ DDM_API int ddm_last_stats(ddm_ctx *ctx, ddm_stats *out) {
     int rc = finish_stats(ctx);
     if (rc) return rc;
     *out = ctx->stats;
+    return DDM_OK;
+}
+
+DDM_API int ddm_last_output_histogram(ddm_ctx *ctx, int n_bins, double rt_max, uint64_t *hist_host) {
+    if (!ctx || !hist_host) return DDM_ERR_INVALID;
+    if (n_bins < 1 || n_bins > 8192 || !(rt_max > 0.0)) return fail(ctx, DDM_ERR_INVALID, "need 1 <= n_bins <= 8192 and rt_max > 0");
+    if (!ctx->have_run || !ctx->out || !ctx->out_resident) return fail(ctx, DDM_ERR_STATE, "no output resident");
+    if (ctx->run_model == DDM_MODEL_GENERAL) return fail(ctx, DDM_ERR_STATE, "histogram is not defined for DDM_MODEL_GENERAL rows");
+    DeviceGuard g(ctx->device);
+    const size_t n_cells = 2 * (size_t)n_bins + 2;
+    DDM_CUDA(ctx, ctx->hist.reserve(n_cells));
+    DDM_CUDA(ctx, cudaMemsetAsync(ctx->hist.p, 0, n_cells * sizeof(unsigned long long), ctx->stream));
+    const bool basic = ctx->run_model == DDM_MODEL_BASIC || ctx->run_model == DDM_MODEL_ETA || ctx->run_model == kRunModelEvidence;
+    DDM_CUDA(ctx, ddm::launch_rt_histogram(ctx->out, ctx->out64, (uint64_t)ctx->run_rows, (uint32_t)ctx->run_cols, basic, (uint32_t)n_bins,
+                                           rt_max, ctx->hist.p, ctx->sm_count, ctx->stream));
+    DDM_CUDA(ctx, cudaMemcpyAsync(hist_host, ctx->hist.p, n_cells * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    DDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return DDM_OK;
 }
 

@@ -319,6 +319,8 @@ struct EvidenceArgs {
     double dt, sqrt_dt;
 };
 
+cudaError_t launch_rt_histogram(const void *rows, bool rows64, uint64_t n_rows, uint32_t cols, bool basic_layout, uint32_t n_bins,
+                                double rt_max, unsigned long long *hist, int sm_count, cudaStream_t s);
 cudaError_t launch_evidence_post(const EvidenceArgs &a, bool out64, uint64_t total, int sm_count, cudaStream_t s);
 cudaError_t launch_evidence_generic(const EvidenceArgs &a, bool buffer_src, uint64_t total, cudaStream_t s);
 cudaError_t launch_evidence_dataset_stats(const double *path_means, double *ds_stats, uint32_t n_datasets,

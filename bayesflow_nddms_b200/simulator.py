@@ -272,6 +272,16 @@ class DDMSimulator:
         self._check(self._lib.ddm_last_stats(self._ctx, C.byref(st)))
         return st.as_dict()
 
+    def last_histogram(self, n_bins: int = 400, rt_max: float = 4.0) -> dict:
+        """Response-time histogram of the last resident batch, reduced on the device: counts per
+        |rt| bin for upper- and lower-boundary responses, trials without a response, and responses
+        beyond ``rt_max``.  Additive over datasets, shards and GPUs."""
+        h = np.zeros(2 * int(n_bins) + 2, dtype=np.uint64)
+        self._check(self._lib.ddm_last_output_histogram(self._ctx, int(n_bins), float(rt_max),
+                                                        h.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return {"upper": h[:n_bins].copy(), "lower": h[n_bins:2 * n_bins].copy(), "missing": int(h[2 * n_bins]),
+                "overflow": int(h[2 * n_bins + 1]), "edges": np.linspace(0.0, float(rt_max), int(n_bins) + 1)}
+
     # ---- parity hooks ---------------------------------------------------------------------
     def set_normals_debug(self, z, offsets):
         """Shared-increment mode: trial t consumes z[offsets[t]:] in the reference's order."""

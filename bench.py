@@ -313,6 +313,16 @@ def main():
         kernel_ms.append(sim.last_stats()["kernel_ms"])
     k_ms = float(np.mean(kernel_ms))
 
+    # the batch is reduced on the device (RT histogram by choice + missing count), nothing is downloaded
+    sim.last_histogram(401, 4.01)
+    t_h = time.perf_counter()
+    hist = sim.last_histogram(401, 4.01)
+    hist_ms = (time.perf_counter() - t_h) * 1e3
+    hist_total = int(hist["upper"].sum() + hist["lower"].sum()) + hist["missing"] + hist["overflow"]
+    reduction = {"kind": "RT histogram, 401 bins of 10 ms x 2 boundaries + missing, over the resident float32 rows",
+                 "ms": hist_ms, "accounts_for_every_trial": bool(hist_total == D * N_TRIALS),
+                 "agrees_with_kernel_counters": bool(int(hist["upper"].sum()) == st["n_upper"] and hist["missing"] == st["n_timeouts"])}
+
     # ---- roofline -----------------------------------------------------------------------------
     peaks = {}
     try:
@@ -432,6 +442,7 @@ def main():
                    "persistent": bool(st["used_persistent"])},
         "clocks": clk, "roofline": roofline, "gpu_launches": launches,
     }
+    line["device_reduction"] = reduction
     if e2e is not None:
         line["e2e"] = e2e
     if training_batch is not None:

@@ -190,6 +190,12 @@ int ddm_simulate_evidence(ddm_ctx *ctx, const double *params, int64_t n_datasets
 /* Per-trial Euler-step counts of the last run (needs DDM_FLAG_KEEP_STEPS). */
 int ddm_last_steps(ddm_ctx *ctx, int32_t *steps_host);
 int ddm_last_stats(ddm_ctx *ctx, ddm_stats *out);
+/* Response-time histogram of the last run's resident output, reduced on the device (no row leaves HBM):
+ * hist_host[0 .. n_bins) counts upper-boundary responses with |rt| in [k, k+1) * rt_max / n_bins,
+ * hist_host[n_bins .. 2 n_bins) the lower-boundary ones, hist_host[2 n_bins] trials without a response
+ * (timeouts: choice 0 / signed rt 0) and hist_host[2 n_bins + 1] responses with |rt| >= rt_max.
+ * n_bins <= 8192.  Additive over datasets: shards and GPUs sum.  Not for DDM_MODEL_GENERAL (mixed layouts). */
+int ddm_last_output_histogram(ddm_ctx *ctx, int n_bins, double rt_max, uint64_t *hist_host);
 
 /* Device hand-off of the last run's output as a DLPack tensor of shape
  * (n_datasets, n_trials, 2) ((n, 2) for trialwise, (n_datasets, n_trials, 2 + n_obs) for evidence runs), dtype per the run's flags,

@@ -168,6 +168,77 @@ def test_full_size_sweep_properties(sim):
     assert sel.size > 300 and np.mean(np.abs(pu - emp)) < 0.015 and np.max(np.abs(pu - emp)) < 0.08
 
 
+def _np_hist(out, basic, n_bins, rt_max):
+    if basic:
+        rt, ch = out[..., 0].ravel().astype(np.float64), np.sign(out[..., 1].ravel())
+    else:
+        rt, ch = np.abs(out[..., 0].ravel()).astype(np.float64), np.sign(out[..., 0].ravel())
+    b = np.floor(rt * (n_bins / rt_max)).astype(np.int64)
+    ok = ch != 0
+    over = ok & (b >= n_bins)
+    up = np.bincount(b[ok & ~over & (ch > 0)], minlength=n_bins)
+    lo = np.bincount(b[ok & ~over & (ch < 0)], minlength=n_bins)
+    return up, lo, int((~ok).sum()), int(over.sum())
+
+
+@pytest.mark.parametrize("model,prior,basic", [(0, "basic", True), (1, "alpha", False), (6, "eta", True)])
+def test_device_histogram_matches_numpy_and_adds_over_shards(sim, model, prior, basic):
+    """The on-device RT histogram (SURVEY 8d, C5's reduction) equals numpy's on the downloaded rows, for both
+    row layouts and dtypes, and the histograms of two dataset shards add up to the whole batch's."""
+    from bayesflow_nddms_b200 import priors
+
+    params = priors.draw_prior_batch(prior, 300, np.random.default_rng(model + 20))
+    kw = dict(dt=0.01, max_steps=150, seed=3)
+    for flags in (0, F_F32):
+        out = sim.simulate(model, params, 211, dataset_offset=10, flags=flags, **kw)
+        h = sim.last_histogram(64, 1.2)
+        up, lo, missing, over = _np_hist(out, basic, 64, 1.2)
+        assert np.array_equal(h["upper"], up) and np.array_equal(h["lower"], lo)
+        assert h["missing"] == missing == sim.last_stats()["n_timeouts"] and h["overflow"] == over and over > 0
+        assert int(h["upper"].sum() + h["lower"].sum()) + missing + over == 300 * 211
+    sim.simulate(model, params[:123], 211, dataset_offset=10, flags=F_F32, **kw)
+    h1 = sim.last_histogram(64, 1.2)
+    sim.simulate(model, params[123:], 211, dataset_offset=133, flags=F_F32, **kw)
+    h2 = sim.last_histogram(64, 1.2)
+    assert np.array_equal(h1["upper"] + h2["upper"], h["upper"]) and np.array_equal(h1["lower"] + h2["lower"], h["lower"])
+    assert h1["missing"] + h2["missing"] == h["missing"]
+
+
+def test_full_size_1e9_trials_histogram_checksum(sim):
+    """BASELINE config 5 at full size on one GPU -- 1e6 datasets x 1000 trials, float32 rows resident in HBM (8 GB):
+    nothing is downloaded; the device histogram must account for every trial, agree with the kernel's own
+    counters, and equal the sum of the histograms of four dataset shards run separately (a checksum of
+    checksums: Philox counters carry the global dataset index, so shards reproduce the batch)."""
+    import torch
+
+    from bayesflow_nddms_b200 import priors
+
+    if torch.cuda.mem_get_info()[0] < 30e9:
+        pytest.skip("needs 30 GB of free HBM")
+    B, N = 1_000_000, 1000
+    params = priors.draw_prior_batch("sweep", B, np.random.default_rng(5))
+    kw = dict(dt=1e-3, max_steps=4000, seed=17)
+    sim.run(0, params, N, dataset_offset=0, flags=F_F32, **kw)
+    st = sim.last_stats()
+    h = sim.last_histogram(401, 4.01)   # a response at the 4000th step has rt = 4.0
+    assert st["n_trials"] == B * N
+    assert int(h["upper"].sum()) == st["n_upper"] and h["missing"] == st["n_timeouts"] and h["overflow"] == 0
+    assert int(h["upper"].sum() + h["lower"].sum()) + h["missing"] == B * N
+    assert 230 * B * N < st["total_steps"] < 290 * B * N
+    # mean RT from the histogram (bin centres) against total_steps * dt (tau = 0 in the sweep), timeouts excluded
+    centres = 0.5 * (h["edges"][:-1] + h["edges"][1:])
+    responded = B * N - h["missing"]
+    mean_rt = float(((h["upper"] + h["lower"]) * centres).sum()) / responded
+    assert abs(mean_rt - (st["total_steps"] - 4000 * h["missing"]) * 1e-3 / responded) < 0.006
+    up = np.zeros_like(h["upper"]); lo = np.zeros_like(h["lower"]); steps = 0
+    for k in range(4):
+        a, b = k * B // 4, (k + 1) * B // 4
+        sim.run(0, params[a:b], N, dataset_offset=a, flags=F_F32, **kw)
+        hk = sim.last_histogram(401, 4.01)   # a response at the 4000th step has rt = 4.0
+        up += hk["upper"]; lo += hk["lower"]; steps += sim.last_stats()["total_steps"]
+    assert np.array_equal(up, h["upper"]) and np.array_equal(lo, h["lower"]) and steps == st["total_steps"]
+
+
 def test_alpha_not_scaled_data_generation(sim):
     """alpha_not_scaled.py:52-131 with the GPU generator in place of simulratcliff: the genparam dict,
     and participant 17 (fixed parameters, drift variability eta = 1) against the reference sampler's
