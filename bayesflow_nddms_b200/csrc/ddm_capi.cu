@@ -432,6 +432,8 @@ int run_common(ddm_ctx *ctx, int model, int64_t n_datasets, int64_t n_trials, do
 // the previous chunk is copied to the host on a second stream, so the batch costs
 // max(kernel, PCIe) instead of kernel + PCIe and needs 2 chunks of HBM instead of the batch.
 constexpr int64_t kPipelineMinRows = 8ll << 20;     // below this one launch + one copy is as fast
+constexpr int64_t kCompactMinRows = 4ll << 20;      // compact records pay off earlier (measured: scripts/midsize_ab.py)
+constexpr int64_t kPipelineMinChunkRows = 2ll << 20;  // a chunk costs ~0.2 ms of launches and kernel tail
 constexpr int64_t kPipelineChunkRows = 32ll << 20;  // trials per chunk (512 MB of float64 pairs)
 
 bool takes_persistent_kernel(const ddm_ctx *ctx, int model, int precision, int flags) {
@@ -456,9 +458,17 @@ int run_pipelined(ddm_ctx *ctx, const double *params_host, int64_t n_trials, dou
     const bool compact = ctx->tune_host_decode >= 0 && cols == 2 && takes_persistent_kernel(ctx, model, precision, flags) &&
                          (uint32_t)max_steps <= ddm::WIRE_MAX_STEPS;
     const size_t wire_bytes = compact ? (basic_cols ? 4 : 8) : row_bytes;
-    const int64_t chunk_rows = ctx->tune_pipeline_chunk_rows > 0 ? ctx->tune_pipeline_chunk_rows : kPipelineChunkRows;
+    // default chunk: a quarter of the batch, so that mid-size batches overlap kernel, copy and host decode too,
+    // between 2 Mi trials and the 32 Mi that the largest batches run best with (profiles/r01_v9c_midsize_ab.txt)
+    int64_t chunk_rows = ctx->tune_pipeline_chunk_rows;
+    if (chunk_rows <= 0) {
+        chunk_rows = n_datasets * n_trials / 4;
+        if (chunk_rows < kPipelineMinChunkRows) chunk_rows = kPipelineMinChunkRows;
+        if (chunk_rows > kPipelineChunkRows) chunk_rows = kPipelineChunkRows;
+    }
     int64_t chunk_ds = chunk_rows / (n_trials > 0 ? n_trials : 1);
     if (chunk_ds < 1) chunk_ds = 1;
+    if (chunk_ds > n_datasets) chunk_ds = n_datasets;  // a batch smaller than a chunk: buffers of its own size
     const size_t chunk_bytes = (size_t)chunk_ds * (size_t)n_trials * wire_bytes;
     const int64_t n_chunks = (n_datasets + chunk_ds - 1) / chunk_ds;
     // the resident-output buffer is not used by this path: hand it back so the pool can reuse it
@@ -557,6 +567,11 @@ int run_pipelined(ddm_ctx *ctx, const double *params_host, int64_t n_trials, dou
         }
     } else {
         // two chunks stay queued on the GPU while the host threads write the rows of the chunk that has landed
+        struct HotWorkers {
+            ddm::HostWorkers *w;
+            explicit HotWorkers(ddm::HostWorkers *w_) : w(w_) { ddm::host_workers_begin(w); }
+            ~HotWorkers() { ddm::host_workers_end(w); }
+        } hot(ctx->workers);
         for (int64_t i = 0; i < 2 && i < n_chunks; i++) {
             rc = enqueue(i);
             if (rc) return rc;
@@ -843,7 +858,10 @@ DDM_API int ddm_simulate(ddm_ctx *ctx, int model, const double *params, int64_t 
                          int precision, int flags, void *out_host) {
     int rc = ddm_upload_params(ctx, model, params, n_datasets, n_params);
     if (rc) return rc;
-    const int64_t min_rows = ctx->tune_pipeline_min_rows >= 0 ? ctx->tune_pipeline_min_rows : kPipelineMinRows;
+    const bool compact_ok = ctx->tune_host_decode >= 0 && n_cols_of(model) == 2 && takes_persistent_kernel(ctx, model, precision, flags) &&
+                            max_steps >= 0 && (uint32_t)max_steps <= ddm::WIRE_MAX_STEPS;
+    const int64_t min_rows = ctx->tune_pipeline_min_rows >= 0 ? ctx->tune_pipeline_min_rows
+                                                              : (compact_ok ? kCompactMinRows : kPipelineMinRows);
     if (out_host && n_trials > 0 && n_datasets * n_trials >= min_rows && n_datasets >= 2 && !(flags & DDM_FLAG_KEEP_STEPS) &&
         !ctx->dbg_on) {
         DeviceGuard g(ctx->device);

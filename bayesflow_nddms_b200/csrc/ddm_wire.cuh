@@ -38,6 +38,9 @@ class HostWorkers;
 HostWorkers *host_workers_create(int n_threads);  // n_threads >= 1 (1 = the calling thread only)
 void host_workers_destroy(HostWorkers *w);
 int host_workers_size(const HostWorkers *w);
+// bracket a streamed call: in between, idle workers poll for the next chunk instead of sleeping
+void host_workers_begin(HostWorkers *w);
+void host_workers_end(HostWorkers *w);
 int host_workers_default_count(int gpus_on_box);
 void wire_decode(HostWorkers *w, const WireDecode &job);
 

@@ -63,7 +63,15 @@ g = timeit(lambda: m1.batch_simulate_trials(P, 1000, sim), 20)
 steps = sim.last_stats()["total_steps"]
 t0 = time.perf_counter()
 orc.simulate_batch_mt(1, P, 1000)
-add("C3 single_trial_alpha_not_scaled 1024x1000 dt=0.01", g, time.perf_counter() - t0, 1024 * 1000, steps)
+cpu3 = time.perf_counter() - t0
+add("C3 single_trial_alpha_not_scaled 1024x1000 dt=0.01", g, cpu3, 1024 * 1000, steps)
+sim.set_host_decode(-1)   # the same call with float64 rows copied straight into the (pageable) result array
+g = timeit(lambda: m1.batch_simulate_trials(P, 1000, sim), 20)
+sim.set_host_decode(0)
+add("C3 as above, float64 rows over PCIe (host decode off)", g, cpu3, 1024 * 1000, steps)
+out3 = sim.pinned_empty((1024, 1000, 2), np.float64)
+g = timeit(lambda: m1.batch_simulate_trials(P, 1000, sim, out=out3), 20)
+add("C3 as above, compact wire into a pinned result array", g, cpu3, 1024 * 1000, steps)
 
 # C4: Stahl-shaped imputation, 19 374 trials / 89 participants, device hand-off
 subj, pe = stahl.synthetic_stahl_like()
