@@ -21,6 +21,78 @@ class DDMError(RuntimeError):
         self.status = status
 
 
+class _PinnedBlock:
+    """One page-locked host block handed out as a result array's base object; goes back to its pool when the
+    last array over it is collected."""
+
+    def __init__(self, pool, ptr: int, cap: int):
+        self._pool, self._ptr, self._cap = pool, ptr, cap
+        self.__array_interface__ = {"shape": (cap,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+    def __del__(self):
+        try:
+            self._pool._give_back(self._ptr, self._cap)
+        except Exception:  # interpreter shutdown
+            pass
+
+
+class _PinnedResultPool:
+    """Result arrays of mid-size host-destined batches live in page-locked memory: a device-to-host copy into a
+    fresh pageable numpy array runs at a third of the PCIe rate (1.1 ms instead of 0.45 ms for the 16 MB of a
+    1024 x 1000 batch).  Blocks are power-of-two sized and reused once the previous result has been dropped;
+    the pool never pins more than ``limit`` bytes, beyond that results are ordinary numpy arrays."""
+
+    MIN_BYTES, MAX_BYTES = 256 << 10, 512 << 20
+
+    def __init__(self, lib, limit: int = 2 << 30):
+        self._lib, self._limit = lib, int(limit)
+        self._free: dict[int, list[int]] = {}
+        self._pinned_bytes = 0
+        self._lock = threading.Lock()
+        self._closed = False
+
+    def empty(self, shape, dtype) -> np.ndarray | None:
+        dtype = np.dtype(dtype)
+        count = int(np.prod(shape, dtype=np.int64))
+        nbytes = count * dtype.itemsize
+        if not (self.MIN_BYTES <= nbytes <= self.MAX_BYTES) or self._closed:
+            return None
+        cap = 1 << (nbytes - 1).bit_length()
+        with self._lock:
+            blocks = self._free.get(cap)
+            ptr = blocks.pop() if blocks else None
+            if ptr is None:
+                if self._pinned_bytes + cap > self._limit:
+                    return None
+                self._pinned_bytes += cap
+        if ptr is None:
+            p = C.c_void_p()
+            if self._lib.ddm_host_alloc(cap, C.byref(p)) != _capi.OK or not p.value:
+                with self._lock:
+                    self._pinned_bytes -= cap
+                return None
+            ptr = p.value
+        raw = np.asarray(_PinnedBlock(self, ptr, cap))
+        return raw[:nbytes].view(dtype).reshape(shape)
+
+    def _give_back(self, ptr: int, cap: int):
+        with self._lock:
+            if not self._closed:
+                self._free.setdefault(cap, []).append(ptr)
+                return
+            self._pinned_bytes -= cap
+        self._lib.ddm_host_free(C.c_void_p(ptr))
+
+    def close(self):
+        with self._lock:
+            self._closed = True
+            blocks = [(p, cap) for cap, ps in self._free.items() for p in ps]
+            self._free = {}
+            self._pinned_bytes -= sum(cap for _, cap in blocks)
+        for p, _ in blocks:
+            self._lib.ddm_host_free(C.c_void_p(p))
+
+
 class DDMSimulator:
     """Owns a device context.  ``seed`` keys Philox; ``dataset_counter`` is the global
     index of the next dataset, so successive batches draw from disjoint counter ranges
@@ -38,6 +110,7 @@ class DDMSimulator:
         self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         self.dataset_counter = 0
         self._pinned = {}
+        self._results = _PinnedResultPool(self._lib)
 
     # ---- plumbing ---------------------------------------------------------------------
     def close(self):
@@ -46,6 +119,7 @@ class DDMSimulator:
             for ptr, _ in self._pinned.values():
                 self._lib.ddm_host_free(ptr)
             self._pinned = {}
+            self._results.close()
             self._lib.ddm_destroy(ctx)
 
     def __del__(self):
@@ -181,7 +255,9 @@ class DDMSimulator:
         shape = (B, int(n_trials), _capi.N_COLS.get(int(model), 2))
         dtype = np.float32 if flags & _capi.FLAG_OUT_F32 else np.float64
         if out is None:
-            out = np.empty(shape, dtype=dtype)
+            out = self._results.empty(shape, dtype)
+            if out is None:
+                out = np.empty(shape, dtype=dtype)
         elif out.dtype != dtype or out.shape != shape or not out.flags.c_contiguous:
             raise ValueError("out must be C-contiguous with the result's shape and dtype")
         off = self._next_offset(B, dataset_offset)

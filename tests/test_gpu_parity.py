@@ -270,6 +270,42 @@ def test_compact_wire_matches_plain_copy(sim, model, prior):
         sim.set_host_decode(0)
 
 
+def test_result_arrays_come_from_a_pinned_pool(sim):
+    """Mid-size results are allocated in page-locked memory (full-rate copies) and the block is reused once the
+    previous result is dropped; a view keeps its block alive; beyond the pool's limit results are plain arrays."""
+    import gc
+
+    from bayesflow_nddms_b200 import priors
+    from bayesflow_nddms_b200.simulator import _PinnedBlock
+
+    def owner(a):
+        while isinstance(a, np.ndarray):
+            a = a.base
+        return a
+
+    params = priors.draw_prior_batch("basic", 64, np.random.default_rng(1))
+    a = sim.simulate(0, params, 500, seed=4, dataset_offset=0)                   # 512 KB
+    assert isinstance(owner(a), _PinnedBlock) and a.flags.writeable and a.flags.c_contiguous
+    ptr_a = a.ctypes.data
+    keep = a[3, :7].copy()
+    view = a[3]
+    del a
+    gc.collect()
+    b = sim.simulate(0, params, 500, seed=5, dataset_offset=0)                   # the view still owns the first block
+    assert b.ctypes.data != ptr_a and np.array_equal(view[:7], keep)
+    ref = b.copy()
+    del view, b
+    gc.collect()
+    c = sim.simulate(0, params, 500, seed=5, dataset_offset=0)
+    assert c.ctypes.data in (ptr_a, ref.ctypes.data) or isinstance(owner(c), _PinnedBlock)
+    assert np.array_equal(c, ref)
+    small = sim.simulate(0, params[:2], 10, seed=5, dataset_offset=0)            # tiny: ordinary array
+    assert not isinstance(owner(small), _PinnedBlock)
+    # a pool at its limit hands out nothing (the caller then falls back to an ordinary array)
+    from bayesflow_nddms_b200.simulator import _PinnedResultPool
+    assert _PinnedResultPool(sim._lib, limit=0).empty((64, 1000, 2), np.float64) is None
+
+
 def test_dc_scaling_is_exact_in_fp32(sim):
     """simulations/Basic_DDM_simulations.py:164-209: (boundary, drift, dc) and (2b, 2d, 2dc) have the
     same choice-RT law; scaling by 2 is exact in binary floating point, so with the same
