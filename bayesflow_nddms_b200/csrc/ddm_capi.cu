@@ -12,6 +12,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/ddm_b200.h"
@@ -458,19 +459,32 @@ int run_pipelined(ddm_ctx *ctx, const double *params_host, int64_t n_trials, dou
     const bool compact = ctx->tune_host_decode >= 0 && cols == 2 && takes_persistent_kernel(ctx, model, precision, flags) &&
                          (uint32_t)max_steps <= ddm::WIRE_MAX_STEPS;
     const size_t wire_bytes = compact ? (basic_cols ? 4 : 8) : row_bytes;
-    // default chunk: a quarter of the batch, so that mid-size batches overlap kernel, copy and host decode too,
-    // between 2 Mi trials and the 32 Mi that the largest batches run best with (profiles/r01_v9c_midsize_ab.txt)
-    int64_t chunk_rows = ctx->tune_pipeline_chunk_rows;
-    if (chunk_rows <= 0) {
-        chunk_rows = n_datasets * n_trials / 4;
-        if (chunk_rows < kPipelineMinChunkRows) chunk_rows = kPipelineMinChunkRows;
-        if (chunk_rows > kPipelineChunkRows) chunk_rows = kPipelineChunkRows;
+    // Chunk schedule (first dataset, datasets).  A fixed chunk_rows if the caller set one; otherwise each chunk is
+    // half of what is left, within 2 Mi .. 32 Mi trials: large batches run in 32 Mi chunks (fewest launches and
+    // kernel tails), the last chunks shrink so that little copy + decode is left exposed after the last kernel, and
+    // mid-size batches overlap kernel, copy and host decode as well (profiles/r01_v9c_midsize_ab.txt).
+    std::vector<std::pair<int64_t, int64_t>> chunks;
+    {
+        const int64_t per_ds = n_trials > 0 ? n_trials : 1;
+        for (int64_t lo = 0; lo < n_datasets;) {
+            int64_t rows_c = ctx->tune_pipeline_chunk_rows;
+            if (rows_c <= 0) {
+                const int64_t quarter = n_datasets * per_ds / 4, half_left = (n_datasets - lo) * per_ds / 2;
+                rows_c = rows_c == -2 ? quarter : (rows_c == -3 ? half_left : (quarter < half_left ? quarter : half_left));
+                if (rows_c < kPipelineMinChunkRows) rows_c = kPipelineMinChunkRows;
+                if (rows_c > kPipelineChunkRows) rows_c = kPipelineChunkRows;
+            }
+            int64_t cnt = rows_c / per_ds;
+            if (cnt < 1) cnt = 1;
+            if (cnt > n_datasets - lo) cnt = n_datasets - lo;
+            chunks.emplace_back(lo, cnt);
+            lo += cnt;
+        }
     }
-    int64_t chunk_ds = chunk_rows / (n_trials > 0 ? n_trials : 1);
-    if (chunk_ds < 1) chunk_ds = 1;
-    if (chunk_ds > n_datasets) chunk_ds = n_datasets;  // a batch smaller than a chunk: buffers of its own size
+    const int64_t n_chunks = (int64_t)chunks.size();
+    int64_t chunk_ds = 0;  // the largest chunk sizes the buffers
+    for (const auto &c : chunks) chunk_ds = c.second > chunk_ds ? c.second : chunk_ds;
     const size_t chunk_bytes = (size_t)chunk_ds * (size_t)n_trials * wire_bytes;
-    const int64_t n_chunks = (n_datasets + chunk_ds - 1) / chunk_ds;
     // the resident-output buffer is not used by this path: hand it back so the pool can reuse it
     if (ctx->out) {
         ctx->pool->give(ctx->out, ctx->out_cap);
@@ -536,8 +550,7 @@ int run_pipelined(ddm_ctx *ctx, const double *params_host, int64_t n_trials, dou
     auto enqueue = [&](int64_t i) -> int {
         const int b = (int)(i & 1), s3 = (int)(i % 3);
         cudaStream_t ks = b ? ctx->pipe_stream2 : ctx->stream;
-        const int64_t lo = i * chunk_ds;
-        const int64_t cnt = (n_datasets - lo < chunk_ds) ? (n_datasets - lo) : chunk_ds;
+        const int64_t lo = chunks[i].first, cnt = chunks[i].second;
         // device buffer free again?  (compact: the host has already waited for that copy)
         if (!compact && i >= 2) DDM_CUDA(ctx, cudaStreamWaitEvent(ks, ctx->pipe_copy_done[(i - 2) % 3], 0));
         ddm::RunArgs a = base;
@@ -582,14 +595,14 @@ int run_pipelined(ddm_ctx *ctx, const double *params_host, int64_t n_trials, dou
                 rc = enqueue(i + 2);
                 if (rc) return rc;
             }
-            const int64_t lo = i * chunk_ds;
+            const int64_t lo = chunks[i].first;
             ddm::WireDecode job;
             job.wire = ctx->wire_host[i % 3];
             job.out = static_cast<char *>(out_host) + (size_t)lo * (size_t)n_trials * row_bytes;
             job.params = params_host + (size_t)lo * ctx->n_params;
             job.n_params = ctx->n_params;
             job.tau_col = 3;
-            job.n_datasets = (n_datasets - lo < chunk_ds) ? (n_datasets - lo) : chunk_ds;
+            job.n_datasets = chunks[i].second;
             job.n_trials = n_trials;
             job.dt = dt;
             job.basic = basic_cols;
