@@ -530,22 +530,15 @@ int run_pipelined(ddm_ctx *ctx, const double *params_host, int64_t n_trials, dou
     DDM_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long) * (1 + ddm::STAT_COUNT), ctx->stream));
     const bool dconst = uses_dconst(ctx, model, precision);
     if (dconst) {
-        if (model == DDM_MODEL_GENERAL) {
-            DDM_CUDA(ctx, ctx->gconst.reserve((size_t)n_datasets));
-            DDM_CUDA(ctx, ddm::launch_prep_general(ctx->params.p, ctx->gconst.p, (uint32_t)n_datasets, dt, ctx->stream));
-        } else {
-            DDM_CUDA(ctx, ctx->dconst.reserve((size_t)n_datasets));
-            DDM_CUDA(ctx, ddm::launch_prep(ctx->params.p, ctx->dconst.p, (uint32_t)n_datasets, (uint32_t)ctx->n_params, model, dt,
-                                           ctx->stream));
-        }
-        st.kernel_launches++;
+        if (model == DDM_MODEL_GENERAL) DDM_CUDA(ctx, ctx->gconst.reserve((size_t)n_datasets));
+        else DDM_CUDA(ctx, ctx->dconst.reserve((size_t)n_datasets));
     }
     DDM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     // Even chunks run on the ctx stream, odd chunks on a second one with their own work counter: a chunk's kernel
     // ends with a tail in which a few warps finish their longest trials (up to max_steps steps, ~0.5 ms at
     // dt = .001) while most SMs idle, and the next chunk's blocks move in as this one's retire.
     DDM_CUDA(ctx, cudaEventRecord(ctx->pipe_ready, ctx->stream));
-    DDM_CUDA(ctx, cudaStreamWaitEvent(ctx->pipe_stream2, ctx->pipe_ready, 0));  // parameters and constants are in place
+    DDM_CUDA(ctx, cudaStreamWaitEvent(ctx->pipe_stream2, ctx->pipe_ready, 0));  // the counters are zeroed
     // chunk i: device buffer and stream i % 2, copy-done event (and wire staging buffer) i % 3
     auto enqueue = [&](int64_t i) -> int {
         const int b = (int)(i & 1), s3 = (int)(i % 3);
@@ -553,6 +546,18 @@ int run_pipelined(ddm_ctx *ctx, const double *params_host, int64_t n_trials, dou
         const int64_t lo = chunks[i].first, cnt = chunks[i].second;
         // device buffer free again?  (compact: the host has already waited for that copy)
         if (!compact && i >= 2) DDM_CUDA(ctx, cudaStreamWaitEvent(ks, ctx->pipe_copy_done[(i - 2) % 3], 0));
+        // the chunk's parameters travel with it (a 1e6-dataset batch is 40 MB of pageable host memory: ~4 ms that
+        // only the first chunk would otherwise wait for), then its per-dataset constants
+        const size_t p_lo = (size_t)lo * ctx->n_params;
+        DDM_CUDA(ctx, cudaMemcpyAsync(ctx->params.p + p_lo, params_host + p_lo, (size_t)cnt * ctx->n_params * sizeof(double),
+                                      cudaMemcpyHostToDevice, ks));
+        if (dconst) {
+            if (model == DDM_MODEL_GENERAL)
+                DDM_CUDA(ctx, ddm::launch_prep_general(ctx->params.p + p_lo, ctx->gconst.p + lo, (uint32_t)cnt, dt, ks));
+            else
+                DDM_CUDA(ctx, ddm::launch_prep(ctx->params.p + p_lo, ctx->dconst.p + lo, (uint32_t)cnt, (uint32_t)ctx->n_params, model, dt, ks));
+            st.kernel_launches++;
+        }
         ddm::RunArgs a = base;
         if (b) a.work_counter = ctx->work_counter2;
         a.params = ctx->params.p + (size_t)lo * ctx->n_params;
@@ -784,7 +789,8 @@ DDM_API int ddm_set_host_decode(ddm_ctx *ctx, int n_threads) {
 }
 
 // ---- the hot path -----------------------------------------------------------------------
-DDM_API int ddm_upload_params(ddm_ctx *ctx, int model, const double *params, int64_t n_datasets, int n_params) {
+// Validates and registers a parameter batch; copies it to the device unless the caller streams it chunk by chunk.
+static int upload_params_impl(ddm_ctx *ctx, int model, const double *params, int64_t n_datasets, int n_params, bool copy) {
     if (!ctx) return DDM_ERR_INVALID;
     const int want = n_params_of(model);
     if (want < 0 || model == DDM_MODEL_TRIALWISE)
@@ -795,7 +801,7 @@ DDM_API int ddm_upload_params(ddm_ctx *ctx, int model, const double *params, int
     DeviceGuard g(ctx->device);
     const size_t n = (size_t)n_datasets * n_params;
     DDM_CUDA(ctx, ctx->params.reserve(n ? n : 1));
-    if (n) DDM_CUDA(ctx, cudaMemcpyAsync(ctx->params.p, params, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (n && copy) DDM_CUDA(ctx, cudaMemcpyAsync(ctx->params.p, params, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     // The production kernel measures the state in units of sqrt(dt)*dc*sqrt(2 ln 2); a dataset without
     // noise (dc == 0; the reference then runs a deterministic drift) has no such unit and goes through
     // the kernel that keeps the reference's formulas.  (Model 2 draws its per-trial dc > 0 itself.)
@@ -812,6 +818,10 @@ DDM_API int ddm_upload_params(ddm_ctx *ctx, int model, const double *params, int
     ctx->n_params = n_params;
     ctx->have_params = true;
     return DDM_OK;
+}
+
+DDM_API int ddm_upload_params(ddm_ctx *ctx, int model, const double *params, int64_t n_datasets, int n_params) {
+    return upload_params_impl(ctx, model, params, n_datasets, n_params, true);
 }
 
 DDM_API int ddm_draw_prior(ddm_ctx *ctx, int prior, int64_t n_draws, uint64_t seed, uint64_t draw_offset, double *params_host) {
@@ -869,7 +879,7 @@ DDM_API int ddm_download(ddm_ctx *ctx, void *out_host) {
 DDM_API int ddm_simulate(ddm_ctx *ctx, int model, const double *params, int64_t n_datasets, int n_params,
                          int64_t n_trials, double dt, int max_steps, uint64_t seed, uint64_t dataset_offset,
                          int precision, int flags, void *out_host) {
-    int rc = ddm_upload_params(ctx, model, params, n_datasets, n_params);
+    int rc = upload_params_impl(ctx, model, params, n_datasets, n_params, false);
     if (rc) return rc;
     const bool compact_ok = ctx->tune_host_decode >= 0 && n_cols_of(model) == 2 && takes_persistent_kernel(ctx, model, precision, flags) &&
                             max_steps >= 0 && (uint32_t)max_steps <= ddm::WIRE_MAX_STEPS;
@@ -879,6 +889,11 @@ DDM_API int ddm_simulate(ddm_ctx *ctx, int model, const double *params, int64_t 
         !ctx->dbg_on) {
         DeviceGuard g(ctx->device);
         return run_pipelined(ctx, params, n_trials, dt, max_steps, seed, dataset_offset, precision, flags, out_host);
+    }
+    if (n_datasets > 0) {
+        DeviceGuard g(ctx->device);
+        DDM_CUDA(ctx, cudaMemcpyAsync(ctx->params.p, params, (size_t)n_datasets * n_params * sizeof(double), cudaMemcpyHostToDevice,
+                                      ctx->stream));
     }
     rc = ddm_run(ctx, n_trials, dt, max_steps, seed, dataset_offset, precision, flags);
     if (rc) return rc;
