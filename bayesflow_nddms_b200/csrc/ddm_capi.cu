@@ -4,6 +4,7 @@
 // buffers (so that a steady-state online-training loop performs no cudaMalloc, even
 // when every batch is handed away through DLPack).  No torch types, no global state
 // except the last-create error string.
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -437,6 +438,19 @@ constexpr int64_t kCompactMinRows = 4ll << 20;      // compact records pay off e
 constexpr int64_t kPipelineMinChunkRows = 2ll << 20;  // a chunk costs ~0.2 ms of launches and kernel tail
 constexpr int64_t kPipelineChunkRows = 32ll << 20;  // trials per chunk (512 MB of float64 pairs)
 
+// The host thread pool (compact-wire decode, parameter scan), sized by ddm_set_host_decode.
+int ensure_workers(ddm_ctx *ctx) {
+    int gpus = 1;
+    if (cudaGetDeviceCount(&gpus) != cudaSuccess) gpus = 1;
+    const int want = ctx->tune_host_decode > 0 ? ctx->tune_host_decode : ddm::host_workers_default_count(gpus);
+    if (ctx->workers && ddm::host_workers_size(ctx->workers) != want) {
+        ddm::host_workers_destroy(ctx->workers);
+        ctx->workers = nullptr;
+    }
+    if (!ctx->workers) ctx->workers = ddm::host_workers_create(want);
+    return ctx->workers ? DDM_OK : DDM_ERR_NOMEM;
+}
+
 bool takes_persistent_kernel(const ddm_ctx *ctx, int model, int precision, int flags) {
     return precision == 32 && !ctx->dbg_on && model != DDM_MODEL_TRIALWISE && !ctx->degenerate_noise &&
            !(flags & (DDM_FLAG_FORCE_GENERIC | DDM_FLAG_OUT_STATE));
@@ -508,14 +522,8 @@ int run_pipelined(ddm_ctx *ctx, const double *params_host, int64_t n_trials, dou
             DDM_CUDA(ctx, cudaHostAlloc(&ctx->wire_host[b], chunk_bytes, cudaHostAllocDefault));
             ctx->wire_cap[b] = chunk_bytes;
         }
-        int gpus = 1;
-        if (cudaGetDeviceCount(&gpus) != cudaSuccess) gpus = 1;
-        const int want = ctx->tune_host_decode > 0 ? ctx->tune_host_decode : ddm::host_workers_default_count(gpus);
-        if (ctx->workers && ddm::host_workers_size(ctx->workers) != want) {
-            ddm::host_workers_destroy(ctx->workers);
-            ctx->workers = nullptr;
-        }
-        if (!ctx->workers) ctx->workers = ddm::host_workers_create(want);
+        rc = ensure_workers(ctx);
+        if (rc) return rc;
     }
     if (!ctx->copy_stream) {
         DDM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -807,12 +815,36 @@ static int upload_params_impl(ddm_ctx *ctx, int model, const double *params, int
     // the kernel that keeps the reference's formulas.  (Model 2 draws its per-trial dc > 0 itself.)
     ctx->degenerate_noise = false;
     const int dc_col = (model == DDM_MODEL_BASIC || model == DDM_MODEL_GENERAL) ? 4 : (model == DDM_MODEL_ALPHA_DC ? -1 : 5);
-    if (dc_col >= 0)
-        for (int64_t d = 0; d < n_datasets; d++) {
-            const double dc = params[(size_t)d * n_params + dc_col];
-            if (model == DDM_MODEL_GENERAL && params[(size_t)d * n_params + 5] != 0.0) continue;  // redrawn until > 0
-            if (!(dc > 1e-30) || !std::isfinite(dc)) { ctx->degenerate_noise = true; break; }
+    if (dc_col >= 0) {
+        struct Scan {
+            const double *params;
+            int64_t n_datasets;
+            int n_params, dc_col;
+            bool general;
+            std::atomic<bool> found;
+        } scan{params, n_datasets, n_params, dc_col, model == DDM_MODEL_GENERAL, {false}};
+        auto slice = [](const void *arg, int id, int n) {
+            Scan &sc = *const_cast<Scan *>(static_cast<const Scan *>(arg));
+            const int64_t per = (sc.n_datasets + n - 1) / n, lo = per * id, hi = std::min<int64_t>(sc.n_datasets, lo + per);
+            for (int64_t d = lo; d < hi; d++) {
+                const double dc = sc.params[(size_t)d * sc.n_params + sc.dc_col];
+                if (sc.general && sc.params[(size_t)d * sc.n_params + 5] != 0.0) continue;  // redrawn until > 0
+                if (!(dc > 1e-30) || !std::isfinite(dc)) {
+                    sc.found.store(true, std::memory_order_relaxed);
+                    break;
+                }
+            }
+        };
+        // a 1e6-dataset batch is 40 MB to walk: 4 ms on one thread, so large batches borrow the decode threads
+        if (n_datasets >= (256 << 10) && ctx->tune_host_decode >= 0) {
+            int rc = ensure_workers(ctx);
+            if (rc) return rc;
+            ddm::host_workers_run(ctx->workers, slice, &scan);
+        } else {
+            slice(&scan, 0, 1);
         }
+        ctx->degenerate_noise = scan.found.load();
+    }
     ctx->model = model;
     ctx->n_datasets = n_datasets;
     ctx->n_params = n_params;

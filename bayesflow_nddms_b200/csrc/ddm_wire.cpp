@@ -172,12 +172,13 @@ class HostWorkers {
         kick();
     }
     void end() { hot_.store(false); }
-    void run(const WireDecode &job) {
-        job_ = &job;
+    void run(HostSliceFn fn, const void *arg) {
+        fn_ = fn;
+        arg_ = arg;
         pending_.store(n_ - 1, std::memory_order_relaxed);
         gen_.fetch_add(1, std::memory_order_release);
         if (!hot_.load(std::memory_order_relaxed)) kick();
-        decode_slice(job, 0, n_);
+        fn(arg, 0, n_);
         while (pending_.load(std::memory_order_acquire) != 0) _mm_pause();
     }
 
@@ -200,7 +201,7 @@ class HostWorkers {
                 wake_.wait(l, [&] { return stop_.load() || hot_.load() || gen_.load() != seen; });
             }
             seen = g;
-            decode_slice(*job_, id, n_);
+            fn_(arg_, id, n_);
             pending_.fetch_sub(1, std::memory_order_acq_rel);
         }
     }
@@ -208,7 +209,8 @@ class HostWorkers {
     std::vector<std::thread> threads_;
     std::mutex m_;
     std::condition_variable wake_;
-    const WireDecode *job_ = nullptr;
+    HostSliceFn fn_ = nullptr;
+    const void *arg_ = nullptr;
     std::atomic<uint64_t> gen_{0};
     std::atomic<int> pending_{0};
     std::atomic<bool> hot_{false}, stop_{false};
@@ -232,6 +234,9 @@ int host_workers_default_count(int gpus) {
     return n < 1 ? 1 : (n > 16 ? 16 : n);
 }
 
-void wire_decode(HostWorkers *w, const WireDecode &job) { w->run(job); }
+void wire_decode(HostWorkers *w, const WireDecode &job) {
+    w->run([](const void *arg, int id, int n) { decode_slice(*static_cast<const WireDecode *>(arg), id, n); }, &job);
+}
+void host_workers_run(HostWorkers *w, HostSliceFn fn, const void *arg) { w->run(fn, arg); }
 
 }  // namespace ddm

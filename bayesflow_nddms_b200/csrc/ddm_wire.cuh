@@ -35,6 +35,7 @@ struct WireDecode {
 
 // A small pool of host threads (the caller takes part) that decode one chunk at a time.
 class HostWorkers;
+typedef void (*HostSliceFn)(const void *arg, int slice, int n_slices);  // runs once per thread, slice = 0 .. n_slices-1
 HostWorkers *host_workers_create(int n_threads);  // n_threads >= 1 (1 = the calling thread only)
 void host_workers_destroy(HostWorkers *w);
 int host_workers_size(const HostWorkers *w);
@@ -43,5 +44,6 @@ void host_workers_begin(HostWorkers *w);
 void host_workers_end(HostWorkers *w);
 int host_workers_default_count(int gpus_on_box);
 void wire_decode(HostWorkers *w, const WireDecode &job);
+void host_workers_run(HostWorkers *w, HostSliceFn fn, const void *arg);
 
 }  // namespace ddm

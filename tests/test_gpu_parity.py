@@ -376,6 +376,15 @@ def test_zero_and_negative_diffusion_coefficient(sim, oracle):
     assert abs((neg[0, :, 1] > 0).mean() - (pos[0, :, 1] > 0).mean()) < 0.05
     ev = sim.simulate_evidence([[2.0, 1.0, 0.5, 0.3, 0.0, 0.1]], 8, 200, 1, seed=1, dataset_offset=0)
     assert np.all(np.isfinite(ev)) and np.all(ev[0, :, 1] == 1)
+    # large batches are scanned for such datasets by several host threads: one dc == 0 anywhere is found
+    big = np.tile([1.0, 1.2, 0.4, 0.2, 1.0], (300_000, 1))
+    sim.simulate(0, big, 2, seed=3, dataset_offset=0)
+    assert sim.last_stats()["used_persistent"] == 1
+    for where in (0, 177_777, 299_999):
+        big[where, 4] = 0.0
+        out = sim.simulate(0, big, 2, seed=3, dataset_offset=0)
+        assert sim.last_stats()["used_persistent"] == 0 and np.all(np.isfinite(out))
+        big[where, 4] = 1.0
 
 
 def test_timeout_flag_and_float32_output(sim):
