@@ -339,8 +339,8 @@ def main():
     roofline = {
         "bound": "issue", "achieved": ach / 1e12, "peak": issue_peak / 1e12, "unit": "T warp-inst/s",
         "frac": ach / issue_peak, "frac_at_survey_28_slots": ach / issue_peak * I_STEP_SURVEY / I_STEP, "traffic": None,
-        "traffic_note": "ncu --set full of this kernel on a 2e7-trial launch (profiles/r01_v8_*): dram read 4.0 MB + write "
-                        "104 MB against 160 MB of algorithmic output (the remainder still in L2 at kernel end)",
+        "traffic_note": "ncu --set full of this kernel on a 2e7-trial launch (profiles/r01_v10_*): dram read 4.1 MB + write "
+                        "106 MB against 160 MB of algorithmic output (the remainder still in L2 at kernel end)",
         "kernel": "ddm::persistent_kernel<KIND_FIXED, f32 out>", "kernel_ms": k_ms,
         "steps_per_launch": st["total_steps"], "issue_slots_per_step": I_STEP,
         "peak_how": f"{sm_count} SMs x 4 schedulers x {f_hz / 1e6:.0f} MHz (median SM clock sampled during the timed region)",
