@@ -10,7 +10,7 @@ sim = pkg.DDMSimulator(0, seed=2023)
 for model, prior, D in ((0, "basic", 200_000), (1, "alpha", 200_000)):
     params = priors.draw_prior_batch(prior, D, np.random.default_rng(1))
     sim._check(sim._lib.ddm_upload_params(sim._ctx, model, params.ctypes.data_as(pkg._capi._dp), D, params.shape[1]))
-    for thr in (0, 5, 12, 16):
+    for thr in (0, 5, 8, 12, 16):
         sim.set_tuning(thr, 0, 0)
         best = None
         for _ in range(3):
