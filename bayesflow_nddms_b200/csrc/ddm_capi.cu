@@ -474,9 +474,10 @@ int run_pipelined(ddm_ctx *ctx, const double *params_host, int64_t n_trials, dou
                          (uint32_t)max_steps <= ddm::WIRE_MAX_STEPS;
     const size_t wire_bytes = compact ? (basic_cols ? 4 : 8) : row_bytes;
     // Chunk schedule (first dataset, datasets).  A fixed chunk_rows if the caller set one; otherwise each chunk is
-    // half of what is left, within 2 Mi .. 32 Mi trials: large batches run in 32 Mi chunks (fewest launches and
-    // kernel tails), the last chunks shrink so that little copy + decode is left exposed after the last kernel, and
-    // mid-size batches overlap kernel, copy and host decode as well (profiles/r01_v9c_midsize_ab.txt).
+    // the smaller of a quarter of the batch and half of what is left, within 2 Mi .. 32 Mi trials: large batches
+    // run in 32 Mi chunks (fewest launches and kernel tails), the last chunks shrink so that little copy + decode is
+    // left exposed after the last kernel, and mid-size batches overlap kernel, copy and host decode as well
+    // (profiles/r01_v9c_midsize_ab.txt, r01_v9d_chunk_policy_ab.txt; codes -2 / -3 select either rule alone).
     std::vector<std::pair<int64_t, int64_t>> chunks;
     {
         const int64_t per_ds = n_trials > 0 ? n_trials : 1;
@@ -555,7 +556,9 @@ int run_pipelined(ddm_ctx *ctx, const double *params_host, int64_t n_trials, dou
         // device buffer free again?  (compact: the host has already waited for that copy)
         if (!compact && i >= 2) DDM_CUDA(ctx, cudaStreamWaitEvent(ks, ctx->pipe_copy_done[(i - 2) % 3], 0));
         // the chunk's parameters travel with it (a 1e6-dataset batch is 40 MB of pageable host memory: ~4 ms that
-        // only the first chunk would otherwise wait for), then its per-dataset constants
+        // only the first chunk would otherwise wait for), then its per-dataset constants.  (A copy from pageable
+        // memory first waits for this stream's earlier work, i.e. for chunk i - 2: the other stream still holds
+        // chunk i - 1, so the GPU stays busy.)
         const size_t p_lo = (size_t)lo * ctx->n_params;
         DDM_CUDA(ctx, cudaMemcpyAsync(ctx->params.p + p_lo, params_host + p_lo, (size_t)cnt * ctx->n_params * sizeof(double),
                                       cudaMemcpyHostToDevice, ks));

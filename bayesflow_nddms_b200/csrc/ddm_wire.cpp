@@ -1,6 +1,6 @@
-// Host side of the compact wire format (ddm_wire.cuh), compiled by g++ (no device code): a few threads turn each chunk's (steps, choice[, draw])
-// records into the caller's float64 (or float32) pairs with non-temporal stores while the GPU simulates the
-// next chunk.  No simulation happens here: the Euler loop, the random numbers and the boundary test are the
+// Host side of the compact wire format (ddm_wire.cuh), compiled by g++ (no device code): a few threads turn each
+// chunk's (steps, choice[, draw]) records into the caller's float64 (or float32) pairs with non-temporal stores
+// while the GPU simulates the next chunk.  No simulation happens here: the Euler loop, the random numbers and the boundary test are the
 // kernel's; this is the output formatting of basic_ddm_dc.py:108-112 applied to the kernel's integers.
 #include "ddm_wire.cuh"
 
@@ -22,7 +22,10 @@ struct WirePair {  // the kernel's int2 {code, fp32 bits}
     int32_t x, y;
 };
 
-const bool g_avx2 = __builtin_cpu_supports("avx2");
+const bool g_avx2 = [] {
+    __builtin_cpu_init();  // this initialiser may run before libgcc's own constructor when the library is dlopen'ed
+    return __builtin_cpu_supports("avx2") != 0;
+}();
 
 struct Segment {  // trials [lo, hi) of the chunk, all of one dataset
     int64_t lo, hi;
