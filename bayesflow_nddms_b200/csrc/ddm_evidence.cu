@@ -27,37 +27,48 @@ namespace ddm {
 // --------------------------------------------------------------------------------------------
 // production, second kernel: a warp per trial finishes the recorded path
 // --------------------------------------------------------------------------------------------
-template <bool OUT64>
+// G lanes work on one trial, 32 / G trials per warp at a time.  A trial's 200 noise normals are 34 Philox blocks:
+// on 32 lanes that is two passes with the second nearly empty; on 8 lanes it is five passes for four trials
+// (1.25 per trial instead of 2), and the reductions are three shuffle steps instead of five.
+template <bool OUT64, int G>
 __global__ void __launch_bounds__(256) evidence_post_kernel(const EvidenceArgs a, uint64_t total) {
-    // Per-warp staging row: every global access below is lane-contiguous (k = lane, lane + 32, ...); the
-    // noise normals, which come six per Philox block and per lane, meet the row in shared memory.
+    // Per-trial staging row: every global access below is contiguous over the G lanes (k = sl, sl + G, ...: whole
+    // 32-byte sectors); the noise normals, which come six per Philox block and per lane, meet the row in shared
+    // memory.
     extern __shared__ float post_smem[];
-    const unsigned lane = threadIdx.x & 31u;
-    float *s = post_smem + (size_t)(threadIdx.x >> 5) * a.n_obs;
+    constexpr unsigned TPW = 32u / G;  // trials per warp
+    const unsigned lane = threadIdx.x & 31u, sl = lane & (G - 1u), sub = lane / G;
+    float *s = post_smem + ((size_t)(threadIdx.x >> 5) * TPW + sub) * a.n_obs;
     const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const uint32_t cols = 2u + a.n_obs;
     const uint32_t n_blocks = (a.n_obs + 5u) / 6u;
     const float inv_n = 1.f / (float)a.n_obs;
-    // (dataset, trial) of the warp's current row, advanced by the grid stride without a 64-bit division per row
-    uint32_t ds = (uint32_t)(warp0 / a.n_trials);
-    uint32_t trial = (uint32_t)(warp0 - (uint64_t)ds * a.n_trials);
-    const uint32_t stride_ds = (uint32_t)(n_warps / a.n_trials);
-    const uint32_t stride_trial = (uint32_t)(n_warps - (uint64_t)stride_ds * a.n_trials);
-    for (uint64_t g = warp0; g < total; g += n_warps) {
+    const bool small = total <= 0xffffffffull;  // 32-bit index arithmetic when the batch allows
+    for (uint64_t base = warp0 * TPW; base < total; base += n_warps * TPW) {
+        const bool valid = base + sub < total;  // the last warp may hold fewer than TPW trials: idle groups redo the
+        const uint64_t g = valid ? base + sub : total - 1;  // last trial and store nothing
+        uint32_t ds, trial;
+        if (small) {
+            ds = (uint32_t)g / a.n_trials;
+            trial = (uint32_t)g - ds * a.n_trials;
+        } else {
+            ds = (uint32_t)(g / a.n_trials);
+            trial = (uint32_t)(g - (uint64_t)ds * a.n_trials);
+        }
         const uint32_t nj = (uint32_t)a.steps[g];
         const float h = a.dconst[ds].v[2], u = a.dconst[ds].v[3];
         const float sigma1 = (float)a.params[(size_t)ds * 6 + 5];
         const float evj = __fmul_rn(__fadd_rn(a.rec_xfinal[g], h), u);
         const float *row_in = a.rec_path + g * a.n_obs;
         // 1. recorded states -> evidence units, held at the final evidence after the crossing
-        for (uint32_t k = lane; k < a.n_obs; k += 32u)
+        for (uint32_t k = sl; k < a.n_obs; k += G)
             s[k] = (k < nj) ? __fmul_rn(__fadd_rn(row_in[k], h), u) : evj;
         __syncwarp();
-        // 2. + sigma1 * z_noise[k]: lane owns Philox blocks lane, lane + 32, ... of the trial's aux stream;
+        // 2. + sigma1 * z_noise[k]: lane owns Philox blocks sl, sl + G, ... of the trial's aux stream;
         //    the row sum is taken on the way
         float sum = 0.f;
-        for (uint32_t b = lane; b < n_blocks; b += 32u) {
+        for (uint32_t b = sl; b < n_blocks; b += G) {
             float z[6];
             philox_normals6_f32(b, trial + a.trial_offset, ds + a.dataset_offset, STREAM_AUX, a.key, z);
 #pragma unroll
@@ -73,23 +84,23 @@ __global__ void __launch_bounds__(256) evidence_post_kernel(const EvidenceArgs a
         __syncwarp();
         // 3. mean (and variance) over the row
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL_MASK, sum, o);
+        for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL_MASK, sum, o);
         const float mean = sum * inv_n;
         float scale = 1.f, shift = 0.f;
         if (a.mode == 1) {
             float ssd = 0.f;
-            for (uint32_t k = lane; k < a.n_obs; k += 32u) {
+            for (uint32_t k = sl; k < a.n_obs; k += G) {
                 const float d = s[k] - mean;
                 ssd = __fmaf_rn(d, d, ssd);
             }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) ssd += __shfl_xor_sync(FULL_MASK, ssd, o);
+            for (int o = G / 2; o > 0; o >>= 1) ssd += __shfl_xor_sync(FULL_MASK, ssd, o);
             scale = 1.f / sqrtf(ssd * inv_n);
             shift = mean;
         }
         // 4. the row
         const uint64_t row = g * cols;
-        if (lane == 0) {
+        if (sl == 0 && valid) {
             const double2 pr = a.pairs[g];  // (rt, choice) from the stepping kernel, reference fp64 arithmetic
             if (OUT64) {
                 double *o = reinterpret_cast<double *>(a.out) + row;
@@ -102,18 +113,14 @@ __global__ void __launch_bounds__(256) evidence_post_kernel(const EvidenceArgs a
             }
             if (a.mode == 2) a.path_means[g] = (double)mean;
         }
-        for (uint32_t k = lane; k < a.n_obs; k += 32u) {
-            const float v = (s[k] - shift) * scale;
-            if (OUT64) reinterpret_cast<double *>(a.out)[row + 2 + k] = (double)v;
-            else reinterpret_cast<float *>(a.out)[row + 2 + k] = v;
+        if (valid) {
+            for (uint32_t k = sl; k < a.n_obs; k += G) {
+                const float v = (s[k] - shift) * scale;
+                if (OUT64) reinterpret_cast<double *>(a.out)[row + 2 + k] = (double)v;
+                else reinterpret_cast<float *>(a.out)[row + 2 + k] = v;
+            }
         }
         __syncwarp();
-        ds += stride_ds;
-        trial += stride_trial;
-        if (trial >= a.n_trials) {
-            trial -= a.n_trials;
-            ds++;
-        }
     }
 }
 
@@ -238,15 +245,26 @@ __global__ void evidence_finalize_kernel(const Src *__restrict__ src, Dst *__res
 // --------------------------------------------------------------------------------------------
 // launchers
 // --------------------------------------------------------------------------------------------
-cudaError_t launch_evidence_post(const EvidenceArgs &a, bool out64, uint64_t total, int sm_count, cudaStream_t s) {
-    if (total == 0) return cudaSuccess;
-    uint64_t grid = (total + 7) / 8;  // 8 warps per block, one trial per warp per pass
+template <int G>
+static cudaError_t launch_evidence_post_g(const EvidenceArgs &a, bool out64, uint64_t total, int sm_count, cudaStream_t s) {
+    constexpr uint64_t per_block = 8ull * (32 / G);  // 8 warps per block, 32 / G trials per warp per pass
+    uint64_t grid = (total + per_block - 1) / per_block;
     const uint64_t cap = (uint64_t)sm_count * 8 * 4;
     if (grid > cap) grid = cap;
-    const size_t smem = (size_t)8 * a.n_obs * sizeof(float);
-    if (out64) evidence_post_kernel<true><<<(unsigned)grid, 256, smem, s>>>(a, total);
-    else evidence_post_kernel<false><<<(unsigned)grid, 256, smem, s>>>(a, total);
+    const size_t smem = (size_t)per_block * a.n_obs * sizeof(float);
+    if (out64) evidence_post_kernel<true, G><<<(unsigned)grid, 256, smem, s>>>(a, total);
+    else evidence_post_kernel<false, G><<<(unsigned)grid, 256, smem, s>>>(a, total);
     return cudaGetLastError();
+}
+
+cudaError_t launch_evidence_post(const EvidenceArgs &a, bool out64, uint64_t total, int sm_count, cudaStream_t s) {
+    if (total == 0) return cudaSuccess;
+    // the widest split whose staging rows fit the 48 KB a block gets without opting in: 8 lanes per trial up to
+    // 384 observations (the reference uses 200 and 400), then 16, then the whole warp
+    const size_t row = (size_t)a.n_obs * sizeof(float);
+    if (32 * row <= 48 * 1024) return launch_evidence_post_g<8>(a, out64, total, sm_count, s);
+    if (16 * row <= 48 * 1024) return launch_evidence_post_g<16>(a, out64, total, sm_count, s);
+    return launch_evidence_post_g<32>(a, out64, total, sm_count, s);
 }
 
 cudaError_t launch_evidence_generic(const EvidenceArgs &a, bool buffer_src, uint64_t total, cudaStream_t s) {
