@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-chunk-rows", type=int, default=-1, help="e2e leg: trials per streamed chunk (-1 = library default)")
     ap.add_argument("--host-decode", type=int, default=0,
                     help="e2e leg: host threads expanding the compact PCIe records (0 auto, < 0 float64 rows over PCIe)")
     ap.add_argument("--microbench", action="store_true", help="also measure per-pipe issue rates")
@@ -371,6 +372,7 @@ def main():
         pe = sweep_params(De, seed=4000 + rank)
         out_host = sim.pinned_empty((De, N_TRIALS, 2), np.float64)
         sim.set_host_decode(args.host_decode)
+        sim.set_pipeline(-1, args.e2e_chunk_rows)
         ke = args.e2e_steps or min(args.steps, 3)
         basic_ddm_dc.batch_simulate_trials(pe, N_TRIALS, sim, dt=DT, max_steps=MAX_STEPS, dataset_offset=ds_base, out=out_host)
         st_e2e = sim.last_stats()
