@@ -48,7 +48,7 @@ class _PinnedResultPool:
         self._lib, self._limit = lib, int(limit)
         self._free: dict[int, list[int]] = {}
         self._pinned_bytes = 0
-        self._lock = threading.Lock()
+        self._lock = threading.RLock()  # re-entrant: a garbage collection inside empty() may run a block's __del__
         self._closed = False
 
     def empty(self, shape, dtype) -> np.ndarray | None:
