@@ -40,6 +40,7 @@ MAX_STEPS = 4000
 # (SURVEY.md section 8d budgeted 28 for a 4-normals-per-block design.)
 I_STEP = 17
 I_STEP_SURVEY = 28
+NCU_DRAM_BYTES_PER_LAUNCH_1E9 = 255_669_760 + 8_083_822_000
 MODEL_BASIC = 0
 FLAG_OUT_F32 = 2
 
@@ -339,9 +340,12 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     roofline = {
         "bound": "issue", "achieved": ach / 1e12, "peak": issue_peak / 1e12, "unit": "T warp-inst/s",
-        "frac": ach / issue_peak, "frac_at_survey_28_slots": ach / issue_peak * I_STEP_SURVEY / I_STEP, "traffic": None,
-        "traffic_note": "ncu --set full of this kernel on a 2e7-trial launch (profiles/r01_v10_*): dram read 4.1 MB + write "
-                        "106 MB against 160 MB of algorithmic output (the remainder still in L2 at kernel end)",
+        "frac": ach / issue_peak, "frac_at_survey_28_slots": ach / issue_peak * I_STEP_SURVEY / I_STEP,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this very size, from the ncu --set full capture
+        # profiles/r01_v11_ncu_persistent_fullsize_details.txt (scripts/gpu_ncu_fullsize.sh); other sizes: not captured
+        "traffic": NCU_DRAM_BYTES_PER_LAUNCH_1E9 if (D == 1_000_000 and N_TRIALS == 1000) else None,
+        "traffic_note": "ncu --set full of this kernel at the bench's launch size (1e9 trials): dram read 0.256 GB + write "
+                        "8.084 GB = 8.339 GB against 8.072 GB algorithmic (8 B/trial out + 72 B/dataset in): 1.03x",
         "kernel": "ddm::persistent_kernel<KIND_FIXED, f32 out>", "kernel_ms": k_ms,
         "steps_per_launch": st["total_steps"], "issue_slots_per_step": I_STEP,
         "peak_how": f"{sm_count} SMs x 4 schedulers x {f_hz / 1e6:.0f} MHz (median SM clock sampled during the timed region)",
