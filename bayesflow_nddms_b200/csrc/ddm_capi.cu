@@ -456,6 +456,27 @@ bool takes_persistent_kernel(const ddm_ctx *ctx, int model, int precision, int f
            !(flags & (DDM_FLAG_FORCE_GENERIC | DDM_FLAG_OUT_STATE));
 }
 
+// The streamed path's chunk schedule: (first dataset, datasets) per chunk, covering [0, n_datasets) in order.
+std::vector<std::pair<int64_t, int64_t>> pipeline_chunks(int64_t n_datasets, int64_t n_trials, int64_t chunk_rows) {
+    std::vector<std::pair<int64_t, int64_t>> chunks;
+    const int64_t per_ds = n_trials > 0 ? n_trials : 1;
+    for (int64_t lo = 0; lo < n_datasets;) {
+        int64_t rows_c = chunk_rows;
+        if (rows_c <= 0) {
+            const int64_t quarter = n_datasets * per_ds / 4, half_left = (n_datasets - lo) * per_ds / 2;
+            rows_c = rows_c == -2 ? quarter : (rows_c == -3 ? half_left : (quarter < half_left ? quarter : half_left));
+            if (rows_c < kPipelineMinChunkRows) rows_c = kPipelineMinChunkRows;
+            if (rows_c > kPipelineChunkRows) rows_c = kPipelineChunkRows;
+        }
+        int64_t cnt = rows_c / per_ds;
+        if (cnt < 1) cnt = 1;
+        if (cnt > n_datasets - lo) cnt = n_datasets - lo;
+        chunks.emplace_back(lo, cnt);
+        lo += cnt;
+    }
+    return chunks;
+}
+
 int run_pipelined(ddm_ctx *ctx, const double *params_host, int64_t n_trials, double dt, int max_steps, uint64_t seed,
                   uint64_t dataset_offset, int precision, int flags, void *out_host) {
     const int model = ctx->model;
@@ -478,24 +499,7 @@ int run_pipelined(ddm_ctx *ctx, const double *params_host, int64_t n_trials, dou
     // run in 32 Mi chunks (fewest launches and kernel tails), the last chunks shrink so that little copy + decode is
     // left exposed after the last kernel, and mid-size batches overlap kernel, copy and host decode as well
     // (profiles/r01_v9c_midsize_ab.txt, r01_v9d_chunk_policy_ab.txt; codes -2 / -3 select either rule alone).
-    std::vector<std::pair<int64_t, int64_t>> chunks;
-    {
-        const int64_t per_ds = n_trials > 0 ? n_trials : 1;
-        for (int64_t lo = 0; lo < n_datasets;) {
-            int64_t rows_c = ctx->tune_pipeline_chunk_rows;
-            if (rows_c <= 0) {
-                const int64_t quarter = n_datasets * per_ds / 4, half_left = (n_datasets - lo) * per_ds / 2;
-                rows_c = rows_c == -2 ? quarter : (rows_c == -3 ? half_left : (quarter < half_left ? quarter : half_left));
-                if (rows_c < kPipelineMinChunkRows) rows_c = kPipelineMinChunkRows;
-                if (rows_c > kPipelineChunkRows) rows_c = kPipelineChunkRows;
-            }
-            int64_t cnt = rows_c / per_ds;
-            if (cnt < 1) cnt = 1;
-            if (cnt > n_datasets - lo) cnt = n_datasets - lo;
-            chunks.emplace_back(lo, cnt);
-            lo += cnt;
-        }
-    }
+    const std::vector<std::pair<int64_t, int64_t>> chunks = pipeline_chunks(n_datasets, n_trials, ctx->tune_pipeline_chunk_rows);
     const int64_t n_chunks = (int64_t)chunks.size();
     int64_t chunk_ds = 0;  // the largest chunk sizes the buffers
     for (const auto &c : chunks) chunk_ds = c.second > chunk_ds ? c.second : chunk_ds;
@@ -1259,6 +1263,17 @@ DDM_API int ddm_export_normals(ddm_ctx *ctx, uint64_t seed, uint32_t dataset, ui
     DDM_CUDA(ctx, cudaMemcpyAsync(out_host, ctx->export_buf.p, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     DDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return DDM_OK;
+}
+
+DDM_API int64_t ddm_pipeline_chunks(int64_t n_datasets, int64_t n_trials, int64_t chunk_rows, int64_t *first, int64_t *count,
+                                    int64_t capacity) {
+    if (n_datasets < 0 || n_trials < 0) return DDM_ERR_INVALID;
+    const auto chunks = pipeline_chunks(n_datasets, n_trials, chunk_rows);
+    for (size_t i = 0; i < chunks.size() && (int64_t)i < capacity; i++) {
+        if (first) first[i] = chunks[i].first;
+        if (count) count[i] = chunks[i].second;
+    }
+    return (int64_t)chunks.size();
 }
 
 DDM_API int ddm_wire_decode_host(const void *wire, void *out_host, const double *params, int n_params, int64_t n_datasets,

@@ -220,6 +220,10 @@ int ddm_export_normals(ddm_ctx *ctx, uint64_t seed, uint32_t dataset, uint32_t t
                        uint32_t first, uint32_t count, int precision, double *out_host);
 /* Raw Philox4x32-10 blocks computed on the device (known-answer tests). */
 int ddm_philox4x32(ddm_ctx *ctx, const uint32_t *ctr4, const uint32_t *key2, uint32_t *out4, int64_t n_blocks);
+/* The chunk schedule ddm_simulate's streamed path uses for a batch (no GPU needed): writes up to `capacity`
+ * (first dataset, datasets) pairs and returns the number of chunks.  chunk_rows as in ddm_set_pipeline. */
+int64_t ddm_pipeline_chunks(int64_t n_datasets, int64_t n_trials, int64_t chunk_rows, int64_t *first, int64_t *count,
+                            int64_t capacity);
 /* The host half of ddm_set_host_decode on its own (no GPU needed): expands n_datasets * n_trials wire
  * records -- int32 (steps << 2 | choice + 1) when basic_columns, else {that, fp32 bits} pairs -- into
  * (rows, 2) float64 / float32 with n_threads threads.  tau = params[d * n_params + 3]. */

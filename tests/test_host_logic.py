@@ -252,3 +252,39 @@ def test_wire_decode_host_formats_rows_like_the_reference(basic, f32):
         assert lib.ddm_wire_decode_host(wire.ctypes.data, out.ctypes.data, params.ctypes.data_as(_capi._dp), 6, D, T, dt,
                                         int(basic), 1, 3) == 0
         assert np.array_equal(out, want)
+
+
+@pytest.mark.parametrize("n_datasets,n_trials", [(1_000_000, 1000), (16_384, 1000), (4_200, 1000), (7, 3_000_000), (3, 5), (0, 10),
+                                                 (100_003, 33)])
+@pytest.mark.parametrize("chunk_rows", [-1, -2, -3, 1, 257 * 7, 32 << 20])
+def test_streamed_path_chunk_schedule(n_datasets, n_trials, chunk_rows):
+    """include/ddm_b200.h: ddm_pipeline_chunks -- the schedule covers every dataset exactly once, in order; the
+    default schedules keep chunks within 2 Mi .. 32 Mi trials (whole datasets) and end with small chunks."""
+    import ctypes as C
+
+    from bayesflow_nddms_b200 import _capi
+
+    lib = _capi.load()
+    cap = 1 << 16
+    first = (C.c_int64 * cap)()
+    count = (C.c_int64 * cap)()
+    n = lib.ddm_pipeline_chunks(n_datasets, n_trials, chunk_rows, first, count, cap)
+    if n_datasets == 0:
+        assert n == 0
+        return
+    assert 1 <= n
+    if n > cap:                                   # tiny fixed chunks of a large batch: count only
+        per = max(1, chunk_rows // n_trials)
+        assert chunk_rows > 0 and n == -(-n_datasets // per)
+        return
+    f, c = np.array(first[:n]), np.array(count[:n])
+    assert f[0] == 0 and np.all(c >= 1) and np.array_equal(f[1:], np.cumsum(c)[:-1]) and f[-1] + c[-1] == n_datasets
+    rows = c * n_trials
+    if chunk_rows < 0:
+        assert np.all(rows <= max(32 << 20, n_trials))                 # at most 32 Mi trials, or one dataset
+        if n > 1:
+            assert np.all(rows[:-1] >= min(2 << 20, rows[:-1].max()) - n_trials)   # at least 2 Mi, up to dataset granularity
+        if n_datasets * n_trials >= 256 << 20 and chunk_rows != -2:
+            assert rows[-1] <= 4 << 20 < rows[0]                        # large batches end with small chunks
+    elif chunk_rows > 0:
+        assert np.all(c[:-1] == max(1, chunk_rows // n_trials))
