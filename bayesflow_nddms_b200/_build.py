@@ -12,7 +12,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libddm_b200.so")
-SOURCES = ["ddm_kernels.cu", "ddm_capi.cu", "ddm_microbench.cu", "ddm_evidence.cu", "ddm_prior.cu", "ddm_reduce.cu"]
+SOURCES = ["ddm_kernels.cu", "ddm_capi.cu", "ddm_microbench.cu", "ddm_evidence.cu", "ddm_prior.cu", "ddm_reduce.cu", "ddm_exact.cu"]
 HOST_SOURCES = ["ddm_wire.cpp"]  # g++ only: host threads of the compact device->host wire format
 HEADERS = ["ddm_kernels.cuh", "ddm_rng.cuh", "ddm_microbench.cuh", "ddm_wire.cuh",
            os.path.join("..", "..", "include", "ddm_b200.h"),

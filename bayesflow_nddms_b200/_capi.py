@@ -107,6 +107,7 @@ SIGNATURES = {
     "ddm_simulate_evidence": (C.c_int, [_vp, _dp, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint64,
                                         C.c_uint64, C.c_int, C.c_int, _vp]),
     "ddm_last_steps": (C.c_int, [_vp, C.POINTER(C.c_int32)]),
+    "ddm_simulate_exact": (C.c_int, [_vp, _dp, C.c_int64, C.c_int64, C.c_uint64, C.c_uint64, _dp]),
     "ddm_last_output_histogram": (C.c_int, [_vp, C.c_int, C.c_double, C.POINTER(C.c_uint64)]),
     "ddm_last_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
     "ddm_last_output_dlpack": (C.c_int, [_vp, C.POINTER(C.POINTER(DLManagedTensor))]),

@@ -8,9 +8,11 @@ The reference draws the participant parameters from NumPy's legacy global state 
 ``np.random.seed(2021)`` (:62-88) -- reproduced here draw for draw, so the parameters are the
 reference's own -- and then calls ``phju.simulratcliff`` per participant (:95-97), a pure-numpy
 rejection sampler of the continuous-time process (~92 us/trial).  Here all participants are one
-launch of the Euler-Maruyama kernel (DDM_MODEL_ETA: drift_trial ~ N(delta, deltatrialsd)) at a fine
-step, dt = 1e-4 by default.  Different algorithm, so parity is distributional: tests
-compare against samples of the reference's sampler.  The JAGS fit and the plots are out of scope.
+launch: by default of the same exact sampler on the GPU (``ddm_simulate_exact``, ``exact=True``), or
+of the Euler-Maruyama kernel (DDM_MODEL_ETA: drift_trial ~ N(delta, deltatrialsd)) at a fine step,
+dt = 1e-4 by default (``exact=False``; a different algorithm).  Streams differ from NumPy's,
+so parity is distributional: tests compare against samples of the reference's sampler.  The JAGS fit
+and the plots are out of scope.
 """
 from __future__ import annotations
 
@@ -40,16 +42,23 @@ def draw_participants(nparts=100, test_num=2, seed=2021):
 
 
 def generate_data(test_num=2, nparts=100, ntrials=100, seed=2021, simulator=None, dt=1e-4, max_time=20.,
-                  sim_seed=None):
+                  sim_seed=None, exact=True):
     """alpha_not_scaled.py:52-131 -> the ``genparam`` dict (same keys, shapes and dtypes)."""
     g, rs = draw_participants(nparts, test_num, seed)
     sim = simulator if simulator is not None else default_simulator()
-    # simulratcliff clips the mean drift to +-5 (pyhddmjagsutils.py:102-103); |delta| <= 4 here anyway
-    nu = np.clip(g['delta'], -5, 5)
-    params = np.stack([nu, g['alpha'], g['beta'], g['ndt'], g['deltatrialsd'], g['varsigma']], axis=-1)
-    out = sim.simulate(_capi.MODEL_ETA, params, ntrials, dt, int(round(max_time / dt)), seed=sim_seed)
-    rt = out[..., 0].reshape(-1)
-    choice = out[..., 1].reshape(-1)
+    if exact:
+        # phju.simulratcliff(N=ntrials, Alpha, Tau, Nu, Beta, Eta, Varsigma) per participant (:95-97)
+        zero = np.zeros(nparts)
+        params = np.stack([g['alpha'], g['ndt'], g['delta'], g['beta'], zero, zero, g['deltatrialsd'], g['varsigma']], axis=-1)
+        y = sim.simulate_exact(params, ntrials, seed=sim_seed).reshape(-1)
+        rt, choice = np.abs(y), np.sign(y)
+    else:
+        # simulratcliff clips the mean drift to +-5 (pyhddmjagsutils.py:102-103); |delta| <= 4 here anyway
+        nu = np.clip(g['delta'], -5, 5)
+        params = np.stack([nu, g['alpha'], g['beta'], g['ndt'], g['deltatrialsd'], g['varsigma']], axis=-1)
+        out = sim.simulate(_capi.MODEL_ETA, params, ntrials, dt, int(round(max_time / dt)), seed=sim_seed)
+        rt = out[..., 0].reshape(-1)
+        choice = out[..., 1].reshape(-1)
     N = ntrials * nparts
     # external data measured per participant (:103-106)
     if test_num != 4:

@@ -144,6 +144,7 @@ int kind_of(int model) {
 
 }  // namespace
 
+constexpr int kRunModelExact = 101;     // ... of ddm_simulate_exact runs ((B, N) signed response times)
 constexpr int kRunModelEvidence = 100;  // run_model of ddm_simulate_evidence runs ((rt, choice, path) rows)
 
 struct ddm_ctx {
@@ -968,6 +969,63 @@ DDM_API int ddm_simulate_trialwise(ddm_ctx *ctx, const int32_t *group, const dou
     }
     int rc = run_common(ctx, DDM_MODEL_TRIALWISE, 1, n, dt, max_steps, seed, 0, trial_offset, precision, flags, n_groups);
     if (rc) return rc;
+    if (out_host) return ddm_download(ctx, out_host);
+    return DDM_OK;
+}
+
+// Exact rejection sampler: pyhddmjagsutils.py:47-176 (simulratcliff).
+DDM_API int ddm_simulate_exact(ddm_ctx *ctx, const double *params, int64_t n_datasets, int64_t n_trials, uint64_t seed,
+                               uint64_t dataset_offset, double *out_host) {
+    if (!ctx) return DDM_ERR_INVALID;
+    if (n_trials < 0 || n_datasets < 0) return fail(ctx, DDM_ERR_INVALID, "negative shape");
+    if (n_trials > 0xffffffffLL || n_datasets > 0xffffffffLL || dataset_offset + (uint64_t)n_datasets > 0xffffffffULL)
+        return fail(ctx, DDM_ERR_INVALID, "shape exceeds the 32-bit Philox counter words");
+    if (n_datasets > 0 && !params) return fail(ctx, DDM_ERR_INVALID, "params is NULL");
+    for (int64_t d = 0; d < n_datasets; d++) {
+        const double *p = params + (size_t)d * 8;
+        for (int j = 0; j < 8; j++)
+            if (!std::isfinite(p[j])) return fail(ctx, DDM_ERR_INVALID, "dataset %lld: parameter %d is not finite", (long long)d, j);
+        if (!(p[0] > 0.0) || !(p[7] > 0.0))
+            return fail(ctx, DDM_ERR_INVALID, "dataset %lld: Alpha and Varsigma must be positive (got %g, %g)", (long long)d, p[0], p[7]);
+        const double b_lo = p[3] - std::fabs(p[5]) / 2, b_hi = p[3] + std::fabs(p[5]) / 2;
+        if (b_lo < 0.0 || b_hi > 1.0)
+            return fail(ctx, DDM_ERR_INVALID, "dataset %lld: start point Beta +- rangeBeta/2 leaves [0, 1]", (long long)d);
+    }
+    DeviceGuard g(ctx->device);
+    const size_t np = (size_t)n_datasets * 8;
+    DDM_CUDA(ctx, ctx->params.reserve(np ? np : 1));
+    if (np) DDM_CUDA(ctx, cudaMemcpyAsync(ctx->params.p, params, np * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->have_params = false;  // the params arena now holds the sampler's parameters
+    const int64_t rows = n_datasets * n_trials;
+    const size_t out_bytes = (size_t)rows * sizeof(double);
+    int rc = ensure_output(ctx, out_bytes);
+    if (rc) return rc;
+    ddm_stats st{};
+    st.n_trials = (uint64_t)rows;
+    DDM_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long) * (1 + ddm::STAT_COUNT), ctx->stream));
+    DDM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    const ddm::PhiloxKey key = ddm::make_philox_key((uint32_t)seed, (uint32_t)(seed >> 32));
+    DDM_CUDA(ctx, ddm::launch_exact_sampler(ctx->params.p, static_cast<double *>(ctx->out), ctx->counters + 1, (uint32_t)n_datasets,
+                                            (uint32_t)n_trials, (uint32_t)dataset_offset, 0u, key, ctx->stream));
+    if (rows) st.kernel_launches++;
+    st.grid = (int)(((uint64_t)rows + 127) / 128);
+    st.block = 128;
+    DDM_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    DDM_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, ctx->counters, sizeof(unsigned long long) * (1 + ddm::STAT_COUNT),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->stats = st;
+    ctx->stats_pending = true;
+    ctx->have_run = true;
+    ctx->out64 = true;
+    ctx->out_bytes = out_bytes;
+    ctx->have_steps = false;
+    ctx->run_rows = rows;
+    ctx->run_datasets = n_datasets;
+    ctx->run_trials = n_trials;
+    ctx->run_trialwise = false;
+    ctx->run_cols = 1;
+    ctx->run_model = kRunModelExact;
+    ctx->out_resident = true;
     if (out_host) return ddm_download(ctx, out_host);
     return DDM_OK;
 }

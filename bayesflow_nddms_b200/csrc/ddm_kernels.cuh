@@ -319,6 +319,9 @@ struct EvidenceArgs {
     double dt, sqrt_dt;
 };
 
+cudaError_t launch_exact_sampler(const double *params, double *out, unsigned long long *stats, uint32_t n_datasets,
+                                 uint32_t n_trials, uint32_t dataset_offset, uint32_t trial_offset, const PhiloxKey &key,
+                                 cudaStream_t s);
 cudaError_t launch_rt_histogram(const void *rows, bool rows64, uint64_t n_rows, uint32_t cols, bool basic_layout, uint32_t n_bins,
                                 double rt_max, unsigned long long *hist, int sm_count, cudaStream_t s);
 cudaError_t launch_evidence_post(const EvidenceArgs &a, bool out64, uint64_t total, int sm_count, cudaStream_t s);

@@ -338,6 +338,23 @@ class DDMSimulator:
         self._check(self._lib.ddm_last_output_device_ptr(self._ctx, C.byref(p), C.byref(n)))
         return p.value, n.value
 
+    def simulate_exact(self, params, n_trials: int, *, seed=None, dataset_offset=None, device: bool = False):
+        """Exact first-passage sampler (``ddm_simulate_exact``; pyhddmjagsutils.py:47-176): params (B, 8) or (8,)
+        = [Alpha, Tau, Nu, Beta, rangeTau, rangeBeta, Eta, Varsigma] -> (B, n_trials) float64 signed response
+        times.  ``device=True`` leaves the batch on the GPU and returns a DLPack producer of shape (B, n_trials, 1)."""
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        if params.ndim == 1:
+            params = params[None, :]
+        if params.ndim != 2 or params.shape[1] != 8:
+            raise ValueError("params must be (8,) or (B, 8): Alpha, Tau, Nu, Beta, rangeTau, rangeBeta, Eta, Varsigma")
+        B = params.shape[0]
+        out = None if device else np.empty((B, int(n_trials)), dtype=np.float64)
+        off = self._next_offset(B, dataset_offset)
+        self._check(self._lib.ddm_simulate_exact(self._ctx, params.ctypes.data_as(_capi._dp), B, int(n_trials),
+                                                 self.seed if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF, off,
+                                                 None if device else out.ctypes.data_as(_capi._dp)))
+        return self.last_output_dlpack() if device else out
+
     def last_steps(self, n: int) -> np.ndarray:
         out = np.empty(int(n), dtype=np.int32)
         self._check(self._lib.ddm_last_steps(self._ctx, out.ctypes.data_as(C.POINTER(C.c_int32))))

@@ -190,6 +190,16 @@ int ddm_simulate_evidence(ddm_ctx *ctx, const double *params, int64_t n_datasets
                           int standardize, double dt, int max_steps, uint64_t seed, uint64_t dataset_offset,
                           int precision, int flags, void *out_host);
 
+/* Replaces B calls of simulratcliff(N, Alpha, Tau, Nu, Beta, rangeTau, rangeBeta, Eta, Varsigma)
+ * (pyhddmjagsutils.py:47-176; caller alpha_not_scaled.py:95-97): the exact rejection sampler of Tuerlinckx et al.
+ * (2001) -- no time step -- with per-trial drift N(Nu, Eta), start point and non-decision time ranges.
+ * params (B, 8) f64 host, columns [Alpha, Tau, Nu, Beta, rangeTau, rangeBeta, Eta, Varsigma];
+ * out_host (B, n_trials) f64 signed response times (+ upper boundary, - lower), may be NULL (resident).
+ * |Nu| is clipped to 5 and Eta == 0 replaced by 1e-16 as in the reference.  Stats: total_steps counts
+ * the symmetric intervals walked, n_upper the upper-boundary responses. */
+int ddm_simulate_exact(ddm_ctx *ctx, const double *params, int64_t n_datasets, int64_t n_trials, uint64_t seed,
+                       uint64_t dataset_offset, double *out_host);
+
 /* Per-trial Euler-step counts of the last run (needs DDM_FLAG_KEEP_STEPS). */
 int ddm_last_steps(ddm_ctx *ctx, int32_t *steps_host);
 int ddm_last_stats(ddm_ctx *ctx, ddm_stats *out);

@@ -245,12 +245,16 @@ def test_alpha_not_scaled_data_generation(sim):
     own samples (different algorithm, distribution-level parity)."""
     from bayesflow_nddms_b200 import alpha_not_scaled as m
 
-    g = m.generate_data(test_num=2, simulator=sim, sim_seed=3)
-    assert g['N'] == 10000 and g['rt'].shape == g['acc'].shape == g['y'].shape == g['participant'].shape == (10000,)
-    assert g['extdata'].shape == (100,) and set(np.unique(g['acc'])) <= {0.0, 0.5, 1.0}
-    assert np.array_equal(g['y'], (2 * g['acc'] - 1) * g['rt']) and np.all(g['rt'] >= np.repeat(g['ndt'], 100))
-    assert abs(np.corrcoef(g['extdata'], g['alpha'])[0, 1]) > 0.7           # sigma = .1 vs sd(alpha) = .17
-    assert abs(g['prop_cog_var'] - 0.03 / 0.04) < 1e-12
+    acc = {}
+    for exact in (True, False):      # the GPU exact sampler (default) and the fine-step Euler kernel
+        g = m.generate_data(test_num=2, simulator=sim, sim_seed=3, exact=exact)
+        assert g['N'] == 10000 and g['rt'].shape == g['acc'].shape == g['y'].shape == g['participant'].shape == (10000,)
+        assert g['extdata'].shape == (100,) and set(np.unique(g['acc'])) <= {0.0, 0.5, 1.0}
+        assert np.array_equal(g['y'], (2 * g['acc'] - 1) * g['rt']) and np.all(g['rt'] >= np.repeat(g['ndt'], 100))
+        assert abs(np.corrcoef(g['extdata'], g['alpha'])[0, 1]) > 0.7           # sigma = .1 vs sd(alpha) = .17
+        assert abs(g['prop_cog_var'] - 0.03 / 0.04) < 1e-12
+        acc[exact] = g['acc'].reshape(100, 100).mean(1)
+    assert np.corrcoef(acc[True], acc[False])[0, 1] > 0.9                      # same participants, same accuracies
     z = np.load(os.path.join(ROOT, "tests", "golden", "simulratcliff_samples.npz"))
     y = z["participant17_eta__y"]
     alpha, tau, nu, beta, eta, vs = z["participant17_eta__params"]
