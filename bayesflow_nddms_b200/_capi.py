@@ -91,6 +91,7 @@ SIGNATURES = {
     "ddm_set_stream": (C.c_int, [_vp, _vp]),
     "ddm_synchronize": (C.c_int, [_vp]),
     "ddm_set_tuning": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
+    "ddm_set_kernel_variant": (C.c_int, [_vp, C.c_int]),
     "ddm_set_pipeline": (C.c_int, [_vp, C.c_int64, C.c_int64]),
     "ddm_set_host_decode": (C.c_int, [_vp, C.c_int]),
     "ddm_pipeline_chunks": (C.c_int64, [C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int64]),
@@ -113,7 +114,7 @@ SIGNATURES = {
     "ddm_last_output_dlpack": (C.c_int, [_vp, C.POINTER(C.POINTER(DLManagedTensor))]),
     "ddm_last_output_device_ptr": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_size_t)]),
     "ddm_set_normals_debug": (C.c_int, [_vp, _dp, C.c_size_t, C.POINTER(C.c_int64), C.c_int64]),
-    "ddm_export_normals": (C.c_int, [_vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+    "ddm_export_normals": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                      C.c_int, _dp]),
     "ddm_philox4x32": (C.c_int, [_vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int64]),
     "ddm_microbench": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp]),

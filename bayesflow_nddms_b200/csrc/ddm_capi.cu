@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <climits>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -207,6 +208,8 @@ struct ddm_ctx {
 
     // tuning (0 = automatic)
     int tune_threshold = 0, tune_blocks_per_sm = 0, tune_tile = 0;
+    int tune_kernel_variant = 0;  // 0 = tile kernel, 1 = the round-1 persistent kernel (A/B measurements)
+    bool trialwise_degenerate = false;  // last trialwise call: some group has dc == 0 (no noise unit)
     int64_t tune_pipeline_min_rows = -1, tune_pipeline_chunk_rows = -1;  // < 0: default
 };
 
@@ -218,9 +221,15 @@ namespace {
 // takes ~0.27 / dt steps (28 at dt = .01, 258 at dt = .001), hence 164 sqrt(dt).  Measured optima on B200: 5-6 at
 // dt = .001, 12-16 at dt = .01.  (An in-kernel estimate of r was tried: 2 % slower on the sweep.)  Results never
 // depend on the threshold; ddm_set_tuning overrides it.
-int default_refill_threshold(double dt) {
-    const int thr = (int)std::lround(164.0 * std::sqrt(dt));
-    return thr < 2 ? 2 : (thr > 16 ? 16 : thr);
+int default_refill_threshold(double dt, bool legacy = false) {
+    if (legacy) {
+        const int thr = (int)std::lround(164.0 * std::sqrt(dt));
+        return thr < 2 ? 2 : (thr > 16 ? 16 : thr);
+    }
+    // tile kernel: the pass is ~45 issue slots (set-up and output arithmetic moved out of it, done a tile at a time),
+    // so the optimum sits lower: sqrt(37.5 r * 45 / 60) = 74 / sqrt(steps per trial) = 142 sqrt(dt)
+    const int thr = (int)std::lround(142.0 * std::sqrt(dt));
+    return thr < 2 ? 2 : (thr > 14 ? 14 : thr);
 }
 
 int fail(ddm_ctx *ctx, int code, const char *fmt, ...) {
@@ -281,10 +290,25 @@ int build_args(ddm_ctx *ctx, int model, int64_t n_datasets, int64_t n_trials, do
     const bool trialwise = (model == DDM_MODEL_TRIALWISE);
     const int64_t rows = trialwise ? n_trials : n_datasets * n_trials;
     if (n_trials > 0xffffffffLL || n_datasets > 0xffffffffLL) return fail(ctx, DDM_ERR_INVALID, "shape exceeds 2^32");
-    if (dataset_offset + (uint64_t)n_datasets > 0xffffffffULL)
-        return fail(ctx, DDM_ERR_INVALID, "dataset_offset + n_datasets must stay below 2^32 (Philox counter word)");
-    if (trial_offset + (uint64_t)n_trials > 0xffffffffULL)
-        return fail(ctx, DDM_ERR_INVALID, "trial_offset + n_trials must stay below 2^32 (Philox counter word)");
+    // 64-bit global indices: the low 32 bits are a Philox counter word, bits 32..55 ride in the stream word
+    // (PhiloxKey::c3_hi), launch-uniform -- so a launch must not straddle a multiple of 2^32.  For the trialwise
+    // model the 64-bit index is the trial's (dataset word = its high part's low 32 bits is not needed: see below).
+    uint64_t index_hi = 0;
+    if (trialwise) {
+        index_hi = trial_offset >> 32;
+        trial_offset &= 0xffffffffULL;
+        if (dataset_offset != 0) return fail(ctx, DDM_ERR_INVALID, "trialwise runs are keyed by trial_offset only");
+    } else {
+        index_hi = dataset_offset >> 32;
+        dataset_offset &= 0xffffffffULL;
+    }
+    if (index_hi >= (1ULL << 24)) return fail(ctx, DDM_ERR_INVALID, "global dataset / trial index must stay below 2^56");
+    if (dataset_offset + (uint64_t)n_datasets > 0x100000000ULL)
+        return fail(ctx, DDM_ERR_INVALID,
+                    "a launch may not straddle a multiple of 2^32 datasets (dataset_offset mod 2^32 + n_datasets > 2^32): "
+                    "start the batch at the next multiple");
+    if (trial_offset + (uint64_t)n_trials > 0x100000000ULL)
+        return fail(ctx, DDM_ERR_INVALID, "trial_offset mod 2^32 + n_trials must not exceed 2^32 (Philox counter word)");
     if (ctx->dbg_on && ctx->dbg_trials != rows)
         return fail(ctx, DDM_ERR_INVALID, "shared-increment buffer was set for %lld trials, run has %lld",
                     (long long)ctx->dbg_trials, (long long)rows);
@@ -304,7 +328,7 @@ int build_args(ddm_ctx *ctx, int model, int64_t n_datasets, int64_t n_trials, do
     a.n_params = (uint32_t)(trialwise ? 4 : ctx->n_params);
     a.dataset_offset = (uint32_t)dataset_offset;
     a.trial_offset = (uint32_t)trial_offset;
-    a.key = ddm::make_philox_key((uint32_t)seed, (uint32_t)(seed >> 32));
+    a.key = ddm::make_philox_key((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)index_hi);
     a.max_steps = (uint32_t)max_steps;
     a.model = model;
     a.flags = flags;
@@ -313,8 +337,21 @@ int build_args(ddm_ctx *ctx, int model, int64_t n_datasets, int64_t n_trials, do
     return DDM_OK;
 }
 
+// Splits a 64-bit global dataset index into the 32-bit counter word and the launch-uniform high part.
+int split_index(ddm_ctx *ctx, uint64_t offset, int64_t count, uint32_t *lo, uint32_t *hi) {
+    if ((offset >> 32) >= (1ULL << 24)) return fail(ctx, DDM_ERR_INVALID, "global dataset index must stay below 2^56");
+    if ((offset & 0xffffffffULL) + (uint64_t)count > 0x100000000ULL)
+        return fail(ctx, DDM_ERR_INVALID,
+                    "a launch may not straddle a multiple of 2^32 datasets (dataset_offset mod 2^32 + n_datasets > 2^32): "
+                    "start the batch at the next multiple");
+    *lo = (uint32_t)offset;
+    *hi = (uint32_t)(offset >> 32);
+    return DDM_OK;
+}
+
 bool uses_dconst(const ddm_ctx *ctx, int model, int precision) {
-    return precision == 32 && model != DDM_MODEL_TRIALWISE && !ctx->dbg_on;
+    if (model == DDM_MODEL_TRIALWISE) return precision == 32 && !ctx->dbg_on && !ctx->trialwise_degenerate;
+    return precision == 32 && !ctx->dbg_on;
 }
 
 // Enqueue the simulator kernel for the datasets described by `a` (pointers already offset to the
@@ -329,34 +366,53 @@ int launch_sim(ddm_ctx *ctx, ddm::RunArgs &a, int precision, ddm_stats &st, cuda
     const int64_t rows = trialwise ? n_trials : n_datasets * n_trials;
     if (rows == 0) return DDM_OK;
     // OUT_STATE (validation) needs the state at exactly max_steps for timeouts: the generic kernel stops there
-    const bool degenerate = ctx->degenerate_noise && !trialwise;
+    const bool degenerate = trialwise ? ctx->trialwise_degenerate : ctx->degenerate_noise;
     if (degenerate) a.flags |= ddm::FLAG_REFERENCE_ARITHMETIC;
-    const bool persistent = precision == 32 && !ctx->dbg_on && !trialwise && !degenerate &&
-                            !(flags & (DDM_FLAG_FORCE_GENERIC | DDM_FLAG_OUT_STATE));
+    const bool persistent = precision == 32 && !ctx->dbg_on && !degenerate &&
+                            !(flags & (DDM_FLAG_FORCE_GENERIC | DDM_FLAG_OUT_STATE)) && (uint32_t)a.max_steps <= ddm::TILE_MAX_STEPS;
     DDM_CUDA(ctx, cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), stream));
     if (persistent) {
         const int block = ddm::persistent_block_size();
-        int per_sm = ctx->tune_blocks_per_sm;
-        const int max_per_sm = ddm::persistent_max_blocks_per_sm(kind, out64, block);
-        if (max_per_sm <= 0) return fail(ctx, DDM_ERR_CUDA, "occupancy query failed for the persistent kernel");
-        if (per_sm <= 0 || per_sm > max_per_sm) per_sm = max_per_sm;
-        // tile: trials of one dataset handed out per atomic claim.  (Whole-dataset claims measured
-        // 15 % slower on the sweep: per-dataset cost varies 400x, so coarse claims unbalance the tail.)
-        uint32_t tile = ctx->tune_tile > 0 ? (uint32_t)ctx->tune_tile : 64u;
+        const bool legacy = ctx->tune_kernel_variant == 1 && !trialwise;  // round-1 kernel, kept for A/B measurements
+        const uint64_t warps_needed = ((uint64_t)rows + 31) / 32;
+        const uint64_t blocks_needed = (warps_needed + (block / 32) - 1) / (block / 32);
+        // tile: consecutive trials of one dataset handed out per atomic claim (and, in the tile kernel, set up and
+        // written out together).  Large batches use the largest tile the shared-memory buffers allow (fewest
+        // stragglers); small ones shrink it so that every warp of the grid still finds a few tiles.  (Whole-dataset
+        // claims measured 15 % slower on the sweep: per-dataset cost varies 400x, coarse claims unbalance the tail.)
+        const uint32_t tile_max = legacy ? 0x40000000u : ddm::tile_kernel_max_tile(kind);
+        uint32_t tile;
+        if (ctx->tune_tile > 0) {
+            tile = (uint32_t)ctx->tune_tile;
+        } else if (legacy) {
+            tile = 64u;
+        } else {
+            const uint64_t warps_grid = std::min<uint64_t>((uint64_t)ctx->sm_count * 6 * (block / 32), warps_needed);
+            const uint64_t want = (uint64_t)rows / (4 * warps_grid);
+            tile = want >= tile_max ? tile_max : (want <= 32 ? 32u : (uint32_t)want & ~31u);
+        }
+        if (tile > tile_max) tile = tile_max;
         if (tile > (uint32_t)n_trials) tile = (uint32_t)n_trials;
         if (tile == 0) tile = 1;
-        while (((uint64_t)n_trials + tile - 1) / tile * (uint64_t)n_datasets > 0xffffffffULL) tile *= 2;  // 32-bit item index
+        if (legacy)
+            while (((uint64_t)n_trials + tile - 1) / tile * (uint64_t)n_datasets > 0xffffffffULL) tile *= 2;  // 32-bit item index
         a.tile = tile;
         a.tiles_per_dataset = (uint32_t)((n_trials + tile - 1) / tile);
         a.n_items = (uint64_t)a.tiles_per_dataset * (uint64_t)n_datasets;
-        a.refill_threshold = ctx->tune_threshold > 0 ? ctx->tune_threshold : default_refill_threshold(a.dt);
+        if (a.n_items > 0xffffffffULL) return fail(ctx, DDM_ERR_INVALID, "batch too large for one launch (more than 2^32 trial tiles)");
+        a.refill_threshold = ctx->tune_threshold > 0 ? ctx->tune_threshold : default_refill_threshold(a.dt, legacy);
         if (a.refill_threshold > 32) a.refill_threshold = 32;
-        const uint64_t warps_needed = ((uint64_t)rows + 31) / 32;
+        const size_t smem = legacy ? 0 : ddm::tile_kernel_smem_bytes(kind, block);
+        int per_sm = ctx->tune_blocks_per_sm;
+        const int max_per_sm = legacy ? ddm::persistent_max_blocks_per_sm(kind, out64, block)
+                                      : ddm::tile_kernel_max_blocks_per_sm(kind, out64, block, smem);
+        if (max_per_sm <= 0) return fail(ctx, DDM_ERR_CUDA, "occupancy query failed for the persistent kernel");
+        if (per_sm <= 0 || per_sm > max_per_sm) per_sm = max_per_sm;
         uint64_t grid = (uint64_t)ctx->sm_count * per_sm;
-        const uint64_t blocks_needed = (warps_needed + (block / 32) - 1) / (block / 32);
         if (grid > blocks_needed) grid = blocks_needed;
         if (grid < 1) grid = 1;
-        DDM_CUDA(ctx, ddm::launch_persistent(a, kind, out64, (int)grid, block, stream));
+        if (legacy) DDM_CUDA(ctx, ddm::launch_persistent(a, kind, out64, (int)grid, block, stream));
+        else DDM_CUDA(ctx, ddm::launch_tile(a, kind, out64, (int)grid, block, smem, stream));
         st.used_persistent = 1;
         st.grid = (int)grid;
         st.block = block;
@@ -375,7 +431,6 @@ int launch_sim(ddm_ctx *ctx, ddm::RunArgs &a, int precision, ddm_stats &st, cuda
 int run_common(ddm_ctx *ctx, int model, int64_t n_datasets, int64_t n_trials, double dt, int max_steps,
                uint64_t seed, uint64_t dataset_offset, uint64_t trial_offset, int precision, int flags,
                int n_groups) {
-    (void)n_groups;
     ddm::RunArgs a;
     int rc = build_args(ctx, model, n_datasets, n_trials, dt, max_steps, seed, dataset_offset, trial_offset, precision, flags, a);
     if (rc) return rc;
@@ -396,7 +451,11 @@ int run_common(ddm_ctx *ctx, int model, int64_t n_datasets, int64_t n_trials, do
     DDM_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long) * (1 + ddm::STAT_COUNT), ctx->stream));
     if (rows > 0) {
         if (uses_dconst(ctx, model, precision)) {
-            if (model == DDM_MODEL_GENERAL) {
+            if (trialwise) {  // per-participant constants; the boundary comes per trial
+                DDM_CUDA(ctx, ctx->dconst.reserve((size_t)(n_groups > 0 ? n_groups : 1)));
+                a.dconst = ctx->dconst.p;
+                DDM_CUDA(ctx, ddm::launch_prep(ctx->params.p, ctx->dconst.p, (uint32_t)n_groups, 4u, model, dt, ctx->stream));
+            } else if (model == DDM_MODEL_GENERAL) {
                 DDM_CUDA(ctx, ctx->gconst.reserve((size_t)n_datasets));
                 a.gconst = ctx->gconst.p;
                 DDM_CUDA(ctx, ddm::launch_prep_general(ctx->params.p, ctx->gconst.p, (uint32_t)n_datasets, dt, ctx->stream));
@@ -790,6 +849,13 @@ DDM_API int ddm_set_tuning(ddm_ctx *ctx, int refill_threshold, int blocks_per_sm
     return DDM_OK;
 }
 
+DDM_API int ddm_set_kernel_variant(ddm_ctx *ctx, int variant) {
+    if (!ctx) return DDM_ERR_INVALID;
+    if (variant < 0 || variant > 1) return fail(ctx, DDM_ERR_INVALID, "kernel variant must be 0 (tile kernel) or 1 (round-1 persistent kernel)");
+    ctx->tune_kernel_variant = variant;
+    return DDM_OK;
+}
+
 DDM_API int ddm_set_pipeline(ddm_ctx *ctx, int64_t min_rows, int64_t chunk_rows) {
     if (!ctx) return DDM_ERR_INVALID;
     ctx->tune_pipeline_min_rows = min_rows;
@@ -947,14 +1013,53 @@ DDM_API int ddm_simulate_trialwise(ddm_ctx *ctx, const int32_t *group, const dou
     if (!ctx) return DDM_ERR_INVALID;
     if (n < 0 || n_groups < 0) return fail(ctx, DDM_ERR_INVALID, "negative shape");
     if (n > 0 && (!group || !bound || !group_params)) return fail(ctx, DDM_ERR_INVALID, "NULL input");
-    for (int64_t i = 0; i < n; i++) {
-        // imputation_from_stahl_not_scaled.py:124-125 raises ValueError; NaN passes there too (NaN < 0 is False)
-        if (bound[i] < 0) {
-            return fail(ctx, DDM_ERR_NEGATIVE_BOUND, "Trial-level boundary cannot be less than zero (trial %lld: %g)",
-                        (long long)i, bound[i]);
+    {
+        // imputation_from_stahl_not_scaled.py:124-125 raises ValueError; NaN passes there too (NaN < 0 is False).
+        // One pass over the inputs, shared among the host threads for large batches; the first offender is reported.
+        struct Scan {
+            const int32_t *group;
+            const double *bound;
+            int64_t n;
+            int n_groups;
+            std::atomic<int64_t> bad_bound, bad_group;
+        } scan{group, bound, n, n_groups, {INT64_MAX}, {INT64_MAX}};
+        auto slice = [](const void *arg, int id, int nthr) {
+            Scan &sc = *const_cast<Scan *>(static_cast<const Scan *>(arg));
+            const int64_t per = (sc.n + nthr - 1) / nthr, lo = per * id, hi = std::min<int64_t>(sc.n, lo + per);
+            for (int64_t i = lo; i < hi; i++) {
+                if (sc.bound[i] < 0) {
+                    int64_t cur = sc.bad_bound.load(std::memory_order_relaxed);
+                    while (i < cur && !sc.bad_bound.compare_exchange_weak(cur, i)) {}
+                    break;
+                }
+                if (sc.group[i] < 0 || sc.group[i] >= sc.n_groups) {
+                    int64_t cur = sc.bad_group.load(std::memory_order_relaxed);
+                    while (i < cur && !sc.bad_group.compare_exchange_weak(cur, i)) {}
+                    break;
+                }
+            }
+        };
+        if (n >= (1 << 20) && ctx->tune_host_decode >= 0) {
+            int rc = ensure_workers(ctx);
+            if (rc) return rc;
+            ddm::host_workers_run(ctx->workers, slice, &scan);
+        } else {
+            slice(&scan, 0, 1);
         }
-        if (group[i] < 0 || group[i] >= n_groups)
-            return fail(ctx, DDM_ERR_INVALID, "group[%lld] = %d outside [0,%d)", (long long)i, group[i], n_groups);
+        const int64_t bb = scan.bad_bound.load(), bg = scan.bad_group.load();
+        if (bb != INT64_MAX && bb < bg)
+            return fail(ctx, DDM_ERR_NEGATIVE_BOUND, "Trial-level boundary cannot be less than zero (trial %lld: %g)",
+                        (long long)bb, bound[bb]);
+        if (bg != INT64_MAX)
+            return fail(ctx, DDM_ERR_INVALID, "group[%lld] = %d outside [0,%d)", (long long)bg, group[bg], n_groups);
+        if (bb != INT64_MAX)
+            return fail(ctx, DDM_ERR_NEGATIVE_BOUND, "Trial-level boundary cannot be less than zero (trial %lld: %g)",
+                        (long long)bb, bound[bb]);
+    }
+    ctx->trialwise_degenerate = false;
+    for (int gidx = 0; gidx < n_groups; gidx++) {
+        const double dc = group_params[(size_t)gidx * 4 + 3];
+        if (!(dc > 1e-30) || !std::isfinite(dc)) ctx->trialwise_degenerate = true;  // no noise unit: reference formulas
     }
     DeviceGuard g(ctx->device);
     DDM_CUDA(ctx, ctx->group.reserve(n ? (size_t)n : 1));
@@ -978,8 +1083,10 @@ DDM_API int ddm_simulate_exact(ddm_ctx *ctx, const double *params, int64_t n_dat
                                uint64_t dataset_offset, double *out_host) {
     if (!ctx) return DDM_ERR_INVALID;
     if (n_trials < 0 || n_datasets < 0) return fail(ctx, DDM_ERR_INVALID, "negative shape");
-    if (n_trials > 0xffffffffLL || n_datasets > 0xffffffffLL || dataset_offset + (uint64_t)n_datasets > 0xffffffffULL)
+    if (n_trials > 0xffffffffLL || n_datasets > 0xffffffffLL)
         return fail(ctx, DDM_ERR_INVALID, "shape exceeds the 32-bit Philox counter words");
+    uint32_t ds_lo = 0, ds_hi = 0;
+    if (int rc0 = split_index(ctx, dataset_offset, n_datasets, &ds_lo, &ds_hi)) return rc0;
     if (n_datasets > 0 && !params) return fail(ctx, DDM_ERR_INVALID, "params is NULL");
     for (int64_t d = 0; d < n_datasets; d++) {
         const double *p = params + (size_t)d * 8;
@@ -1004,9 +1111,9 @@ DDM_API int ddm_simulate_exact(ddm_ctx *ctx, const double *params, int64_t n_dat
     st.n_trials = (uint64_t)rows;
     DDM_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long) * (1 + ddm::STAT_COUNT), ctx->stream));
     DDM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    const ddm::PhiloxKey key = ddm::make_philox_key((uint32_t)seed, (uint32_t)(seed >> 32));
+    const ddm::PhiloxKey key = ddm::make_philox_key((uint32_t)seed, (uint32_t)(seed >> 32), ds_hi);
     DDM_CUDA(ctx, ddm::launch_exact_sampler(ctx->params.p, static_cast<double *>(ctx->out), ctx->counters + 1, (uint32_t)n_datasets,
-                                            (uint32_t)n_trials, (uint32_t)dataset_offset, 0u, key, ctx->stream));
+                                            (uint32_t)n_trials, ds_lo, 0u, key, ctx->stream));
     if (rows) st.kernel_launches++;
     st.grid = (int)(((uint64_t)rows + 127) / 128);
     st.block = 128;
@@ -1041,8 +1148,10 @@ DDM_API int ddm_simulate_evidence(ddm_ctx *ctx, const double *params, int64_t n_
     if (max_steps < 0 || n_trials < 0 || n_datasets < 0) return fail(ctx, DDM_ERR_INVALID, "negative argument");
     if (n_obs < 1 || n_obs > 32 * 6 * 4) return fail(ctx, DDM_ERR_INVALID, "n_obs must be in [1, 768], got %d", n_obs);
     if (standardize < 0 || standardize > 2) return fail(ctx, DDM_ERR_INVALID, "standardize must be 0, 1 or 2");
-    if (n_trials > 0xffffffffLL || n_datasets > 0xffffffffLL || dataset_offset + (uint64_t)n_datasets > 0xffffffffULL)
+    if (n_trials > 0xffffffffLL || n_datasets > 0xffffffffLL)
         return fail(ctx, DDM_ERR_INVALID, "shape exceeds the 32-bit Philox counter words");
+    uint32_t ds_lo = 0, ds_hi = 0;
+    if (int rc0 = split_index(ctx, dataset_offset, n_datasets, &ds_lo, &ds_hi)) return rc0;
     if (n_datasets > 0 && !params) return fail(ctx, DDM_ERR_INVALID, "params is NULL");
     const int64_t rows = n_datasets * n_trials;
     if (ctx->dbg_on && precision != 64) return fail(ctx, DDM_ERR_INVALID, "shared-increment mode needs precision 64 for the evidence model");
@@ -1082,12 +1191,12 @@ DDM_API int ddm_simulate_evidence(ddm_ctx *ctx, const double *params, int64_t n_
     a.tiles_per_dataset = (uint32_t)((n_trials + 31) / 32);
     a.n_items = (uint64_t)a.tiles_per_dataset * (uint64_t)n_datasets;
     if (a.n_items > 0xffffffffULL) return fail(ctx, DDM_ERR_INVALID, "too many trial tiles for one launch");
-    a.dataset_offset = (uint32_t)dataset_offset;
+    a.dataset_offset = ds_lo;
     a.trial_offset = 0;
     a.max_steps = (uint32_t)max_steps;
     a.mode = standardize;
     a.flags = flags;
-    a.key = ddm::make_philox_key((uint32_t)seed, (uint32_t)(seed >> 32));
+    a.key = ddm::make_philox_key((uint32_t)seed, (uint32_t)(seed >> 32), ds_hi);
     a.dt = dt;
     a.sqrt_dt = std::sqrt(dt);
     if (standardize == 2) {
@@ -1307,7 +1416,7 @@ DDM_API int ddm_set_normals_debug(ddm_ctx *ctx, const double *z, size_t n, const
     return DDM_OK;
 }
 
-DDM_API int ddm_export_normals(ddm_ctx *ctx, uint64_t seed, uint32_t dataset, uint32_t trial, uint32_t stream,
+DDM_API int ddm_export_normals(ddm_ctx *ctx, uint64_t seed, uint64_t dataset, uint32_t trial, uint32_t stream,
                                uint32_t first, uint32_t count, int precision, double *out_host) {
     if (!ctx) return DDM_ERR_INVALID;
     if (precision != 32 && precision != 64) return fail(ctx, DDM_ERR_INVALID, "precision must be 32 or 64");
@@ -1316,8 +1425,10 @@ DDM_API int ddm_export_normals(ddm_ctx *ctx, uint64_t seed, uint32_t dataset, ui
     if (!out_host) return fail(ctx, DDM_ERR_INVALID, "out_host is NULL");
     DeviceGuard g(ctx->device);
     DDM_CUDA(ctx, ctx->export_buf.reserve(count));
-    const ddm::PhiloxKey key = ddm::make_philox_key((uint32_t)seed, (uint32_t)(seed >> 32));
-    DDM_CUDA(ctx, ddm::launch_export_normals(key, dataset, trial, stream, first, count, precision == 64, ctx->export_buf.p, ctx->stream));
+    if ((dataset >> 32) >= (1ULL << 24)) return fail(ctx, DDM_ERR_INVALID, "global dataset index must stay below 2^56");
+    const ddm::PhiloxKey key = ddm::make_philox_key((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)(dataset >> 32));
+    DDM_CUDA(ctx, ddm::launch_export_normals(key, (uint32_t)dataset, trial, stream, first, count, precision == 64, ctx->export_buf.p,
+                                             ctx->stream));
     DDM_CUDA(ctx, cudaMemcpyAsync(out_host, ctx->export_buf.p, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     DDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return DDM_OK;

@@ -227,7 +227,9 @@ __global__ void evidence_dataset_stats_kernel(const double *__restrict__ path_me
 // scratch (fp64 rows) or the output itself (in place) -> output dtype, applying mode 2's dataset-level
 // standardisation to the path columns
 template <typename Src, typename Dst>
-__global__ void evidence_finalize_kernel(const Src *__restrict__ src, Dst *__restrict__ dst,
+// src and dst may be the same buffer (mode 2 standardises the production rows in place: each thread reads and
+// writes its own element only), so neither is __restrict__.
+__global__ void evidence_finalize_kernel(const Src *src, Dst *dst,
                                          const double *__restrict__ ds_stats, uint64_t total, uint32_t cols,
                                          uint32_t n_trials, int standardize) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

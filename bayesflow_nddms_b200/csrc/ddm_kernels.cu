@@ -40,6 +40,12 @@ __global__ void prep_kernel(const double *__restrict__ params, DsConst *__restri
         c.v[2] = (float)(0.5 * p[1] / U);
         c.v[3] = (float)U;
         c.v[4] = (float)(p[4] * dt / U);
+    } else if (model == 5) {  // trialwise groups: [drift, beta, ter, dc] in the BOUND layout (boundary supplied per trial)
+        const double U = unit1 * p[3];
+        c.v[0] = (float)(p[0] * dt / U);
+        c.v[1] = (float)((p[1] - 0.5) / U);
+        c.v[4] = (float)(0.5 / U);
+        c.v[7] = (float)U;
     } else if (model == 2) {  // alt: [drift, alpha, beta, ter, std_dc, mu_dc, sigma1]
         c.v[0] = (float)(p[0] * dt / unit1);
         c.v[1] = (float)(p[1] * (p[2] - 0.5) / unit1);
@@ -328,6 +334,348 @@ __global__ void __launch_bounds__(DDM_PERSISTENT_BLOCK, RECORD ? (1024 / DDM_PER
     }
 }
 
+
+// --------------------------------------------------------------------------------
+// tile kernel (production)
+// --------------------------------------------------------------------------------
+// The persistent kernel above pays for every finished trial inside the divergent finish + refill pass: the
+// per-trial set-up (an aux Philox block, three Box-Muller pairs, the redraw loop) and the fp64 output arithmetic
+// run with only the refilled lanes active.  At the reference's own dt = .01 a trial lasts ~7 blocks and that
+// pass was more than half of all instructions (round 1: 39 lane-instructions per Euler step against 17 in the
+// stepping loop).  Here both ends of a trial are done a whole tile at a time with all 32 lanes busy:
+//   claim    a warp claims a tile of <= tile_cap consecutive trials of one dataset and sets all of them up at
+//            once (lane i takes trials i, i + 32, ...), staging each trial's start state (x0, h, c0) and its
+//            external columns in shared memory (north_star: "per-dataset parameters staged in shared memory");
+//   refill   a lane that needs a trial takes the tile's next one: two or three LDS;
+//   finish   a finished lane parks (steps << 2 | choice + 1) in the tile's result slot: one STS;
+//   flush    when the tile's last trial has finished the warp turns the 4-byte results into output rows --
+//            fp64 arithmetic of the reference, lane-contiguous vector stores.
+// A warp works on two tiles at a time (the one being handed out and the previous one, draining).  When a third
+// is claimed while the oldest still has trials running (first-passage times are heavy-tailed), that tile is
+// flushed as far as it has got and its stragglers write their own rows when they finish ("direct").
+// Philox counters, set-up and step arithmetic are those of the generic kernel: results are bit-identical.
+constexpr uint32_t SLOT_EMPTY = 0xffffffffu;   // the lane holds no trial
+constexpr uint32_t SLOT_DIRECT = 0xfffffffeu;  // its tile's buffer was recycled: the lane emits its own row
+constexpr uint32_t CODE_PENDING = 0xffffffffu; // result slot of a trial that has not finished (choice + 1 is never 3)
+
+template <int KIND>
+struct TileLayout {
+    static constexpr bool XH = KIND == KIND_BOUND || KIND == KIND_DC || KIND == KIND_GENERAL || KIND == KIND_TRIALWISE;
+    static constexpr bool C0 = KIND == KIND_DC || KIND == KIND_GENERAL || KIND == KIND_DRIFT || KIND == KIND_TRIALWISE;
+    static constexpr bool EXT = KIND == KIND_BOUND || KIND == KIND_DC || KIND == KIND_GENERAL;
+    static constexpr bool EXT2 = KIND == KIND_GENERAL;
+    // 32-bit words per tile slot: result codes and external columns are double-buffered, the start state is not
+    static constexpr uint32_t WORDS = 2u + (XH ? 2u : 0u) + (C0 ? 1u : 0u) + (EXT ? 2u : 0u) + (EXT2 ? 2u : 0u);
+    // slots per tile buffer, a compile-time constant so that every buffer is the warp's base address plus an
+    // immediate: the largest tile that still leaves room for six resident blocks of eight warps per SM
+    static constexpr uint32_t T = WORDS <= 7u ? 128u : 96u;
+};
+
+template <bool OUT64>
+__device__ __forceinline__ void store_col(void *out, uint64_t at, double v) {
+    if (OUT64) reinterpret_cast<double *>(out)[at] = v;
+    else reinterpret_cast<float *>(out)[at] = (float)v;
+}
+
+struct TileStats {
+    unsigned long long steps;
+    uint32_t timeouts, upper;
+};
+
+// Per-warp bookkeeping lives in shared memory next to the tile buffers (registers are for the stepping loop):
+// the two tiles' identities and outstanding-trial counts, and the warp's statistics.
+enum TileMeta : uint32_t {
+    M_CDS = 0, M_CFIRST, M_CCOUNT, M_CLEFT,   // current tile: dataset, first trial, trials, trials not finished
+    M_ODS, M_OFIRST, M_OCOUNT, M_OLEFT,       // the tile before it (draining)
+    M_STEPS = 8,                              // 64-bit, two words
+    M_TIMEOUTS = 10, M_UPPER, M_CAP,
+    M_WORDS = 16
+};
+
+// One finished trial -> its output row.  COLS: 0 = the whole row; 1 = only the columns that depend on the
+// trial's outcome (a straggler whose external columns the partial flush has already written).
+template <int KIND, bool OUT64, int COLS>
+__device__ __forceinline__ void tile_emit(const RunArgs &a, uint64_t idx, uint32_t c, uint32_t ds, float ext, float ext2,
+                                          TileStats &st) {
+    constexpr bool BASIC = (KIND == KIND_FIXED || KIND == KIND_DRIFT);
+    const uint32_t n = c >> 2;
+    const int choice = (int)(c & 3u) - 1;
+    double o0, o1;
+    if (KIND == KIND_GENERAL) {
+        const double tau = a.params[(size_t)ds * a.n_params + 7];
+        if (a.gconst[ds].v[21] == 0.f) {  // (rt, choice, ext1)
+            trial_outputs<true>(a.flags, choice, n, a.dt, tau, 0.0, o0, o1);
+            store_col<OUT64>(a.out, 3 * idx, o0);
+            store_col<OUT64>(a.out, 3 * idx + 1, o1);
+            if (COLS == 0) store_col<OUT64>(a.out, 3 * idx + 2, (double)ext);
+        } else {                          // (signed rt, ext1, ext2)
+            trial_outputs<false>(a.flags, choice, n, a.dt, tau, 0.0, o0, o1);
+            store_col<OUT64>(a.out, 3 * idx, o0);
+            if (COLS == 0) {
+                store_col<OUT64>(a.out, 3 * idx + 1, (double)ext);
+                store_col<OUT64>(a.out, 3 * idx + 2, (double)ext2);
+            }
+        }
+    } else if (a.flags & FLAG_WIRE_COMPACT) {  // chunked host pipeline: the host writes the rows (ddm_wire.cpp)
+        if (BASIC) reinterpret_cast<int32_t *>(a.out)[idx] = (int32_t)c;
+        else if (COLS == 0) reinterpret_cast<int2 *>(a.out)[idx] = make_int2((int32_t)c, __float_as_int(ext));
+        else reinterpret_cast<int32_t *>(a.out)[2 * idx] = (int32_t)c;
+    } else {
+        double tau, e = (double)ext;
+        if (KIND == KIND_TRIALWISE) {
+            tau = a.params[(size_t)a.group[idx] * 4 + 2];
+            e = a.bound_in[idx];
+        } else {
+            tau = a.params[(size_t)ds * a.n_params + 3];
+        }
+        trial_outputs<BASIC>(a.flags, choice, n, a.dt, tau, e, o0, o1);
+        if (BASIC || COLS == 0) store_pair<OUT64>(a.out, idx, o0, o1);
+        else store_col<OUT64>(a.out, 2 * idx, o0);
+    }
+    if (a.steps_out) a.steps_out[idx] = (int32_t)n;
+    st.steps += n;
+    st.timeouts += (choice == 0);
+    st.upper += (choice > 0);
+}
+
+// The external columns of a trial that is still running when its tile's buffer is recycled.
+template <int KIND, bool OUT64>
+__device__ __forceinline__ void tile_emit_ext_only(const RunArgs &a, uint64_t idx, uint32_t ds, float ext, float ext2) {
+    if (KIND == KIND_GENERAL) {
+        if (a.gconst[ds].v[21] == 0.f) {
+            store_col<OUT64>(a.out, 3 * idx + 2, (double)ext);
+        } else {
+            store_col<OUT64>(a.out, 3 * idx + 1, (double)ext);
+            store_col<OUT64>(a.out, 3 * idx + 2, (double)ext2);
+        }
+    } else if (KIND == KIND_TRIALWISE) {
+        store_col<OUT64>(a.out, 2 * idx + 1, a.bound_in[idx]);
+    } else if (KIND == KIND_BOUND || KIND == KIND_DC) {
+        if (a.flags & FLAG_WIRE_COMPACT) reinterpret_cast<int32_t *>(a.out)[2 * idx + 1] = __float_as_int(ext);
+        else store_col<OUT64>(a.out, 2 * idx + 1, (double)ext);
+    }
+}
+
+// All 32 lanes: the rows of the tile described by meta[0..2] (dataset, first trial, trials) from its result
+// slots, statistics into the warp's counters.  partial: trials whose slot is still CODE_PENDING get their
+// external columns only (they will write the rest themselves when they finish).
+template <int KIND, bool OUT64>
+__device__ __forceinline__ void tile_flush(const RunArgs &a, const uint32_t *code, const float *ext, const float *ext2,
+                                        uint32_t *stats, uint32_t ds, uint32_t first, uint32_t count, bool partial) {
+    using L = TileLayout<KIND>;
+    TileStats st{0ull, 0u, 0u};
+    const unsigned lane = threadIdx.x & 31u;
+    const uint64_t idx0 = (uint64_t)ds * a.n_trials + first;
+    for (uint32_t i = lane; i < count; i += 32u) {
+        const uint32_t c = code[i];
+        const float e1 = L::EXT ? ext[i] : 0.f, e2 = L::EXT2 ? ext2[i] : 0.f;
+        if (c != CODE_PENDING) tile_emit<KIND, OUT64, 0>(a, idx0 + i, c, ds, e1, e2, st);
+        else if (partial) tile_emit_ext_only<KIND, OUT64>(a, idx0 + i, ds, e1, e2);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        st.steps += __shfl_xor_sync(FULL_MASK, st.steps, o);
+        st.timeouts += __shfl_xor_sync(FULL_MASK, st.timeouts, o);
+        st.upper += __shfl_xor_sync(FULL_MASK, st.upper, o);
+    }
+    if (lane == 0) {
+        *reinterpret_cast<unsigned long long *>(stats) += st.steps;
+        stats[M_TIMEOUTS - M_STEPS] += st.timeouts;
+        stats[M_UPPER - M_STEPS] += st.upper;
+    }
+    __syncwarp();
+}
+
+// Resident blocks per SM: the kinds whose tile set-up draws normals (a Philox block and three Box-Muller pairs live
+// next to the stepping state) get 48 registers and five blocks; at 40 registers ptxas spilled a loop-carried
+// register of the stepping loop.  (Round 1 measured 5 x 48 equal to 6 x 40 on the sweep.)
+template <int KIND>
+constexpr int tile_min_blocks() {
+    return (KIND == KIND_BOUND || KIND == KIND_DC || KIND == KIND_GENERAL) ? (1280 / DDM_PERSISTENT_BLOCK) : DDM_PERSISTENT_MIN_BLOCKS;
+}
+
+template <int KIND, bool OUT64>
+__global__ void __launch_bounds__(DDM_PERSISTENT_BLOCK, tile_min_blocks<KIND>()) tile_kernel(const __grid_constant__ RunArgs a) {
+    using L = TileLayout<KIND>;
+    extern __shared__ uint32_t tile_smem[];
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    constexpr uint32_t T = L::T;
+    uint32_t *meta = tile_smem + (threadIdx.x >> 5) * (L::WORDS * T + M_WORDS);
+    uint32_t *code = meta + M_WORDS;                                      // [2][T] result slots
+    float *sext = reinterpret_cast<float *>(code + 2u * T);               // [2][T] external column (EXT)
+    float *sext2 = sext + (L::EXT ? 2u * T : 0u);                         // [2][T] second external column (EXT2)
+    float *sx = sext2 + (L::EXT2 ? 2u * T : 0u);                          // [T] staged start state of the current tile
+    float *sh = sx + (L::XH ? T : 0u);
+    float *sc0 = sh + (L::XH ? T : 0u);
+    if (lane < M_WORDS) meta[lane] = 0u;
+    __syncwarp();
+
+    // warp-uniform registers: hand-out cursor of the current tile (slot indices), its buffer
+    uint32_t ci = 0, cn = 0, cb = 0;
+    bool more = true;
+    DsConst tile_c;
+#pragma unroll
+    for (int i = 0; i < 8; i++) tile_c.v[i] = 0.f;
+
+    // per-lane trial
+    float x = 0.f, h = 0.f, c0 = 0.f;
+    uint32_t n = 0, blk = 0, trial = 0, ds = 0, p = 0;
+    uint32_t slot = SLOT_EMPTY;  // buffer * T + index within the tile, or SLOT_EMPTY / SLOT_DIRECT
+
+    const int thr = a.refill_threshold;
+
+    for (;;) {
+        // ---- finish: park the results of frozen lanes, flush tiles that are complete ---------------------
+        {
+            const bool fin = (slot != SLOT_EMPTY) && (p == 0u);
+            if (__any_sync(FULL_MASK, fin)) {
+                bool in_cur = false, in_old = false;
+                if (fin) {
+                    int choice = (x >= h) ? 1 : ((x <= -h) ? -1 : 0);
+                    // lanes always run whole 6-step blocks; a trial still inside the boundaries after max_steps
+                    // steps is a timeout whatever it did in the surplus steps of its last block
+                    if (n > a.max_steps) { n = a.max_steps; choice = 0; }
+                    const uint32_t c = (uint32_t)wire_pack(n, choice);
+                    if (slot == SLOT_DIRECT) {
+                        TileStats st{0ull, 0u, 0u};
+                        tile_emit<KIND, OUT64, 1>(a, (uint64_t)ds * a.n_trials + trial, c, ds, 0.f, 0.f, st);
+                        atomicAdd(reinterpret_cast<unsigned long long *>(meta + M_STEPS), st.steps);
+                        if (st.timeouts) atomicAdd(meta + M_TIMEOUTS, st.timeouts);
+                        if (st.upper) atomicAdd(meta + M_UPPER, st.upper);
+                    } else {
+                        code[slot] = c;
+                        in_cur = (slot >= T) == (cb != 0u);
+                        in_old = !in_cur;
+                    }
+                    slot = SLOT_EMPTY;
+                }
+                const uint32_t c_left = meta[M_CLEFT] - __popc(__ballot_sync(FULL_MASK, in_cur));
+                const uint32_t o_left = meta[M_OLEFT] - __popc(__ballot_sync(FULL_MASK, in_old));
+                const uint32_t c_count = meta[M_CCOUNT], o_count = meta[M_OCOUNT];
+                __syncwarp();
+                if (lane == 0) { meta[M_CLEFT] = c_left; meta[M_OLEFT] = o_left; }
+                if (o_count != 0u && o_left == 0u) {
+                    const uint32_t ob = (cb ^ 1u) * T;
+                    tile_flush<KIND, OUT64>(a, code + ob, sext + ob, sext2 + ob, meta + M_STEPS, meta[M_ODS], meta[M_OFIRST], o_count, false);
+                    if (lane == 0) meta[M_OCOUNT] = 0u;
+                }
+                if (c_count != 0u && c_left == 0u) {
+                    const uint32_t nb = cb * T;
+                    tile_flush<KIND, OUT64>(a, code + nb, sext + nb, sext2 + nb, meta + M_STEPS, meta[M_CDS], meta[M_CFIRST], c_count, false);
+                    if (lane == 0) meta[M_CCOUNT] = 0u;
+                }
+                __syncwarp();
+            }
+        }
+        // ---- refill: hand out trials of the current tile, claiming (and setting up) tiles as needed --------
+        for (;;) {
+            const unsigned empty = __ballot_sync(FULL_MASK, slot == SLOT_EMPTY);
+            if (empty == 0u) break;
+            if (ci == cn) {
+                if (!more) break;
+                unsigned long long w = 0;
+                if (lane == 0) w = atomicAdd(a.work_counter, 1ull);
+                w = __shfl_sync(FULL_MASK, w, 0);
+                if (w >= a.n_items) { more = false; break; }
+                // the buffer the new tile goes into still belongs to the old tile if that has stragglers: write out
+                // what it has; the stragglers emit their own rows from now on
+                const uint32_t o_count = meta[M_OCOUNT];
+                if (o_count != 0u) {
+                    const uint32_t ob = (cb ^ 1u) * T;
+                    tile_flush<KIND, OUT64>(a, code + ob, sext + ob, sext2 + ob, meta + M_STEPS, meta[M_ODS], meta[M_OFIRST], o_count, true);
+                    if (slot < SLOT_DIRECT && ((slot >= T) != (cb != 0u))) slot = SLOT_DIRECT;
+                }
+                cb ^= 1u;
+                uint32_t c_ds, ti = 0;
+                if (a.tiles_per_dataset == 1u) {  // a claim is a whole dataset, no division
+                    c_ds = (uint32_t)w;
+                } else {
+                    c_ds = (uint32_t)w / a.tiles_per_dataset;  // host keeps n_items < 2^32
+                    ti = (uint32_t)w - c_ds * a.tiles_per_dataset;
+                }
+                const uint32_t c_first = ti * a.tile;
+                cn = min(a.tile, a.n_trials - c_first);
+                ci = 0;
+                if (lane < 4u) meta[M_ODS + lane] = meta[M_CDS + lane];   // the current tile becomes the draining one
+                __syncwarp();
+                if (lane == 0) {
+                    meta[M_CDS] = c_ds; meta[M_CFIRST] = c_first; meta[M_CCOUNT] = cn; meta[M_CLEFT] = cn;
+                }
+                if (KIND != KIND_GENERAL && KIND != KIND_TRIALWISE) {
+                    const float4 *src = reinterpret_cast<const float4 *>(a.dconst + c_ds);
+                    const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
+                    tile_c.v[0] = v0.x; tile_c.v[1] = v0.y; tile_c.v[2] = v0.z; tile_c.v[3] = v0.w;
+                    tile_c.v[4] = v1.x; tile_c.v[5] = v1.y; tile_c.v[6] = v1.z; tile_c.v[7] = v1.w;
+                }
+                // set the whole tile up, all lanes busy
+                const uint32_t nb = cb * T;
+                uint32_t cap_hits = 0;
+                for (uint32_t i = lane; i < cn; i += 32u) {
+                    if (KIND != KIND_FIXED) {
+                        TrialF32 t;
+                        t.x = 0.f; t.h = 0.f; t.c0 = 0.f; t.u = 0.f; t.ext = 0.f; t.ext2 = 0.f;
+                        if (KIND == KIND_GENERAL) {
+                            trial_setup_general(a.gconst[c_ds], c_first + i + a.trial_offset, c_ds + a.dataset_offset, a.key, t, cap_hits);
+                        } else if (KIND == KIND_TRIALWISE) {
+                            const uint64_t g = (uint64_t)c_first + i;
+                            trial_setup_trialwise(a.dconst[a.group[g]], (float)a.bound_in[g], t);
+                        } else {
+                            trial_setup_f32<KIND>(tile_c, c_first + i + a.trial_offset, c_ds + a.dataset_offset, a.key, t, cap_hits);
+                        }
+                        if (L::XH) { sx[i] = t.x; sh[i] = t.h; }
+                        if (L::C0) sc0[i] = t.c0;
+                        if (L::EXT) sext[nb + i] = t.ext;
+                        if (L::EXT2) sext2[nb + i] = t.ext2;
+                    }
+                    code[nb + i] = CODE_PENDING;
+                }
+                if (cap_hits) atomicAdd(meta + M_CAP, cap_hits);
+                __syncwarp();
+            }
+            const uint32_t rank = __popc(empty & lt_mask);
+            const uint32_t avail = cn - ci;
+            if (slot == SLOT_EMPTY && rank < avail) {
+                const uint32_t i = ci + rank;
+                slot = cb * T + i;
+                ds = meta[M_CDS];
+                trial = meta[M_CFIRST] + i;
+                x = L::XH ? sx[i] : tile_c.v[1];
+                h = L::XH ? sh[i] : tile_c.v[2];
+                c0 = L::C0 ? sc0[i] : tile_c.v[0];
+                n = 0;
+                blk = 0;
+                p = ((fabsf(x) < h) && (a.max_steps > 0u)) ? 1u : 0u;
+            }
+            ci += min((uint32_t)__popc(empty), avail);
+        }
+        if (__all_sync(FULL_MASK, slot == SLOT_EMPTY)) break;
+        // once the work has run out there is nothing to refill with: run the warp's last trials to the end
+        const int thr_now = (more || ci != cn) ? thr : 32;
+
+        // ---- step: tight, branch-free inner loop (round keys and constants stay in uniform registers)
+        __syncwarp();
+        unsigned alive = __ballot_sync(FULL_MASK, p != 0u);
+        const int live_min = 32 - thr_now;  // keep stepping while more than this many lanes are alive
+        do {
+            Normals6Scaled z;
+            philox_pairs_lg2(blk, trial + a.trial_offset, ds + a.dataset_offset, STREAM_STEP, a.key, z);
+            euler6_warp(x, n, alive, c0, h, z, a.max_steps);
+            blk++;
+        } while (__popc(alive) > live_min);
+        p = (alive >> lane) & 1u;
+    }
+
+    // ---- per-warp statistics --------------------------------------------------------
+    __syncwarp();
+    if (lane == 0) {
+        atomicAdd(a.stats + STAT_STEPS, *reinterpret_cast<unsigned long long *>(meta + M_STEPS));
+        atomicAdd(a.stats + STAT_TIMEOUTS, (unsigned long long)meta[M_TIMEOUTS]);
+        atomicAdd(a.stats + STAT_UPPER, (unsigned long long)meta[M_UPPER]);
+        if (meta[M_CAP]) atomicAdd(a.stats + STAT_REJECT_CAP, (unsigned long long)meta[M_CAP]);
+    }
+}
+
 // --------------------------------------------------------------------------------
 // generic kernel: one thread per trial
 // --------------------------------------------------------------------------------
@@ -364,17 +712,21 @@ __global__ void __launch_bounds__(128) generic_kernel(const RunArgs a, uint64_t 
         int choice = 0;
         double ext = 0.0, final_ev = 0.0;
 
-        if (sizeof(Real) == 4 && !BUFFER && KIND != KIND_TRIALWISE && !(a.flags & FLAG_REFERENCE_ARITHMETIC)) {
+        if (sizeof(Real) == 4 && !BUFFER && !(a.flags & FLAG_REFERENCE_ARITHMETIC)) {
             // ---- fp32 / Philox: the persistent kernel's arithmetic, naive scheduling ----
-            const DsConst dc = a.dconst[ds];
             TrialF32 t;
-            trial_setup_f32<(KIND == KIND_TRIALWISE ? KIND_FIXED : KIND)>(dc, trial_g, ds_g, a.key, t, cap);
+            if (KIND == KIND_TRIALWISE) {
+                trial_setup_trialwise(a.dconst[a.group[g]], (float)a.bound_in[g], t);
+            } else {
+                const DsConst dc = a.dconst[ds];
+                trial_setup_f32<(KIND == KIND_TRIALWISE ? KIND_FIXED : KIND)>(dc, trial_g, ds_g, a.key, t, cap);
+            }
             float x = t.x;
             uint32_t p = ((fabsf(x) < t.h) && (a.max_steps > 0u)) ? 1u : 0u;
             for (uint32_t blk = 0; p != 0u; blk++)
                 step_block_f32<true>(blk, trial_g, ds_g, a.key, t, x, n, p, a.max_steps);
             choice = (x >= t.h) ? 1 : ((x <= -t.h) ? -1 : 0);
-            ext = (double)t.ext;
+            ext = (KIND == KIND_TRIALWISE) ? a.bound_in[g] : (double)t.ext;
             final_ev = (double)__fmul_rn(__fadd_rn(x, t.h), t.u);
         } else {
             // ---- reference arithmetic in Real (fp64: the reference's exact operation order;
@@ -648,6 +1000,67 @@ cudaError_t launch_persistent(const RunArgs &a, int kind, bool out64, int grid, 
     case KIND_GENERAL: return launch_persistent_kind<KIND_GENERAL>(a, out64, grid, block, s);
     default: return cudaErrorInvalidValue;
     }
+}
+
+template <int KIND>
+static cudaError_t launch_tile_kind(const RunArgs &a, bool out64, int grid, int block, size_t smem, cudaStream_t s) {
+    // the tile buffers want most of the SM's 228 KB as shared memory (6 blocks x up to 28 KB)
+    static bool configured[2] = {false, false};
+    if (!configured[out64 ? 1 : 0]) {
+        cudaError_t e = out64 ? cudaFuncSetAttribute(tile_kernel<KIND, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                     cudaSharedmemCarveoutMaxShared)
+                              : cudaFuncSetAttribute(tile_kernel<KIND, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                     cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        configured[out64 ? 1 : 0] = true;
+    }
+    if (out64) tile_kernel<KIND, true><<<grid, block, smem, s>>>(a);
+    else tile_kernel<KIND, false><<<grid, block, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tile(const RunArgs &a, int kind, bool out64, int grid, int block, size_t smem, cudaStream_t s) {
+    switch (kind) {
+    case KIND_FIXED: return launch_tile_kind<KIND_FIXED>(a, out64, grid, block, smem, s);
+    case KIND_BOUND: return launch_tile_kind<KIND_BOUND>(a, out64, grid, block, smem, s);
+    case KIND_DC: return launch_tile_kind<KIND_DC>(a, out64, grid, block, smem, s);
+    case KIND_TRIALWISE: return launch_tile_kind<KIND_TRIALWISE>(a, out64, grid, block, smem, s);
+    case KIND_DRIFT: return launch_tile_kind<KIND_DRIFT>(a, out64, grid, block, smem, s);
+    case KIND_GENERAL: return launch_tile_kind<KIND_GENERAL>(a, out64, grid, block, smem, s);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+template <int KIND>
+static size_t tile_smem_of(int block) {
+    return (size_t)(block / 32) * ((size_t)TileLayout<KIND>::WORDS * TileLayout<KIND>::T + M_WORDS) * sizeof(uint32_t);
+}
+
+size_t tile_kernel_smem_bytes(int kind, int block) {
+    switch (kind) {
+    case KIND_FIXED: return tile_smem_of<KIND_FIXED>(block);
+    case KIND_BOUND: return tile_smem_of<KIND_BOUND>(block);
+    case KIND_DC: return tile_smem_of<KIND_DC>(block);
+    case KIND_TRIALWISE: return tile_smem_of<KIND_TRIALWISE>(block);
+    case KIND_DRIFT: return tile_smem_of<KIND_DRIFT>(block);
+    default: return tile_smem_of<KIND_GENERAL>(block);
+    }
+}
+
+uint32_t tile_kernel_max_tile(int kind) { return kind == KIND_GENERAL ? TileLayout<KIND_GENERAL>::T : 128u; }
+
+int tile_kernel_max_blocks_per_sm(int kind, bool out64, int block, size_t smem) {
+    int nb = 0;
+    cudaError_t e = cudaErrorInvalidValue;
+#define DDM_OCC(K, O) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tile_kernel<K, O>, block, smem)
+    if (kind == KIND_FIXED) { if (out64) DDM_OCC(KIND_FIXED, true); else DDM_OCC(KIND_FIXED, false); }
+    else if (kind == KIND_BOUND) { if (out64) DDM_OCC(KIND_BOUND, true); else DDM_OCC(KIND_BOUND, false); }
+    else if (kind == KIND_DC) { if (out64) DDM_OCC(KIND_DC, true); else DDM_OCC(KIND_DC, false); }
+    else if (kind == KIND_TRIALWISE) { if (out64) DDM_OCC(KIND_TRIALWISE, true); else DDM_OCC(KIND_TRIALWISE, false); }
+    else if (kind == KIND_DRIFT) { if (out64) DDM_OCC(KIND_DRIFT, true); else DDM_OCC(KIND_DRIFT, false); }
+    else if (kind == KIND_GENERAL) { if (out64) DDM_OCC(KIND_GENERAL, true); else DDM_OCC(KIND_GENERAL, false); }
+#undef DDM_OCC
+    return (e == cudaSuccess) ? nb : -1;
 }
 
 static size_t record_smem_bytes(int block) { return (size_t)block * (REC_RING + 1) * sizeof(float); }

@@ -39,6 +39,7 @@ struct __align__(16) GenConst {
     float v[24];
 };
 
+constexpr uint32_t TILE_MAX_STEPS = (1u << 30) - 1u;  // tile kernel: a trial's result is (steps << 2 | choice + 1) in 32 bits
 constexpr int REJECT_CAP_BLOCKS = 1024;  // ~6000 candidates before giving up on a redraw loop
 
 struct RunArgs {
@@ -146,6 +147,18 @@ __device__ __forceinline__ void trial_setup_f32(const DsConst &dc, uint32_t tria
         t.u = __fmul_rn(dc.v[7], latent);
         t.ext = __fmaf_rn(dc.v[5], z_ext, latent);
     }
+}
+
+// KIND_TRIALWISE (imputation_from_stahl_not_scaled.py:120-148): the boundary is supplied, the constants are the
+// trial's participant's (BOUND layout: c0, (beta-.5)/U, -, -, .5/U, -, -, U).  bound == 0 gives h = x = 0: no step
+// is taken and x >= h reports the upper boundary, as the reference does (ev >= bound_trial -> +ter).
+__device__ __forceinline__ void trial_setup_trialwise(const DsConst &gc, float bound, TrialF32 &t) {
+    t.c0 = gc.v[0];
+    t.h = __fmul_rn(gc.v[4], bound);
+    t.x = __fmul_rn(bound, gc.v[1]);
+    t.u = gc.v[7];
+    t.ext = bound;
+    t.ext2 = 0.f;
 }
 
 // KIND_GENERAL: aux stream normal 0 = z_ext1, 1 = z_ext2, 2 = z_drift, boundary candidate i = 4 + 2i,
@@ -339,6 +352,11 @@ cudaError_t launch_prior(double *params, int prior, uint32_t n_params, uint64_t 
 cudaError_t launch_prep(const double *params, DsConst *dconst, uint32_t n_datasets, uint32_t n_params,
                         int model, double dt, cudaStream_t s);
 cudaError_t launch_persistent(const RunArgs &a, int kind, bool out64, int grid, int block, cudaStream_t s);
+// the tile-staged persistent kernel (production): a.tile_cap and the shared-memory size come from tile_kernel_config
+cudaError_t launch_tile(const RunArgs &a, int kind, bool out64, int grid, int block, size_t smem, cudaStream_t s);
+size_t tile_kernel_smem_bytes(int kind, int block);
+int tile_kernel_max_blocks_per_sm(int kind, bool out64, int block, size_t smem);
+uint32_t tile_kernel_max_tile(int kind);
 cudaError_t launch_persistent_record(const RunArgs &a, int grid, int block, cudaStream_t s);  // KIND_FIXED, float64 pairs
 cudaError_t launch_prep_general(const double *params, GenConst *gconst, uint32_t n_datasets, double dt, cudaStream_t s);
 cudaError_t launch_generic(const RunArgs &a, int kind, bool f64, bool buffer_src, bool out64,

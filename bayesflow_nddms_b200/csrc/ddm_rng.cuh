@@ -3,7 +3,7 @@
 // Philox4x32-10 (Salmon et al., SC'11).  key = (seed_lo, seed_hi) is uniform for
 // a launch, so the ten round keys live in uniform registers / the constant bank
 // and a round costs 2 IMAD.WIDE.U32 + 2 LOP3 per lane.
-// counter = (block, trial, dataset, stream); one block yields SIX normals:
+// counter = (block, trial, dataset [low 32 bits], stream | dataset [bits 32..55] << 8); one block yields SIX normals:
 //   stream 0 ("step"):  block b yields the normals of Euler steps 6b..6b+5
 //   stream 1 ("aux"):   normal 0 = the ext-data normal z_ext (drawn after the
 //                       loop in the reference, single_trial_alpha_not_scaled.py:131),
@@ -45,14 +45,19 @@ constexpr uint32_t STREAM_AUX = 1u;
 // an extra uniform-datapath add per round per block.
 struct PhiloxKey {
     uint32_t rk[20];  // rk[2r] = k0 + r*W0, rk[2r+1] = k1 + r*W1
+    // Bits 8..31 of counter word 3 (bits 0..7 = stream): the high part of the 64-bit global dataset
+    // index, launch-uniform (a launch never straddles a multiple of 2^32 datasets, ddm_capi.cu:
+    // build_args), so long runs roll over into fresh counters instead of running out of them.
+    uint32_t c3_hi;
 };
 
-__host__ __device__ inline PhiloxKey make_philox_key(uint32_t k0, uint32_t k1) {
+__host__ __device__ inline PhiloxKey make_philox_key(uint32_t k0, uint32_t k1, uint32_t index_hi = 0u) {
     PhiloxKey k;
     for (int r = 0; r < 10; r++) {
         k.rk[2 * r] = k0 + (uint32_t)r * 0x9E3779B9u;
         k.rk[2 * r + 1] = k1 + (uint32_t)r * 0xBB67AE85u;
     }
+    k.c3_hi = index_hi << 8;
     return k;
 }
 
@@ -77,6 +82,7 @@ __device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2
 
 __device__ __forceinline__ void philox4x32_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                               const PhiloxKey &key, uint32_t (&o)[4]) {
+    c3 |= key.c3_hi;  // uniform: folds into the first round's key operand
 #pragma unroll
     for (int r = 0; r < 10; r++) {
         const uint64_t p0 = (uint64_t)PHILOX_M0 * c0;

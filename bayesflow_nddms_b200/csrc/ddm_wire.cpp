@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -83,9 +84,43 @@ void decode_basic64(const int32_t *w, double *o, const Segment &s, double dt, do
     }
 }
 
-void decode_basic32(const int32_t *w, float *o, const Segment &s, double dt, double timeout_val) {
+// Eight trials per iteration: int32 codes -> (float)(n*dt + tau), choice as float32 pairs, two 32-byte streaming
+// stores.  The response time is formed in double (multiply, add, then one rounding to float), exactly like the
+// kernel's float32 store path (store_pair<false> over trial_outputs<true>).
+__attribute__((target("avx2"))) int64_t decode_basic32_avx2(const int32_t *w, float *o, int64_t lo, int64_t hi, double dt,
+                                                            double tau, float timeout_val) {
+    const __m256d vdt = _mm256_set1_pd(dt), vtau = _mm256_set1_pd(tau);
+    const __m256 vto = _mm256_set1_ps(timeout_val), zero = _mm256_setzero_ps();
+    const __m256i three = _mm256_set1_epi32(3), one = _mm256_set1_epi32(1);
+    int64_t i = lo;
+    for (; i + 8 <= hi; i += 8) {
+        const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(w + i));
+        const __m256i n = _mm256_srli_epi32(c, 2);
+        const __m256d rt0 = _mm256_add_pd(_mm256_mul_pd(_mm256_cvtepi32_pd(_mm256_castsi256_si128(n)), vdt), vtau);
+        const __m256d rt1 = _mm256_add_pd(_mm256_mul_pd(_mm256_cvtepi32_pd(_mm256_extracti128_si256(n, 1)), vdt), vtau);
+        const __m256 rt = _mm256_set_m128(_mm256_cvtpd_ps(rt1), _mm256_cvtpd_ps(rt0));
+        __m256 ch = _mm256_cvtepi32_ps(_mm256_sub_epi32(_mm256_and_si256(c, three), one));
+        ch = _mm256_blendv_ps(ch, vto, _mm256_cmp_ps(ch, zero, _CMP_EQ_OQ));
+        const __m256 a = _mm256_unpacklo_ps(rt, ch);  // rt0 ch0 rt1 ch1 | rt4 ch4 rt5 ch5
+        const __m256 b = _mm256_unpackhi_ps(rt, ch);  // rt2 ch2 rt3 ch3 | rt6 ch6 rt7 ch7
+        _mm256_stream_ps(o + 2 * i, _mm256_permute2f128_ps(a, b, 0x20));
+        _mm256_stream_ps(o + 2 * i + 8, _mm256_permute2f128_ps(a, b, 0x31));
+    }
+    return i;
+}
+
+void decode_basic32(const int32_t *w, float *o, const Segment &s, double dt, double timeout_val, bool stream) {
     const float lut[3] = {-1.f, (float)timeout_val, 1.f};
-    for (int64_t i = s.lo; i < s.hi; i++) {
+    int64_t i = s.lo;
+    if (stream && g_avx2) {
+        for (; i < s.hi && ((reinterpret_cast<uintptr_t>(o + 2 * i) & 31u) != 0u); i++) {  // reach a 32-byte boundary
+            const uint32_t c = (uint32_t)w[i];
+            o[2 * i] = (float)((double)(int32_t)(c >> 2) * dt + s.tau);
+            o[2 * i + 1] = lut[c & 3u];
+        }
+        i = decode_basic32_avx2(w, o, i, s.hi, dt, s.tau, (float)timeout_val);
+    }
+    for (; i < s.hi; i++) {
         const uint32_t c = (uint32_t)w[i];
         const double rt = (double)(int32_t)(c >> 2) * dt;
         o[2 * i] = (float)(rt + s.tau);
@@ -134,7 +169,7 @@ void decode_slice(const WireDecode &j, int id, int n_threads) {
     per = (per + 1) & ~int64_t(1);
     const int64_t lo = std::min<int64_t>(total, per * id), hi = std::min<int64_t>(total, lo + per);
     if (lo >= hi) return;
-    const bool stream = j.out64 && (reinterpret_cast<uintptr_t>(j.out) & 15u) == 0u;
+    const bool stream = (reinterpret_cast<uintptr_t>(j.out) & (j.out64 ? 15u : 7u)) == 0u;  // rows are 16 / 8 bytes
     const double timeout_val = j.timeout_choice_one ? 1.0 : 0.0;
     int64_t ds = lo / j.n_trials;
     for (int64_t at = lo; at < hi; ds++) {
@@ -144,9 +179,9 @@ void decode_slice(const WireDecode &j, int id, int n_threads) {
         s.tau = j.params[(size_t)ds * j.n_params + j.tau_col];
         if (j.basic) {
             if (j.out64) decode_basic64(static_cast<const int32_t *>(j.wire), static_cast<double *>(j.out), s, j.dt, timeout_val, stream);
-            else decode_basic32(static_cast<const int32_t *>(j.wire), static_cast<float *>(j.out), s, j.dt, timeout_val);
+            else decode_basic32(static_cast<const int32_t *>(j.wire), static_cast<float *>(j.out), s, j.dt, timeout_val, stream);
         } else {
-            if (j.out64) decode_ext64(static_cast<const WirePair *>(j.wire), static_cast<double *>(j.out), s, j.dt, stream);
+            if (j.out64) decode_ext64(static_cast<const WirePair *>(j.wire), static_cast<double *>(j.out), s, j.dt, stream && j.out64);
             else decode_ext32(static_cast<const WirePair *>(j.wire), static_cast<float *>(j.out), s, j.dt);
         }
         at = s.hi;
@@ -192,18 +227,23 @@ class HostWorkers {
     }
     void loop(int id) {
         uint64_t seen = 0;
+        unsigned spins = 0;
         for (;;) {
             uint64_t g;
             while ((g = gen_.load(std::memory_order_acquire)) == seen) {
                 if (stop_.load(std::memory_order_relaxed)) return;
                 if (hot_.load(std::memory_order_relaxed)) {
-                    _mm_pause();
+                    // between the chunks of one streamed call: spin briefly (a chunk lands every few ms), then
+                    // give the core away -- on a box with one rank per GPU the other ranks' threads want it
+                    if (++spins < 4096) _mm_pause();
+                    else std::this_thread::yield();
                     continue;
                 }
                 std::unique_lock<std::mutex> l(m_);
                 wake_.wait(l, [&] { return stop_.load() || hot_.load() || gen_.load() != seen; });
             }
             seen = g;
+            spins = 0;
             fn_(arg_, id, n_);
             pending_.fetch_sub(1, std::memory_order_acq_rel);
         }
@@ -235,6 +275,44 @@ int host_workers_default_count(int gpus) {
     if (gpus < 1) gpus = 1;
     const int n = cpus / gpus;
     return n < 1 ? 1 : (n > 16 ? 16 : n);
+}
+
+// The host-memory ceiling of the decode: n_threads threads fill `bytes` of `buf` with non-temporal 32-byte
+// stores (the decode's own store instruction), nothing read.  Returns bytes per second.
+namespace {
+struct FillJob {
+    char *buf;
+    size_t bytes;
+};
+__attribute__((target("avx2"))) void fill_avx2(char *p, char *end) {
+    const __m256d v = _mm256_set1_pd(1.0);
+    for (; p + 32 <= end; p += 32) _mm256_stream_pd(reinterpret_cast<double *>(p), v);
+}
+void fill_slice(const void *arg, int id, int n) {
+    const FillJob &j = *static_cast<const FillJob *>(arg);
+    size_t per = (j.bytes / (size_t)n) & ~size_t(63);
+    char *lo = j.buf + per * (size_t)id, *hi = (id == n - 1) ? j.buf + (j.bytes & ~size_t(63)) : lo + per;
+    if (g_avx2) {
+        fill_avx2(lo, hi);
+    } else {
+        const __m128d v = _mm_set1_pd(1.0);
+        for (char *p = lo; p + 16 <= hi; p += 16) _mm_stream_pd(reinterpret_cast<double *>(p), v);
+    }
+    _mm_sfence();
+}
+}  // namespace
+
+double host_stream_store_rate(HostWorkers *w, void *buf, size_t bytes, int reps) {
+    FillJob j{static_cast<char *>(buf), bytes};
+    w->run(fill_slice, &j);  // touch the pages
+    double best = 0.0;
+    for (int r = 0; r < reps; r++) {
+        const auto t0 = std::chrono::steady_clock::now();
+        w->run(fill_slice, &j);
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (dt > 0.0 && (double)bytes / dt > best) best = (double)bytes / dt;
+    }
+    return best;
 }
 
 void wire_decode(HostWorkers *w, const WireDecode &job) {

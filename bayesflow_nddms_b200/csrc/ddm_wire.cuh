@@ -45,5 +45,7 @@ void host_workers_end(HostWorkers *w);
 int host_workers_default_count(int gpus_on_box);
 void wire_decode(HostWorkers *w, const WireDecode &job);
 void host_workers_run(HostWorkers *w, HostSliceFn fn, const void *arg);
+// bytes per second the pool's threads reach filling `buf` with streaming stores (the decode's ceiling)
+double host_stream_store_rate(HostWorkers *w, void *buf, size_t bytes, int reps);
 
 }  // namespace ddm

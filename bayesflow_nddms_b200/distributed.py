@@ -31,9 +31,16 @@ def world():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
 
-def simulate_sharded(simulate_fn, params, n_trials, *, rank=None, world_size=None, dataset_base=0, gather=False,
+_batch_base = 0  # global dataset index of the next sharded batch (advances by B on every rank alike)
+
+
+def simulate_sharded(simulate_fn, params, n_trials, *, rank=None, world_size=None, dataset_base=None, gather=False,
                      **kw):
     """Simulate this rank's slice of a (B, P) parameter batch.
+
+    ``dataset_base`` is the global index of the batch's first dataset.  ``None`` (default) takes it from a
+    process-wide counter that advances by B per call -- every rank calls with the same B, so the ranks stay
+    in step and successive batches use fresh Philox counters; pass an explicit base to regenerate a batch.
 
     ``simulate_fn(params_local, n_trials, dataset_offset=..., **kw)`` is a model module's
     ``batch_simulate_trials`` (numpy out) or ``batch_simulate_trials_device`` (DLPack out).
@@ -45,6 +52,13 @@ def simulate_sharded(simulate_fn, params, n_trials, *, rank=None, world_size=Non
     world_size = w if world_size is None else world_size
     params = np.asarray(params, dtype=np.float64)
     lo, hi = shard_range(params.shape[0], rank, world_size)
+    if dataset_base is None:
+        global _batch_base
+        B = int(params.shape[0])
+        if (_batch_base & 0xFFFFFFFF) + B > 1 << 32:   # a launch may not straddle a multiple of 2^32
+            _batch_base = ((_batch_base >> 32) + 1) << 32
+        dataset_base = _batch_base
+        _batch_base += B
     local = simulate_fn(params[lo:hi], n_trials, dataset_offset=int(dataset_base) + lo, **kw)
     if not gather or world_size == 1:
         return local, (lo, hi)

@@ -34,25 +34,28 @@ def draw_participant_params(nsubs, rng=None):
 
 
 def diffusion_trial(drift, bound_trial, beta, ter, dc, dt=.01, max_steps=400., simulator=None):
-    """:120-148 -> choicert.  Raises ValueError for a negative boundary, as the reference does."""
+    """:120-148 -> choicert.  Raises ValueError for a negative boundary, as the reference does.
+    Every call consumes fresh randomness (the simulator's trial counter advances), like the reference's."""
     out = impute_choicert([0], [bound_trial], [[drift, beta, ter, dc]], dt=dt, max_steps=max_steps,
                           simulator=simulator)
     return float(out[0])
 
 
 def impute_choicert(part_index, single_trial_alphas, part_params, dt=.01, max_steps=400., simulator=None,
-                    seed=None, trial_offset=0, precision=32):
+                    seed=None, trial_offset=None, precision=32):
     """The per-row loop :205-213 as one launch.
 
     part_index (n,) int -- row of ``part_params`` for each trial; single_trial_alphas (n,);
-    part_params (G, 4) [Drift, Beta, Ter, Dc].  Returns imputed_choicert (n,) float64."""
+    part_params (G, 4) [Drift, Beta, Ter, Dc].  Returns imputed_choicert (n,) float64.
+    ``trial_offset=None``: the simulator's trial counter keys the trials and advances by n, so repeated
+    imputations differ (as repeated runs of the reference's loop do); an explicit offset reproduces one."""
     sim = simulator if simulator is not None else default_simulator()
     out = sim.simulate_trialwise(part_index, single_trial_alphas, part_params, dt, int(max_steps), seed=seed,
                                  trial_offset=trial_offset, precision=precision)
     return out[:, 0].copy()
 
 
-def impute_dataset(subj_idx, all_Pe, part_params=None, simulator=None, device=False, seed=None):
+def impute_dataset(subj_idx, all_Pe, part_params=None, simulator=None, device=False, seed=None, trial_offset=None):
     """Lines 82-228 end to end on arrays: returns (input_data (n, 2), part_ids, part_index).
 
     ``input_data`` = column_stack((imputed_choicert, alpha_like_Pe)) (:228); with
@@ -65,11 +68,11 @@ def impute_dataset(subj_idx, all_Pe, part_params=None, simulator=None, device=Fa
         part_params = draw_participant_params(part_ids.size)
     sim = simulator if simulator is not None else default_simulator()
     if not device:
-        cr = impute_choicert(part_index, single_trial_alphas, part_params, simulator=sim, seed=seed)
+        cr = impute_choicert(part_index, single_trial_alphas, part_params, simulator=sim, seed=seed, trial_offset=trial_offset)
         return np.column_stack((cr, alpha_like_Pe)), part_ids, part_index
     import torch
 
-    batch = sim.simulate_trialwise(part_index, single_trial_alphas, part_params, seed=seed,
+    batch = sim.simulate_trialwise(part_index, single_trial_alphas, part_params, seed=seed, trial_offset=trial_offset,
                                    flags=_capi.FLAG_OUT_F32, device=True)
     t = torch.from_dlpack(batch)  # (n, 2): choicert, boundary used
     t[:, 1] = torch.as_tensor(alpha_like_Pe.astype(np.float32), device=t.device)

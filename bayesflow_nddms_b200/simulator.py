@@ -36,6 +36,17 @@ class _PinnedBlock:
             pass
 
 
+class _FreeingPool:
+    """Owner of a single page-locked block (``DDMSimulator.pinned_empty``): the block is freed when the last
+    array over it goes away."""
+
+    def __init__(self, lib):
+        self._lib = lib
+
+    def _give_back(self, ptr: int, cap: int):
+        self._lib.ddm_host_free(C.c_void_p(ptr))
+
+
 class _PinnedResultPool:
     """Result arrays of mid-size host-destined batches live in page-locked memory: a device-to-host copy into a
     fresh pageable numpy array runs at a third of the PCIe rate (1.1 ms instead of 0.45 ms for the 16 MB of a
@@ -109,6 +120,7 @@ class DDMSimulator:
         self.device = int(device)
         self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         self.dataset_counter = 0
+        self.trial_counter = 0  # trialwise (Stahl) path: global index of the next trial, see simulate_trialwise
         self._pinned = {}
         self._results = _PinnedResultPool(self._lib)
 
@@ -116,9 +128,7 @@ class DDMSimulator:
     def close(self):
         ctx, self._ctx = getattr(self, "_ctx", None), C.c_void_p()
         if ctx:
-            for ptr, _ in self._pinned.values():
-                self._lib.ddm_host_free(ptr)
-            self._pinned = {}
+            self._pinned = {}   # blocks are freed as the last arrays over them are collected
             self._results.close()
             self._lib.ddm_destroy(ctx)
 
@@ -148,6 +158,10 @@ class DDMSimulator:
     def set_tuning(self, refill_threshold: int = 0, blocks_per_sm: int = 0, tile: int = 0):
         self._check(self._lib.ddm_set_tuning(self._ctx, refill_threshold, blocks_per_sm, tile))
 
+    def set_kernel_variant(self, variant: int = 0):
+        """0: the tile-staged persistent kernel (default); 1: the round-1 persistent kernel (A/B measurements)."""
+        self._check(self._lib.ddm_set_kernel_variant(self._ctx, int(variant)))
+
     def set_stream(self, cuda_stream_ptr: int | None):
         self._check(self._lib.ddm_set_stream(self._ctx, C.c_void_p(cuda_stream_ptr or 0)))
 
@@ -169,27 +183,35 @@ class DDMSimulator:
             return False
 
     def pinned_empty(self, shape, dtype=np.float64, slot: str = "out") -> np.ndarray:
-        """A numpy array over page-locked host memory, reused per slot (full-rate D2H)."""
+        """A numpy array over page-locked host memory, reused per slot (full-rate D2H).  The block belongs to
+        the arrays handed out over it: asking the slot for more than it holds allocates a new block and the
+        old one is freed when the last array over it is collected (never under a live array)."""
         dtype = np.dtype(dtype)
-        nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
-        ptr, cap = self._pinned.get(slot, (None, 0))
-        if cap < nbytes:
-            if ptr:
-                self._lib.ddm_host_free(ptr)
+        count = int(np.prod(shape, dtype=np.int64))
+        nbytes = count * dtype.itemsize
+        blk = self._pinned.get(slot)
+        if blk is None or blk._cap < nbytes:
             p = C.c_void_p()
             rc = self._lib.ddm_host_alloc(max(nbytes, 1), C.byref(p))
             if rc != _capi.OK:
                 raise DDMError(rc, "pinned host allocation failed")
-            ptr, cap = p, max(nbytes, 1)
-            self._pinned[slot] = (ptr, cap)
-        buf = (C.c_char * max(nbytes, 1)).from_address(ptr.value)
-        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
+            blk = _PinnedBlock(_FreeingPool(self._lib), p.value, max(nbytes, 1))
+            self._pinned[slot] = blk
+        return np.asarray(blk)[:nbytes].view(dtype).reshape(shape)
 
     # ---- the hot path -----------------------------------------------------------------
+    @staticmethod
+    def _roll(counter: int, n: int) -> int:
+        """A launch must not straddle a multiple of 2^32 of the global index (its low 32 bits are one Philox
+        counter word, the high part is launch-uniform): skip to the next multiple when it would."""
+        if (counter & 0xFFFFFFFF) + int(n) > 1 << 32:
+            counter = ((counter >> 32) + 1) << 32
+        return counter
+
     def _next_offset(self, n_datasets: int, dataset_offset):
         if dataset_offset is None:
-            dataset_offset = self.dataset_counter
-            self.dataset_counter += int(n_datasets)
+            dataset_offset = self._roll(self.dataset_counter, n_datasets)
+            self.dataset_counter = dataset_offset + int(n_datasets)
         return int(dataset_offset)
 
     def draw_prior(self, prior: str, n_draws: int, *, seed=None, draw_offset=None, to_host: bool = True):
@@ -285,8 +307,13 @@ class DDMSimulator:
         return self.last_output_dlpack()
 
     def simulate_trialwise(self, group, bound, group_params, dt: float = 0.01, max_steps: int = 400, *, seed=None,
-                           trial_offset: int = 0, precision: int = 32, flags: int = 0, device: bool = False):
-        """Per-trial supplied boundary, parameters gathered by group (Stahl imputation)."""
+                           trial_offset: int | None = None, precision: int = 32, flags: int = 0, device: bool = False):
+        """Per-trial supplied boundary, parameters gathered by group (Stahl imputation).
+
+        Trial i is keyed by the global trial index ``trial_offset + i``.  With ``trial_offset=None`` the
+        simulator's ``trial_counter`` supplies it and advances by n, so successive calls -- the reference calls
+        ``diffusion_trial`` once per CSV row (imputation_from_stahl_not_scaled.py:205-213) -- draw fresh noise,
+        as ``dataset_counter`` does for the dataset-wise models; pass an explicit offset to regenerate a call."""
         group = np.ascontiguousarray(group, dtype=np.int32).ravel()
         bound = np.ascontiguousarray(bound, dtype=np.float64).ravel()
         group_params = np.ascontiguousarray(group_params, dtype=np.float64)
@@ -297,6 +324,9 @@ class DDMSimulator:
         if group.size != bound.size:
             raise ValueError("group and bound must have one entry per trial")
         n = group.size
+        if trial_offset is None:
+            trial_offset = self._roll(self.trial_counter, n)
+            self.trial_counter = trial_offset + int(n)
         f32 = bool(flags & _capi.FLAG_OUT_F32)
         out = None if device else np.empty((n, 2), dtype=np.float32 if f32 else np.float64)
         self._check(self._lib.ddm_simulate_trialwise(
@@ -424,6 +454,11 @@ def default_simulator() -> DDMSimulator:
         if _default is None:
             _default = DDMSimulator(device=int(os.environ.get("LOCAL_RANK", "0")),
                                     seed=int(os.environ.get("DDM_SEED", "2023")))
+            # one process per GPU: every rank draws its own batches, so each starts in its own 2^40-dataset
+            # range of the global index (same seed, disjoint Philox counters); rank 0 starts at 0 as before
+            rank = int(os.environ.get("RANK", "0"))
+            _default.dataset_counter = rank << 40
+            _default.trial_counter = rank << 40
         return _default
 
 

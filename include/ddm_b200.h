@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DDM_B200_VERSION 100
+#define DDM_B200_VERSION 200
 
 typedef struct ddm_ctx ddm_ctx;
 struct DLManagedTensor; /* include/ddm_dlpack.h (DLPack v0.8 ABI) */
@@ -126,6 +126,9 @@ int ddm_set_stream(ddm_ctx *ctx, void *cuda_stream); /* NULL restores the ctx-ow
 int ddm_synchronize(ddm_ctx *ctx);
 /* tuning knobs; 0 = automatic */
 int ddm_set_tuning(ddm_ctx *ctx, int refill_threshold, int blocks_per_sm, int tile);
+/* 0 (default): the tile-staged persistent kernel; 1: the round-1 persistent kernel (per-lane set-up and emission
+ * inside the refill pass), kept for A/B measurements.  Results are bit-identical. */
+int ddm_set_kernel_variant(ddm_ctx *ctx, int variant);
 /* ddm_simulate with a host destination streams batches of at least min_rows trials to the host in
  * chunks of about chunk_rows trials, overlapping kernel and PCIe copy (defaults: min_rows 8 Mi trials,
  * 4 Mi when the rows travel as compact records, see ddm_set_host_decode; chunk_rows: the smaller of a
@@ -149,7 +152,10 @@ int ddm_set_host_decode(ddm_ctx *ctx, int n_threads);
  * NULL: results stay on the device (ddm_last_output_dlpack / ddm_download).
  * dt, max_steps: the reference's default kwargs (.01, 400).  Philox key = seed;
  * counters = (step block, trial, dataset_offset + b, stream), so the result of
- * dataset b does not depend on how datasets are sharded over GPUs.
+ * dataset b does not depend on how datasets are sharded over GPUs.  dataset_offset is a
+ * 64-bit global index below 2^56: its low 32 bits are a counter word, the rest rides in the
+ * stream word, so a long run rolls over into fresh counters; one call must not straddle a
+ * multiple of 2^32 (DDM_ERR_INVALID: start the batch at the next multiple).
  * precision: 32 (production) or 64 (validation; reference operation order). */
 int ddm_simulate(ddm_ctx *ctx, int model, const double *params, int64_t n_datasets, int n_params,
                  int64_t n_trials, double dt, int max_steps, uint64_t seed, uint64_t dataset_offset,
@@ -226,7 +232,7 @@ int ddm_last_output_device_ptr(ddm_ctx *ctx, void **ptr, size_t *bytes);
 int ddm_set_normals_debug(ddm_ctx *ctx, const double *z, size_t n, const int64_t *offsets, int64_t n_trials);
 /* The normals the production (precision 32) or validation (64) kernels use for
  * counters (dataset, trial, stream), indices first..first+count-1, as doubles. */
-int ddm_export_normals(ddm_ctx *ctx, uint64_t seed, uint32_t dataset, uint32_t trial, uint32_t stream,
+int ddm_export_normals(ddm_ctx *ctx, uint64_t seed, uint64_t dataset, uint32_t trial, uint32_t stream,
                        uint32_t first, uint32_t count, int precision, double *out_host);
 /* Raw Philox4x32-10 blocks computed on the device (known-answer tests). */
 int ddm_philox4x32(ddm_ctx *ctx, const uint32_t *ctr4, const uint32_t *key2, uint32_t *out4, int64_t n_blocks);

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} is declared in include/ddm_b200.h but not exported"
     # the ctypes prototypes cover the same surface
     assert sorted(_capi.SIGNATURES) == _declared_functions()
-    assert _capi.load().ddm_version() == 100
+    assert _capi.load().ddm_version() == 200
 
 
 def test_enums_match_header():

@@ -16,6 +16,60 @@ def _offsets(consumed):
     return off
 
 
+def _trial_increments(sim, model, params, ds, t, n_step_normals, seed):
+    """The production kernel's own normals of one trial in the reference's consumption order
+    (pre-draws, ``n_step_normals`` step normals, ext-data draw): north_star's exported increments."""
+    zs = sim.export_normals(ds, t, 0, 0, int(n_step_normals), seed=seed) if n_step_normals else np.empty(0)
+    if model in (0, 5):
+        return zs
+    if model == 6:
+        return np.concatenate([sim.export_normals(ds, t, 1, 1, 1, seed=seed), zs])
+    aux = sim.export_normals(ds, t, 1, 0, 4097, seed=seed)
+    mu, sd = (params[5], params[4]) if model == 2 else (params[1], params[4])
+    cand = np.float32(mu) + np.float32(sd) * aux[1:].astype(np.float32)
+    k = int(np.argmax(cand > 0))          # index of the first positive candidate
+    return np.concatenate([aux[1:k + 2], zs, aux[:1]])
+
+
+def _reference_trial(sim, oracle, model, params, ds, t, n_gpu, seed, kw, bound_in=None):
+    """The reference's fp64 loop (CPU oracle) on the kernel's exported increments of one trial.  The
+    buffer first holds exactly the kernel's step count of step normals (so that the draw made after the
+    loop lands where the reference draws it); if the fp64 path wants more steps it is rerun with more."""
+    for extra in (0, 64, int(kw["max_steps"])):
+        S = min(int(n_gpu) + extra, int(kw["max_steps"]))
+        z = _trial_increments(sim, model, params, ds, t, S, seed)
+        try:
+            r = oracle.simulate_buffer(model, params, 1, z, bound_in=bound_in, **kw)
+        except IndexError:
+            continue
+        if int(r.n_steps[0]) <= S:
+            return r, z
+    raise AssertionError(f"trial {t}: the reference loop did not finish on {S} step normals")
+
+
+ULP32 = 2.0 ** -23
+TIE_ULPS = 64   # a tie = the fp64 path is within this many fp32 ulps (of the boundary scale) of a boundary
+
+
+def _assert_boundary_tie(sim, oracle, model, params, ds, t, n_gpu, n_ref, seed, kw, bound_in=None):
+    """SURVEY 7 / VERDICT r1: a trial whose crossing step differs between the fp32 kernel and the fp64
+    reference loop on the same increments is a *documented boundary tie* only if, at the step where the
+    two paths part (the earlier of the two crossing steps), the fp64 evidence sits within a few fp32 ulps
+    of the boundary it is compared with.  Returns that distance in fp32 ulps of the boundary scale."""
+    m = int(min(n_gpu, n_ref))
+    what = f"model {model} dataset {ds} trial {t}"
+    assert m >= 1, f"{what}: paths part before the first step"
+    z = _trial_increments(sim, model, params, ds, t, m, seed)
+    r = oracle.simulate_buffer(model, params, 1, z, bound_in=bound_in, **dict(kw, max_steps=float(m)))
+    assert int(r.n_steps[0]) == m, what
+    ev, bound = float(r.evidence[0]), float(r.bound[0])
+    dist = min(abs(ev), abs(ev - bound))
+    ulps = dist / (ULP32 * max(bound, abs(ev), 1e-30))
+    assert ulps <= TIE_ULPS, (f"{what}: crossing steps {n_gpu} (fp32 kernel) vs {n_ref} (fp64 loop) but the fp64 evidence "
+                              f"{ev!r} at step {m} is {ulps:.1f} fp32 ulps from a boundary (0, {bound!r}): not a tie")
+    return ulps
+
+
 # --------------------------------------------------------------------------------------------
 # Philox and the normal map
 # --------------------------------------------------------------------------------------------
@@ -122,38 +176,21 @@ def test_fp32_production_vs_reference_loop_on_exported_increments(sim, oracle, m
     steps = sim.last_steps(n)
     assert sim.last_stats()["used_persistent"] == 1
     state = sim.simulate(model, params, n, precision=32, flags=F_STATE, seed=seed, dataset_offset=ds, **kw)[0, :, 1]
-    # per-trial increments, in the reference's consumption order: pre-draws, steps, ext
-    chunks, consumed = [], []
-    for t in range(n):
-        zs = sim.export_normals(ds, t, 0, 0, int(steps[t]) + 8, seed=seed)
-        if model == 0:
-            c = [zs]
-        elif model == 6:
-            c = [sim.export_normals(ds, t, 1, 1, 1, seed=seed), zs[:int(steps[t])]]
-        else:
-            aux = sim.export_normals(ds, t, 1, 0, 4097, seed=seed)
-            mu, sd = (params[5], params[4]) if model == 2 else (params[1], params[4])
-            cand = np.float32(mu) + np.float32(sd) * aux[1:].astype(np.float32)
-            k = int(np.argmax(cand > 0))          # index of the first positive candidate
-            c = [aux[1:k + 2], zs[:int(steps[t])], aux[:1]]
-            zs = None
-        chunks.append(np.concatenate(c))
-        consumed.append(chunks[-1].size)
-    normals = np.concatenate(chunks)
-    off = _offsets(np.array(consumed))
     ref_steps = np.empty(n, np.int64)
     ref_choice = np.empty(n, np.int32)
     ref_ev = np.empty(n)
     ref_out = np.empty((n, 2))
     ref_bound = np.empty(n)
-    for t in range(n):  # one oracle call per trial so each starts at its own offset
-        r = oracle.simulate_buffer(model, params, 1, normals[off[t]:off[t] + consumed[t]], **kw)
+    for t in range(n):  # the reference loop on this trial's exported increments (pre-draws, steps, ext)
+        r, _ = _reference_trial(sim, oracle, model, params, ds, t, steps[t], seed, kw)
         ref_steps[t], ref_choice[t], ref_ev[t], ref_out[t], ref_bound[t] = (
             r.n_steps[0], r.choice[0], r.evidence[0], r.sim_data[0], r.bound[0])
     same = (steps == ref_steps)
-    # documented boundary ties: fp32 rounding flips a strict comparison only when the fp64
-    # path passes within rounding distance of a boundary
-    assert same.mean() >= 0.98, f"{(~same).sum()} of {n} crossing steps differ"
+    # documented boundary ties: fp32 rounding flips a strict comparison only when the fp64 path passes
+    # within rounding distance of a boundary -- at most one of the 384 trials, and it must *be* such a tie
+    assert (~same).sum() <= 1, f"{(~same).sum()} of {n} crossing steps differ"
+    for t in np.flatnonzero(~same):
+        _assert_boundary_tie(sim, oracle, model, params, ds, t, steps[t], ref_steps[t], seed, kw)
     rt_col = out[:, 0]
     if model in (0, 6):
         gpu_choice = out[:, 1].astype(np.int32)
@@ -432,7 +469,7 @@ def test_trialwise_ragged_groups(sim, oracle):
     z = alphas == 0
     assert np.array_equal(cr[z], pp[part_index[z], 2])
     # same trials through the oracle on the ideal Philox stream (fp64 mode)
-    cr64 = sim.simulate_trialwise(part_index, alphas, pp, seed=77, precision=64)[:, 0]
+    cr64 = sim.simulate_trialwise(part_index, alphas, pp, seed=77, precision=64, trial_offset=0)[:, 0]
     pick = np.random.default_rng(0).choice(19374, 300, replace=False)
     for i in pick:
         o = oracle.simulate_philox(5, pp[part_index[i]], 1, 77, dataset=0, trial_offset=int(i), bound_in=[alphas[i]])
@@ -677,7 +714,7 @@ def test_two_contexts_on_two_host_threads(sim):
 @pytest.mark.parametrize("model,prior,kw", [(0, "basic", dict(dt=0.001, max_steps=4000)), (0, "basic", dict(dt=0.01, max_steps=400)),
                                             (1, "alpha", dict(dt=0.01, max_steps=400)), (2, "alpha_dc", dict(dt=0.01, max_steps=400)),
                                             (6, "eta", dict(dt=0.001, max_steps=4000))])
-def test_check1_at_scale_fp32_kernel_vs_fp64_reference_arithmetic_on_the_same_increments(sim, model, prior, kw):
+def test_check1_at_scale_fp32_kernel_vs_fp64_reference_arithmetic_on_the_same_increments(sim, oracle, model, prior, kw):
     """Check #1 on 1e6 trials per model: the fp32 production kernel against the reference's fp64 loop
     (the validation kernel, itself bit-equal to the CPU oracle) consuming the production kernel's own
     fp32 normals.  Crossing steps and choices must agree except for boundary ties; the tie rate is
@@ -695,7 +732,16 @@ def test_check1_at_scale_fp32_kernel_vs_fp64_reference_arithmetic_on_the_same_in
     same = sa == sb
     tie_rate = 1.0 - same.mean()
     print(f"model {model} dt={kw['dt']}: {int((~same).sum())} of {B * N} crossing steps differ (tie rate {tie_rate:.2e})")
-    assert tie_rate < 5e-4
+    assert tie_rate < 5e-5            # measured 1e-6 .. 1.4e-5
+    # ... and every one of them is a boundary tie: at the step where the paths part, the reference's fp64
+    # evidence (CPU oracle on the exported increments) is within TIE_ULPS fp32 ulps of the boundary
+    ulps = []
+    for idx in np.flatnonzero(~same)[:64]:
+        d, t = divmod(int(idx), N)
+        ulps.append(_assert_boundary_tie(sim, oracle, model, P[d], d, t, sa[idx], sb[idx], 13, kw))
+    if ulps:
+        print(f"    distance of the fp64 evidence from the boundary at the parting step: max {max(ulps):.2f}, "
+              f"median {np.median(ulps):.2f} fp32 ulps")
     # where the step count agrees, the reported RT is bit-identical and the choice equal
     assert np.array_equal(a2[same, 0].view(np.uint64), b2[same, 0].view(np.uint64))
     if model in (0, 6):
@@ -708,3 +754,227 @@ def test_check1_at_scale_fp32_kernel_vs_fp64_reference_arithmetic_on_the_same_in
     d = (sa.astype(np.int64) - sb.astype(np.int64))[~same]
     if d.size > 20:
         assert abs(np.mean(np.sign(d))) < 0.5
+
+
+# --------------------------------------------------------------------------------------------
+# Check #1 for DDM_MODEL_TRIALWISE (imputation_from_stahl_not_scaled.py:120-148) at its default precision 32
+# --------------------------------------------------------------------------------------------
+def _stahl_like_bounds(rng, n):
+    """Boundaries shaped like the reference's (z(pre_Pe) + 3) / 3 clipped at 0 (imputation...:82-105), with the
+    clipped zeros and a band of tiny positive values (a start point within rounding of both boundaries)."""
+    b = np.clip((rng.standard_normal(n) * 1.05 + 3.0) / 3.0, 0.0, None)
+    b[rng.random(n) < 0.01] = 0.0
+    tiny = rng.random(n) < 0.01
+    b[tiny] = 10.0 ** rng.uniform(-6, -2, tiny.sum())
+    return b
+
+
+TRIALWISE_CASES = [
+    ([3.0, 0.5, 0.4, 1.0], dict(dt=0.01, max_steps=400)),
+    ([-1.2, 0.42, 0.25, 0.8], dict(dt=0.001, max_steps=4000)),
+    ([0.1, 0.55, 0.3, 0.25], dict(dt=0.01, max_steps=400)),          # small dc: many timeouts
+]
+
+
+@pytest.mark.parametrize("gp,kw", TRIALWISE_CASES)
+def test_trialwise_fp32_vs_reference_loop_on_exported_increments(sim, oracle, gp, kw):
+    """The product path of the Stahl imputation (precision 32) against the reference's pure-Python loop (CPU
+    oracle, fp64) on the kernel's own exported increments: crossing steps and choices equal except boundary
+    ties (at most 1 of 384, classified), reported RTs then bit-identical, final states within 1e-5."""
+    n, seed, toff = 384, 31, 1000
+    rng = np.random.default_rng(int(abs(gp[0]) * 100))
+    bounds = _stahl_like_bounds(rng, n)
+    bounds[:4] = [0.0, 1e-7, 1e-4, 2.5]
+    group = np.zeros(n, np.int32)
+    out = sim.simulate_trialwise(group, bounds, [gp], seed=seed, trial_offset=toff, precision=32, flags=F_STEPS, **kw)
+    steps = sim.last_steps(n)
+    state = sim.simulate_trialwise(group, bounds, [gp], seed=seed, trial_offset=toff, precision=32, flags=F_STATE, **kw)[:, 1]
+    assert np.array_equal(out[:, 1], bounds)
+    differ = 0
+    for t in range(n):
+        r, _ = _reference_trial(sim, oracle, 5, gp, 0, toff + t, steps[t], seed, kw, bound_in=[bounds[t]])
+        if int(r.n_steps[0]) != steps[t]:
+            differ += 1
+            _assert_boundary_tie(sim, oracle, 5, gp, 0, toff + t, steps[t], r.n_steps[0], seed, kw, bound_in=[bounds[t]])
+            continue
+        assert np.sign(out[t, 0]) == r.choice[0], t
+        assert out[t, 0].view(np.uint64) == r.sim_data[0, 0].view(np.uint64), t
+        assert abs(state[t] - r.evidence[0]) <= 1e-5 * max(bounds[t], 1e-3), t
+    assert differ <= 1, f"{differ} of {n} crossing steps differ"
+    assert np.all(steps[bounds == 0] == 0) and np.all(out[bounds == 0, 0] == gp[2])   # :131-133: zero steps, +ter
+
+
+def test_trialwise_check1_at_scale(sim, oracle):
+    """1e6 Stahl-shaped trials over 89 participants: the precision-32 product path vs the reference's fp64
+    arithmetic on the same fp32 normals (DDM_FLAG_F32_NORMALS), incl. bound == 0 and tiny bounds."""
+    from bayesflow_nddms_b200 import imputation_from_stahl_not_scaled as stahl
+
+    n, G, seed = 1_000_000, 89, 17
+    rng = np.random.default_rng(5)
+    pp = stahl.draw_participant_params(G, np.random.default_rng(2024))
+    group = rng.integers(0, G, n).astype(np.int32)
+    bounds = _stahl_like_bounds(rng, n)
+    kw = dict(dt=0.01, max_steps=400)
+    a = sim.simulate_trialwise(group, bounds, pp, seed=seed, precision=32, flags=F_STEPS, trial_offset=0, **kw)
+    sa = sim.last_steps(n)
+    b = sim.simulate_trialwise(group, bounds, pp, seed=seed, precision=64, flags=F_STEPS | 32, trial_offset=0, **kw)
+    sb = sim.last_steps(n)
+    same = sa == sb
+    tie_rate = 1.0 - same.mean()
+    print(f"trialwise: {int((~same).sum())} of {n} crossing steps differ (tie rate {tie_rate:.2e})")
+    assert tie_rate < 5e-5
+    assert np.array_equal(a[same, 0].view(np.uint64), b[same, 0].view(np.uint64))
+    assert np.array_equal(a[:, 1], bounds) and np.array_equal(b[:, 1], bounds)
+    for idx in np.flatnonzero(~same)[:64]:
+        i = int(idx)
+        _assert_boundary_tie(sim, oracle, 5, pp[group[i]], 0, i, sa[i], sb[i], seed, kw, bound_in=[bounds[i]])
+
+
+def test_trialwise_calls_consume_fresh_randomness(sim):
+    """the reference's per-row loop (imputation...:205-213) draws new noise on every call of
+    diffusion_trial; the drop-in must too (a per-simulator trial counter), and stay reproducible on request."""
+    from bayesflow_nddms_b200 import imputation_from_stahl_not_scaled as stahl
+    from bayesflow_nddms_b200 import set_default_simulator
+
+    set_default_simulator(sim)
+    try:
+        rts = {stahl.diffusion_trial(1.0, 1.4, 0.5, 0.3, 1.0) for _ in range(12)}
+        assert len(rts) >= 6                              # 12 identical values before the fix
+        part_index = np.zeros(500, np.int32)
+        alphas = np.full(500, 1.2)
+        pp = np.array([[1.0, 0.5, 0.3, 1.0]])
+        x = stahl.impute_choicert(part_index, alphas, pp, simulator=sim)
+        y = stahl.impute_choicert(part_index, alphas, pp, simulator=sim)
+        assert not np.array_equal(x, y)
+        u = stahl.impute_choicert(part_index, alphas, pp, simulator=sim, seed=5, trial_offset=0)
+        v = stahl.impute_choicert(part_index, alphas, pp, simulator=sim, seed=5, trial_offset=0)
+        assert np.array_equal(u, v)
+        # one launch over 500 trials == 500 single-trial calls at the same counters
+        w = np.array([sim.simulate_trialwise([0], [1.2], pp, seed=5, trial_offset=i)[0, 0] for i in range(40)])
+        assert np.array_equal(w, u[:40])
+    finally:
+        set_default_simulator(None)
+
+
+# --------------------------------------------------------------------------------------------
+# Round 2: the tile-staged persistent kernel
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("model", [0, 1, 2, 3, 4, 6])
+def test_tile_kernel_equals_round1_persistent_kernel(sim, model):
+    """Both schedulers of the same trials (ddm_set_kernel_variant) give the same bits, for host rows, float32
+    rows and the compact wire, over tile sizes that do and do not divide the dataset and thresholds that force
+    stragglers (a tile recycled while its slow trials still run: they write their own rows)."""
+    from bayesflow_nddms_b200 import priors
+
+    name = ["basic", "alpha", "alpha_dc", "alpha_scale", "alpha_scale2", None, "eta"][model]
+    params = priors.draw_prior_batch(name, 53, np.random.default_rng(40 + model))
+    try:
+        for kw in (dict(dt=0.01, max_steps=400), dict(dt=0.001, max_steps=1000)):
+            sim.set_kernel_variant(1)
+            sim.set_tuning(0, 0, 0)
+            ref = sim.simulate(model, params, 307, seed=9, dataset_offset=3, flags=F_STEPS, **kw)
+            ref_steps, ref_st = sim.last_steps(53 * 307), sim.last_stats()
+            sim.set_kernel_variant(0)
+            for thr, bps, tile in [(0, 0, 0), (1, 1, 5), (3, 2, 33), (32, 0, 128), (8, 0, 64), (2, 1, 1000)]:
+                sim.set_tuning(thr, bps, tile)
+                out = sim.simulate(model, params, 307, seed=9, dataset_offset=3, flags=F_STEPS, **kw)
+                steps, st = sim.last_steps(53 * 307), sim.last_stats()
+                assert st["used_persistent"] == 1 and st["tile"] <= 128
+                assert np.array_equal(out.view(np.uint64), ref.view(np.uint64)), (kw, thr, bps, tile)
+                assert np.array_equal(steps, ref_steps)
+                for k in ("total_steps", "n_timeouts", "n_upper", "reject_cap_hits", "n_trials"):
+                    assert st[k] == ref_st[k], (k, thr, bps, tile)
+            sim.set_tuning(2, 1, 16)   # few warps, small tiles: most tiles are recycled with trials still running
+            f32 = sim.simulate(model, params, 307, seed=9, dataset_offset=3, flags=F_F32, **kw)
+            assert np.array_equal(f32, ref.astype(np.float32))
+    finally:
+        sim.set_kernel_variant(0)
+        sim.set_tuning(0, 0, 0)
+
+
+def test_tile_kernel_general_model_and_wire(sim):
+    """Three-column rows (DDM_MODEL_GENERAL, both output styles) and the compact wire through the tile kernel."""
+    from bayesflow_nddms_b200 import priors, two_channel
+
+    rng = np.random.default_rng(3)
+    raw = np.column_stack([rng.normal(0, 2, 31), 1.0 + rng.random(31), np.full(31, 0.5), np.full(31, 0.3), 0.5 + rng.random(31),
+                           0.6 + rng.random(31), np.full(31, 0.3), np.full(31, 0.5), np.full(31, 0.6), np.full(31, 0.2), np.full(31, 0.1)])
+    for P in (two_channel.canonical_drift_dc5(raw), two_channel.canonical_alpha_dc(raw)):   # both output styles' cousins
+        try:
+            sim.set_kernel_variant(1)
+            sim.set_tuning(0, 0, 0)
+            ref = sim.simulate(7, P, 211, seed=4, dataset_offset=0)
+            sim.set_kernel_variant(0)
+            for thr, bps, tile in [(0, 0, 0), (2, 1, 16), (8, 0, 96)]:
+                sim.set_tuning(thr, bps, tile)
+                assert np.array_equal(sim.simulate(7, P, 211, seed=4, dataset_offset=0).view(np.uint64), ref.view(np.uint64))
+        finally:
+            sim.set_kernel_variant(0)
+            sim.set_tuning(0, 0, 0)
+    params = priors.draw_prior_batch("alpha", 97, np.random.default_rng(6))
+    try:
+        sim.set_pipeline(1 << 60, -1)
+        base = sim.simulate(1, params, 131, seed=2, dataset_offset=0, dt=0.01, max_steps=61)
+        sim.set_pipeline(1, 131 * 10)
+        sim.set_tuning(2, 1, 8)
+        again = sim.simulate(1, params, 131, seed=2, dataset_offset=0, dt=0.01, max_steps=61)
+        assert np.array_equal(base, again)
+    finally:
+        sim.set_pipeline(-1, -1)
+        sim.set_tuning(0, 0, 0)
+
+
+def test_trialwise_persistent_equals_generic_bitwise(sim):
+    """DDM_MODEL_TRIALWISE at precision 32 now runs on the persistent tile kernel (VERDICT r1 missing #4):
+    same bits as the one-thread-per-trial kernel, ragged tails, zero and tiny boundaries included."""
+    from bayesflow_nddms_b200 import imputation_from_stahl_not_scaled as stahl
+
+    rng = np.random.default_rng(12)
+    n, G = 100_003, 89
+    pp = stahl.draw_participant_params(G, np.random.default_rng(2024))
+    group = rng.integers(0, G, n).astype(np.int32)
+    bounds = _stahl_like_bounds(rng, n)
+    for kw in (dict(dt=0.01, max_steps=400), dict(dt=0.001, max_steps=777)):
+        a = sim.simulate_trialwise(group, bounds, pp, seed=3, trial_offset=11, flags=F_STEPS, **kw)
+        sa, st = sim.last_steps(n), sim.last_stats()
+        assert st["used_persistent"] == 1
+        b = sim.simulate_trialwise(group, bounds, pp, seed=3, trial_offset=11, flags=F_STEPS | F_GENERIC, **kw)
+        sb, st2 = sim.last_steps(n), sim.last_stats()
+        assert st2["used_persistent"] == 0
+        assert np.array_equal(a.view(np.uint64), b.view(np.uint64)) and np.array_equal(sa, sb)
+        for k in ("total_steps", "n_timeouts", "n_upper", "n_trials"):
+            assert st[k] == st2[k]
+        f32 = sim.simulate_trialwise(group, bounds, pp, seed=3, trial_offset=11, flags=F_F32, **kw)
+        assert np.array_equal(f32, a.astype(np.float32))
+    # a participant without noise (dc == 0) has no state unit: the library keeps the reference's formulas
+    pp0 = pp.copy()
+    pp0[5, 3] = 0.0
+    out = sim.simulate_trialwise(group[:5000], bounds[:5000], pp0, seed=3, trial_offset=0)
+    assert sim.last_stats()["used_persistent"] == 0 and np.all(np.isfinite(out))
+
+
+def test_global_dataset_index_is_64_bit(sim, oracle):
+    """dataset_counter grows without bound; the index is now 64-bit (low word = Philox
+    counter word 2, the rest in the stream word), a launch must not straddle a multiple of 2^32 and the
+    Python counter skips to the next multiple instead."""
+    p = np.array([[1.0, 1.2, 0.5, 0.3, 1.0]] * 3)
+    base = sim.simulate(0, p, 50, seed=5, dataset_offset=7)
+    far = sim.simulate(0, p, 50, seed=5, dataset_offset=(9 << 32) + 7)
+    again = sim.simulate(0, p, 50, seed=5, dataset_offset=(9 << 32) + 7)
+    assert not np.array_equal(base, far) and np.array_equal(far, again)
+    big = (9 << 32) + 8
+    z = sim.export_normals(big, 4, 0, 0, 60, seed=5, precision=64)
+    assert np.max(np.abs(z - oracle.philox_normals(5, big, 4, 0, 0, 60))) < 1e-13
+    assert not np.array_equal(z, sim.export_normals(8, 4, 0, 0, 60, seed=5, precision=64))
+    with pytest.raises(ValueError, match="straddle"):
+        sim.simulate(0, p, 50, seed=5, dataset_offset=(1 << 32) - 2)
+    with pytest.raises(ValueError):
+        sim.simulate(0, p, 50, seed=5, dataset_offset=1 << 56)
+    keep = sim.dataset_counter
+    try:
+        sim.dataset_counter = (1 << 32) - 2
+        out = sim.simulate(0, p, 50, seed=5)                       # rolls to 2^32 instead of failing
+        assert sim.dataset_counter == (1 << 32) + 3
+        assert np.array_equal(out, sim.simulate(0, p, 50, seed=5, dataset_offset=1 << 32))
+    finally:
+        sim.dataset_counter = keep

@@ -150,9 +150,10 @@ def _gloo_worker(rank, world, port, n_total, q):
         return np.stack([orc.simulate_philox(0, p[i], n_trials, 99, dataset=dataset_offset + i).sim_data
                          for i in range(p.shape[0])]) if p.shape[0] else np.empty((0, n_trials, 2))
 
-    full, (lo, hi) = D.simulate_sharded(fake_simulate, params, 20, gather=True)
-    local, _ = D.simulate_sharded(fake_simulate, params, 20, gather=False)
-    q.put((rank, lo, hi, full, local))
+    full, (lo, hi) = D.simulate_sharded(fake_simulate, params, 20, gather=True)           # batch counter: base 0
+    nxt, _ = D.simulate_sharded(fake_simulate, params, 20, gather=True)                   # ... advanced by n_total
+    local, _ = D.simulate_sharded(fake_simulate, params, 20, gather=False, dataset_base=0)  # an explicit base regenerates
+    q.put((rank, lo, hi, full, local, nxt))
     dist.destroy_process_group()
 
 
@@ -173,10 +174,13 @@ def test_sharded_simulation_with_gloo_gather_world2(n_total, oracle):
     params = np.tile(np.array([[1.0, 1.2, 0.5, 0.3, 1.0]]), (n_total, 1))
     params[:, 0] = np.linspace(-2, 2, n_total)
     single = np.stack([oracle.simulate_philox(0, params[i], 20, 99, dataset=i).sim_data for i in range(n_total)])
-    (r0, lo0, hi0, full0, loc0), (r1, lo1, hi1, full1, loc1) = res
+    (r0, lo0, hi0, full0, loc0, nxt0), (r1, lo1, hi1, full1, loc1, nxt1) = res
     assert (lo0, hi1) == (0, n_total) and hi0 == lo1
     assert np.array_equal(full0, single) and np.array_equal(full1, single)   # independent of world size
     assert np.array_equal(np.concatenate([loc0, loc1]), single)
+    # successive batches use fresh counters: the second one is keyed n_total datasets further on, on every rank
+    second = np.stack([oracle.simulate_philox(0, params[i], 20, 99, dataset=n_total + i).sim_data for i in range(n_total)])
+    assert np.array_equal(nxt0, second) and np.array_equal(nxt1, second) and not np.array_equal(second, single)
 
 
 # ---- alpha_not_scaled.py data generation (:52-131): participant parameters are the reference's own ---------
