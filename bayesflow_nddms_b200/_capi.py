@@ -44,7 +44,8 @@ FLAG_OUT_STATE = 16
 FLAG_F32_NORMALS = 32
 
 MB_NAMES = ["ffma", "imad_wide", "lop3", "iadd3", "mufu_lg2", "mufu_sin", "mix_fma_alu", "fsetp", "philox",
-            "sim_block", "mix_imadw_lop3", "mix_mufu_lop3", "mix_mufu_imadw", "mix_blocklike"]
+            "sim_block", "mix_imadw_lop3", "mix_mufu_lop3", "mix_mufu_imadw", "mix_blocklike", "ffma_3reg", "fadd_2reg",
+            "imad_wide_noacc", "imad_hi", "ffma2_packed", "philox7", "sim_block_x2"]
 
 
 class Stats(C.Structure):
@@ -110,12 +111,16 @@ SIGNATURES = {
     "ddm_last_steps": (C.c_int, [_vp, C.POINTER(C.c_int32)]),
     "ddm_simulate_exact": (C.c_int, [_vp, _dp, C.c_int64, C.c_int64, C.c_uint64, C.c_uint64, _dp]),
     "ddm_last_output_histogram": (C.c_int, [_vp, C.c_int, C.c_double, C.POINTER(C.c_uint64)]),
+    "ddm_simulate_histogram": (C.c_int, [_vp, C.c_int, _dp, C.c_int64, C.c_int, C.c_int64, C.c_double, C.c_int, C.c_uint64,
+                                         C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_uint64)]),
+    "ddm_host_stream_peak": (C.c_int, [C.c_int, C.c_size_t, _dp]),
     "ddm_last_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
     "ddm_last_output_dlpack": (C.c_int, [_vp, C.POINTER(C.POINTER(DLManagedTensor))]),
     "ddm_last_output_device_ptr": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_size_t)]),
     "ddm_set_normals_debug": (C.c_int, [_vp, _dp, C.c_size_t, C.POINTER(C.c_int64), C.c_int64]),
     "ddm_export_normals": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                      C.c_int, _dp]),
+    "ddm_normals_histogram": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_uint64), _dp]),
     "ddm_philox4x32": (C.c_int, [_vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int64]),
     "ddm_microbench": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp]),
     "ddm_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),

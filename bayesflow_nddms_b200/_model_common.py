@@ -66,6 +66,16 @@ class ModelAPI:
             int(self.max_steps if max_steps is None else max_steps), precision=precision,
             flags=self.flags if flags is None else flags, seed=seed, dataset_offset=dataset_offset, out=out)
 
+    def batch_simulate_histogram(self, params, n_trials, simulator=None, *, dt=None, max_steps=None, precision=32,
+                                 flags=None, seed=None, dataset_offset=None, n_bins=400, rt_max=4.0):
+        """(B, P) f64 host parameters -> the batch's response-time histogram by boundary, reduced on the device
+        ("outputs reduced on device"); only 2 n_bins + 2 counters come back."""
+        return self.sim(simulator).simulate_histogram(
+            self.model_id, params, int(n_trials), self.dt if dt is None else dt,
+            int(self.max_steps if max_steps is None else max_steps), precision=precision,
+            flags=self.flags if flags is None else flags, seed=seed, dataset_offset=dataset_offset, n_bins=n_bins,
+            rt_max=rt_max)
+
     def batch_simulate_trials_device(self, params, n_trials, simulator=None, *, dt=None, max_steps=None,
                                      precision=32, flags=None, seed=None, dataset_offset=None):
         """Device-resident variant: returns a DLPack producer of shape (B, n_trials, 2) float32."""

@@ -56,6 +56,11 @@ def batch_simulate_trials(params, n_trials, simulator=None, **kw):
     return _api.batch_simulate_trials(params, n_trials, simulator, **kw)
 
 
+def batch_simulate_histogram(params, n_trials, simulator=None, **kw):
+    """(B, P) host parameters -> RT histogram by boundary of the B x n_trials simulated trials, reduced on the GPU."""
+    return _api.batch_simulate_histogram(params, n_trials, simulator, **kw)
+
+
 def batch_simulate_trials_device(params, n_trials, simulator=None, **kw):
     kw.setdefault("flags", _flags())
     return _api.batch_simulate_trials_device(params, n_trials, simulator, **kw)

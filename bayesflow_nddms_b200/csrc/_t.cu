@@ -693,495 +693,7 @@ __global__ void __launch_bounds__(DDM_PERSISTENT_BLOCK, tile_min_blocks<KIND>())
     }
 }
 
-// --------------------------------------------------------------------------------
-// generic kernel: one thread per trial
-// --------------------------------------------------------------------------------
-struct NormalStreamBuf {
-    const double *z, *end;
-    bool overrun;
-    __device__ __forceinline__ double next() {
-        if (z >= end) { overrun = true; return 0.0; }
-        return *z++;
-    }
-};
 
-template <typename Real, int KIND, bool BUFFER, bool OUT64>
-__global__ void __launch_bounds__(128) generic_kernel(const RunArgs a, uint64_t total) {
-    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = g < total;
-    unsigned long long acc_steps = 0;
-    uint32_t tout = 0, upper = 0, cap = 0;
-
-    if (active) {
-        uint32_t ds, trial;
-        if (KIND == KIND_TRIALWISE) {
-            ds = 0;
-            trial = (uint32_t)g;
-        } else {
-            ds = (uint32_t)(g / a.n_trials);
-            trial = (uint32_t)(g - (uint64_t)ds * a.n_trials);
-        }
-        const uint32_t ds_g = ds + a.dataset_offset, trial_g = trial + a.trial_offset;
-        const double *prm = (KIND == KIND_TRIALWISE) ? a.params + (size_t)a.group[g] * 4
-                                                     : a.params + (size_t)ds * a.n_params;
-        const double tau = (KIND == KIND_TRIALWISE) ? prm[2] : prm[3];
-        uint32_t n = 0;
-        int choice = 0;
-        double ext = 0.0, final_ev = 0.0;
-
-        if (sizeof(Real) == 4 && !BUFFER && !(a.flags & FLAG_REFERENCE_ARITHMETIC)) {
-            // ---- fp32 / Philox: the persistent kernel's arithmetic, naive scheduling ----
-            TrialF32 t;
-            if (KIND == KIND_TRIALWISE) {
-                trial_setup_trialwise(a.dconst[a.group[g]], (float)a.bound_in[g], t);
-            } else {
-                const DsConst dc = a.dconst[ds];
-                trial_setup_f32<(KIND == KIND_TRIALWISE ? KIND_FIXED : KIND)>(dc, trial_g, ds_g, a.key, t, cap);
-            }
-            float x = t.x;
-            uint32_t p = ((fabsf(x) < t.h) && (a.max_steps > 0u)) ? 1u : 0u;
-            for (uint32_t blk = 0; p != 0u; blk++)
-                step_block_f32<true>(blk, trial_g, ds_g, a.key, t, x, n, p, a.max_steps);
-            choice = (x >= t.h) ? 1 : ((x <= -t.h) ? -1 : 0);
-            ext = (KIND == KIND_TRIALWISE) ? a.bound_in[g] : (double)t.ext;
-            final_ev = (double)__fmul_rn(__fadd_rn(x, t.h), t.u);
-        } else {
-            // ---- reference arithmetic in Real (fp64: the reference's exact operation order;
-            //      fp32: the same formulas rounded to float), normals from Philox or a buffer ----
-            NormalStreamBuf buf{BUFFER ? a.dbg_z + a.dbg_off[g] : nullptr, BUFFER ? a.dbg_z + a.dbg_n : nullptr, false};
-            double zc[6];
-            uint32_t zblk = 0xffffffffu;
-            auto philox_normal = [&](uint32_t stream, uint32_t idx) -> double {
-                const uint32_t b = idx / 6u;
-                const uint32_t tag = b | (stream << 31);  // cache tag
-                if (tag != zblk) {
-                    if (sizeof(Real) == 8 && !(a.flags & 32)) {
-                        philox_normals6_f64(b, trial_g, ds_g, stream, a.key, zc);
-                    } else {
-                        float zf[6];
-                        philox_normals6_f32(b, trial_g, ds_g, stream, a.key, zf);
-#pragma unroll
-                        for (int i = 0; i < 6; i++) zc[i] = zf[i];
-                    }
-                    zblk = tag;
-                }
-                return zc[idx - 6u * b];
-            };
-            Real drift, beta, bound, dcoef, sigma1 = 0, gain = 1, latent = 0;
-            if (KIND == KIND_TRIALWISE) {
-                drift = (Real)prm[0]; beta = (Real)prm[1]; dcoef = (Real)prm[3];
-                bound = (Real)a.bound_in[g];
-                latent = bound;
-            } else if (KIND == KIND_FIXED) {
-                drift = (Real)prm[0]; bound = (Real)prm[1]; beta = (Real)prm[2]; dcoef = (Real)prm[4];
-            } else if (KIND == KIND_DRIFT) {  // basic_ddm_eta_dc.py:87-88
-                bound = (Real)prm[1]; beta = (Real)prm[2]; dcoef = (Real)prm[5];
-                const Real z = (Real)(BUFFER ? buf.next() : philox_normal(STREAM_AUX, 1u));
-                drift = (Real)prm[0] + (Real)prm[4] * z;
-            } else {
-                drift = (Real)prm[0]; beta = (Real)prm[2]; sigma1 = (Real)prm[6];
-                const Real mu = (KIND == KIND_BOUND) ? (Real)prm[1] : (Real)prm[5];
-                const Real sd = (Real)prm[4];
-                uint32_t i = 0;
-                for (;;) {
-                    const Real z = (Real)(BUFFER ? buf.next() : philox_normal(STREAM_AUX, 1u + i));
-                    latent = mu + sd * z;  // separate mul and add: see -fmad=false in build
-                    i++;
-                    if (latent > (Real)0) break;
-                    if (i >= 6u * REJECT_CAP_BLOCKS - 1u) { cap++; latent = (Real)1e-30; break; }
-                }
-                if (KIND == KIND_BOUND) {
-                    bound = latent; dcoef = (Real)prm[5];
-                    gain = (a.model == 3) ? (Real)prm[7] : ((a.model == 4) ? (Real)2 : (Real)1);
-                } else {
-                    bound = (Real)prm[1]; dcoef = latent; gain = (Real)1;
-                }
-            }
-            const Real dt = (Real)a.dt, sqrt_dt = (Real)a.sqrt_dt;
-            Real ev = bound * beta;
-            while ((ev > (Real)0) && (ev < bound) && (n < a.max_steps)) {
-                const Real z = (Real)(BUFFER ? buf.next() : philox_normal(STREAM_STEP, n));
-                const Real t1 = drift * dt;
-                const Real t2 = sqrt_dt * dcoef;
-                const Real t3 = t2 * z;
-                ev = ev + (t1 + t3);
-                n++;
-            }
-            choice = (ev >= bound) ? 1 : ((ev <= (Real)0) ? -1 : 0);
-            final_ev = (double)ev;
-            if (KIND == KIND_TRIALWISE) {
-                ext = (double)bound;
-            } else if (KIND != KIND_FIXED && KIND != KIND_DRIFT) {
-                const Real z = (Real)(BUFFER ? buf.next() : philox_normal(STREAM_AUX, 0u));
-                const Real e = gain * latent + sigma1 * z;
-                ext = (double)e;
-            }
-            if (BUFFER && buf.overrun) atomicAdd(a.stats + STAT_DBG_OVERRUN, 1ull);
-        }
-        double o0, o1;
-        trial_outputs<(KIND == KIND_FIXED || KIND == KIND_DRIFT)>(a.flags, choice, n, a.dt, tau, ext, o0, o1);
-        if (a.flags & 16) o1 = final_ev;
-        store_pair<OUT64>(a.out, g, o0, o1);
-        if (a.steps_out) a.steps_out[g] = (int32_t)n;
-        acc_steps = n;
-        tout = (choice == 0);
-        upper = (choice > 0);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        acc_steps += __shfl_xor_sync(FULL_MASK, acc_steps, o);
-        tout += __shfl_xor_sync(FULL_MASK, tout, o);
-        upper += __shfl_xor_sync(FULL_MASK, upper, o);
-        cap += __shfl_xor_sync(FULL_MASK, cap, o);
-    }
-    if ((threadIdx.x & 31u) == 0u) {
-        atomicAdd(a.stats + STAT_STEPS, acc_steps);
-        if (tout) atomicAdd(a.stats + STAT_TIMEOUTS, (unsigned long long)tout);
-        if (upper) atomicAdd(a.stats + STAT_UPPER, (unsigned long long)upper);
-        if (cap) atomicAdd(a.stats + STAT_REJECT_CAP, (unsigned long long)cap);
-    }
+template __global__ void tile_kernel<KIND_FIXED,false>(const __grid_constant__ RunArgs);
+template __global__ void tile_kernel<KIND_BOUND,false>(const __grid_constant__ RunArgs);
 }
-
-// --------------------------------------------------------------------------------
-// general (two-latent, two-channel) model, one thread per trial: validation twin of
-// persistent_kernel<KIND_GENERAL>
-// --------------------------------------------------------------------------------
-template <typename Real, bool BUFFER, bool OUT64>
-__global__ void __launch_bounds__(128) general_generic_kernel(const RunArgs a, uint64_t total) {
-    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long acc_steps = 0;
-    uint32_t tout = 0, upper = 0, cap = 0;
-    if (g < total) {
-        const uint32_t ds = (uint32_t)(g / a.n_trials);
-        const uint32_t trial = (uint32_t)(g - (uint64_t)ds * a.n_trials);
-        const uint32_t ds_g = ds + a.dataset_offset, trial_g = trial + a.trial_offset;
-        const double *p = a.params + (size_t)ds * 24;
-        uint32_t n = 0;
-        int choice = 0;
-        double e1 = 0.0, e2 = 0.0, final_ev = 0.0;
-        if (sizeof(Real) == 4 && !BUFFER && !(a.flags & FLAG_REFERENCE_ARITHMETIC)) {
-            // the persistent kernel's arithmetic, naive scheduling
-            TrialF32 t;
-            trial_setup_general(a.gconst[ds], trial_g, ds_g, a.key, t, cap);
-            float x = t.x;
-            uint32_t alive = ((fabsf(x) < t.h) && (a.max_steps > 0u)) ? 1u : 0u;
-            for (uint32_t blk = 0; alive != 0u; blk++)
-                step_block_f32<true>(blk, trial_g, ds_g, a.key, t, x, n, alive, a.max_steps);
-            choice = (x >= t.h) ? 1 : ((x <= -t.h) ? -1 : 0);
-            e1 = (double)t.ext;
-            e2 = (double)t.ext2;
-            final_ev = (double)__fmul_rn(__fadd_rn(x, t.h), t.u);
-        } else {
-            // the reference's formulas in Real, operation for operation (fp64: bit-equal to the numba loop)
-            NormalStreamBuf buf{BUFFER ? a.dbg_z + a.dbg_off[g] : nullptr, BUFFER ? a.dbg_z + a.dbg_n : nullptr, false};
-            double zc[6];
-            uint32_t ztag = 0xffffffffu;
-            auto normal = [&](uint32_t stream, uint32_t idx) -> double {
-                if (BUFFER) return buf.next();
-                const uint32_t b = idx / 6u, tag = b | (stream << 31);
-                if (tag != ztag) {
-                    if (sizeof(Real) == 8 && !(a.flags & 32)) {
-                        philox_normals6_f64(b, trial_g, ds_g, stream, a.key, zc);
-                    } else {
-                        float zf[6];
-                        philox_normals6_f32(b, trial_g, ds_g, stream, a.key, zf);
-#pragma unroll
-                        for (int i = 0; i < 6; i++) zc[i] = zf[i];
-                    }
-                    ztag = tag;
-                }
-                return zc[idx - 6u * b];
-            };
-            int ord = (int)p[20];
-            if (ord < 0 || ord > 5) ord = 0;
-            Real lat[3] = {(Real)p[0], (Real)p[2], (Real)p[4]};
-            uint32_t cand[3] = {0u, 0u, 0u};
-            for (int k = 0; k < 3; k++) {
-                // permutations of (drift, boundary, dc): 012 021 102 120 201 210
-                const int which = (k == 0) ? (ord >> 1) : ((k == 1) ? ((0x102021 >> (4 * ord)) & 3) : ((0x010212 >> (4 * ord)) & 3));
-                const Real mu = (Real)p[2 * which], sd = (Real)p[2 * which + 1];
-                if (sd == (Real)0) continue;
-                for (;;) {
-                    const uint32_t idx = (which == 0) ? 2u : (which == 1 ? 4u + 2u * cand[1] : 5u + 2u * cand[2]);
-                    lat[which] = mu + sd * (Real)normal(STREAM_AUX, idx);
-                    cand[which]++;
-                    if (which == 0 || lat[which] > (Real)0) break;
-                    if (cand[which] >= 3u * REJECT_CAP_BLOCKS - 2u) { cap++; lat[which] = (Real)1e-30; break; }
-                }
-            }
-            const Real drift_t = lat[0], bound_t = lat[1], dc_t = lat[2];
-            const Real dt = (Real)a.dt, sqrt_dt = (Real)a.sqrt_dt, beta = (Real)p[6];
-            Real ev = bound_t * beta;
-            while ((ev > (Real)0) && (ev < bound_t) && (n < a.max_steps)) {
-                const Real z = (Real)normal(STREAM_STEP, n);
-                const Real t1 = drift_t * dt;
-                const Real t2 = sqrt_dt * dc_t;
-                const Real t3 = t2 * z;
-                ev = ev + (t1 + t3);
-                n++;
-            }
-            choice = (ev >= bound_t) ? 1 : ((ev <= (Real)0) ? -1 : 0);
-            final_ev = (double)ev;
-            const int n_ext = (int)p[21];
-            Real ext[2] = {(Real)0, (Real)0};
-            for (int c = 0; c < 2 && c < n_ext; c++) {
-                const double *e = p + 8 + 6 * c;
-                const Real loc = ((Real)e[0] * drift_t + (Real)e[1] * bound_t) + (Real)e[2] * dc_t;
-                const Real temp = loc + (Real)e[3] * (Real)normal(STREAM_AUX, (uint32_t)c);
-                ext[c] = (temp - (Real)e[4]) / (Real)e[5];
-            }
-            e1 = (double)ext[0];
-            e2 = (double)ext[1];
-            if (BUFFER && buf.overrun) atomicAdd(a.stats + STAT_DBG_OVERRUN, 1ull);
-        }
-        double o0, o1;
-        if ((int)p[22] == 0) {
-            trial_outputs<true>(a.flags, choice, n, a.dt, p[7], 0.0, o0, o1);
-            store_triple<OUT64>(a.out, g, o0, o1, (a.flags & 16) ? final_ev : e1);
-        } else {
-            trial_outputs<false>(a.flags, choice, n, a.dt, p[7], e1, o0, o1);
-            store_triple<OUT64>(a.out, g, o0, o1, (a.flags & 16) ? final_ev : e2);
-        }
-        if (a.steps_out) a.steps_out[g] = (int32_t)n;
-        acc_steps = n;
-        tout = (choice == 0);
-        upper = (choice > 0);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        acc_steps += __shfl_xor_sync(FULL_MASK, acc_steps, o);
-        tout += __shfl_xor_sync(FULL_MASK, tout, o);
-        upper += __shfl_xor_sync(FULL_MASK, upper, o);
-        cap += __shfl_xor_sync(FULL_MASK, cap, o);
-    }
-    if ((threadIdx.x & 31u) == 0u) {
-        atomicAdd(a.stats + STAT_STEPS, acc_steps);
-        if (tout) atomicAdd(a.stats + STAT_TIMEOUTS, (unsigned long long)tout);
-        if (upper) atomicAdd(a.stats + STAT_UPPER, (unsigned long long)upper);
-        if (cap) atomicAdd(a.stats + STAT_REJECT_CAP, (unsigned long long)cap);
-    }
-}
-
-// --------------------------------------------------------------------------------
-// parity hooks
-// --------------------------------------------------------------------------------
-__global__ void export_normals_kernel(PhiloxKey key, uint32_t dataset, uint32_t trial, uint32_t stream,
-                                      uint32_t first, uint32_t count, int f64, double *out) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    const uint32_t idx = first + i;
-    const uint32_t b = idx / 6u, j = idx - 6u * b;
-    if (f64) {
-        double z[6];
-        philox_normals6_f64(b, trial, dataset, stream, key, z);
-        out[i] = z[j];
-    } else {
-        float z[6];
-        philox_normals6_f32(b, trial, dataset, stream, key, z);
-        out[i] = (double)z[j];
-    }
-}
-
-__global__ void philox_blocks_kernel(const uint32_t *ctr, const uint32_t *key, uint32_t *out, int64_t n) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t o[4];
-    philox4x32<10>(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], key[2 * i], key[2 * i + 1], o);
-    out[4 * i] = o[0]; out[4 * i + 1] = o[1]; out[4 * i + 2] = o[2]; out[4 * i + 3] = o[3];
-}
-
-// --------------------------------------------------------------------------------
-// launchers
-// --------------------------------------------------------------------------------
-cudaError_t launch_prep(const double *params, DsConst *dconst, uint32_t n_datasets, uint32_t n_params,
-                        int model, double dt, cudaStream_t s) {
-    const int block = 128;
-    const unsigned grid = (n_datasets + block - 1) / block;
-    prep_kernel<<<grid, block, 0, s>>>(params, dconst, n_datasets, n_params, model, dt);
-    return cudaGetLastError();
-}
-
-template <int KIND>
-static cudaError_t launch_persistent_kind(const RunArgs &a, bool out64, int grid, int block, cudaStream_t s) {
-    if (out64) persistent_kernel<KIND, true><<<grid, block, 0, s>>>(a);
-    else persistent_kernel<KIND, false><<<grid, block, 0, s>>>(a);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_persistent(const RunArgs &a, int kind, bool out64, int grid, int block, cudaStream_t s) {
-    switch (kind) {
-    case KIND_FIXED: return launch_persistent_kind<KIND_FIXED>(a, out64, grid, block, s);
-    case KIND_BOUND: return launch_persistent_kind<KIND_BOUND>(a, out64, grid, block, s);
-    case KIND_DC: return launch_persistent_kind<KIND_DC>(a, out64, grid, block, s);
-    case KIND_DRIFT: return launch_persistent_kind<KIND_DRIFT>(a, out64, grid, block, s);
-    case KIND_GENERAL: return launch_persistent_kind<KIND_GENERAL>(a, out64, grid, block, s);
-    default: return cudaErrorInvalidValue;
-    }
-}
-
-template <int KIND>
-static cudaError_t launch_tile_kind(const RunArgs &a, bool out64, int grid, int block, size_t smem, cudaStream_t s) {
-    // the tile buffers want most of the SM's 228 KB as shared memory (6 blocks x up to 28 KB)
-    static bool configured[2] = {false, false};
-    if (!configured[out64 ? 1 : 0]) {
-        cudaError_t e = out64 ? cudaFuncSetAttribute(tile_kernel<KIND, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                                     cudaSharedmemCarveoutMaxShared)
-                              : cudaFuncSetAttribute(tile_kernel<KIND, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                                     cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return e;
-        configured[out64 ? 1 : 0] = true;
-    }
-    if (out64) tile_kernel<KIND, true><<<grid, block, smem, s>>>(a);
-    else tile_kernel<KIND, false><<<grid, block, smem, s>>>(a);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_tile(const RunArgs &a, int kind, bool out64, int grid, int block, size_t smem, cudaStream_t s) {
-    switch (kind) {
-    case KIND_FIXED: return launch_tile_kind<KIND_FIXED>(a, out64, grid, block, smem, s);
-    case KIND_BOUND: return launch_tile_kind<KIND_BOUND>(a, out64, grid, block, smem, s);
-    case KIND_DC: return launch_tile_kind<KIND_DC>(a, out64, grid, block, smem, s);
-    case KIND_TRIALWISE: return launch_tile_kind<KIND_TRIALWISE>(a, out64, grid, block, smem, s);
-    case KIND_DRIFT: return launch_tile_kind<KIND_DRIFT>(a, out64, grid, block, smem, s);
-    case KIND_GENERAL: return launch_tile_kind<KIND_GENERAL>(a, out64, grid, block, smem, s);
-    default: return cudaErrorInvalidValue;
-    }
-}
-
-template <int KIND>
-static size_t tile_smem_of(int block) {
-    return (size_t)(block / 32) * ((size_t)TileLayout<KIND>::WORDS * TileLayout<KIND>::T + M_WORDS) * sizeof(uint32_t);
-}
-
-size_t tile_kernel_smem_bytes(int kind, int block) {
-    switch (kind) {
-    case KIND_FIXED: return tile_smem_of<KIND_FIXED>(block);
-    case KIND_BOUND: return tile_smem_of<KIND_BOUND>(block);
-    case KIND_DC: return tile_smem_of<KIND_DC>(block);
-    case KIND_TRIALWISE: return tile_smem_of<KIND_TRIALWISE>(block);
-    case KIND_DRIFT: return tile_smem_of<KIND_DRIFT>(block);
-    default: return tile_smem_of<KIND_GENERAL>(block);
-    }
-}
-
-uint32_t tile_kernel_max_tile(int kind) { return kind == KIND_GENERAL ? TileLayout<KIND_GENERAL>::T : 128u; }
-
-int tile_kernel_max_blocks_per_sm(int kind, bool out64, int block, size_t smem) {
-    int nb = 0;
-    cudaError_t e = cudaErrorInvalidValue;
-#define DDM_OCC(K, O) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tile_kernel<K, O>, block, smem)
-    if (kind == KIND_FIXED) { if (out64) DDM_OCC(KIND_FIXED, true); else DDM_OCC(KIND_FIXED, false); }
-    else if (kind == KIND_BOUND) { if (out64) DDM_OCC(KIND_BOUND, true); else DDM_OCC(KIND_BOUND, false); }
-    else if (kind == KIND_DC) { if (out64) DDM_OCC(KIND_DC, true); else DDM_OCC(KIND_DC, false); }
-    else if (kind == KIND_TRIALWISE) { if (out64) DDM_OCC(KIND_TRIALWISE, true); else DDM_OCC(KIND_TRIALWISE, false); }
-    else if (kind == KIND_DRIFT) { if (out64) DDM_OCC(KIND_DRIFT, true); else DDM_OCC(KIND_DRIFT, false); }
-    else if (kind == KIND_GENERAL) { if (out64) DDM_OCC(KIND_GENERAL, true); else DDM_OCC(KIND_GENERAL, false); }
-#undef DDM_OCC
-    return (e == cudaSuccess) ? nb : -1;
-}
-
-static size_t record_smem_bytes(int block) { return (size_t)block * (REC_RING + 1) * sizeof(float); }
-
-cudaError_t launch_persistent_record(const RunArgs &a, int grid, int block, cudaStream_t s) {
-    persistent_kernel<KIND_FIXED, true, true><<<grid, block, record_smem_bytes(block), s>>>(a);
-    return cudaGetLastError();
-}
-
-int persistent_record_max_blocks_per_sm(int block) {
-    int nb = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, persistent_kernel<KIND_FIXED, true, true>, block,
-                                                                  record_smem_bytes(block));
-    return (e == cudaSuccess) ? nb : -1;
-}
-
-int persistent_block_size() { return DDM_PERSISTENT_BLOCK; }
-
-int persistent_max_blocks_per_sm(int kind, bool out64, int block) {
-    int nb = 0;
-    cudaError_t e = cudaErrorInvalidValue;
-#define DDM_OCC(K, O) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, persistent_kernel<K, O>, block, 0)
-    if (kind == KIND_FIXED) { if (out64) DDM_OCC(KIND_FIXED, true); else DDM_OCC(KIND_FIXED, false); }
-    else if (kind == KIND_BOUND) { if (out64) DDM_OCC(KIND_BOUND, true); else DDM_OCC(KIND_BOUND, false); }
-    else if (kind == KIND_DC) { if (out64) DDM_OCC(KIND_DC, true); else DDM_OCC(KIND_DC, false); }
-    else if (kind == KIND_DRIFT) { if (out64) DDM_OCC(KIND_DRIFT, true); else DDM_OCC(KIND_DRIFT, false); }
-    else if (kind == KIND_GENERAL) { if (out64) DDM_OCC(KIND_GENERAL, true); else DDM_OCC(KIND_GENERAL, false); }
-#undef DDM_OCC
-    return (e == cudaSuccess) ? nb : -1;
-}
-
-template <typename Real, int KIND, bool BUFFER>
-static cudaError_t launch_generic_3(const RunArgs &a, bool out64, uint64_t total, cudaStream_t s) {
-    const int block = 128;
-    const unsigned grid = (unsigned)((total + block - 1) / block);
-    if (grid == 0) return cudaSuccess;
-    if (out64) generic_kernel<Real, KIND, BUFFER, true><<<grid, block, 0, s>>>(a, total);
-    else generic_kernel<Real, KIND, BUFFER, false><<<grid, block, 0, s>>>(a, total);
-    return cudaGetLastError();
-}
-
-template <typename Real, int KIND>
-static cudaError_t launch_generic_2(const RunArgs &a, bool buffer_src, bool out64, uint64_t total, cudaStream_t s) {
-    return buffer_src ? launch_generic_3<Real, KIND, true>(a, out64, total, s)
-                      : launch_generic_3<Real, KIND, false>(a, out64, total, s);
-}
-
-template <typename Real>
-static cudaError_t launch_generic_1(const RunArgs &a, int kind, bool buffer_src, bool out64, uint64_t total,
-                                    cudaStream_t s) {
-    switch (kind) {
-    case KIND_FIXED: return launch_generic_2<Real, KIND_FIXED>(a, buffer_src, out64, total, s);
-    case KIND_BOUND: return launch_generic_2<Real, KIND_BOUND>(a, buffer_src, out64, total, s);
-    case KIND_DC: return launch_generic_2<Real, KIND_DC>(a, buffer_src, out64, total, s);
-    case KIND_TRIALWISE: return launch_generic_2<Real, KIND_TRIALWISE>(a, buffer_src, out64, total, s);
-    case KIND_DRIFT: return launch_generic_2<Real, KIND_DRIFT>(a, buffer_src, out64, total, s);
-    default: return cudaErrorInvalidValue;
-    }
-}
-
-template <typename Real>
-static cudaError_t launch_general_generic(const RunArgs &a, bool buffer_src, bool out64, uint64_t total, cudaStream_t s) {
-    const unsigned grid = (unsigned)((total + 127) / 128);
-    if (grid == 0) return cudaSuccess;
-    if (buffer_src) {
-        if (out64) general_generic_kernel<Real, true, true><<<grid, 128, 0, s>>>(a, total);
-        else general_generic_kernel<Real, true, false><<<grid, 128, 0, s>>>(a, total);
-    } else {
-        if (out64) general_generic_kernel<Real, false, true><<<grid, 128, 0, s>>>(a, total);
-        else general_generic_kernel<Real, false, false><<<grid, 128, 0, s>>>(a, total);
-    }
-    return cudaGetLastError();
-}
-
-cudaError_t launch_prep_general(const double *params, GenConst *gconst, uint32_t n_datasets, double dt, cudaStream_t s) {
-    if (n_datasets == 0) return cudaSuccess;
-    prep_general_kernel<<<(n_datasets + 127) / 128, 128, 0, s>>>(params, gconst, n_datasets, dt);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_generic(const RunArgs &a, int kind, bool f64, bool buffer_src, bool out64,
-                           uint64_t total_trials, cudaStream_t s) {
-    if (kind == KIND_GENERAL)
-        return f64 ? launch_general_generic<double>(a, buffer_src, out64, total_trials, s)
-                   : launch_general_generic<float>(a, buffer_src, out64, total_trials, s);
-    return f64 ? launch_generic_1<double>(a, kind, buffer_src, out64, total_trials, s)
-               : launch_generic_1<float>(a, kind, buffer_src, out64, total_trials, s);
-}
-
-cudaError_t launch_export_normals(PhiloxKey key, uint32_t dataset, uint32_t trial, uint32_t stream,
-                                  uint32_t first, uint32_t count, bool f64, double *out_dev, cudaStream_t s) {
-    if (count == 0) return cudaSuccess;
-    const int block = 128;
-    export_normals_kernel<<<(count + block - 1) / block, block, 0, s>>>(key, dataset, trial, stream, first,
-                                                                         count, f64 ? 1 : 0, out_dev);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_philox_blocks(const uint32_t *ctr, const uint32_t *key, uint32_t *out, int64_t n,
-                                 cudaStream_t s) {
-    if (n <= 0) return cudaSuccess;
-    const int block = 128;
-    philox_blocks_kernel<<<(unsigned)((n + block - 1) / block), block, 0, s>>>(ctr, key, out, n);
-    return cudaGetLastError();
-}
-
-}  // namespace ddm

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <climits>
 #include <cstring>
 #include <mutex>
@@ -1345,6 +1346,27 @@ DDM_API int ddm_last_output_histogram(ddm_ctx *ctx, int n_bins, double rt_max, u
     return DDM_OK;
 }
 
+// C5 as SURVEY.md section 8d specifies it: host parameters in, the batch simulated and reduced on the device, only the
+// histogram comes back.  One call = H2D of the parameters, prep + simulator kernel (float32 rows, resident),
+// histogram kernel, D2H of 2 n_bins + 2 counters.
+DDM_API int ddm_simulate_histogram(ddm_ctx *ctx, int model, const double *params, int64_t n_datasets, int n_params,
+                                   int64_t n_trials, double dt, int max_steps, uint64_t seed, uint64_t dataset_offset,
+                                   int precision, int flags, int n_bins, double rt_max, uint64_t *hist_host) {
+    if (!ctx || !hist_host) return DDM_ERR_INVALID;
+    if (n_bins < 1 || n_bins > 8192 || !(rt_max > 0.0)) return fail(ctx, DDM_ERR_INVALID, "need 1 <= n_bins <= 8192 and rt_max > 0");
+    if (model == DDM_MODEL_GENERAL || model == DDM_MODEL_TRIALWISE)
+        return fail(ctx, DDM_ERR_INVALID, "ddm_simulate_histogram takes the two-column dataset-wise models");
+    int rc = ddm_upload_params(ctx, model, params, n_datasets, n_params);
+    if (rc) return rc;
+    rc = ddm_run(ctx, n_trials, dt, max_steps, seed, dataset_offset, precision, (flags | DDM_FLAG_OUT_F32) & ~DDM_FLAG_KEEP_STEPS);
+    if (rc) return rc;
+    if (n_datasets * n_trials == 0) {
+        std::memset(hist_host, 0, (2 * (size_t)n_bins + 2) * sizeof(uint64_t));
+        return DDM_OK;
+    }
+    return ddm_last_output_histogram(ctx, n_bins, rt_max, hist_host);
+}
+
 DDM_API int ddm_last_output_device_ptr(ddm_ctx *ctx, void **ptr, size_t *bytes) {
     if (!ctx || !ptr) return DDM_ERR_INVALID;
     if (!ctx->have_run || !ctx->out || !ctx->out_resident) return fail(ctx, DDM_ERR_STATE, "no output resident");
@@ -1434,6 +1456,25 @@ DDM_API int ddm_export_normals(ddm_ctx *ctx, uint64_t seed, uint64_t dataset, ui
     return DDM_OK;
 }
 
+DDM_API int ddm_normals_histogram(ddm_ctx *ctx, uint64_t seed, uint64_t n_normals, int n_bins_abs, double z_max, int n_bins_angle,
+                                  uint64_t *hist_host, double *moments_host) {
+    if (!ctx || !hist_host || !moments_host) return DDM_ERR_INVALID;
+    if (n_bins_abs < 1 || n_bins_abs > 4096 || n_bins_angle < 1 || n_bins_angle > 4096 || !(z_max > 0.0))
+        return fail(ctx, DDM_ERR_INVALID, "need 1 <= bins <= 4096 and z_max > 0");
+    DeviceGuard g(ctx->device);
+    const size_t n_cells = (size_t)n_bins_abs + 1 + (size_t)n_bins_angle;
+    DDM_CUDA(ctx, ctx->hist.reserve(n_cells + 4));  // histogram + four double moments behind it
+    DDM_CUDA(ctx, cudaMemsetAsync(ctx->hist.p, 0, (n_cells + 4) * sizeof(unsigned long long), ctx->stream));
+    double *mom = reinterpret_cast<double *>(ctx->hist.p + n_cells);
+    const ddm::PhiloxKey key = ddm::make_philox_key((uint32_t)seed, (uint32_t)(seed >> 32));
+    DDM_CUDA(ctx, ddm::launch_normals_histogram(key, (n_normals + 5) / 6, (uint32_t)n_bins_abs, z_max, (uint32_t)n_bins_angle, ctx->hist.p, mom,
+                                                ctx->sm_count, ctx->stream));
+    DDM_CUDA(ctx, cudaMemcpyAsync(hist_host, ctx->hist.p, n_cells * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    DDM_CUDA(ctx, cudaMemcpyAsync(moments_host, mom, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    DDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DDM_OK;
+}
+
 DDM_API int64_t ddm_pipeline_chunks(int64_t n_datasets, int64_t n_trials, int64_t chunk_rows, int64_t *first, int64_t *count,
                                     int64_t capacity) {
     if (n_datasets < 0 || n_trials < 0) return DDM_ERR_INVALID;
@@ -1464,6 +1505,24 @@ DDM_API int ddm_wire_decode_host(const void *wire, void *out_host, const double 
     job.timeout_choice_one = (flags & DDM_FLAG_TIMEOUT_CHOICE_ONE) != 0;
     ddm::wire_decode(w, job);
     ddm::host_workers_destroy(w);
+    return DDM_OK;
+}
+
+DDM_API int ddm_host_stream_peak(int n_threads, size_t bytes, double *bytes_per_s) {
+    if (!bytes_per_s || n_threads < 0 || n_threads > 256 || bytes < (1u << 20)) return DDM_ERR_INVALID;
+    if (n_threads == 0) {
+        int gpus = 1;
+        if (cudaGetDeviceCount(&gpus) != cudaSuccess) gpus = 1;
+        n_threads = ddm::host_workers_default_count(gpus);
+    }
+    void *buf = nullptr;
+    if (posix_memalign(&buf, 4096, bytes) != 0 || !buf) return DDM_ERR_NOMEM;
+    ddm::HostWorkers *w = ddm::host_workers_create(n_threads);
+    ddm::host_workers_begin(w);
+    *bytes_per_s = ddm::host_stream_store_rate(w, buf, bytes, 5);
+    ddm::host_workers_end(w);
+    ddm::host_workers_destroy(w);
+    free(buf);
     return DDM_OK;
 }
 

@@ -261,6 +261,22 @@ __device__ __forceinline__ void euler6_warp(float &x, uint32_t &n, unsigned &ali
                    "f"(z.s[2]), "f"(z.c[2]), "f"(z.sn[2]), "r"(max_steps));
 }
 
+// The same with the lane's own bit handed in (the tile kernel holds it in a register anyway; reading
+// %lanemask_eq costs an S2R per block when the compiler does not hoist it).
+__device__ __forceinline__ void euler6_warp_lb(float &x, uint32_t &n, unsigned &alive, unsigned lane_bit, float c0, float h,
+                                               const Normals6Scaled &z, uint32_t max_steps) {
+    asm volatile("{\n\t.reg .pred q;\n\t.reg .f32 ax, inc;\n\t.reg .b32 t;\n\t"
+                 "and.b32 t, %15, %2;\n\t"
+                 "setp.ne.u32 q, t, 0;\n\t"
+                 DDM_STEP("%5", "%6") DDM_STEP("%5", "%7") DDM_STEP("%8", "%9")
+                 DDM_STEP("%8", "%10") DDM_STEP("%11", "%12") DDM_STEP("%11", "%13")
+                 "setp.lt.and.u32 q, %1, %14, q;\n\t"
+                 "vote.sync.ballot.b32 %2, q, 0xffffffff;\n\t}"
+                 : "+f"(x), "+r"(n), "+r"(alive)
+                 : "f"(c0), "f"(h), "f"(z.s[0]), "f"(z.c[0]), "f"(z.sn[0]), "f"(z.s[1]), "f"(z.c[1]), "f"(z.sn[1]),
+                   "f"(z.s[2]), "f"(z.c[2]), "f"(z.sn[2]), "r"(max_steps), "r"(lane_bit));
+}
+
 // The same block for the evidence-path models: also hands back the state after each of the six
 // steps (r[k] = x after step k+1; frozen at the crossing value once the lane has stopped), which the
 // caller stores as the observed path.
@@ -337,6 +353,8 @@ cudaError_t launch_exact_sampler(const double *params, double *out, unsigned lon
                                  cudaStream_t s);
 cudaError_t launch_rt_histogram(const void *rows, bool rows64, uint64_t n_rows, uint32_t cols, bool basic_layout, uint32_t n_bins,
                                 double rt_max, unsigned long long *hist, int sm_count, cudaStream_t s);
+cudaError_t launch_normals_histogram(const PhiloxKey &key, uint64_t n_blocks, uint32_t nb_abs, double z_max, uint32_t nb_ang,
+                                     unsigned long long *hist, double *moments, int sm_count, cudaStream_t s);
 cudaError_t launch_evidence_post(const EvidenceArgs &a, bool out64, uint64_t total, int sm_count, cudaStream_t s);
 cudaError_t launch_evidence_generic(const EvidenceArgs &a, bool buffer_src, uint64_t total, cudaStream_t s);
 cudaError_t launch_evidence_dataset_stats(const double *path_means, double *ds_stats, uint32_t n_datasets,

@@ -3,6 +3,7 @@
 // a roofline").  Every kernel runs 8 blocks x 256 threads per SM (64 resident warps, the
 // simulator's own occupancy class) with 8 independent dependency chains per thread.
 #include <cstdint>
+#include <cstdlib>
 
 #include "../../include/ddm_b200.h"
 #include "ddm_kernels.cuh"
@@ -69,6 +70,17 @@ __global__ void __launch_bounds__(256) microbench_kernel(int iters, uint32_t see
                     else if (c == 1 || c == 2) xl[c] = (uint64_t)(uint32_t)xl[c] * (uint64_t)PHILOX_M0 + xl[c];
                     else if (c <= 5) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(xi[c]) : "r"(ka), "r"(kb));
                     else xf[c] = __fmaf_rn(xf[c], fa, fb);
+                } else if (WHICH == DDM_MB_FFMA_REG) {        // three register operands (the Euler step's form)
+                    xf[c] = __fmaf_rn(xf[c], xf[(c + 3) & 7], xf[(c + 5) & 7]);
+                } else if (WHICH == DDM_MB_FADD_REG) {
+                    xf[c] = __fadd_rn(xf[c], xf[(c + 3) & 7]);
+                } else if (WHICH == DDM_MB_IMAD_WIDE_NOACC) {  // the Philox round's form: 32 x 32 -> 64, no addend
+                    xl[c] = (uint64_t)((uint32_t)xl[c] ^ (uint32_t)(xl[c] >> 32)) * (uint64_t)PHILOX_M0;
+                } else if (WHICH == DDM_MB_IMAD_HI) {
+                    xi[c] = __umulhi(xi[c], PHILOX_M0) + ka;
+                } else if (WHICH == DDM_MB_FFMA2) {            // packed fp32 pair (sm_100 fma.rn.f32x2), counted as one instruction
+                    asm volatile("{ .reg .b64 a, b, d; mov.b64 a, {%0, %1}; mov.b64 b, {%2, %3}; fma.rn.f32x2 d, a, b, b; mov.b64 {%0, %1}, d; }"
+                                 : "+f"(xf[c]), "+f"(xf[(c + 4) & 7]) : "f"(fa), "f"(fb));
                 } else if (WHICH == DDM_MB_FSETP) {
                     asm volatile("{ .reg .pred p; setp.lt.f32 p, %1, %2; @p add.u32 %0, %0, 1; }" : "+r"(xi[c]) : "f"(xf[c]), "f"(fa));
                 }
@@ -78,6 +90,18 @@ __global__ void __launch_bounds__(256) microbench_kernel(int iters, uint32_t see
             uint32_t w[4];
             philox4x32<10>((uint32_t)it, tid, xi[0], 0u, ka, kb, w);
             xi[0] ^= w[0] ^ w[1] ^ w[2] ^ w[3];
+        } else if (WHICH == DDM_MB_PHILOX7) {
+            uint32_t w[4];
+            philox4x32<7>((uint32_t)it, tid, xi[0], 0u, ka, kb, w);
+            xi[0] ^= w[0] ^ w[1] ^ w[2] ^ w[3];
+        } else if (WHICH == DDM_MB_NORMALS2) {
+            // two independent trials per lane: does instruction-level parallelism inside a warp buy issue slots?
+            TrialF32 t;
+            t.h = 3.4e38f; t.c0 = fb; t.u = fa; t.x = 0.f; t.ext = 0.f;
+            uint32_t n = 0u, p = 1u, n2 = 0u, p2 = 1u;
+            step_block_f32<false>((uint32_t)it, tid, xi[0], key, t, xf[0], n, p, 0xffffffffu);
+            step_block_f32<false>((uint32_t)it, tid + 0x40000000u, xi[0], key, t, xf[1], n2, p2, 0xffffffffu);
+            acc += n + n2;
         } else if (WHICH == DDM_MB_NORMALS) {
             // the simulator's own inner block: Philox -> 6 scaled normals -> 6 predicated Euler steps
             TrialF32 t;
@@ -94,9 +118,24 @@ __global__ void __launch_bounds__(256) microbench_kernel(int iters, uint32_t see
     if (threadIdx.x == 0) o.cycles[blockIdx.x] = (unsigned long long)(t1 - t0);
 }
 
+// DDM_MB_BLOCKS_PER_SM (1..8, default 8) limits the resident blocks per SM through the dynamic shared memory
+// request, to measure a mix at the occupancy the simulator kernels actually run at.
+static int mb_blocks_per_sm() {
+    const char *e = getenv("DDM_MB_BLOCKS_PER_SM");
+    const int v = e ? atoi(e) : 8;
+    return v < 1 ? 1 : (v > 8 ? 8 : v);
+}
+
 template <int WHICH>
 static cudaError_t launch_one(int grid, int iters, MbOut o, cudaStream_t s) {
-    microbench_kernel<WHICH><<<grid, 256, 0, s>>>(iters, 12345u, 1.0000001f, 1e-9f, o, make_philox_key(12345u, 678u));
+    const int bps = mb_blocks_per_sm();
+    size_t smem = 0;
+    if (bps < 8) {
+        smem = (size_t)(220 * 1024 / bps) & ~size_t(1023);
+        cudaError_t e = cudaFuncSetAttribute(microbench_kernel<WHICH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    microbench_kernel<WHICH><<<grid, 256, smem, s>>>(iters, 12345u, 1.0000001f, 1e-9f, o, make_philox_key(12345u, 678u));
     return cudaGetLastError();
 }
 
@@ -116,12 +155,19 @@ static cudaError_t launch_which(int which, int grid, int iters, MbOut o, cudaStr
     case DDM_MB_MIX_MUFU_LOP3: return launch_one<DDM_MB_MIX_MUFU_LOP3>(grid, iters, o, s);
     case DDM_MB_MIX_MUFU_IMADW: return launch_one<DDM_MB_MIX_MUFU_IMADW>(grid, iters, o, s);
     case DDM_MB_MIX_BLOCKLIKE: return launch_one<DDM_MB_MIX_BLOCKLIKE>(grid, iters, o, s);
+    case DDM_MB_FFMA_REG: return launch_one<DDM_MB_FFMA_REG>(grid, iters, o, s);
+    case DDM_MB_FADD_REG: return launch_one<DDM_MB_FADD_REG>(grid, iters, o, s);
+    case DDM_MB_IMAD_WIDE_NOACC: return launch_one<DDM_MB_IMAD_WIDE_NOACC>(grid, iters, o, s);
+    case DDM_MB_IMAD_HI: return launch_one<DDM_MB_IMAD_HI>(grid, iters, o, s);
+    case DDM_MB_FFMA2: return launch_one<DDM_MB_FFMA2>(grid, iters, o, s);
+    case DDM_MB_PHILOX7: return launch_one<DDM_MB_PHILOX7>(grid, iters, o, s);
+    case DDM_MB_NORMALS2: return launch_one<DDM_MB_NORMALS2>(grid, iters, o, s);
     default: return cudaErrorInvalidValue;
     }
 }
 
 cudaError_t run_microbench(int which, int iters, int sm_count, cudaStream_t s, double *inst_per_s, double *sm_hz) {
-    const int grid = sm_count * 8;
+    const int grid = sm_count * mb_blocks_per_sm();
     MbOut o{};
     cudaError_t e;
     if ((e = cudaMalloc(&o.cycles, sizeof(unsigned long long) * grid)) != cudaSuccess) return e;
@@ -151,7 +197,8 @@ cudaError_t run_microbench(int which, int iters, int sm_count, cudaStream_t s, d
     cudaFree(o.sink);
     if (e != cudaSuccess) return e;
     const double warps = (double)grid * 256.0 / 32.0;
-    const double per_iter = (which == DDM_MB_PHILOX || which == DDM_MB_NORMALS) ? 1.0
+    const double per_iter = (which == DDM_MB_PHILOX || which == DDM_MB_NORMALS || which == DDM_MB_PHILOX7) ? 1.0
+                          : which == DDM_MB_NORMALS2 ? 2.0
                           : (which == DDM_MB_MIX_FMA_ALU ? (double)(MB_CHAINS * MB_UNROLL) : (double)(MB_CHAINS * MB_UNROLL));
     *inst_per_s = warps * (double)iters * per_iter / best_s;
     // the kernel's longest block spans (almost) the whole launch: cycles / time = SM clock

@@ -405,6 +405,33 @@ class DDMSimulator:
         return {"upper": h[:n_bins].copy(), "lower": h[n_bins:2 * n_bins].copy(), "missing": int(h[2 * n_bins]),
                 "overflow": int(h[2 * n_bins + 1]), "edges": np.linspace(0.0, float(rt_max), int(n_bins) + 1)}
 
+    def simulate_histogram(self, model: int, params, n_trials: int, dt: float = 0.01, max_steps: int = 400, *, seed=None,
+                           dataset_offset=None, precision: int = 32, flags: int = 0, n_bins: int = 400,
+                           rt_max: float = 4.0) -> dict:
+        """Simulate (B, P) host parameters and return only the response-time histogram, reduced on the device
+        (``ddm_simulate_histogram``): the throughput sweep's own output.  The float32
+        rows stay resident (``last_output_dlpack``)."""
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        if params.ndim == 1:
+            params = params[None, :]
+        if params.ndim != 2:
+            raise ValueError("params must be (P,) or (B, P)")
+        B, P = params.shape
+        off = self._next_offset(B, dataset_offset)
+        h = np.zeros(2 * int(n_bins) + 2, dtype=np.uint64)
+        self._check(self._lib.ddm_simulate_histogram(
+            self._ctx, int(model), params.ctypes.data_as(_capi._dp), B, P, int(n_trials), float(dt), int(max_steps),
+            self.seed if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF, off, int(precision), int(flags), int(n_bins),
+            float(rt_max), h.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return {"upper": h[:n_bins].copy(), "lower": h[n_bins:2 * n_bins].copy(), "missing": int(h[2 * n_bins]),
+                "overflow": int(h[2 * n_bins + 1]), "edges": np.linspace(0.0, float(rt_max), int(n_bins) + 1)}
+
+    def host_stream_peak(self, n_threads: int = 0, nbytes: int = 1 << 30) -> float:
+        """Bytes per second this box's host threads reach with the compact wire decode's streaming stores."""
+        v = C.c_double()
+        self._check(self._lib.ddm_host_stream_peak(int(n_threads), int(nbytes), C.byref(v)))
+        return v.value
+
     # ---- parity hooks ---------------------------------------------------------------------
     def set_normals_debug(self, z, offsets):
         """Shared-increment mode: trial t consumes z[offsets[t]:] in the reference's order."""
@@ -423,6 +450,17 @@ class DDMSimulator:
                                                  int(trial), int(stream), int(first), int(count), int(precision),
                                                  out.ctypes.data_as(_capi._dp)))
         return out
+
+    def normals_histogram(self, n_normals: int, n_bins_abs: int = 112, z_max: float = 5.6, n_bins_angle: int = 256, *, seed=None):
+        """|z| and pair-angle histograms and raw moments of ``n_normals`` production-map normals, reduced on the device."""
+        h = np.zeros(int(n_bins_abs) + 1 + int(n_bins_angle), dtype=np.uint64)
+        m = np.zeros(4, dtype=np.float64)
+        self._check(self._lib.ddm_normals_histogram(self._ctx, self.seed if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                                    int(n_normals), int(n_bins_abs), float(z_max), int(n_bins_angle),
+                                                    h.ctypes.data_as(C.POINTER(C.c_uint64)), m.ctypes.data_as(_capi._dp)))
+        n = 6 * ((int(n_normals) + 5) // 6)
+        return {"n": n, "abs": h[:n_bins_abs].copy(), "beyond": int(h[n_bins_abs]), "angle": h[n_bins_abs + 1:].copy(),
+                "edges": np.linspace(0.0, float(z_max), int(n_bins_abs) + 1), "moments": m / n}
 
     def philox4x32(self, ctr, key) -> np.ndarray:
         ctr = np.ascontiguousarray(ctr, dtype=np.uint32).reshape(-1, 4)

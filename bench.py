@@ -9,10 +9,15 @@ every rank simulates its own D datasets at disjoint global dataset indices (disj
 counter ranges), no data-path collective.
 
   value     Euler steps/s, whole job, parameters resident in HBM, output left in HBM
-  e2e       same metric through the reference-facing call
-            basic_ddm_dc.batch_simulate_trials(params_host, n_trials) -> (B, N, 2) float64
-            host array: H2D of the parameters, kernel, D2H of the batch, all inside the timed region
-  roofline  issue-slot roofline of the persistent kernel (not HBM, not tensor: no contraction)
+  e2e       same metric through the reference-facing call with HOST buffers, as SURVEY.md section 8d specifies C5
+            ("outputs reduced on device"): basic_ddm_dc.batch_simulate_histogram(params_host, n_trials)
+            = H2D of the parameters, simulator kernel, histogram kernel, D2H of the histogram, all timed
+  e2e_host_rows  the same batch delivered as (B, N, 2) host arrays (float64 as the reference returns them, and
+            float32 as its configurator casts them), against this host's measured streaming-store rate
+  roofline  issue-slot roofline of the stepping kernel (not HBM, not tensor: no contraction)
+  configs   BASELINE.json's other configurations (C1, C3, C4) through the reference-facing calls and device-
+            resident, with their kernels' roofline fractions; fp64 validation-mode throughput on C5
+  allgather_batch  (N > 1) the one collective of the path: C3-sized training-batch shards -> every rank
   cpu_baseline  the CPU oracle port of the reference's numba loop on this box's host cores
 
 `--impl reference` times that CPU implementation alone (rank 0 only).
@@ -61,6 +66,9 @@ def parse_args():
     ap.add_argument("--host-decode", type=int, default=0,
                     help="e2e leg: host threads expanding the compact PCIe records (0 auto, < 0 float64 rows over PCIe)")
     ap.add_argument("--microbench", action="store_true", help="also measure per-pipe issue rates")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C1/C3/C4/fp64 legs")
+    ap.add_argument("--no-host-rows", action="store_true", help="skip the host-row legs of the end-to-end section")
+    ap.add_argument("--kernel-variant", type=int, default=0, help="0 tile kernel (default), 1 the round-1 persistent kernel")
     return ap.parse_args()
 
 
@@ -226,6 +234,183 @@ def workload_config(datasets_per_gpu: int, note: str = "") -> dict:
     return c
 
 
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json's other configurations (rank 0)
+# ------------------------------------------------------------------------------------------------
+def _median_ms(fn, sim, reps):
+    fn()
+    sim.synchronize()
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        sim.synchronize()
+        ts.append((time.perf_counter() - t0) * 1e3)
+    return float(np.median(ts))
+
+
+def other_configs(sim, issue_peak, want_cpu=True) -> dict:
+    """C1 (1 x 300), C3 (1024 x 1000, per-trial boundary), C4 (Stahl-shaped, 19 374 trials) through the reference-facing
+    calls (host arrays in and out) and device-resident, each with its kernel's time and roofline fraction; and C5's
+    sweep in the fp64 validation mode (the reference's own precision)."""
+    from bayesflow_nddms_b200 import _capi as capi
+    from bayesflow_nddms_b200 import basic_ddm_dc as m0
+    from bayesflow_nddms_b200 import imputation_from_stahl_not_scaled as stahl
+    from bayesflow_nddms_b200 import priors
+    from bayesflow_nddms_b200 import single_trial_alpha_not_scaled as m1
+
+    def kernel_fields(st):
+        k_s = st["kernel_ms"] * 1e-3
+        d = {"kernel_ms": st["kernel_ms"], "euler_steps": st["total_steps"], "persistent": bool(st["used_persistent"])}
+        if k_s > 0:
+            d["kernel_steps_per_s"] = st["total_steps"] / k_s
+            d["kernel_roofline_frac"] = st["total_steps"] * I_STEP / 32.0 / k_s / issue_peak
+        return d
+
+    out = {}
+    orc = None
+    if want_cpu:
+        from oracle import cpu as orc  # the checker, timed beside (cpu_baseline leg)
+
+    # ---- C1: one prior draw x 300 trials (reference defaults dt=.01/400, and the dt=1e-3 BASELINE.json names)
+    p = np.array([3.0, 1.5, 0.5, 0.4, 1.0])          # single_trial_alpha_not_scaled.py:853-883's fixed vector, basic layout
+    for dt, ms, key in ((0.01, 400, "C1_dt0.01"), (0.001, 4000, "C1_dt0.001")):
+        g = _median_ms(lambda: m0.batch_simulate_trials(p[None], 300, sim, dt=dt, max_steps=ms)[0], sim, 200)
+        st = sim.last_stats()
+        dev_ms = _median_ms(lambda: sim.run(0, p[None], 300, dt, ms, flags=capi.FLAG_OUT_F32), sim, 200)
+        out[key] = {"workload": f"basic_ddm_dc: one parameter vector x 300 trials, dt={dt}, max_steps={ms}",
+                    "call_ms": g, "call": "simulate_trials(params (5,), 300) -> (300, 2) float64 host array",
+                    "device_resident_ms": dev_ms, "trials_per_s_call": 300 / (g * 1e-3), **kernel_fields(st)}
+        if orc is not None:
+            t0 = time.perf_counter()
+            for _ in range(20):
+                orc.simulate_batch_mt(0, p[None], 300, dt=dt, max_steps=float(ms))
+            out[key]["cpu_port_1thread_ms"] = (time.perf_counter() - t0) / 20 * 1e3
+
+    # ---- C3: single_trial_alpha_not_scaled, 1024 datasets x 1000 trials, dt=.01
+    P = priors.draw_prior_batch("alpha", 1024, np.random.default_rng(2023))
+    g = _median_ms(lambda: m1.batch_simulate_trials(P, 1000, sim), sim, 30)
+    st = sim.last_stats()
+
+    def c3_device():
+        b = m1.batch_simulate_trials_device(P, 1000, sim)
+        del b
+
+    dev_ms = _median_ms(c3_device, sim, 50)
+    out["C3"] = {"workload": "single_trial_alpha_not_scaled: 1024 datasets x 1000 trials, per-trial boundary, dt=.01, max_steps=400",
+                 "call_ms": g, "call": "batch_simulate_trials(params (1024,7), 1000) -> (1024, 1000, 2) float64 host array (16 MB, pinned pool)",
+                 "device_resident_ms": dev_ms, "device_call": "batch_simulate_trials_device -> DLPack (1024, 1000, 2) float32",
+                 "steps_per_s_call": st["total_steps"] / (g * 1e-3), "steps_per_s_device_resident": st["total_steps"] / (dev_ms * 1e-3),
+                 **kernel_fields(st)}
+    # the same model at a launch size that fills the GPU (20 000 datasets): the kernel's own rate in this regime
+    Pb = priors.draw_prior_batch("alpha", 20_000, np.random.default_rng(2))
+    best = None
+    for _ in range(3):
+        sim.run(1, Pb, 1000, 0.01, 400, flags=capi.FLAG_OUT_F32)
+        stb = sim.last_stats()
+        best = stb if best is None or stb["kernel_ms"] < best["kernel_ms"] else best
+    out["C3_model_at_2e7_trials"] = {"workload": "the same model and dt, 20 000 datasets x 1000 trials (short trials: 43 steps each)",
+                                     "mean_steps_per_trial": best["total_steps"] / best["n_trials"], **kernel_fields(best)}
+    if orc is not None:
+        t0 = time.perf_counter()
+        orc.simulate_batch_mt(1, P[:128], 1000)
+        out["C3"]["cpu_port_1thread_ms"] = (time.perf_counter() - t0) * 8 * 1e3
+        out["C3"]["cpu_port_note"] = "128 of the 1024 datasets timed on one thread, scaled by 8"
+
+    # ---- C4: Stahl-shaped imputation (19 374 trials, 89 participants), fed to training via DLPack
+    subj, pe = stahl.synthetic_stahl_like()
+    pp = stahl.draw_participant_params(89, np.random.default_rng(2024))
+
+    def c4_device():
+        t, _, _ = stahl.impute_dataset(subj, pe, pp, simulator=sim, device=True)
+        del t
+
+    g_dev = _median_ms(c4_device, sim, 50)
+    st = sim.last_stats()
+    g_host = _median_ms(lambda: stahl.impute_dataset(subj, pe, pp, simulator=sim), sim, 50)
+    out["C4"] = {"workload": "imputation_from_stahl_not_scaled: 19 374 Stahl-shaped trials, 89 participants, per-trial boundary from the EEG "
+                             "channel, dt=.01 (synthetic data with the CSV's shape)",
+                 "call_ms": g_host, "call": "impute_dataset(subj_idx, pre_Pe, participant params) -> (19374, 2) float64 host array",
+                 "device_resident_ms": g_dev, "device_call": "impute_dataset(..., device=True) -> torch tensor over the DLPack capsule",
+                 "trials_per_s_device": 19374 / (g_dev * 1e-3), **kernel_fields(st)}
+    if orc is not None:
+        _, alphas = stahl.boundaries_from_pe(pe)
+        _, idx = np.unique(subj, return_inverse=True)
+        t0 = time.perf_counter()
+        for i in range(0, 19374, 97):   # every 97th trial through the scalar oracle, scaled up
+            orc.simulate_mt(5, pp[idx[i]], 1, seed=i, bound_in=[alphas[i]])
+        out["C4"]["cpu_port_1thread_ms"] = (time.perf_counter() - t0) * 97 * 1e3
+
+    # ---- C5 in the fp64 validation mode (the reference's own precision): bounded sample
+    Ps = sweep_params(2000, seed=99)
+    best = None
+    for _ in range(2):
+        sim.run(0, Ps, N_TRIALS, DT, MAX_STEPS, precision=64, flags=0)
+        st64 = sim.last_stats()
+        best = st64 if best is None or st64["kernel_ms"] < best["kernel_ms"] else best
+    sim.run(0, Ps, N_TRIALS, DT, MAX_STEPS, precision=32, flags=capi.FLAG_OUT_F32)
+    st32 = sim.last_stats()
+    out["C5_fp64_validation_mode"] = {
+        "workload": "the sweep's prior, 2000 datasets x 1000 trials, precision 64: reference operation order in double, fp64 "
+                    "Box-Muller (libdevice log/sincospi), one thread per trial (generic kernel), float64 rows",
+        "kernel_ms": best["kernel_ms"], "steps_per_s": best["total_steps"] / (best["kernel_ms"] * 1e-3),
+        "fp32_production_steps_per_s_same_batch": st32["total_steps"] / (st32["kernel_ms"] * 1e-3),
+        "note": "B200 issues fp64 at a fraction of the fp32 rate and the validation kernel has no lane refill; it exists to check "
+                "the production kernel, not to be fast"}
+    return out
+
+
+def allgather_leg(sim, rank, world, dev, stream, barrier, max_over_ranks) -> dict:
+    """the path's only collective.  Every rank simulates its shard of a C3-sized training batch
+    (single_trial_alpha_not_scaled: 1024 x 1000 x 2 float32) and the shards are all-gathered so that the training
+    rank holds the batch (bayesflow_nddms_b200.distributed.all_gather_batch, NCCL).  Timed on the device, max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    from bayesflow_nddms_b200 import distributed as D
+    from bayesflow_nddms_b200 import priors
+    from bayesflow_nddms_b200 import single_trial_alpha_not_scaled as m1
+
+    B, N = 1024, 1000
+    P = priors.draw_prior_batch("alpha", B, np.random.default_rng(77))     # same draws on every rank
+    lo, hi = D.shard_range(B, rank, world)
+    local = torch.from_dlpack(m1.batch_simulate_trials_device(P[lo:hi], N, sim, dataset_offset=5000 + lo))
+    torch.cuda.synchronize()
+    full = D.all_gather_batch(local, B, world)                              # warm-up (communicator set-up)
+    ok = True
+    if rank == 0:   # the assembled batch is what one GPU produces alone, bit for bit
+        alone = torch.from_dlpack(m1.batch_simulate_trials_device(P, N, sim, dataset_offset=5000))
+        ok = bool(torch.equal(alone, full))
+        del alone
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 50
+    barrier()
+    e0.record()
+    for _ in range(reps):
+        full = D.all_gather_batch(local, B, world)
+    e1.record()
+    torch.cuda.synchronize()
+    us = max_over_ranks(e0.elapsed_time(e1)) / reps * 1e3
+    # one step of the data-parallel generator: simulate the shard + gather
+    barrier()
+    e0.record()
+    for _ in range(reps):
+        local = torch.from_dlpack(m1.batch_simulate_trials_device(P[lo:hi], N, sim, dataset_offset=5000 + lo))
+        full = D.all_gather_batch(local, B, world)
+    e1.record()
+    torch.cuda.synchronize()
+    step_us = max_over_ranks(e0.elapsed_time(e1)) / reps * 1e3
+    nbytes = B * N * 2 * 4
+    recv = nbytes * (world - 1) / world
+    return {"workload": "C3-sized training batch: (1024/R, 1000, 2) float32 shards -> (1024, 1000, 2) on every rank",
+            "collective": "torch.distributed.all_gather_into_tensor (NCCL)", "batch_bytes": nbytes,
+            "bytes_received_per_rank": int(recv), "us_per_allgather": us,
+            "algorithm_gbs_per_rank": recv / (us * 1e-6) / 1e9, "bus_gbs": nbytes * (world - 1) / world / (us * 1e-6) / 1e9,
+            "us_per_simulate_plus_allgather": step_us, "assembled_batch_equals_single_gpu_batch": ok,
+            "note": "8 MB: latency-bound on NVLink 5 / NVSwitch, as SURVEY.md section 5 expects"}
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
@@ -271,6 +456,7 @@ def main():
 
     D = args.datasets
     sim = pkg.DDMSimulator(device=local_rank, seed=2023)
+    sim.set_kernel_variant(args.kernel_variant)
     numa_bound = sim.bind_host_thread_near_gpu() if world > 1 else False  # host staging on the GPU's own NUMA node
     stream = torch.cuda.Stream(device=dev)
     sim.set_stream(stream.cuda_stream)
@@ -354,6 +540,17 @@ def main():
                 "peak_gbs": hbm_peak, "frac": out_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
     }
+    # the stepping loop's own ceiling on this chip: one Philox block + three Box-Muller pairs + six Euler steps per warp in
+    # a bare loop (no refill, no output), measured now.  The loop is bound by the FMA-heavy pipe (20 IMAD.WIDE of ~4.6
+    # cycles each per block): this rate does not depend on occupancy or on instruction-level parallelism.
+    try:
+        blocks_per_s, _hz = sim.microbench(pkg._capi.MB_NAMES.index("sim_block"), 2048)
+        ceil_steps = blocks_per_s * 32 * 6
+        roofline["bare_loop_ceiling_steps_per_s"] = ceil_steps
+        roofline["frac_of_bare_loop_ceiling"] = st["total_steps"] / (k_ms * 1e-3) / ceil_steps
+    except Exception as e:
+        roofline["bare_loop_ceiling_steps_per_s"] = None
+        roofline["bare_loop_note"] = repr(e)[:120]
     if args.microbench and rank == 0:
         mb = {}
         for i, name in enumerate(pkg._capi.MB_NAMES):
@@ -361,47 +558,111 @@ def main():
             mb[name] = {"warp_inst_per_s": ips, "sm_mhz": hz / 1e6, "per_smsp_per_clk": ips / (sm_count * 4 * hz)}
         roofline["microbench"] = mb
 
-    # ---- end to end through the reference-facing call ------------------------------------------------
-    e2e = None
+    # ---- end to end through the reference-facing calls, host buffers on both sides ----------------------
+    e2e, e2e_rows = None, None
     if not args.no_e2e:
         import psutil
 
-        De = args.e2e_datasets or D
-        need = De * N_TRIALS * 16
-        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-        avail = psutil.virtual_memory().available
-        while De > 1000 and need * local_world * 3 > avail:
-            De //= 2
-            need = De * N_TRIALS * 16
-        pe = sweep_params(De, seed=4000 + rank)
-        out_host = sim.pinned_empty((De, N_TRIALS, 2), np.float64)
-        sim.set_host_decode(args.host_decode)
-        sim.set_pipeline(-1, args.e2e_chunk_rows)
+        N_BINS, RT_MAX = 401, 4.01
+        pe = sweep_params(D, seed=4000 + rank)   # host (pageable) parameters, as a caller holds them
         ke = args.e2e_steps or min(args.steps, 3)
-        basic_ddm_dc.batch_simulate_trials(pe, N_TRIALS, sim, dt=DT, max_steps=MAX_STEPS, dataset_offset=ds_base, out=out_host)
-        st_e2e = sim.last_stats()
-        steps_e2e = float(st_e2e["total_steps"])
+
+        # (1) C5 as specified: parameters in, batch simulated and reduced on the device, histogram out
+        def hist_step():
+            return basic_ddm_dc.batch_simulate_histogram(pe, N_TRIALS, sim, dt=DT, max_steps=MAX_STEPS, dataset_offset=ds_base,
+                                                         n_bins=N_BINS, rt_max=RT_MAX)
+
+        h = hist_step()
+        st_h = sim.last_stats()
+        h_total = int(h["upper"].sum() + h["lower"].sum()) + h["missing"] + h["overflow"]
         barrier()
         with torch.cuda.stream(stream):
             e0.record(stream)
             for k in range(ke):
-                basic_ddm_dc.batch_simulate_trials(pe, N_TRIALS, sim, dt=DT, max_steps=MAX_STEPS, dataset_offset=ds_base,
-                                                   out=out_host)
+                h = hist_step()
             e1.record(stream)
         torch.cuda.synchronize()
         barrier()
         ms = max_over_ranks(e0.elapsed_time(e1))
-        tot = sum_over_ranks(steps_e2e)
-        e2e = {"value": tot * ke / (ms * 1e-3), "unit": "steps/s", "trials_per_s": De * N_TRIALS * world * ke / (ms * 1e-3),
-               "h2d_bytes_per_step": int(pe.nbytes), "d2h_bytes_per_step": int(st_e2e["d2h_bytes"] or out_host.nbytes),
-               "host_rows_bytes_per_step": int(out_host.nbytes), "host_decode_threads": int(st_e2e["host_decode_threads"]),
-               "steps": ke,
-               "datasets_per_gpu": De, "ms_per_step": ms / ke, "host_thread_bound_near_gpu": bool(numa_bound),
-               "api": "basic_ddm_dc.batch_simulate_trials(params (B,5) f64 host, n_trials) -> (B, n_trials, 2) f64 pinned host "
-                      "array; one ddm_simulate call: H2D params, chunked kernels overlapped with the D2H of the previous chunk; "
-                      "trials cross PCIe as 4-byte (steps, choice) records and host threads write the float64 rows "
-                      "(rt = n*dt + ndt, choice) while the next chunk is simulated"}
-        launches += sim.last_stats()["kernel_launches"] * ke
+        tot = sum_over_ranks(float(st_h["total_steps"]))
+        e2e = {"value": tot * ke / (ms * 1e-3), "unit": "steps/s", "trials_per_s": D * N_TRIALS * world * ke / (ms * 1e-3),
+               "h2d_bytes_per_step": int(pe.nbytes), "d2h_bytes_per_step": int((2 * N_BINS + 2) * 8), "steps": ke,
+               "datasets_per_gpu": D, "ms_per_step": ms / ke,
+               "result_accounts_for_every_trial": bool(h_total == D * N_TRIALS),
+               "result_agrees_with_kernel_counters": bool(int(h["upper"].sum()) == st_h["n_upper"] and h["missing"] == st_h["n_timeouts"]),
+               "api": "basic_ddm_dc.batch_simulate_histogram(params (B,5) f64 host, n_trials) -> RT histogram by boundary (401 bins "
+                      "of 10 ms x 2 + missing + overflow) as host arrays; one ddm_simulate_histogram call: H2D of the parameters, "
+                      "prep + stepping kernel (float32 rows stay in HBM), histogram kernel, D2H of 804 counters -- C5 as SURVEY.md "
+                      "section 8d specifies it (outputs reduced on device)"}
+        launches += (st_h["kernel_launches"] + 1) * ke
+
+        # (2) the same batch delivered as host rows: float64 (what simulate_trials returns) and float32 (what the
+        # reference's configurator turns it into at once, basic_ddm_dc.py:146), against the host's streaming-store rate
+        if not args.no_host_rows:
+            De = args.e2e_datasets or D
+            local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+            avail = psutil.virtual_memory().available
+            while De > 1000 and De * N_TRIALS * 16 * local_world * 3 > avail:
+                De //= 2
+            pr = pe[:De]
+            sim.set_host_decode(args.host_decode)
+            sim.set_pipeline(-1, args.e2e_chunk_rows)
+            e2e_rows = {"datasets_per_gpu": De, "h2d_bytes_per_step": int(pr.nbytes)}
+            for label, dtype, fl in (("float64", np.float64, 0), ("float32", np.float32, FLAG_OUT_F32)):
+                out_host = sim.pinned_empty((De, N_TRIALS, 2), dtype, slot="rows_" + label)
+                basic_ddm_dc.batch_simulate_trials(pr, N_TRIALS, sim, dt=DT, max_steps=MAX_STEPS, dataset_offset=ds_base, out=out_host,
+                                                   flags=fl)
+                st_r = sim.last_stats()
+                barrier()
+                with torch.cuda.stream(stream):
+                    e0.record(stream)
+                    for k in range(ke):
+                        basic_ddm_dc.batch_simulate_trials(pr, N_TRIALS, sim, dt=DT, max_steps=MAX_STEPS, dataset_offset=ds_base,
+                                                           out=out_host, flags=fl)
+                    e1.record(stream)
+                torch.cuda.synchronize()
+                barrier()
+                ms_r = max_over_ranks(e0.elapsed_time(e1))
+                tot_r = sum_over_ranks(float(st_r["total_steps"]))
+                e2e_rows[label] = {"value": tot_r * ke / (ms_r * 1e-3), "unit": "steps/s", "ms_per_step": ms_r / ke,
+                                   "d2h_bytes_per_step": int(st_r["d2h_bytes"] or out_host.nbytes),
+                                   "host_rows_bytes_per_step": int(out_host.nbytes),
+                                   "host_decode_threads": int(st_r["host_decode_threads"]),
+                                   "host_row_write_gbs_all_ranks": out_host.nbytes * world * ke / (ms_r * 1e-3) / 1e9}
+                launches += st_r["kernel_launches"] * ke
+                del out_host
+            # the ceiling of the row-writing side: every rank's decode threads filling memory with the decode's own
+            # streaming stores, all ranks at once (they share the host's memory controllers)
+            barrier()
+            t0 = time.perf_counter()
+            peak = sim.host_stream_peak(args.host_decode if args.host_decode > 0 else 0, 1 << 30)
+            peak_all = sum_over_ranks(peak)
+            e2e_rows["host_stream_store_peak_gbs_all_ranks"] = peak_all / 1e9
+            e2e_rows["host_stream_store_peak_how"] = ("ddm_host_stream_peak: each rank's decode threads fill 1 GiB with non-temporal 32-byte "
+                                                     "stores, best of 5 passes, all ranks concurrently; sum over ranks")
+            for label in ("float64", "float32"):
+                e2e_rows[label]["frac_of_host_store_peak"] = e2e_rows[label]["host_row_write_gbs_all_ranks"] / (peak_all / 1e9)
+            e2e_rows["api"] = ("basic_ddm_dc.batch_simulate_trials(params (B,5) f64 host, n_trials[, flags=OUT_F32]) -> (B, n_trials, 2) pinned "
+                               "host array; one ddm_simulate call: chunked kernels overlapped with the D2H of the previous chunk; trials "
+                               "cross PCIe as 4-byte (steps, choice) records and host threads write the rows (rt = n*dt + ndt, choice)")
+            e2e_rows["host_thread_bound_near_gpu"] = bool(numa_bound)
+            sim.set_pipeline(-1, -1)
+
+    # ---- BASELINE.json's other configurations, through the reference-facing calls and device-resident ----------
+    configs = None
+    if rank == 0 and not args.no_configs:
+        try:
+            configs = other_configs(sim, issue_peak, want_cpu=(not args.no_cpu_baseline and world == 1))
+        except Exception as e:  # secondary figures must not take the headline down
+            configs = {"error": repr(e)[:300]}
+
+    # ---- the one collective of the path: all-gather of a training batch's shards (N > 1) ------------------------
+    allgather = None
+    if world > 1:
+        try:
+            allgather = allgather_leg(sim, rank, world, dev, stream, barrier, max_over_ranks)
+        except Exception as e:
+            allgather = {"error": repr(e)[:300]}
 
     # ---- BASELINE config 2: one online-training batch (64 datasets x 500 trials, dt=.01), latency -------------
     training_batch = None
@@ -421,7 +682,7 @@ def main():
                 batch = sim.last_output_dlpack()                                  # hand-off (syncs the stream)
                 del batch
             lat = (time.perf_counter() - t0) / reps
-            training_batch = {"workload": "basic_ddm_dc online-training batch: 64 datasets x 500 trials, dt=.01, max_steps=400",
+            training_batch = {"workload": "C2 basic_ddm_dc online-training batch: 64 datasets x 500 trials, dt=.01, max_steps=400",
                               "path": "ddm_draw_prior -> ddm_run -> ddm_last_output_dlpack (device-resident f32 batch)",
                               "ms_per_batch": lat * 1e3, "trials_per_s": B2 * N2 / lat, "launches_per_batch": 3}
             if not args.no_cpu_baseline and world == 1:
@@ -451,6 +712,12 @@ def main():
     line["device_reduction"] = reduction
     if e2e is not None:
         line["e2e"] = e2e
+    if e2e_rows is not None:
+        line["e2e_host_rows"] = e2e_rows
+    if configs is not None:
+        line["configs"] = configs
+    if allgather is not None:
+        line["allgather_batch"] = allgather
     if training_batch is not None:
         line["training_batch"] = training_batch
     if rank == 0 and not args.no_cpu_baseline and world == 1:

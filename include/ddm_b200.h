@@ -216,6 +216,15 @@ int ddm_last_stats(ddm_ctx *ctx, ddm_stats *out);
  * n_bins <= 8192.  Additive over datasets: shards and GPUs sum.  Not for DDM_MODEL_GENERAL (mixed layouts). */
 int ddm_last_output_histogram(ddm_ctx *ctx, int n_bins, double rt_max, uint64_t *hist_host);
 
+/* The throughput sweep as SURVEY.md section 8d specifies it ("outputs reduced on device -- no host copy"): one
+ * call takes host parameters, simulates the batch into resident float32 rows, reduces them on the device and
+ * returns only the histogram of ddm_last_output_histogram (2 n_bins + 2 counters).  Replaces
+ * [simulate_trials(p, n_trials) for p in params] followed by a histogram of the stacked rows; two-column
+ * dataset-wise models only.  The rows stay resident afterwards (ddm_last_output_dlpack / ddm_download). */
+int ddm_simulate_histogram(ddm_ctx *ctx, int model, const double *params, int64_t n_datasets, int n_params,
+                           int64_t n_trials, double dt, int max_steps, uint64_t seed, uint64_t dataset_offset,
+                           int precision, int flags, int n_bins, double rt_max, uint64_t *hist_host);
+
 /* Device hand-off of the last run's output as a DLPack tensor of shape
  * (n_datasets, n_trials, 2) ((n, 2) for trialwise, (n_datasets, n_trials, 2 + n_obs) for evidence runs), dtype per the run's flags,
  * on this ctx's device.  Ownership of the buffer moves to the consumer; its
@@ -234,6 +243,12 @@ int ddm_set_normals_debug(ddm_ctx *ctx, const double *z, size_t n, const int64_t
  * counters (dataset, trial, stream), indices first..first+count-1, as doubles. */
 int ddm_export_normals(ddm_ctx *ctx, uint64_t seed, uint64_t dataset, uint32_t trial, uint32_t stream,
                        uint32_t first, uint32_t count, int precision, double *out_host);
+/* The production normal generator under the microscope: ceil(n_normals / 6) Philox blocks through the fp32 map of the
+ * stepping kernels (21-bit Box-Muller fields, MUFU lg2/sqrt/sin/cos), reduced on the device.  hist_host receives
+ * n_bins_abs counts of |z| in equal bins over [0, z_max), one count of |z| >= z_max, then n_bins_angle counts of the
+ * Box-Muller pairs' angles in equal sectors; moments_host[4] = sum z, z^2, z^3, z^4. */
+int ddm_normals_histogram(ddm_ctx *ctx, uint64_t seed, uint64_t n_normals, int n_bins_abs, double z_max, int n_bins_angle,
+                          uint64_t *hist_host, double *moments_host);
 /* Raw Philox4x32-10 blocks computed on the device (known-answer tests). */
 int ddm_philox4x32(ddm_ctx *ctx, const uint32_t *ctr4, const uint32_t *key2, uint32_t *out4, int64_t n_blocks);
 /* The chunk schedule ddm_simulate's streamed path uses for a batch (no GPU needed): writes up to `capacity`
@@ -254,9 +269,17 @@ enum ddm_microbench_id {
     DDM_MB_FFMA = 0, DDM_MB_IMAD_WIDE = 1, DDM_MB_LOP3 = 2, DDM_MB_IADD3 = 3,
     DDM_MB_MUFU_LG2 = 4, DDM_MB_MUFU_SIN = 5, DDM_MB_MIX_FMA_ALU = 6, DDM_MB_FSETP = 7,
     DDM_MB_PHILOX = 8, DDM_MB_NORMALS = 9, DDM_MB_MIX_IMADW_LOP3 = 10, DDM_MB_MIX_MUFU_LOP3 = 11,
-    DDM_MB_MIX_MUFU_IMADW = 12, DDM_MB_MIX_BLOCKLIKE = 13, DDM_MB_COUNT = 14
+    DDM_MB_MIX_MUFU_IMADW = 12, DDM_MB_MIX_BLOCKLIKE = 13,
+    /* round 2: register-operand forms, the Philox round's multiply, packed fp32, 7 rounds, two trials per lane */
+    DDM_MB_FFMA_REG = 14, DDM_MB_FADD_REG = 15, DDM_MB_IMAD_WIDE_NOACC = 16, DDM_MB_IMAD_HI = 17, DDM_MB_FFMA2 = 18,
+    DDM_MB_PHILOX7 = 19, DDM_MB_NORMALS2 = 20, DDM_MB_COUNT = 21
 };
 int ddm_microbench(ddm_ctx *ctx, int which, int iters, double *inst_per_s, double *sm_hz);
+
+/* The ceiling of the host side of ddm_set_host_decode on this box: n_threads host threads (0 = the automatic
+ * count) fill `bytes` of host memory with the decode's own non-temporal stores; *bytes_per_s = the best of five
+ * passes.  No GPU needed. */
+int ddm_host_stream_peak(int n_threads, size_t bytes, double *bytes_per_s);
 
 /* pinned host memory helpers (for callers that want full-rate D2H) */
 int ddm_host_alloc(size_t bytes, void **ptr);

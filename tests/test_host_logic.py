@@ -258,6 +258,64 @@ def test_wire_decode_host_formats_rows_like_the_reference(basic, f32):
         assert np.array_equal(out, want)
 
 
+def test_wire_decode_float32_streaming_path_any_alignment():
+    """Round 2: float32 rows are written with 32-byte streaming stores, eight trials at a time (ddm_wire.cpp:
+    decode_basic32_avx2).  Destinations at every 4-byte phase of a 32-byte line, lengths around the vector width,
+    per-dataset non-decision times: always (float)(n*dt + tau) rounded once from double, like the kernel's own rows."""
+    from bayesflow_nddms_b200 import _capi
+
+    lib = _capi.load()
+    rng = np.random.default_rng(8)
+    dt = 1e-3
+    for D, T in ((3, 1000), (5, 17), (1, 7), (2, 8), (1, 40_003)):
+        params = rng.uniform(0.0, 1.5, (D, 5))
+        n = rng.integers(0, 4001, (D, T)).astype(np.uint32)
+        ch = rng.integers(-1, 2, (D, T))
+        code = ((n << 2) | (ch + 1).astype(np.uint32)).astype(np.int32)
+        want = np.stack([(n.astype(np.float64) * dt + params[:, 3:4]).astype(np.float32), ch.astype(np.float32)], axis=-1)
+        for phase in range(8):
+            raw = np.full(D * T * 2 + 16, np.nan, dtype=np.float32)
+            base = (-raw.ctypes.data // 4) % 8             # first 32-byte aligned element
+            out = raw[base + phase: base + phase + D * T * 2].reshape(D, T, 2)
+            for threads in (1, 3):
+                out[...] = np.nan
+                assert lib.ddm_wire_decode_host(code.ctypes.data, out.ctypes.data, params.ctypes.data_as(_capi._dp), 5, D, T, dt, 1,
+                                                _capi.FLAG_OUT_F32, threads) == 0
+                assert np.array_equal(out, want), (D, T, phase, threads)
+            assert np.isnan(raw[:base + phase]).all() and np.isnan(raw[base + phase + D * T * 2:]).all()   # nothing outside the rows
+
+
+def test_host_stream_store_peak_is_measurable():
+    import ctypes as C
+
+    from bayesflow_nddms_b200 import _capi
+
+    lib = _capi.load()
+    v = C.c_double()
+    assert lib.ddm_host_stream_peak(2, 64 << 20, C.byref(v)) == 0 and v.value > 1e8      # > 0.1 GB/s on anything
+    assert lib.ddm_host_stream_peak(2, 1000, C.byref(v)) == _capi.ERR_INVALID
+
+
+def test_simulator_counters_roll_over_multiples_of_2_32():
+    """The 64-bit global index: a launch must not straddle a multiple of 2^32, the Python counters skip
+    ahead instead of failing; distributed.simulate_sharded's batch counter does the same."""
+    from bayesflow_nddms_b200 import distributed as D
+    from bayesflow_nddms_b200.simulator import DDMSimulator
+
+    roll = DDMSimulator._roll
+    assert roll(10, 5) == 10 and roll((1 << 32) - 5, 5) == (1 << 32) - 5 and roll((1 << 32) - 4, 5) == 1 << 32
+    assert roll((7 << 32) + 12, 1 << 32) == 8 << 32 and roll(0, 1 << 32) == 0
+    seen = []
+    D._batch_base = (1 << 32) - 3
+    try:
+        for _ in range(2):
+            D.simulate_sharded(lambda p, n, dataset_offset: seen.append(dataset_offset) or np.zeros((p.shape[0], n, 2)),
+                               np.zeros((8, 5)), 4, rank=0, world_size=1)
+    finally:
+        D._batch_base = 0
+    assert seen == [1 << 32, (1 << 32) + 8]
+
+
 @pytest.mark.parametrize("n_datasets,n_trials", [(1_000_000, 1000), (16_384, 1000), (4_200, 1000), (7, 3_000_000), (3, 5), (0, 10),
                                                  (100_003, 33)])
 @pytest.mark.parametrize("chunk_rows", [-1, -2, -3, 1, 257 * 7, 32 << 20])
