@@ -66,5 +66,17 @@ def build(force: bool = False, verbose: bool = False, out_path: str | None = Non
     return target
 
 
+PHILOX7_LIB_PATH = os.path.join(HERE, "libddm_b200_philox7.so")
+
+
+def build_philox7(force: bool = False) -> str:
+    """The measurement-only 7-round variant (ddm_rng.cuh: DDM_PHILOX_ROUNDS), selected with DDM_B200_LIB."""
+    if not force and os.path.exists(PHILOX7_LIB_PATH) and not any(
+            os.path.getmtime(os.path.join(CSRC, f)) > os.path.getmtime(PHILOX7_LIB_PATH)
+            for f in SOURCES + HOST_SOURCES + HEADERS if os.path.exists(os.path.join(CSRC, f))):
+        return PHILOX7_LIB_PATH
+    return build(out_path=PHILOX7_LIB_PATH, defines=("DDM_PHILOX_ROUNDS=7",))
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))

@@ -86,6 +86,7 @@ _lib = None
 _dp, _vp = C.POINTER(C.c_double), C.c_void_p
 SIGNATURES = {
     "ddm_version": (C.c_int, []),
+    "ddm_philox_rounds": (C.c_int, []),
     "ddm_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "ddm_destroy": (C.c_int, [_vp]),
     "ddm_last_error": (C.c_char_p, [_vp]),

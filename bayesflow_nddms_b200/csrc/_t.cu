@@ -493,7 +493,7 @@ __device__ __forceinline__ void tile_flush(const RunArgs &a, const uint32_t *cod
 #endif
 template <int KIND>
 constexpr int tile_min_blocks() {
-    return DDM_TILE_MIN_BLOCKS;
+    return (KIND == KIND_FIXED || KIND == KIND_DRIFT) ? 6 : DDM_TILE_MIN_BLOCKS;
 }
 
 // A straggler's own row (its tile's buffer has been recycled).  Not inlined: the fp64 output arithmetic and the

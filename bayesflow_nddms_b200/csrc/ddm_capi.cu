@@ -209,7 +209,7 @@ struct ddm_ctx {
 
     // tuning (0 = automatic)
     int tune_threshold = 0, tune_blocks_per_sm = 0, tune_tile = 0;
-    int tune_kernel_variant = 0;  // 0 = tile kernel, 1 = the round-1 persistent kernel (A/B measurements)
+    int tune_kernel_variant = -1;  // -1 = the faster of the two per model family (measured), 0 = tile kernel, 1 = round-1 persistent kernel
     bool trialwise_degenerate = false;  // last trialwise call: some group has dc == 0 (no noise unit)
     int64_t tune_pipeline_min_rows = -1, tune_pipeline_chunk_rows = -1;  // < 0: default
 };
@@ -227,10 +227,10 @@ int default_refill_threshold(double dt, bool legacy = false) {
         const int thr = (int)std::lround(164.0 * std::sqrt(dt));
         return thr < 2 ? 2 : (thr > 16 ? 16 : thr);
     }
-    // tile kernel: the pass is ~45 issue slots (set-up and output arithmetic moved out of it, done a tile at a time),
-    // so the optimum sits lower: sqrt(37.5 r * 45 / 60) = 74 / sqrt(steps per trial) = 142 sqrt(dt)
-    const int thr = (int)std::lround(142.0 * std::sqrt(dt));
-    return thr < 2 ? 2 : (thr > 14 ? 14 : thr);
+    // tile kernel: measured optima on B200 (profiles/r02_ab_kernels_v3b.jsonl) are 5 at dt = .001 (4: -0.4 %, 6: -0.3 %) and
+    // 10-12 at dt = .01 for every model family; 46 dt^0.32 passes through both
+    const int thr = (int)std::lround(46.0 * std::pow(dt, 0.32));
+    return thr < 2 ? 2 : (thr > 12 ? 12 : thr);
 }
 
 int fail(ddm_ctx *ctx, int code, const char *fmt, ...) {
@@ -374,7 +374,12 @@ int launch_sim(ddm_ctx *ctx, ddm::RunArgs &a, int precision, ddm_stats &st, cuda
     DDM_CUDA(ctx, cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), stream));
     if (persistent) {
         const int block = ddm::persistent_block_size();
-        const bool legacy = ctx->tune_kernel_variant == 1 && !trialwise;  // round-1 kernel, kept for A/B measurements
+        // Two schedulers of the same trials, bit-identical results.  The tile kernel wins wherever a trial needs set-up
+        // draws (per-trial boundary / diffusion coefficient / the general model: +3 .. +11 %, profiles/r02_ab_kernels*.jsonl)
+        // and is the only one for the trialwise model; for the models without per-trial set-up (basic, per-trial drift)
+        // the round-1 kernel's two-instruction-shorter stepping loop keeps it 1-2 % ahead, so it stays their default.
+        const bool fixed_kind = (kind == ddm::KIND_FIXED || kind == ddm::KIND_DRIFT);
+        const bool legacy = !trialwise && (ctx->tune_kernel_variant == 1 || (ctx->tune_kernel_variant < 0 && fixed_kind));
         const uint64_t warps_needed = ((uint64_t)rows + 31) / 32;
         const uint64_t blocks_needed = (warps_needed + (block / 32) - 1) / (block / 32);
         // tile: consecutive trials of one dataset handed out per atomic claim (and, in the tile kernel, set up and
@@ -738,6 +743,8 @@ int finish_stats(ddm_ctx *ctx) {
 // ---- lifecycle --------------------------------------------------------------------------
 DDM_API int ddm_version(void) { return DDM_B200_VERSION; }
 
+DDM_API int ddm_philox_rounds(void) { return DDM_PHILOX_ROUNDS; }
+
 DDM_API const char *ddm_last_error(const ddm_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 DDM_API int ddm_create(int device, ddm_ctx **out) {
@@ -852,7 +859,8 @@ DDM_API int ddm_set_tuning(ddm_ctx *ctx, int refill_threshold, int blocks_per_sm
 
 DDM_API int ddm_set_kernel_variant(ddm_ctx *ctx, int variant) {
     if (!ctx) return DDM_ERR_INVALID;
-    if (variant < 0 || variant > 1) return fail(ctx, DDM_ERR_INVALID, "kernel variant must be 0 (tile kernel) or 1 (round-1 persistent kernel)");
+    if (variant < -1 || variant > 1)
+        return fail(ctx, DDM_ERR_INVALID, "kernel variant must be -1 (automatic), 0 (tile kernel) or 1 (round-1 persistent kernel)");
     ctx->tune_kernel_variant = variant;
     return DDM_OK;
 }

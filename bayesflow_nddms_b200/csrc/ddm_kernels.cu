@@ -486,14 +486,18 @@ __device__ __forceinline__ void tile_flush(const RunArgs &a, const uint32_t *cod
 }
 
 // Resident blocks per SM: the kinds whose tile set-up draws normals (a Philox block and three Box-Muller pairs live
-// next to the stepping state) get 48 registers and five blocks; at 40 registers ptxas spilled a loop-carried
-// register of the stepping loop.  (Round 1 measured 5 x 48 equal to 6 x 40 on the sweep.)
+// next to the stepping state) get 48 registers and five blocks -- at 40 registers ptxas spilled a loop-carried register
+// of the stepping loop; the kinds without set-up draws keep six blocks of 40.  (The bare stepping loop is bound by the
+// FMA-heavy pipe and loses 1 % from 12 to 10 warps per scheduler: profiles/r02_microbench_occupancy.txt.)
 #ifndef DDM_TILE_MIN_BLOCKS
 #define DDM_TILE_MIN_BLOCKS (1280 / DDM_PERSISTENT_BLOCK)
 #endif
+#ifndef DDM_TILE_MIN_BLOCKS_FIXED
+#define DDM_TILE_MIN_BLOCKS_FIXED (1536 / DDM_PERSISTENT_BLOCK)  // no set-up draws: 40 registers do (A/B: +1 % over five blocks)
+#endif
 template <int KIND>
 constexpr int tile_min_blocks() {
-    return DDM_TILE_MIN_BLOCKS;
+    return (KIND == KIND_FIXED || KIND == KIND_DRIFT) ? DDM_TILE_MIN_BLOCKS_FIXED : DDM_TILE_MIN_BLOCKS;
 }
 
 // A straggler's own row (its tile's buffer has been recycled).  Not inlined: the fp64 output arithmetic and the

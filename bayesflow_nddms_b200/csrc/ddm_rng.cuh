@@ -80,11 +80,21 @@ __device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2
     o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
 }
 
+// Rounds of the simulator's generator.  10 is Random123's and cuRAND's default and what every shipped number is
+// measured with; the build option -DDDM_PHILOX_ROUNDS=7 (Philox4x32-7: the fewest rounds that pass BigCrush in
+// Salmon et al., SC'11, table 2) exists to measure what the round count costs (bench.py: philox7_variant) -- the
+// stepping loop is bound by the 20 IMAD.WIDE of a 10-round block.  The known-answer tests (philox4x32<10>) and the
+// CPU oracle are 10-round: a 7-round library is checked by the distribution tests only.
+#ifndef DDM_PHILOX_ROUNDS
+#define DDM_PHILOX_ROUNDS 10
+#endif
+static_assert(DDM_PHILOX_ROUNDS >= 7 && DDM_PHILOX_ROUNDS <= 10, "Philox4x32 rounds: 7 .. 10");
+
 __device__ __forceinline__ void philox4x32_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                               const PhiloxKey &key, uint32_t (&o)[4]) {
     c3 |= key.c3_hi;  // uniform: folds into the first round's key operand
 #pragma unroll
-    for (int r = 0; r < 10; r++) {
+    for (int r = 0; r < DDM_PHILOX_ROUNDS; r++) {
         const uint64_t p0 = (uint64_t)PHILOX_M0 * c0;
         const uint64_t p1 = (uint64_t)PHILOX_M1 * c2;
         const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ key.rk[2 * r];

@@ -158,8 +158,9 @@ class DDMSimulator:
     def set_tuning(self, refill_threshold: int = 0, blocks_per_sm: int = 0, tile: int = 0):
         self._check(self._lib.ddm_set_tuning(self._ctx, refill_threshold, blocks_per_sm, tile))
 
-    def set_kernel_variant(self, variant: int = 0):
-        """0: the tile-staged persistent kernel (default); 1: the round-1 persistent kernel (A/B measurements)."""
+    def set_kernel_variant(self, variant: int = -1):
+        """-1 (default): the faster scheduler per model family; 0: the tile-staged persistent kernel; 1: the round-1
+        persistent kernel.  Bit-identical results (A/B measurements, tests)."""
         self._check(self._lib.ddm_set_kernel_variant(self._ctx, int(variant)))
 
     def set_stream(self, cuda_stream_ptr: int | None):

@@ -68,7 +68,7 @@ def parse_args():
     ap.add_argument("--microbench", action="store_true", help="also measure per-pipe issue rates")
     ap.add_argument("--no-configs", action="store_true", help="skip the C1/C3/C4/fp64 legs")
     ap.add_argument("--no-host-rows", action="store_true", help="skip the host-row legs of the end-to-end section")
-    ap.add_argument("--kernel-variant", type=int, default=0, help="0 tile kernel (default), 1 the round-1 persistent kernel")
+    ap.add_argument("--kernel-variant", type=int, default=-1, help="-1 automatic (default), 0 tile kernel, 1 the round-1 persistent kernel")
     return ap.parse_args()
 
 
@@ -358,6 +358,51 @@ def other_configs(sim, issue_peak, want_cpu=True) -> dict:
         "fp32_production_steps_per_s_same_batch": st32["total_steps"] / (st32["kernel_ms"] * 1e-3),
         "note": "B200 issues fp64 at a fraction of the fp32 rate and the validation kernel has no lane refill; it exists to check "
                 "the production kernel, not to be fast"}
+    return out
+
+
+PHILOX7_PROBE = r"""
+import json, sys
+import numpy as np
+sys.path.insert(0, %r)
+import bayesflow_nddms_b200 as pkg
+from bayesflow_nddms_b200 import priors
+sim = pkg.DDMSimulator(device=%d, seed=2023)
+rounds = sim._lib.ddm_philox_rounds()
+P = priors.draw_prior_batch("sweep", 100_000, np.random.default_rng(2023))
+best = None
+for _ in range(4):
+    sim.run(0, P, 1000, 1e-3, 4000, flags=2)
+    st = sim.last_stats()
+    best = st if best is None or st["kernel_ms"] < best["kernel_ms"] else best
+print(json.dumps({"rounds": rounds, "kernel_ms": best["kernel_ms"], "steps": best["total_steps"],
+                  "steps_per_s": best["total_steps"] / (best["kernel_ms"] * 1e-3)}))
+"""
+
+
+def philox_rounds_leg(device: int) -> dict:
+    """What the generator's round count costs: the sweep kernel (1e8 trials) from the shipped 10-round library and from
+    the measurement-only 7-round build (ddm_rng.cuh: DDM_PHILOX_ROUNDS), each in its own process (DDM_B200_LIB)."""
+    import subprocess
+
+    from bayesflow_nddms_b200 import _build
+
+    out = {}
+    for name, lib in (("philox10_shipped", _build.LIB_PATH), ("philox7_variant", _build.PHILOX7_LIB_PATH)):
+        if not os.path.exists(lib):
+            out[name] = {"unavailable": os.path.basename(lib) + " not built"}
+            continue
+        env = dict(os.environ, DDM_B200_LIB=lib)
+        r = subprocess.run([sys.executable, "-c", PHILOX7_PROBE % (ROOT, device)], env=env, capture_output=True, text=True, timeout=300)
+        try:
+            out[name] = json.loads(r.stdout.strip().split("\n")[-1])
+        except Exception:
+            out[name] = {"error": (r.stderr or r.stdout)[-300:]}
+    a, b = out.get("philox10_shipped", {}), out.get("philox7_variant", {})
+    if "steps_per_s" in a and "steps_per_s" in b:
+        out["speedup_7_over_10"] = b["steps_per_s"] / a["steps_per_s"]
+    out["note"] = ("10 rounds is the shipped generator (Random123 / cuRAND default) and what every other figure uses; 7 rounds is the "
+                   "fewest that pass BigCrush (Salmon et al. 2011) and is built only to measure the cost of the 20 IMAD.WIDE per block")
     return out
 
 
@@ -655,6 +700,12 @@ def main():
             configs = other_configs(sim, issue_peak, want_cpu=(not args.no_cpu_baseline and world == 1))
         except Exception as e:  # secondary figures must not take the headline down
             configs = {"error": repr(e)[:300]}
+
+    if rank == 0 and world == 1 and not args.no_configs and isinstance(configs, dict):
+        try:
+            configs["philox_rounds"] = philox_rounds_leg(local_rank)
+        except Exception as e:
+            configs["philox_rounds"] = {"error": repr(e)[:300]}
 
     # ---- the one collective of the path: all-gather of a training batch's shards (N > 1) ------------------------
     allgather = None

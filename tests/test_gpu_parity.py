@@ -888,7 +888,7 @@ def test_tile_kernel_equals_round1_persistent_kernel(sim, model):
             f32 = sim.simulate(model, params, 307, seed=9, dataset_offset=3, flags=F_F32, **kw)
             assert np.array_equal(f32, ref.astype(np.float32))
     finally:
-        sim.set_kernel_variant(0)
+        sim.set_kernel_variant(-1)
         sim.set_tuning(0, 0, 0)
 
 
@@ -909,7 +909,7 @@ def test_tile_kernel_general_model_and_wire(sim):
                 sim.set_tuning(thr, bps, tile)
                 assert np.array_equal(sim.simulate(7, P, 211, seed=4, dataset_offset=0).view(np.uint64), ref.view(np.uint64))
         finally:
-            sim.set_kernel_variant(0)
+            sim.set_kernel_variant(-1)
             sim.set_tuning(0, 0, 0)
     params = priors.draw_prior_batch("alpha", 97, np.random.default_rng(6))
     try:
