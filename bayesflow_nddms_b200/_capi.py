@@ -54,7 +54,7 @@ class Stats(C.Structure):
                 ("kernel_launches", C.c_int32), ("used_persistent", C.c_int32), ("grid", C.c_int32),
                 ("block", C.c_int32), ("refill_threshold", C.c_int32), ("tile", C.c_int32),
                 ("debug_overruns", C.c_uint64), ("d2h_bytes", C.c_uint64), ("host_decode_threads", C.c_int32),
-                ("reserved_", C.c_int32)]
+                ("scheduler", C.c_int32)]
 
     def as_dict(self) -> dict:
         return {k: getattr(self, k) for k, _ in self._fields_}

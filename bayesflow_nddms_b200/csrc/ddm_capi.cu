@@ -55,8 +55,13 @@ struct BufferPool {
             std::lock_guard<std::mutex> g(mu);
             free_list.emplace_back(p, cap);
             if (free_list.size() > kMaxCachedBuffers) {
-                drop = free_list.front().first;
-                free_list.erase(free_list.begin());
+                // over capacity: let the largest go (a multi-GB buffer of an earlier, bigger batch is what costs memory,
+                // and what a small-batch loop will never take again)
+                size_t big = 0;
+                for (size_t i = 1; i < free_list.size(); i++)
+                    if (free_list[i].second > free_list[big].second) big = i;
+                drop = free_list[big].first;
+                free_list.erase(free_list.begin() + big);
             }
         }
         if (drop) {
@@ -264,7 +269,9 @@ struct DeviceGuard {
 };
 
 int ensure_output(ddm_ctx *ctx, size_t bytes) {
-    if (ctx->out && ctx->out_cap >= bytes) return DDM_OK;
+    // reuse the resident buffer only if it is about the right size: a DLPack hand-off gives the whole buffer to the
+    // consumer, and a 256 KB training batch must not travel in (and keep alive) the 8 GB buffer of an earlier sweep
+    if (ctx->out && ctx->out_cap >= bytes && ctx->out_cap <= 2 * bytes + (1u << 20)) return DDM_OK;
     if (ctx->out) {
         ctx->pool->give(ctx->out, ctx->out_cap);
         ctx->out = nullptr;
@@ -420,6 +427,7 @@ int launch_sim(ddm_ctx *ctx, ddm::RunArgs &a, int precision, ddm_stats &st, cuda
         if (legacy) DDM_CUDA(ctx, ddm::launch_persistent(a, kind, out64, (int)grid, block, stream));
         else DDM_CUDA(ctx, ddm::launch_tile(a, kind, out64, (int)grid, block, smem, stream));
         st.used_persistent = 1;
+        st.scheduler = legacy ? 1 : 2;
         st.grid = (int)grid;
         st.block = block;
         st.refill_threshold = a.refill_threshold;
@@ -1273,6 +1281,7 @@ DDM_API int ddm_simulate_evidence(ddm_ctx *ctx, const double *params, int64_t n_
             st.grid = (int)grid;
             st.block = block;
             st.used_persistent = 1;
+            st.scheduler = 1;
             st.refill_threshold = r.refill_threshold;
             st.tile = (int)tile;
             if (standardize == 2) {
@@ -1570,7 +1579,8 @@ DDM_API int ddm_host_alloc(size_t bytes, void **ptr) {
     *ptr = nullptr;
     cudaError_t e = cudaMallocHost(ptr, bytes ? bytes : 1);
     if (e != cudaSuccess) {
-        g_create_error = std::string("cudaMallocHost: ") + cudaGetErrorString(e);
+        g_create_error = std::string("cudaMallocHost(") + std::to_string(bytes) + "): " + cudaGetErrorName(e) + ": " + cudaGetErrorString(e);
+        cudaGetLastError();  // a failed allocation is not sticky: clear it
         return e == cudaErrorMemoryAllocation ? DDM_ERR_NOMEM : DDM_ERR_CUDA;
     }
     return DDM_OK;

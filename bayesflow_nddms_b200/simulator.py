@@ -195,7 +195,8 @@ class DDMSimulator:
             p = C.c_void_p()
             rc = self._lib.ddm_host_alloc(max(nbytes, 1), C.byref(p))
             if rc != _capi.OK:
-                raise DDMError(rc, "pinned host allocation failed")
+                why = (self._lib.ddm_last_error(None) or b"").decode()
+                raise DDMError(rc, f"pinned host allocation of {nbytes} bytes failed: {why}")
             blk = _PinnedBlock(_FreeingPool(self._lib), p.value, max(nbytes, 1))
             self._pinned[slot] = blk
         return np.asarray(blk)[:nbytes].view(dtype).reshape(shape)

@@ -45,7 +45,7 @@ MAX_STEPS = 4000
 # (SURVEY.md section 8d budgeted 28 for a 4-normals-per-block design.)
 I_STEP = 17
 I_STEP_SURVEY = 28
-NCU_DRAM_BYTES_PER_LAUNCH_1E9 = 255_669_760 + 8_083_822_000
+NCU_DRAM_BYTES_PER_LAUNCH_1E9 = 247_497_216 + 8_079_781_376  # profiles/r02_ncu_sweep_fullsize_details.txt
 MODEL_BASIC = 0
 FLAG_OUT_F32 = 2
 
@@ -262,7 +262,8 @@ def other_configs(sim, issue_peak, want_cpu=True) -> dict:
 
     def kernel_fields(st):
         k_s = st["kernel_ms"] * 1e-3
-        d = {"kernel_ms": st["kernel_ms"], "euler_steps": st["total_steps"], "persistent": bool(st["used_persistent"])}
+        d = {"kernel_ms": st["kernel_ms"], "euler_steps": st["total_steps"],
+             "scheduler": {1: "round-1 persistent kernel", 2: "tile kernel"}.get(st["scheduler"], "generic")}
         if k_s > 0:
             d["kernel_steps_per_s"] = st["total_steps"] / k_s
             d["kernel_roofline_frac"] = st["total_steps"] * I_STEP / 32.0 / k_s / issue_peak
@@ -437,15 +438,18 @@ def allgather_leg(sim, rank, world, dev, stream, barrier, max_over_ranks) -> dic
     e1.record()
     torch.cuda.synchronize()
     us = max_over_ranks(e0.elapsed_time(e1)) / reps * 1e3
-    # one step of the data-parallel generator: simulate the shard + gather
+    # one step of the data-parallel generator: simulate the shard + gather (the simulator call blocks the host until
+    # its batch is ready for hand-off, so this one is a host clock around the loop, device drained on both sides)
+    for _ in range(5):
+        local = torch.from_dlpack(m1.batch_simulate_trials_device(P[lo:hi], N, sim, dataset_offset=5000 + lo))
+        full = D.all_gather_batch(local, B, world)
     barrier()
-    e0.record()
+    t0 = time.perf_counter()
     for _ in range(reps):
         local = torch.from_dlpack(m1.batch_simulate_trials_device(P[lo:hi], N, sim, dataset_offset=5000 + lo))
         full = D.all_gather_batch(local, B, world)
-    e1.record()
     torch.cuda.synchronize()
-    step_us = max_over_ranks(e0.elapsed_time(e1)) / reps * 1e3
+    step_us = max_over_ranks((time.perf_counter() - t0) * 1e6) / reps
     nbytes = B * N * 2 * 4
     recv = nbytes * (world - 1) / world
     return {"workload": "C3-sized training batch: (1024/R, 1000, 2) float32 shards -> (1024, 1000, 2) on every rank",
@@ -490,6 +494,13 @@ def main():
             return x
         t = torch.tensor([x], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def min_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
         return float(t.item())
 
     def sum_over_ranks(x: float) -> float:
@@ -573,11 +584,12 @@ def main():
         "bound": "issue", "achieved": ach / 1e12, "peak": issue_peak / 1e12, "unit": "T warp-inst/s",
         "frac": ach / issue_peak, "frac_at_survey_28_slots": ach / issue_peak * I_STEP_SURVEY / I_STEP,
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this very size, from the ncu --set full capture
-        # profiles/r01_v11_ncu_persistent_fullsize_details.txt (scripts/gpu_ncu_fullsize.sh); other sizes: not captured
-        "traffic": NCU_DRAM_BYTES_PER_LAUNCH_1E9 if (D == 1_000_000 and N_TRIALS == 1000) else None,
-        "traffic_note": "ncu --set full of this kernel at the bench's launch size (1e9 trials): dram read 0.256 GB + write "
-                        "8.084 GB = 8.339 GB against 8.072 GB algorithmic (8 B/trial out + 72 B/dataset in): 1.03x",
-        "kernel": "ddm::persistent_kernel<KIND_FIXED, f32 out>", "kernel_ms": k_ms,
+        # profiles/r02_ncu_sweep_fullsize_details.txt (scripts/r02_gpu_ncu_full.sh); other sizes: not captured
+        "traffic": NCU_DRAM_BYTES_PER_LAUNCH_1E9 if (D == 1_000_000 and N_TRIALS == 1000 and st["scheduler"] == 1) else None,
+        "traffic_note": "ncu --set full of this kernel at the bench's launch size (1e9 trials): dram read 0.247 GB + write "
+                        "8.080 GB = 8.327 GB against 8.072 GB algorithmic (8 B/trial out + 72 B/dataset in): 1.03x",
+        "kernel": ("ddm::persistent_kernel<KIND_FIXED, f32 out>" if st["scheduler"] == 1 else "ddm::tile_kernel<KIND_FIXED, f32 out>"),
+        "kernel_ms": k_ms,
         "steps_per_launch": st["total_steps"], "issue_slots_per_step": I_STEP,
         "peak_how": f"{sm_count} SMs x 4 schedulers x {f_hz / 1e6:.0f} MHz (median SM clock sampled during the timed region)",
         "steps_per_s_kernel": st["total_steps"] / (k_ms * 1e-3),
@@ -654,7 +666,23 @@ def main():
             sim.set_pipeline(-1, args.e2e_chunk_rows)
             e2e_rows = {"datasets_per_gpu": De, "h2d_bytes_per_step": int(pr.nbytes)}
             for label, dtype, fl in (("float64", np.float64, 0), ("float32", np.float32, FLAG_OUT_F32)):
-                out_host = sim.pinned_empty((De, N_TRIALS, 2), dtype, slot="rows_" + label)
+                # page-locked destination; every rank must get one (the legs below contain barriers): agree, else halve
+                out_host, why = None, ""
+                for _attempt in range(4):
+                    try:
+                        out_host = sim.pinned_empty((De, N_TRIALS, 2), dtype, slot="rows_" + label)
+                    except Exception as e:
+                        out_host, why = None, repr(e)[:200]
+                    if min_over_ranks(0.0 if out_host is None else 1.0) > 0.5:
+                        break
+                    out_host = None
+                    sim._pinned.pop("rows_" + label, None)
+                    De //= 2
+                    pr = pe[:De]
+                if out_host is None:
+                    e2e_rows[label] = {"error": "no rank-wide page-locked destination: " + why}
+                    continue
+                e2e_rows["datasets_per_gpu"] = De
                 basic_ddm_dc.batch_simulate_trials(pr, N_TRIALS, sim, dt=DT, max_steps=MAX_STEPS, dataset_offset=ds_base, out=out_host,
                                                    flags=fl)
                 st_r = sim.last_stats()
@@ -670,12 +698,13 @@ def main():
                 ms_r = max_over_ranks(e0.elapsed_time(e1))
                 tot_r = sum_over_ranks(float(st_r["total_steps"]))
                 e2e_rows[label] = {"value": tot_r * ke / (ms_r * 1e-3), "unit": "steps/s", "ms_per_step": ms_r / ke,
-                                   "d2h_bytes_per_step": int(st_r["d2h_bytes"] or out_host.nbytes),
+                                   "datasets_per_gpu": De, "d2h_bytes_per_step": int(st_r["d2h_bytes"] or out_host.nbytes),
                                    "host_rows_bytes_per_step": int(out_host.nbytes),
                                    "host_decode_threads": int(st_r["host_decode_threads"]),
                                    "host_row_write_gbs_all_ranks": out_host.nbytes * world * ke / (ms_r * 1e-3) / 1e9}
                 launches += st_r["kernel_launches"] * ke
                 del out_host
+                sim._pinned.pop("rows_" + label, None)   # give the page-locked block back before the next layout takes its own
             # the ceiling of the row-writing side: every rank's decode threads filling memory with the decode's own
             # streaming stores, all ranks at once (they share the host's memory controllers)
             barrier()
@@ -686,7 +715,8 @@ def main():
             e2e_rows["host_stream_store_peak_how"] = ("ddm_host_stream_peak: each rank's decode threads fill 1 GiB with non-temporal 32-byte "
                                                      "stores, best of 5 passes, all ranks concurrently; sum over ranks")
             for label in ("float64", "float32"):
-                e2e_rows[label]["frac_of_host_store_peak"] = e2e_rows[label]["host_row_write_gbs_all_ranks"] / (peak_all / 1e9)
+                if "host_row_write_gbs_all_ranks" in e2e_rows.get(label, {}):
+                    e2e_rows[label]["frac_of_host_store_peak"] = e2e_rows[label]["host_row_write_gbs_all_ranks"] / (peak_all / 1e9)
             e2e_rows["api"] = ("basic_ddm_dc.batch_simulate_trials(params (B,5) f64 host, n_trials[, flags=OUT_F32]) -> (B, n_trials, 2) pinned "
                                "host array; one ddm_simulate call: chunked kernels overlapped with the D2H of the previous chunk; trials "
                                "cross PCIe as 4-byte (steps, choice) records and host threads write the rows (rt = n*dt + ndt, choice)")
@@ -726,16 +756,20 @@ def main():
                 sim.draw_prior("basic", B2)
                 sim.run_uploaded(N2, 0.01, 400, flags=capi.FLAG_OUT_F32)
             sim.synchronize()
-            t0 = time.perf_counter()
-            for _ in range(reps):
-                pd = sim.draw_prior("basic", B2)                                  # device prior + (64,5) copy out
-                sim.run_uploaded(N2, 0.01, 400, flags=capi.FLAG_OUT_F32)          # simulate on the resident draws
-                batch = sim.last_output_dlpack()                                  # hand-off (syncs the stream)
-                del batch
-            lat = (time.perf_counter() - t0) / reps
+            blocks = []
+            for _ in range(5):                                                    # five blocks of 40 batches: the median block
+                t0 = time.perf_counter()
+                for _ in range(reps // 5):
+                    pd = sim.draw_prior("basic", B2)                              # device prior + (64,5) copy out
+                    sim.run_uploaded(N2, 0.01, 400, flags=capi.FLAG_OUT_F32)      # simulate on the resident draws
+                    batch = sim.last_output_dlpack()                              # hand-off (syncs the stream)
+                    del batch
+                blocks.append((time.perf_counter() - t0) / (reps // 5))
+            lat = float(np.median(blocks))
             training_batch = {"workload": "C2 basic_ddm_dc online-training batch: 64 datasets x 500 trials, dt=.01, max_steps=400",
                               "path": "ddm_draw_prior -> ddm_run -> ddm_last_output_dlpack (device-resident f32 batch)",
-                              "ms_per_batch": lat * 1e3, "trials_per_s": B2 * N2 / lat, "launches_per_batch": 3}
+                              "ms_per_batch": lat * 1e3, "ms_per_batch_blocks_of_40": [b * 1e3 for b in blocks],
+                              "trials_per_s": B2 * N2 / lat, "launches_per_batch": 3}
             if not args.no_cpu_baseline and world == 1:
                 from oracle import cpu as orc
 
@@ -757,7 +791,7 @@ def main():
         "mean_steps_per_trial": steps_per_step / trials_per_step,
         "timeout_frac": sum_over_ranks(float(st["n_timeouts"])) / trials_per_step,
         "kernel": {"grid": st["grid"], "block": st["block"], "refill_threshold": st["refill_threshold"], "tile": st["tile"],
-                   "persistent": bool(st["used_persistent"])},
+                   "persistent": bool(st["used_persistent"]), "scheduler": {1: "round-1 persistent kernel", 2: "tile kernel"}.get(st["scheduler"], "generic")},
         "clocks": clk, "roofline": roofline, "gpu_launches": launches,
     }
     line["device_reduction"] = reduction

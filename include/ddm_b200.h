@@ -114,7 +114,7 @@ typedef struct ddm_stats {
     uint64_t debug_overruns; /* shared-increment mode: trials that ran past the normals buffer */
     uint64_t d2h_bytes;      /* output bytes the run copied device -> host itself (0: batch left resident) */
     int32_t host_decode_threads; /* > 0: compact wire records were expanded by that many host threads */
-    int32_t reserved_;
+    int32_t scheduler;       /* 0 one thread per trial (generic / validation), 1 round-1 persistent kernel, 2 tile kernel */
 } ddm_stats;
 
 /* ---- lifecycle -------------------------------------------------------- */

@@ -874,12 +874,13 @@ def test_tile_kernel_equals_round1_persistent_kernel(sim, model):
             sim.set_tuning(0, 0, 0)
             ref = sim.simulate(model, params, 307, seed=9, dataset_offset=3, flags=F_STEPS, **kw)
             ref_steps, ref_st = sim.last_steps(53 * 307), sim.last_stats()
+            assert ref_st["scheduler"] == 1
             sim.set_kernel_variant(0)
             for thr, bps, tile in [(0, 0, 0), (1, 1, 5), (3, 2, 33), (32, 0, 128), (8, 0, 64), (2, 1, 1000)]:
                 sim.set_tuning(thr, bps, tile)
                 out = sim.simulate(model, params, 307, seed=9, dataset_offset=3, flags=F_STEPS, **kw)
                 steps, st = sim.last_steps(53 * 307), sim.last_stats()
-                assert st["used_persistent"] == 1 and st["tile"] <= 128
+                assert st["used_persistent"] == 1 and st["scheduler"] == 2 and st["tile"] <= 128
                 assert np.array_equal(out.view(np.uint64), ref.view(np.uint64)), (kw, thr, bps, tile)
                 assert np.array_equal(steps, ref_steps)
                 for k in ("total_steps", "n_timeouts", "n_upper", "reject_cap_hits", "n_trials"):
@@ -937,7 +938,7 @@ def test_trialwise_persistent_equals_generic_bitwise(sim):
     for kw in (dict(dt=0.01, max_steps=400), dict(dt=0.001, max_steps=777)):
         a = sim.simulate_trialwise(group, bounds, pp, seed=3, trial_offset=11, flags=F_STEPS, **kw)
         sa, st = sim.last_steps(n), sim.last_stats()
-        assert st["used_persistent"] == 1
+        assert st["used_persistent"] == 1 and st["scheduler"] == 2
         b = sim.simulate_trialwise(group, bounds, pp, seed=3, trial_offset=11, flags=F_STEPS | F_GENERIC, **kw)
         sb, st2 = sim.last_steps(n), sim.last_stats()
         assert st2["used_persistent"] == 0
