@@ -508,8 +508,17 @@ int run_common(ddm_ctx *ctx, int model, int64_t n_datasets, int64_t n_trials, do
 // the previous chunk is copied to the host on a second stream, so the batch costs
 // max(kernel, PCIe) instead of kernel + PCIe and needs 2 chunks of HBM instead of the batch.
 constexpr int64_t kPipelineMinRows = 8ll << 20;     // below this one launch + one copy is as fast
-constexpr int64_t kCompactMinRows = 4ll << 20;      // compact records pay off earlier (measured: scripts/midsize_ab.py)
+// Compact records pay off from 10^6 trials on for the (rt, choice) layout -- 1024 x 1000 rows 0.44 -> 0.32-0.37 ms in two
+// chunks -- and from 4 Mi for the (signed rt, external column) layout, whose 8-byte records and wider decode only break
+// even at 10^6 (scripts/r02_c3_pipeline_ab.py, profiles/r02_c3_pipeline_ab.txt); 256 x 1000 gains from nothing.
+constexpr int64_t kCompactMinRows = 1000000;
+constexpr int64_t kCompactMinRowsExt = 4ll << 20;
+// Into a page-locked destination two plain chunks already beat one launch + one copy at 10^6 trials (C3: 0.49 -> 0.44 ms);
+// into pageable memory each chunk's copy blocks the host and nothing overlaps, so the old threshold stays.
+constexpr int64_t kPinnedPipelineMinRows = 1000000;
 constexpr int64_t kPipelineMinChunkRows = 2ll << 20;  // a chunk costs ~0.2 ms of launches and kernel tail
+constexpr int64_t kPipelineSmallBatchRows = 4ll << 20;     // batches below this are halved / quartered ...
+constexpr int64_t kPipelineSmallBatchChunkRows = 512ll << 10;  // ... down to chunks of 512 Ki trials
 constexpr int64_t kPipelineChunkRows = 32ll << 20;  // trials per chunk (512 MB of float64 pairs)
 
 // The host thread pool (compact-wire decode, parameter scan), sized by ddm_set_host_decode.
@@ -539,7 +548,8 @@ std::vector<std::pair<int64_t, int64_t>> pipeline_chunks(int64_t n_datasets, int
         if (rows_c <= 0) {
             const int64_t quarter = n_datasets * per_ds / 4, half_left = (n_datasets - lo) * per_ds / 2;
             rows_c = rows_c == -2 ? quarter : (rows_c == -3 ? half_left : (quarter < half_left ? quarter : half_left));
-            if (rows_c < kPipelineMinChunkRows) rows_c = kPipelineMinChunkRows;
+            const int64_t min_chunk = n_datasets * per_ds < kPipelineSmallBatchRows ? kPipelineSmallBatchChunkRows : kPipelineMinChunkRows;
+            if (rows_c < min_chunk) rows_c = min_chunk;
             if (rows_c > kPipelineChunkRows) rows_c = kPipelineChunkRows;
         }
         int64_t cnt = rows_c / per_ds;
@@ -552,7 +562,7 @@ std::vector<std::pair<int64_t, int64_t>> pipeline_chunks(int64_t n_datasets, int
 }
 
 int run_pipelined(ddm_ctx *ctx, const double *params_host, int64_t n_trials, double dt, int max_steps, uint64_t seed,
-                  uint64_t dataset_offset, int precision, int flags, void *out_host) {
+                  uint64_t dataset_offset, int precision, int flags, void *out_host, bool want_compact) {
     const int model = ctx->model;
     const int64_t n_datasets = ctx->n_datasets;
     ddm::RunArgs base;
@@ -565,7 +575,7 @@ int run_pipelined(ddm_ctx *ctx, const double *params_host, int64_t n_trials, dou
     // host threads write the rows, so the PCIe copy moves 4 or 8 bytes per trial instead of 16.
     const int kind = kind_of(model);
     const bool basic_cols = (kind == ddm::KIND_FIXED || kind == ddm::KIND_DRIFT);
-    const bool compact = ctx->tune_host_decode >= 0 && cols == 2 && takes_persistent_kernel(ctx, model, precision, flags) &&
+    const bool compact = want_compact && ctx->tune_host_decode >= 0 && cols == 2 && takes_persistent_kernel(ctx, model, precision, flags) &&
                          (uint32_t)max_steps <= ddm::WIRE_MAX_STEPS;
     const size_t wire_bytes = compact ? (basic_cols ? 4 : 8) : row_bytes;
     // Chunk schedule (first dataset, datasets).  A fixed chunk_rows if the caller set one; otherwise each chunk is
@@ -1006,12 +1016,33 @@ DDM_API int ddm_simulate(ddm_ctx *ctx, int model, const double *params, int64_t 
     if (rc) return rc;
     const bool compact_ok = ctx->tune_host_decode >= 0 && n_cols_of(model) == 2 && takes_persistent_kernel(ctx, model, precision, flags) &&
                             max_steps >= 0 && (uint32_t)max_steps <= ddm::WIRE_MAX_STEPS;
-    const int64_t min_rows = ctx->tune_pipeline_min_rows >= 0 ? ctx->tune_pipeline_min_rows
-                                                              : (compact_ok ? kCompactMinRows : kPipelineMinRows);
-    if (out_host && n_trials > 0 && n_datasets * n_trials >= min_rows && n_datasets >= 2 && !(flags & DDM_FLAG_KEEP_STEPS) &&
-        !ctx->dbg_on) {
+    // How a host-destined batch travels: one launch + one copy, plain chunks (kernel of chunk i+1 over the copy of chunk i),
+    // or compact records + host decode.  A caller's ddm_set_pipeline(min_rows) overrides the measured defaults.
+    const int64_t rows_total = n_datasets * n_trials;
+    bool stream = false, want_compact = compact_ok;
+    if (out_host && n_trials > 0 && n_datasets >= 2 && !(flags & DDM_FLAG_KEEP_STEPS) && !ctx->dbg_on) {
+        if (ctx->tune_pipeline_min_rows >= 0) {
+            stream = rows_total >= ctx->tune_pipeline_min_rows;
+        } else {
+            const int k = kind_of(model);
+            const bool basic_cols = (k == ddm::KIND_FIXED || k == ddm::KIND_DRIFT);
+            if (compact_ok && rows_total >= (basic_cols ? kCompactMinRows : kCompactMinRowsExt)) {
+                stream = true;
+            } else if (rows_total >= kPipelineMinRows) {
+                stream = true;
+                want_compact = false;
+            } else if (rows_total >= kPinnedPipelineMinRows) {
+                cudaPointerAttributes attr{};
+                const bool pinned = cudaPointerGetAttributes(&attr, out_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+                cudaGetLastError();  // an unregistered pointer is not an error worth keeping
+                stream = pinned;
+                want_compact = false;
+            }
+        }
+    }
+    if (stream) {
         DeviceGuard g(ctx->device);
-        return run_pipelined(ctx, params, n_trials, dt, max_steps, seed, dataset_offset, precision, flags, out_host);
+        return run_pipelined(ctx, params, n_trials, dt, max_steps, seed, dataset_offset, precision, flags, out_host, want_compact);
     }
     if (n_datasets > 0) {
         DeviceGuard g(ctx->device);

@@ -135,7 +135,79 @@ inline double signed_rt(uint32_t c, double dt, double tau) {
     return choice > 0 ? tau + rt : (choice < 0 ? -tau - rt : 0.0);
 }
 
+// Four (code, fp32 bits) records per iteration -> (signed rt, external measurement) float64 pairs, two 32-byte streaming
+// stores.  signed rt = +(tau + n*dt) / -(tau + n*dt) / 0 by choice: -tau - rt of trial_outputs<false> is the same double
+// as -(tau + rt) (rounding is symmetric), and the blends keep a missing response at +0.0 whatever tau's sign.
+__attribute__((target("avx2"))) int64_t decode_ext64_avx2(const WirePair *w, double *o, int64_t lo, int64_t hi, double dt, double tau) {
+    const __m256d vdt = _mm256_set1_pd(dt), vtau = _mm256_set1_pd(tau), zero = _mm256_setzero_pd();
+    const __m256d sign = _mm256_set1_pd(-0.0);
+    const __m256i pick = _mm256_setr_epi32(0, 2, 4, 6, 1, 3, 5, 7);  // codes to the low half, fp32 bits to the high half
+    const __m128i three = _mm_set1_epi32(3), one = _mm_set1_epi32(1);
+    int64_t i = lo;
+    for (; i + 4 <= hi; i += 4) {
+        const __m256i r = _mm256_permutevar8x32_epi32(_mm256_loadu_si256(reinterpret_cast<const __m256i *>(w + i)), pick);
+        const __m128i c = _mm256_castsi256_si128(r);
+        const __m256d ext = _mm256_cvtps_pd(_mm_castsi128_ps(_mm256_extracti128_si256(r, 1)));
+        const __m256d t = _mm256_add_pd(vtau, _mm256_mul_pd(_mm256_cvtepi32_pd(_mm_srli_epi32(c, 2)), vdt));
+        const __m256d ch = _mm256_cvtepi32_pd(_mm_sub_epi32(_mm_and_si128(c, three), one));
+        __m256d v = _mm256_blendv_pd(zero, _mm256_xor_pd(t, sign), _mm256_cmp_pd(ch, zero, _CMP_LT_OQ));
+        v = _mm256_blendv_pd(v, t, _mm256_cmp_pd(ch, zero, _CMP_GT_OQ));
+        const __m256d a = _mm256_unpacklo_pd(v, ext);  // v0 e0 | v2 e2
+        const __m256d b = _mm256_unpackhi_pd(v, ext);  // v1 e1 | v3 e3
+        _mm256_stream_pd(o + 2 * i, _mm256_permute2f128_pd(a, b, 0x20));
+        _mm256_stream_pd(o + 2 * i + 4, _mm256_permute2f128_pd(a, b, 0x31));
+    }
+    return i;
+}
+
+// Eight records per iteration -> (float signed rt, external measurement) float32 pairs.
+__attribute__((target("avx2"))) int64_t decode_ext32_avx2(const WirePair *w, float *o, int64_t lo, int64_t hi, double dt, double tau) {
+    const __m256d vdt = _mm256_set1_pd(dt), vtau = _mm256_set1_pd(tau), zero = _mm256_setzero_pd();
+    const __m256d sign = _mm256_set1_pd(-0.0);
+    const __m256i pick = _mm256_setr_epi32(0, 2, 4, 6, 1, 3, 5, 7);
+    const __m128i three = _mm_set1_epi32(3), one = _mm_set1_epi32(1);
+    int64_t i = lo;
+    for (; i + 8 <= hi; i += 8) {
+        __m128 rt[2];
+        __m128i eb[2];
+        for (int half = 0; half < 2; half++) {
+            const __m256i r = _mm256_permutevar8x32_epi32(_mm256_loadu_si256(reinterpret_cast<const __m256i *>(w + i + 4 * half)), pick);
+            const __m128i c = _mm256_castsi256_si128(r);
+            eb[half] = _mm256_extracti128_si256(r, 1);
+            const __m256d t = _mm256_add_pd(vtau, _mm256_mul_pd(_mm256_cvtepi32_pd(_mm_srli_epi32(c, 2)), vdt));
+            const __m256d ch = _mm256_cvtepi32_pd(_mm_sub_epi32(_mm_and_si128(c, three), one));
+            __m256d v = _mm256_blendv_pd(zero, _mm256_xor_pd(t, sign), _mm256_cmp_pd(ch, zero, _CMP_LT_OQ));
+            v = _mm256_blendv_pd(v, t, _mm256_cmp_pd(ch, zero, _CMP_GT_OQ));
+            rt[half] = _mm256_cvtpd_ps(v);
+        }
+        const __m256 vrt = _mm256_set_m128(rt[1], rt[0]);
+        const __m256 vext = _mm256_castsi256_ps(_mm256_set_m128i(eb[1], eb[0]));
+        const __m256 a = _mm256_unpacklo_ps(vrt, vext);  // r0 e0 r1 e1 | r4 e4 r5 e5
+        const __m256 b = _mm256_unpackhi_ps(vrt, vext);  // r2 e2 r3 e3 | r6 e6 r7 e7
+        _mm256_stream_ps(o + 2 * i, _mm256_permute2f128_ps(a, b, 0x20));
+        _mm256_stream_ps(o + 2 * i + 8, _mm256_permute2f128_ps(a, b, 0x31));
+    }
+    return i;
+}
+
 void decode_ext64(const WirePair *w, double *o, const Segment &s, double dt, bool stream) {
+    if (stream && g_avx2) {
+        int64_t i = s.lo;
+        for (; i < s.hi && ((reinterpret_cast<uintptr_t>(o + 2 * i) & 31u) != 0u); i++) {  // reach a 32-byte boundary
+            float ext;
+            __builtin_memcpy(&ext, &w[i].y, sizeof(ext));
+            o[2 * i] = signed_rt((uint32_t)w[i].x, dt, s.tau);
+            o[2 * i + 1] = (double)ext;
+        }
+        i = decode_ext64_avx2(w, o, i, s.hi, dt, s.tau);
+        for (; i < s.hi; i++) {
+            float ext;
+            __builtin_memcpy(&ext, &w[i].y, sizeof(ext));
+            o[2 * i] = signed_rt((uint32_t)w[i].x, dt, s.tau);
+            o[2 * i + 1] = (double)ext;
+        }
+        return;
+    }
     for (int64_t i = s.lo; i < s.hi; i++) {
         const WirePair r = w[i];
         float ext;
@@ -151,8 +223,18 @@ void decode_ext64(const WirePair *w, double *o, const Segment &s, double dt, boo
     }
 }
 
-void decode_ext32(const WirePair *w, float *o, const Segment &s, double dt) {
-    for (int64_t i = s.lo; i < s.hi; i++) {
+void decode_ext32(const WirePair *w, float *o, const Segment &s, double dt, bool stream) {
+    int64_t i0 = s.lo;
+    if (stream && g_avx2) {
+        for (; i0 < s.hi && ((reinterpret_cast<uintptr_t>(o + 2 * i0) & 31u) != 0u); i0++) {  // reach a 32-byte boundary
+            float ext;
+            __builtin_memcpy(&ext, &w[i0].y, sizeof(ext));
+            o[2 * i0] = (float)signed_rt((uint32_t)w[i0].x, dt, s.tau);
+            o[2 * i0 + 1] = ext;
+        }
+        i0 = decode_ext32_avx2(w, o, i0, s.hi, dt, s.tau);
+    }
+    for (int64_t i = i0; i < s.hi; i++) {
         const WirePair r = w[i];
         float ext;
         __builtin_memcpy(&ext, &r.y, sizeof(ext));
@@ -182,7 +264,7 @@ void decode_slice(const WireDecode &j, int id, int n_threads) {
             else decode_basic32(static_cast<const int32_t *>(j.wire), static_cast<float *>(j.out), s, j.dt, timeout_val, stream);
         } else {
             if (j.out64) decode_ext64(static_cast<const WirePair *>(j.wire), static_cast<double *>(j.out), s, j.dt, stream && j.out64);
-            else decode_ext32(static_cast<const WirePair *>(j.wire), static_cast<float *>(j.out), s, j.dt);
+            else decode_ext32(static_cast<const WirePair *>(j.wire), static_cast<float *>(j.out), s, j.dt, stream);
         }
         at = s.hi;
     }

@@ -135,10 +135,11 @@ int ddm_set_tuning(ddm_ctx *ctx, int refill_threshold, int blocks_per_sm, int ti
  * draws and for DDM_MODEL_TRIALWISE, the round-1 kernel for DDM_MODEL_BASIC / DDM_MODEL_ETA.  Results are bit-identical. */
 int ddm_set_kernel_variant(ddm_ctx *ctx, int variant);
 /* ddm_simulate with a host destination streams batches of at least min_rows trials to the host in
- * chunks of about chunk_rows trials, overlapping kernel and PCIe copy (defaults: min_rows 8 Mi trials,
- * 4 Mi when the rows travel as compact records, see ddm_set_host_decode; chunk_rows: the smaller of a
- * quarter of the batch and half of what is left, within 2 Mi .. 32 Mi, so that the last chunks are
- * small; values < 0 restore them -- chunk_rows -2 / -3 select "a quarter" / "half of what is left"
+ * chunks of about chunk_rows trials, overlapping kernel and PCIe copy (defaults: min_rows 8 Mi trials, 10^6 into a
+ * page-locked destination; 10^6 -- 4 Mi for the layouts with an external column -- when the rows travel as compact
+ * records, see ddm_set_host_decode; chunk_rows: the smaller of a
+ * quarter of the batch and half of what is left, within 2 Mi .. 32 Mi -- 512 Ki for batches below 4 Mi --
+ * so that the last chunks are small; values < 0 restore them -- chunk_rows -2 / -3 select "a quarter" / "half of what is left"
  * alone, for measurements; a huge min_rows switches the pipeline off).  After such a run the batch
  * is not resident on the device.  Results do not depend on the chunking. */
 int ddm_set_pipeline(ddm_ctx *ctx, int64_t min_rows, int64_t chunk_rows);

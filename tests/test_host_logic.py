@@ -285,6 +285,40 @@ def test_wire_decode_float32_streaming_path_any_alignment():
             assert np.isnan(raw[:base + phase]).all() and np.isnan(raw[base + phase + D * T * 2:]).all()   # nothing outside the rows
 
 
+@pytest.mark.parametrize("f32", [False, True])
+def test_wire_decode_external_column_layout_streaming_path_any_alignment(f32):
+    """The (signed rt, external measurement) rows of the single-trial-boundary models through the vectorised decoders
+    (decode_ext64_avx2 / decode_ext32_avx2): every phase of the destination, lengths around the vector width, negative
+    and zero non-decision times (a missing response must stay +0.0), all three choices."""
+    from bayesflow_nddms_b200 import _capi
+
+    lib = _capi.load()
+    rng = np.random.default_rng(9)
+    dt = 0.01
+    dtype = np.float32 if f32 else np.float64
+    for D, T in ((3, 1000), (5, 17), (1, 3), (2, 8), (1, 20_003)):
+        params = rng.uniform(-0.5, 1.5, (D, 7))
+        params[0, 3] = 0.0
+        n = rng.integers(0, 401, (D, T)).astype(np.uint32)
+        ch = rng.integers(-1, 2, (D, T))
+        code = ((n << 2) | (ch + 1).astype(np.uint32)).astype(np.int32)
+        ext = rng.standard_normal((D, T)).astype(np.float32)
+        wire = np.stack([code, ext.view(np.int32)], axis=-1).copy()
+        rt, tau = n.astype(np.float64) * dt, params[:, 3:4]
+        want = np.stack([np.where(ch > 0, tau + rt, np.where(ch < 0, -tau - rt, 0.0)), ext.astype(np.float64)], axis=-1).astype(dtype)
+        per = 32 // dtype().itemsize
+        for phase in range(per):
+            raw = np.full(D * T * 2 + 2 * per, np.nan, dtype=dtype)
+            base = (-raw.ctypes.data // dtype().itemsize) % per
+            out = raw[base + phase: base + phase + D * T * 2].reshape(D, T, 2)
+            for threads in (1, 3):
+                out[...] = np.nan
+                assert lib.ddm_wire_decode_host(wire.ctypes.data, out.ctypes.data, params.ctypes.data_as(_capi._dp), 7, D, T, dt, 0,
+                                                _capi.FLAG_OUT_F32 if f32 else 0, threads) == 0
+                assert np.array_equal(out, want) and not np.signbit(out[..., 0][ch == 0]).any(), (D, T, phase, threads)
+            assert np.isnan(raw[:base + phase]).all() and np.isnan(raw[base + phase + D * T * 2:]).all()
+
+
 def test_host_stream_store_peak_is_measurable():
     import ctypes as C
 
@@ -321,7 +355,8 @@ def test_simulator_counters_roll_over_multiples_of_2_32():
 @pytest.mark.parametrize("chunk_rows", [-1, -2, -3, 1, 257 * 7, 32 << 20])
 def test_streamed_path_chunk_schedule(n_datasets, n_trials, chunk_rows):
     """include/ddm_b200.h: ddm_pipeline_chunks -- the schedule covers every dataset exactly once, in order; the
-    default schedules keep chunks within 2 Mi .. 32 Mi trials (whole datasets) and end with small chunks."""
+    default schedules keep chunks within 2 Mi .. 32 Mi trials (512 Ki for batches below 4 Mi; whole datasets) and end with
+    small chunks."""
     import ctypes as C
 
     from bayesflow_nddms_b200 import _capi
@@ -345,7 +380,8 @@ def test_streamed_path_chunk_schedule(n_datasets, n_trials, chunk_rows):
     if chunk_rows < 0:
         assert np.all(rows <= max(32 << 20, n_trials))                 # at most 32 Mi trials, or one dataset
         if n > 1:
-            assert np.all(rows[:-1] >= min(2 << 20, rows[:-1].max()) - n_trials)   # at least 2 Mi, up to dataset granularity
+            floor = (512 << 10) if n_datasets * n_trials < (4 << 20) else (2 << 20)   # small batches: 512 Ki-trial chunks
+            assert np.all(rows[:-1] >= min(floor, rows[:-1].max()) - n_trials)        # ... up to dataset granularity
         if n_datasets * n_trials >= 256 << 20 and chunk_rows != -2:
             assert rows[-1] <= 4 << 20 < rows[0]                        # large batches end with small chunks
     elif chunk_rows > 0:
