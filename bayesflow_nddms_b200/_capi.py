@@ -130,8 +130,14 @@ SIGNATURES = {
 
 
 def library_path() -> str:
-    # DDM_B200_LIB selects an experimental build of the same library (A/B measurements only)
-    return os.environ.get("DDM_B200_LIB") or _build.LIB_PATH
+    # DDM_B200_LIB selects an experimental build of the same library (A/B measurements only);
+    # DDM_PHILOX_ROUNDS=7 the 7-round build of the generator (1.16x the steps/s; same counters and maps, a different
+    # stream: the known-answer tests and the CPU oracle are 10-round, its distribution suite passes -- DESIGN.md section 5)
+    if os.environ.get("DDM_B200_LIB"):
+        return os.environ["DDM_B200_LIB"]
+    if os.environ.get("DDM_PHILOX_ROUNDS", "10") == "7":
+        return _build.PHILOX7_LIB_PATH
+    return _build.LIB_PATH
 
 
 def load() -> C.CDLL:

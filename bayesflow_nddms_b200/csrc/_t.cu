@@ -486,14 +486,18 @@ __device__ __forceinline__ void tile_flush(const RunArgs &a, const uint32_t *cod
 }
 
 // Resident blocks per SM: the kinds whose tile set-up draws normals (a Philox block and three Box-Muller pairs live
-// next to the stepping state) get 48 registers and five blocks; at 40 registers ptxas spilled a loop-carried
-// register of the stepping loop.  (Round 1 measured 5 x 48 equal to 6 x 40 on the sweep.)
+// next to the stepping state) get 48 registers and five blocks -- at 40 registers ptxas spilled a loop-carried register
+// of the stepping loop; the kinds without set-up draws keep six blocks of 40.  (The bare stepping loop is bound by the
+// FMA-heavy pipe and loses 1 % from 12 to 10 warps per scheduler: profiles/r02_microbench_occupancy.txt.)
 #ifndef DDM_TILE_MIN_BLOCKS
 #define DDM_TILE_MIN_BLOCKS (1280 / DDM_PERSISTENT_BLOCK)
 #endif
+#ifndef DDM_TILE_MIN_BLOCKS_FIXED
+#define DDM_TILE_MIN_BLOCKS_FIXED (1536 / DDM_PERSISTENT_BLOCK)  // no set-up draws: 40 registers do (A/B: +1 % over five blocks)
+#endif
 template <int KIND>
 constexpr int tile_min_blocks() {
-    return (KIND == KIND_FIXED || KIND == KIND_DRIFT) ? 6 : DDM_TILE_MIN_BLOCKS;
+    return (KIND == KIND_FIXED || KIND == KIND_DRIFT) ? DDM_TILE_MIN_BLOCKS_FIXED : DDM_TILE_MIN_BLOCKS;
 }
 
 // A straggler's own row (its tile's buffer has been recycled).  Not inlined: the fp64 output arithmetic and the
@@ -620,8 +624,8 @@ __global__ void __launch_bounds__(DDM_PERSISTENT_BLOCK, tile_min_blocks<KIND>())
                 int choice = (x >= h) ? 1 : ((x <= -h) ? -1 : 0);
                 // lanes always run whole 6-step blocks; a trial still inside the boundaries after max_steps
                 // steps is a timeout whatever it did in the surplus steps of its last block
-                if (n > a.max_steps) { n = a.max_steps; choice = 0; }
-                const uint32_t c = (uint32_t)wire_pack(n, choice);
+                if (n > a.max_steps) choice = 0;
+                const uint32_t c = (uint32_t)wire_pack(min(n, a.max_steps), choice);
                 if (direct & lane_bit) {  // rare: the trial outlived its tile's buffer
                     tile_emit_direct<KIND, OUT64>(a, ds, trial, c, meta);
                 } else {
