@@ -979,3 +979,66 @@ def test_global_dataset_index_is_64_bit(sim, oracle):
         assert np.array_equal(out, sim.simulate(0, p, 50, seed=5, dataset_offset=1 << 32))
     finally:
         sim.dataset_counter = keep
+
+
+def test_simulate_histogram_is_the_histogram_of_the_rows(sim):
+    """ddm_simulate_histogram (C5 as SURVEY 8d specifies it: host parameters in, device-reduced histogram out) returns
+    exactly the histogram of the rows the same call leaves resident, for both row layouts, and agrees with the kernel's
+    counters; the rows remain available for DLPack hand-off."""
+    import torch
+
+    from bayesflow_nddms_b200 import basic_ddm_dc as m0
+    from bayesflow_nddms_b200 import priors
+    from bayesflow_nddms_b200 import single_trial_alpha_not_scaled as m1
+
+    for mod, prior, basic in ((m0, "sweep", True), (m1, "alpha", False)):
+        P = priors.draw_prior_batch(prior, 300, np.random.default_rng(5))
+        kw = dict(dt=1e-3, max_steps=4000) if basic else dict(dt=0.01, max_steps=400)
+        h = mod.batch_simulate_histogram(P, 700, sim, seed=4, dataset_offset=9, n_bins=97, rt_max=3.3, **kw)
+        st = sim.last_stats()
+        rows = torch.from_dlpack(sim.last_output_dlpack()).cpu().numpy().astype(np.float64).reshape(-1, 2)
+        assert rows.shape[0] == 300 * 700
+        if basic:
+            rt, choice = rows[:, 0], np.sign(rows[:, 1])
+        else:
+            rt, choice = np.abs(rows[:, 0]), np.sign(rows[:, 0])
+        b = rt * (97 / 3.3)
+        inside = b < 97
+        for sign, key in ((1, "upper"), (-1, "lower")):
+            want = np.bincount(b[(choice == sign) & inside].astype(np.int64), minlength=97)
+            assert np.array_equal(h[key].astype(np.int64), want), key
+        assert h["missing"] == int((choice == 0).sum()) == st["n_timeouts"]
+        assert h["overflow"] == int(((choice != 0) & ~inside).sum())
+        assert int(h["upper"].sum() + h["lower"].sum()) + h["missing"] + h["overflow"] == 300 * 700
+        # same trials as the row-returning call
+        again = mod.batch_simulate_trials(P, 700, sim, seed=4, dataset_offset=9, flags=F_F32, **kw)
+        assert np.array_equal(again.reshape(-1, 2).astype(np.float64), rows)
+    with pytest.raises(ValueError):
+        sim.simulate_histogram(7, np.zeros((2, 24)), 10)
+
+
+@pytest.mark.parametrize("model,prior", [(0, "basic"), (1, "alpha")])
+def test_default_transfer_plan_at_a_million_trials(sim, model, prior):
+    """Round 2 lowered the streaming thresholds to 1e6 trials (compact records for (rt, choice) rows, two plain chunks
+    into a page-locked destination for the layouts with an external column): the defaults return the bits of one launch +
+    one copy, into the pool's pinned result array and into a caller's pageable one."""
+    from bayesflow_nddms_b200 import priors
+
+    P = priors.draw_prior_batch(prior, 1003, np.random.default_rng(2))
+    for flags in (0, F_F32):
+        try:
+            sim.set_pipeline(1 << 60, -1)
+            base = sim.simulate(model, P, 1000, seed=3, dataset_offset=1, flags=flags)
+        finally:
+            sim.set_pipeline(-1, -1)
+        got = sim.simulate(model, P, 1000, seed=3, dataset_offset=1, flags=flags)             # pinned pool array
+        st = sim.last_stats()
+        assert np.array_equal(base, got)
+        assert st["d2h_bytes"] > 0                                                           # it was streamed
+        if model == 0:
+            assert st["host_decode_threads"] > 0 and st["d2h_bytes"] == 1003 * 1000 * 4          # compact records
+        else:
+            assert st["host_decode_threads"] == 0                                                # plain chunks at this size
+        mine = np.empty_like(base)                                                            # pageable destination
+        out = sim.simulate(model, P, 1000, seed=3, dataset_offset=1, flags=flags, out=mine)
+        assert out is mine and np.array_equal(base, mine)
