@@ -214,7 +214,7 @@ struct ddm_ctx {
 
     // tuning (0 = automatic)
     int tune_threshold = 0, tune_blocks_per_sm = 0, tune_tile = 0;
-    int tune_kernel_variant = -1;  // -1 = the faster of the two per model family (measured), 0 = tile kernel, 1 = round-1 persistent kernel
+    int tune_kernel_variant = -1;  // -1 / 0 = tile kernel (production), 1 = round-1 persistent kernel (A/B measurements)
     bool trialwise_degenerate = false;  // last trialwise call: some group has dc == 0 (no noise unit)
     int64_t tune_pipeline_min_rows = -1, tune_pipeline_chunk_rows = -1;  // < 0: default
 };
@@ -232,10 +232,11 @@ int default_refill_threshold(double dt, bool legacy = false) {
         const int thr = (int)std::lround(164.0 * std::sqrt(dt));
         return thr < 2 ? 2 : (thr > 16 ? 16 : thr);
     }
-    // tile kernel: measured optima on B200 (profiles/r02_ab_kernels_v3b.jsonl) are 5 at dt = .001 (4: -0.4 %, 6: -0.3 %) and
-    // 10-12 at dt = .01 for every model family; 46 dt^0.32 passes through both
-    const int thr = (int)std::lround(46.0 * std::pow(dt, 0.32));
-    return thr < 2 ? 2 : (thr > 12 ? 12 : thr);
+    // tile kernel: finished lanes are refilled in place (~45 issue slots per refill, no loop re-entry), so the optimum sits
+    // lower than the round-1 kernel's: measured 3-4 at dt = .001 and 8 at dt = .01 for every model family
+    // (profiles/r02_ab_kernels.jsonl); 42 dt^0.36 passes through both
+    const int thr = (int)std::lround(42.0 * std::pow(dt, 0.36));
+    return thr < 2 ? 2 : (thr > 10 ? 10 : thr);
 }
 
 int fail(ddm_ctx *ctx, int code, const char *fmt, ...) {
@@ -381,12 +382,10 @@ int launch_sim(ddm_ctx *ctx, ddm::RunArgs &a, int precision, ddm_stats &st, cuda
     DDM_CUDA(ctx, cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), stream));
     if (persistent) {
         const int block = ddm::persistent_block_size();
-        // Two schedulers of the same trials, bit-identical results.  The tile kernel wins wherever a trial needs set-up
-        // draws (per-trial boundary / diffusion coefficient / the general model: +3 .. +11 %, profiles/r02_ab_kernels*.jsonl)
-        // and is the only one for the trialwise model; for the models without per-trial set-up (basic, per-trial drift)
-        // the round-1 kernel's two-instruction-shorter stepping loop keeps it 1-2 % ahead, so it stays their default.
-        const bool fixed_kind = (kind == ddm::KIND_FIXED || kind == ddm::KIND_DRIFT);
-        const bool legacy = !trialwise && (ctx->tune_kernel_variant == 1 || (ctx->tune_kernel_variant < 0 && fixed_kind));
+        // Two schedulers of the same trials, bit-identical results.  The tile kernel (round 2) is the production one for
+        // every model family: +3 % on the sweep, +7 % on the basic model at dt = .01, +18-20 % on the per-trial-boundary /
+        // per-trial-dc models at dt = .01 (profiles/r02_ab_kernels.jsonl); the round-1 kernel stays selectable for A/B.
+        const bool legacy = !trialwise && ctx->tune_kernel_variant == 1;
         const uint64_t warps_needed = ((uint64_t)rows + 31) / 32;
         const uint64_t blocks_needed = (warps_needed + (block / 32) - 1) / (block / 32);
         // tile: consecutive trials of one dataset handed out per atomic claim (and, in the tile kernel, set up and

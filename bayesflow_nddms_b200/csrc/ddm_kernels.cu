@@ -346,9 +346,10 @@ __global__ void __launch_bounds__(DDM_PERSISTENT_BLOCK, RECORD ? (1024 / DDM_PER
 //   claim    a warp claims a tile of <= tile_cap consecutive trials of one dataset and sets all of them up at
 //            once (lane i takes trials i, i + 32, ...), staging each trial's start state (x0, h, c0) and its
 //            external columns in shared memory (north_star: "per-dataset parameters staged in shared memory");
-//   refill   a lane that needs a trial takes the tile's next one: two or three LDS;
 //   finish   a finished lane parks (steps << 2 | choice + 1) in the tile's result slot: one STS;
-//   flush    when the tile's last trial has finished the warp turns the 4-byte results into output rows --
+//   refill   ... and takes the tile's next trial: a ballot/popc prefix and two or three LDS -- right inside the stepping
+//            loop (the "fast path", ~45 issue slots, no loop re-entry) as long as the tile can serve every finished lane;
+//   flush    when the next tile but one is claimed the warp turns the 4-byte results into output rows --
 //            fp64 arithmetic of the reference, lane-contiguous vector stores.
 // A warp works on two tiles at a time (the one being handed out and the previous one, draining).  When a third
 // is claimed while the oldest still has trials running (first-passage times are heavy-tailed), that tile is
@@ -485,15 +486,15 @@ __device__ __forceinline__ void tile_flush(const RunArgs &a, const uint32_t *cod
     __syncwarp();
 }
 
-// Resident blocks per SM: the kinds whose tile set-up draws normals (a Philox block and three Box-Muller pairs live
-// next to the stepping state) get 48 registers and five blocks -- at 40 registers ptxas spilled a loop-carried register
-// of the stepping loop; the kinds without set-up draws keep six blocks of 40.  (The bare stepping loop is bound by the
-// FMA-heavy pipe and loses 1 % from 12 to 10 warps per scheduler: profiles/r02_microbench_occupancy.txt.)
+// Resident blocks per SM: five blocks of 256 threads at 48 registers for every kind.  At 40 registers (six blocks) ptxas
+// either spilled a loop-carried register of the stepping loop (the kinds whose tile set-up draws normals) or rebuilt the
+// lane mask inside it (the others); the bare stepping loop is bound by the FMA-heavy pipe and loses 1 % from 12 to 10
+// warps per scheduler (profiles/r02_microbench_occupancy.txt), and the A/B has five blocks 1-3 % ahead for every kind.
 #ifndef DDM_TILE_MIN_BLOCKS
 #define DDM_TILE_MIN_BLOCKS (1280 / DDM_PERSISTENT_BLOCK)
 #endif
 #ifndef DDM_TILE_MIN_BLOCKS_FIXED
-#define DDM_TILE_MIN_BLOCKS_FIXED (1536 / DDM_PERSISTENT_BLOCK)  // no set-up draws: 40 registers do (A/B: +1 % over five blocks)
+#define DDM_TILE_MIN_BLOCKS_FIXED (1280 / DDM_PERSISTENT_BLOCK)
 #endif
 template <int KIND>
 constexpr int tile_min_blocks() {
@@ -516,11 +517,17 @@ __global__ void __launch_bounds__(DDM_PERSISTENT_BLOCK, tile_min_blocks<KIND>())
     using L = TileLayout<KIND>;
     extern __shared__ uint32_t tile_smem[];
     const unsigned lane = threadIdx.x & 31u;
-    const unsigned lane_bit = 1u << lane;
-    const unsigned lt_mask = lane_bit - 1u;
+    // The lane's masks and the shared address of the warp's result slots are read in every refill; left alone, ptxas
+    // rebuilds them each time from the thread index (S2R, shifts, a multiply-add chain for the shared-memory base)
+    // rather than keep three registers.  Values that come out of a volatile asm cannot be rematerialised.
+    unsigned lane_bit, lt_mask;
+    asm volatile("mov.u32 %0, %%lanemask_eq;" : "=r"(lane_bit));
+    asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
     constexpr uint32_t T = L::T;
     uint32_t *meta = tile_smem + (threadIdx.x >> 5) * (L::WORDS * T + M_WORDS);
     uint32_t *code = meta + M_WORDS;                                      // [2][T] result slots
+    uint32_t code_s = (uint32_t)__cvta_generic_to_shared(code);           // the same, as a 32-bit shared-window address
+    asm volatile("" : "+r"(code_s));
     float *sext = reinterpret_cast<float *>(code + 2u * T);               // [2][T] external column (EXT)
     float *sext2 = sext + (L::EXT ? 2u * T : 0u);                         // [2][T] second external column (EXT2)
     float *sx = sext2 + (L::EXT2 ? 2u * T : 0u);                          // [T] staged start state of the current tile
@@ -629,7 +636,7 @@ __global__ void __launch_bounds__(DDM_PERSISTENT_BLOCK, tile_min_blocks<KIND>())
                 if (direct & lane_bit) {  // rare: the trial outlived its tile's buffer
                     tile_emit_direct<KIND, OUT64>(a, ds, trial, c, meta);
                 } else {
-                    code[slot] = c;
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(code_s + 4u * slot), "r"(c) : "memory");
                 }
             }
             held &= ~fin;
@@ -659,19 +666,51 @@ __global__ void __launch_bounds__(DDM_PERSISTENT_BLOCK, tile_min_blocks<KIND>())
             if (__any_sync(FULL_MASK, more && ci == cn && held != FULL_MASK)) break;  // lanes are waiting, the tile is used up: next tile
             if (__all_sync(FULL_MASK, held == 0u)) { done = true; break; }            // no trial left in the warp and none to be had
 
-            // ---- step: tight, branch-free inner loop (round keys and constants stay in uniform registers) until
-            // `thr` of the warp's trials have finished -- all of them once the work has run out and there is nothing
-            // to refill with.  alive is a subset of held, which does not change in the loop: one POPC per block.
-            // (the votes only make warp-uniform values provably so: with a loop bound the compiler cannot prove uniform,
-            // ptxas guards the loop's vote with a divergence check and reloads the round keys every block)
-            const int n_held = __popc(__ballot_sync(FULL_MASK, (held & lane_bit) != 0u));
-            const int live_min = __any_sync(FULL_MASK, more || ci != cn) ? max(n_held - thr, 0) : 0;  // step while more lanes than this are alive
-            do {
-                Normals6Scaled z;
-                philox_pairs_lg2(blk, trial + a.trial_offset, ds + a.dataset_offset, STREAM_STEP, a.key, z);
-                euler6_warp_lb(x, n, alive, lane_bit, c0, h, z, a.max_steps);
-                blk++;
-            } while (__popc(alive) > live_min);
+            // ---- step, and refill in place -------------------------------------------------------------------
+            // The stepping loop (round keys and constants in uniform registers) runs until `thr` of the warp's trials have
+            // finished -- all of them once the work has run out.  If the current tile can serve every finished lane and
+            // none of them is a straggler, the lanes park their results and take their next trials right here (the fast
+            // path: ~30 issue slots, no loop re-entry); only a used-up tile, a straggler's own row or the end of the work
+            // leave the loop for the pass above.  Every value that decides control flow in here goes through a vote or a
+            // warp reduction first: they are warp-uniform by construction, but derived from a shuffled work index, and
+            // with bounds it cannot *prove* uniform ptxas guards the loop's votes with BRA.DIV and reloads the round keys
+            // on every block.
+            const unsigned held_u = __ballot_sync(FULL_MASK, (held & lane_bit) != 0u);
+            const unsigned direct_u = __ballot_sync(FULL_MASK, (direct & lane_bit) != 0u);
+            const int live_min = __any_sync(FULL_MASK, more || ci != cn) ? max(__popc(held_u) - thr, 0) : 0;
+            uint32_t ci_u = __reduce_max_sync(FULL_MASK, ci);
+            const uint32_t cn_u = __reduce_max_sync(FULL_MASK, cn);
+            const uint32_t slot0 = cb * T;
+            for (;;) {
+                do {  // the tight loop: one Philox block, three Box-Muller pairs, six predicated steps
+                    Normals6Scaled z;
+                    philox_pairs_lg2(blk, trial + a.trial_offset, ds + a.dataset_offset, STREAM_STEP, a.key, z);
+                    euler6_warp_lb(x, n, alive, lane_bit, c0, h, z, a.max_steps);
+                    blk++;
+                } while (__popc(alive) > live_min);  // keep stepping while more lanes than this are alive
+                const unsigned fin = held_u & ~alive;
+                const uint32_t nf = __popc(fin);
+                if (ci_u + nf > cn_u || (fin & direct_u) != 0u) break;
+                const bool mine = (fin & lane_bit) != 0u;
+                if (mine) {
+                    int choice = (x >= h) ? 1 : ((x <= -h) ? -1 : 0);
+                    if (n > a.max_steps) choice = 0;  // whole blocks: see the pass
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(code_s + 4u * slot), "r"((uint32_t)wire_pack(min(n, a.max_steps), choice)) : "memory");
+                    const uint32_t i = ci_u + __popc(fin & lt_mask);
+                    slot = slot0 + i;
+                    ds = c_ds;
+                    trial = c_first + i;
+                    x = L::XH ? sx[i] : tile_c.v[1];
+                    h = L::XH ? sh[i] : tile_c.v[2];
+                    c0 = L::C0 ? sc0[i] : tile_c.v[0];
+                    n = 0;
+                    blk = 0;
+                }
+                ci_u += nf;
+                const bool stepping = mine ? ((fabsf(x) < h) && (a.max_steps > 0u)) : ((alive & lane_bit) != 0u);
+                alive = __ballot_sync(FULL_MASK, stepping);
+            }
+            ci = ci_u;
         }
         if (__any_sync(FULL_MASK, done)) break;
     }

@@ -159,8 +159,8 @@ class DDMSimulator:
         self._check(self._lib.ddm_set_tuning(self._ctx, refill_threshold, blocks_per_sm, tile))
 
     def set_kernel_variant(self, variant: int = -1):
-        """-1 (default): the faster scheduler per model family; 0: the tile-staged persistent kernel; 1: the round-1
-        persistent kernel.  Bit-identical results (A/B measurements, tests)."""
+        """-1 / 0 (default): the tile-staged persistent kernel; 1: the round-1 persistent kernel.  Bit-identical
+        results (A/B measurements, tests)."""
         self._check(self._lib.ddm_set_kernel_variant(self._ctx, int(variant)))
 
     def set_stream(self, cuda_stream_ptr: int | None):

@@ -129,10 +129,10 @@ int ddm_set_stream(ddm_ctx *ctx, void *cuda_stream); /* NULL restores the ctx-ow
 int ddm_synchronize(ddm_ctx *ctx);
 /* tuning knobs; 0 = automatic */
 int ddm_set_tuning(ddm_ctx *ctx, int refill_threshold, int blocks_per_sm, int tile);
-/* Scheduler of the production (precision 32) path: 0 the tile-staged persistent kernel (set-up and emission a tile at a
- * time through shared memory), 1 the round-1 persistent kernel (per-lane set-up and emission inside the refill pass),
- * -1 (default) whichever measured faster for the model family: the tile kernel for the models with per-trial set-up
- * draws and for DDM_MODEL_TRIALWISE, the round-1 kernel for DDM_MODEL_BASIC / DDM_MODEL_ETA.  Results are bit-identical. */
+/* Scheduler of the production (precision 32) path: 0 (and -1, the default) the tile-staged persistent kernel (set-up and
+ * emission a tile at a time through shared memory, finished lanes refilled inside the stepping loop), 1 the round-1
+ * persistent kernel (per-lane set-up and emission inside a refill pass), kept for A/B measurements.  Results are
+ * bit-identical. */
 int ddm_set_kernel_variant(ddm_ctx *ctx, int variant);
 /* ddm_simulate with a host destination streams batches of at least min_rows trials to the host in
  * chunks of about chunk_rows trials, overlapping kernel and PCIe copy (defaults: min_rows 8 Mi trials, 10^6 into a

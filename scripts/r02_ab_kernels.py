@@ -33,15 +33,15 @@ def checksum(model, params, n, dt, ms, variant):
 
 cases = [
     ("sweep basic dt=.001", 0, priors.draw_prior_batch("sweep", 100_000, np.random.default_rng(1)), 1000, 1e-3, 4000,
-     [(1, 5, 64), (0, 3, 128), (0, 4, 128), (0, 5, 128), (0, 6, 128), (0, 8, 128), (0, 5, 64), (0, 4, 64), (0, 5, 96)]),
+     [(1, 5, 64), (0, 1, 128), (0, 2, 128), (0, 3, 128), (0, 4, 128), (0, 5, 128), (0, 6, 128), (0, 8, 128), (0, 3, 64)]),
     ("C3 alpha dt=.01", 1, priors.draw_prior_batch("alpha", 20_000, np.random.default_rng(2)), 1000, 0.01, 400,
-     [(1, 16, 64), (1, 12, 64), (0, 4, 128), (0, 6, 128), (0, 8, 128), (0, 10, 128), (0, 12, 128), (0, 14, 128), (0, 8, 64), (0, 10, 64)]),
+     [(1, 16, 64), (0, 1, 128), (0, 2, 128), (0, 3, 128), (0, 4, 128), (0, 6, 128), (0, 8, 128), (0, 10, 128), (0, 12, 128), (0, 4, 64)]),
     ("basic dt=.01", 0, priors.draw_prior_batch("basic", 40_000, np.random.default_rng(3)), 1000, 0.01, 400,
-     [(1, 16, 64), (0, 4, 128), (0, 6, 128), (0, 8, 128), (0, 10, 128), (0, 12, 128), (0, 8, 64)]),
+     [(1, 16, 64), (0, 1, 128), (0, 2, 128), (0, 4, 128), (0, 6, 128), (0, 8, 128), (0, 10, 128), (0, 12, 128)]),
     ("alpha_dc dt=.01", 2, priors.draw_prior_batch("alpha_dc", 20_000, np.random.default_rng(4)), 1000, 0.01, 400,
-     [(1, 16, 64), (0, 6, 128), (0, 8, 128), (0, 10, 128)]),
+     [(1, 16, 64), (0, 2, 128), (0, 4, 128), (0, 8, 128), (0, 10, 128)]),
     ("alpha dt=.001 (fine)", 1, priors.draw_prior_batch("alpha", 20_000, np.random.default_rng(5)), 1000, 1e-3, 4000,
-     [(1, 5, 64), (0, 4, 128), (0, 5, 128), (0, 6, 128)]),
+     [(1, 5, 64), (0, 2, 128), (0, 3, 128), (0, 4, 128), (0, 5, 128)]),
 ]
 for name, model, params, n, dt, ms, grid in cases:
     c1, c0 = checksum(model, params, n, dt, ms, 1), checksum(model, params, n, dt, ms, 0)

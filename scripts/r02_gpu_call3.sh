@@ -2,18 +2,18 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/r02_call3_pytest.txt
 tail -4 gpurun_out/r02_call3_pytest.txt
-timeout 600 python scripts/r02_ab_kernels.py > gpurun_out/r02_ab_kernels_v3b.jsonl 2> gpurun_out/r02_ab_kernels_v3b.err
-tail -3 gpurun_out/r02_ab_kernels_v3b.err
+timeout 600 python scripts/r02_ab_kernels.py > gpurun_out/r02_ab_kernels_v4.jsonl 2> gpurun_out/r02_ab_kernels_v4.err
+tail -3 gpurun_out/r02_ab_kernels_v4.err
 python - <<'PY'
 import json
-for l in open("gpurun_out/r02_ab_kernels_v3b.jsonl"):
+for l in open("gpurun_out/r02_ab_kernels_v4.jsonl"):
     d = json.loads(l)
     if "variant" in d:
         print(d["case"].ljust(22), d["variant"].ljust(7), "thr", str(d["thr"]).ljust(3), "tile", str(d["tile"]).ljust(4), "ms %8.4f" % d["kernel_ms"], "steps/s %.4g" % d["steps_per_s"])
     else:
         print(d["case"], "identical:", d["identical_output_checksums"])
 PY
-timeout 900 python bench.py --steps 3 --warmup 3 --datasets 200000 --cpu-seconds 4 > gpurun_out/r02_bench_small.json 2> gpurun_out/r02_bench_small.err
+timeout 900 python bench.py --steps 3 --warmup 3 --datasets 100000 --cpu-seconds 2 --no-host-rows > gpurun_out/r02_bench_small.json 2> gpurun_out/r02_bench_small.err
 tail -5 gpurun_out/r02_bench_small.err
 python - <<'PY'
 import json

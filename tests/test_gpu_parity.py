@@ -874,7 +874,7 @@ def test_tile_kernel_equals_round1_persistent_kernel(sim, model):
             sim.set_tuning(0, 0, 0)
             ref = sim.simulate(model, params, 307, seed=9, dataset_offset=3, flags=F_STEPS, **kw)
             ref_steps, ref_st = sim.last_steps(53 * 307), sim.last_stats()
-            assert ref_st["scheduler"] == 1
+            assert ref_st["scheduler"] == 1 and ref_st["tile"] == 64
             sim.set_kernel_variant(0)
             for thr, bps, tile in [(0, 0, 0), (1, 1, 5), (3, 2, 33), (32, 0, 128), (8, 0, 64), (2, 1, 1000)]:
                 sim.set_tuning(thr, bps, tile)
