@@ -346,9 +346,10 @@ __global__ void __launch_bounds__(DDM_PERSISTENT_BLOCK, RECORD ? (1024 / DDM_PER
 //   claim    a warp claims a tile of <= tile_cap consecutive trials of one dataset and sets all of them up at
 //            once (lane i takes trials i, i + 32, ...), staging each trial's start state (x0, h, c0) and its
 //            external columns in shared memory (north_star: "per-dataset parameters staged in shared memory");
-//   refill   a lane that needs a trial takes the tile's next one: two or three LDS;
 //   finish   a finished lane parks (steps << 2 | choice + 1) in the tile's result slot: one STS;
-//   flush    when the tile's last trial has finished the warp turns the 4-byte results into output rows --
+//   refill   ... and takes the tile's next trial: a ballot/popc prefix and two or three LDS -- right inside the stepping
+//            loop (the "fast path", ~45 issue slots, no loop re-entry) as long as the tile can serve every finished lane;
+//   flush    when the next tile but one is claimed the warp turns the 4-byte results into output rows --
 //            fp64 arithmetic of the reference, lane-contiguous vector stores.
 // A warp works on two tiles at a time (the one being handed out and the previous one, draining).  When a third
 // is claimed while the oldest still has trials running (first-passage times are heavy-tailed), that tile is
@@ -485,10 +486,10 @@ __device__ __forceinline__ void tile_flush(const RunArgs &a, const uint32_t *cod
     __syncwarp();
 }
 
-// Resident blocks per SM: the kinds whose tile set-up draws normals (a Philox block and three Box-Muller pairs live
-// next to the stepping state) get 48 registers and five blocks -- at 40 registers ptxas spilled a loop-carried register
-// of the stepping loop; the kinds without set-up draws keep six blocks of 40.  (The bare stepping loop is bound by the
-// FMA-heavy pipe and loses 1 % from 12 to 10 warps per scheduler: profiles/r02_microbench_occupancy.txt.)
+// Resident blocks per SM: five blocks of 256 threads at 48 registers for every kind.  At 40 registers (six blocks) ptxas
+// either spilled a loop-carried register of the stepping loop (the kinds whose tile set-up draws normals) or rebuilt the
+// lane mask inside it (the others); the bare stepping loop is bound by the FMA-heavy pipe and loses 1 % from 12 to 10
+// warps per scheduler (profiles/r02_microbench_occupancy.txt), and the A/B has five blocks 1-3 % ahead for every kind.
 #ifndef DDM_TILE_MIN_BLOCKS
 #define DDM_TILE_MIN_BLOCKS (1280 / DDM_PERSISTENT_BLOCK)
 #endif

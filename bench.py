@@ -45,7 +45,7 @@ MAX_STEPS = 4000
 # (SURVEY.md section 8d budgeted 28 for a 4-normals-per-block design.)
 I_STEP = 17
 I_STEP_SURVEY = 28
-NCU_DRAM_BYTES_PER_LAUNCH_1E9 = 247_497_216 + 8_079_781_376  # profiles/r02_ncu_sweep_fullsize_details.txt
+NCU_DRAM_BYTES_PER_LAUNCH_1E9 = 131_922_944 + 7_955_124_480  # profiles/r02_ncu_sweep_fullsize_details.txt (tile kernel)
 MODEL_BASIC = 0
 FLAG_OUT_F32 = 2
 
@@ -292,13 +292,13 @@ def other_configs(sim, issue_peak, want_cpu=True) -> dict:
     # ---- C3: single_trial_alpha_not_scaled, 1024 datasets x 1000 trials, dt=.01
     P = priors.draw_prior_batch("alpha", 1024, np.random.default_rng(2023))
     g = _median_ms(lambda: m1.batch_simulate_trials(P, 1000, sim), sim, 30)
-    st = sim.last_stats()
 
     def c3_device():
         b = m1.batch_simulate_trials_device(P, 1000, sim)
         del b
 
     dev_ms = _median_ms(c3_device, sim, 50)
+    st = sim.last_stats()   # of the resident launch (the host call streams the rows in two chunks: its event window spans copies)
     out["C3"] = {"workload": "single_trial_alpha_not_scaled: 1024 datasets x 1000 trials, per-trial boundary, dt=.01, max_steps=400",
                  "call_ms": g, "call": "batch_simulate_trials(params (1024,7), 1000) -> (1024, 1000, 2) float64 host array (16 MB, pinned pool)",
                  "device_resident_ms": dev_ms, "device_call": "batch_simulate_trials_device -> DLPack (1024, 1000, 2) float32",
@@ -585,9 +585,10 @@ def main():
         "frac": ach / issue_peak, "frac_at_survey_28_slots": ach / issue_peak * I_STEP_SURVEY / I_STEP,
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this very size, from the ncu --set full capture
         # profiles/r02_ncu_sweep_fullsize_details.txt (scripts/r02_gpu_ncu_full.sh); other sizes: not captured
-        "traffic": NCU_DRAM_BYTES_PER_LAUNCH_1E9 if (D == 1_000_000 and N_TRIALS == 1000 and st["scheduler"] == 1) else None,
-        "traffic_note": "ncu --set full of this kernel at the bench's launch size (1e9 trials): dram read 0.247 GB + write "
-                        "8.080 GB = 8.327 GB against 8.072 GB algorithmic (8 B/trial out + 72 B/dataset in): 1.03x",
+        "traffic": NCU_DRAM_BYTES_PER_LAUNCH_1E9 if (D == 1_000_000 and N_TRIALS == 1000 and st["scheduler"] == 2) else None,
+        "traffic_note": "ncu --set full of this kernel at the bench's launch size (1e9 trials): dram read 0.132 GB + write "
+                        "7.955 GB = 8.087 GB against 8.072 GB algorithmic (8 B/trial out + 72 B/dataset in): 1.00x (the tile "
+                        "kernel writes rows a tile at a time, lane-contiguous; ~45 MB of the last rows are still in L2 at kernel end)",
         "kernel": ("ddm::persistent_kernel<KIND_FIXED, f32 out>" if st["scheduler"] == 1 else "ddm::tile_kernel<KIND_FIXED, f32 out>"),
         "kernel_ms": k_ms,
         "steps_per_launch": st["total_steps"], "issue_slots_per_step": I_STEP,
