@@ -78,5 +78,14 @@ def build_philox7(force: bool = False) -> str:
     return build(out_path=PHILOX7_LIB_PATH, defines=("DDM_PHILOX_ROUNDS=7",))
 
 
+CHECKED_LIB_PATH = os.path.join(HERE, "libddm_b200_checked.so")
+
+
+def build_checked() -> str:
+    """The bounds-checked build (ddm_kernels.cuh: DDM_CHECKED), the in-tree stand-in for compute-sanitizer's memcheck;
+    select it with DDM_B200_LIB (scripts/r02_checked_run.py)."""
+    return build(out_path=CHECKED_LIB_PATH, defines=("DDM_CHECKED",))
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))

@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(DDM_PERSISTENT_BLOCK, RECORD ? (1024 / DDM_PER
             const double tau = (KIND == KIND_GENERAL) ? 0.0 : a.params[(size_t)ds * a.n_params + 3];
             double o0, o1;
             const uint64_t idx = (uint64_t)ds * a.n_trials + trial;
+            if (!DDM_CHECK(a.stats, ds < a.n_datasets && trial < a.n_trials && n <= a.max_steps)) { has = false; continue; }
             if (KIND == KIND_GENERAL) {
                 const double tau_g = a.params[(size_t)ds * a.n_params + 7];
                 const bool style0 = a.gconst[ds].v[21] == 0.f;
@@ -400,6 +401,7 @@ __device__ __forceinline__ void tile_emit(const RunArgs &a, uint64_t idx, uint32
     constexpr bool BASIC = (KIND == KIND_FIXED || KIND == KIND_DRIFT);
     const uint32_t n = c >> 2;
     const int choice = (int)(c & 3u) - 1;
+    if (!DDM_CHECK(a.stats, idx < (uint64_t)a.n_datasets * a.n_trials && ds < a.n_datasets && n <= a.max_steps && (c & 3u) != 3u)) return;
     double o0, o1;
     if (KIND == KIND_GENERAL) {
         const double tau = a.params[(size_t)ds * a.n_params + 7];
@@ -466,6 +468,7 @@ __device__ __forceinline__ void tile_flush(const RunArgs &a, const uint32_t *cod
     TileStats st{0ull, 0u, 0u};
     const unsigned lane = threadIdx.x & 31u;
     const uint64_t idx0 = (uint64_t)ds * a.n_trials + first;
+    if (!DDM_CHECK(a.stats, count <= TileLayout<KIND>::T && (uint64_t)first + count <= a.n_trials)) return;
     for (uint32_t i = lane; i < count; i += 32u) {
         const uint32_t c = code[i];
         const float e1 = L::EXT ? ext[i] : 0.f, e2 = L::EXT2 ? ext2[i] : 0.f;
@@ -596,6 +599,7 @@ __global__ void __launch_bounds__(DDM_PERSISTENT_BLOCK, tile_min_blocks<KIND>())
                 // set the whole tile up, all lanes busy
                 const uint32_t nb = cb * T;
                 uint32_t cap_hits = 0;
+                if (!DDM_CHECK(a.stats, cn >= 1u && cn <= T && c_ds < a.n_datasets && c_first + cn <= a.n_trials)) cn = 0;
                 for (uint32_t i = lane; i < cn; i += 32u) {
                     if (KIND != KIND_FIXED) {
                         TrialF32 t;
@@ -635,7 +639,7 @@ __global__ void __launch_bounds__(DDM_PERSISTENT_BLOCK, tile_min_blocks<KIND>())
                 const uint32_t c = (uint32_t)wire_pack(n, choice);
                 if (direct & lane_bit) {  // rare: the trial outlived its tile's buffer
                     tile_emit_direct<KIND, OUT64>(a, ds, trial, c, meta);
-                } else {
+                } else if (DDM_CHECK(a.stats, slot < 2u * T)) {
                     asm volatile("st.shared.u32 [%0], %1;" ::"r"(code_s + 4u * slot), "r"(c) : "memory");
                 }
             }
@@ -646,6 +650,7 @@ __global__ void __launch_bounds__(DDM_PERSISTENT_BLOCK, tile_min_blocks<KIND>())
             const uint32_t i = ci + __popc(need & lt_mask);
             const bool take = (need & lane_bit) && i < cn;
             if (take) {
+                DDM_CHECK(a.stats, i < T);
                 slot = cb * T + i;
                 ds = c_ds;
                 trial = c_first + i;
@@ -695,8 +700,10 @@ __global__ void __launch_bounds__(DDM_PERSISTENT_BLOCK, tile_min_blocks<KIND>())
                 if (mine) {
                     int choice = (x >= h) ? 1 : ((x <= -h) ? -1 : 0);
                     if (n > a.max_steps) choice = 0;  // whole blocks: see the pass
-                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(code_s + 4u * slot), "r"((uint32_t)wire_pack(min(n, a.max_steps), choice)) : "memory");
+                    if (DDM_CHECK(a.stats, slot < 2u * T))
+                        asm volatile("st.shared.u32 [%0], %1;" ::"r"(code_s + 4u * slot), "r"((uint32_t)wire_pack(min(n, a.max_steps), choice)) : "memory");
                     const uint32_t i = ci_u + __popc(fin & lt_mask);
+                    DDM_CHECK(a.stats, i < cn_u && cn_u <= T);
                     slot = slot0 + i;
                     ds = c_ds;
                     trial = c_first + i;

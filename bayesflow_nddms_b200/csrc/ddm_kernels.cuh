@@ -75,6 +75,17 @@ struct RunArgs {
 };
 
 constexpr unsigned FULL_MASK = 0xffffffffu;
+
+// compute-sanitizer is closed on the GPU pool this library is developed on, so the kernels carry their own bounds
+// checks: a build with -DDDM_CHECKED (bayesflow_nddms_b200/_build.py: build_checked) verifies every shared-memory slot
+// index, every output row index and every gathered input index before use and counts violations in the
+// STAT_DBG_OVERRUN slot (ddm_stats.debug_overruns); a violating access is skipped.  scripts/r02_checked_run.py drives
+// every kernel family through it.  In the shipped build the macro compiles to nothing.
+#ifdef DDM_CHECKED
+#define DDM_CHECK(stats, cond) ((cond) ? true : (atomicAdd((stats) + STAT_DBG_OVERRUN, 1ull), false))
+#else
+#define DDM_CHECK(stats, cond) true
+#endif
 // internal run flag (not part of the C ABI): the fp32 generic kernel uses the reference's formulas in
 // float instead of the unit-scaled production arithmetic (a dataset with dc == 0 has no noise unit)
 constexpr int FLAG_REFERENCE_ARITHMETIC = 1 << 30;

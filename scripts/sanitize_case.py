@@ -16,6 +16,22 @@ for model, name in [(0, "basic"), (1, "alpha"), (2, "alpha_dc"), (3, "alpha_scal
     b = sim.simulate(model, p, 77, flags=8, precision=32)
     c = sim.simulate(model, p, 77, precision=64)
     assert a.shape == b.shape == c.shape == (9, 77, 2)
+# round 2: both schedulers, tiles that force recycling with trials still running (stragglers write their own rows),
+# the general model, the histogram call, the generator histogram
+from bayesflow_nddms_b200 import two_channel  # noqa: E402
+
+for variant, thr, bps, tile in ((0, 2, 1, 8), (0, 0, 0, 0), (1, 0, 0, 0)):
+    sim.set_kernel_variant(variant)
+    sim.set_tuning(thr, bps, tile)
+    for model, name in [(0, "basic"), (1, "alpha"), (2, "alpha_dc")]:
+        sim.simulate(model, priors.draw_prior_batch(name, 23, rng), 301, dt=0.01, max_steps=400)
+    raw = np.column_stack([rng.normal(0, 2, 7), 1.0 + rng.random(7), np.full(7, 0.5), np.full(7, 0.3), 0.5 + rng.random(7),
+                           0.6 + rng.random(7), np.full(7, 0.3), np.full(7, 0.5), np.full(7, 0.6), np.full(7, 0.2), np.full(7, 0.1)])
+    sim.simulate(7, two_channel.canonical_drift_dc5(raw), 130)
+sim.set_kernel_variant(-1)
+sim.set_tuning(0, 0, 0)
+sim.simulate_histogram(0, priors.draw_prior_batch("sweep", 11, rng), 500, 1e-3, 4000, n_bins=64, rt_max=4.0)
+sim.normals_histogram(600_000, 56, 5.6, 64)
 sim.set_pipeline(1, 77 * 3)
 sim.simulate(0, priors.draw_prior_batch("basic", 9, rng), 77)
 sim.set_pipeline(-1, -1)
