@@ -526,6 +526,7 @@ __global__ void __launch_bounds__(DDM_PERSISTENT_BLOCK, tile_min_blocks<KIND>())
     unsigned lane_bit, lt_mask;
     asm volatile("mov.u32 %0, %%lanemask_eq;" : "=r"(lane_bit));
     asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
+    const RngConsts rk = pinned_rng_consts();
     constexpr uint32_t T = L::T;
     uint32_t *meta = tile_smem + (threadIdx.x >> 5) * (L::WORDS * T + M_WORDS);
     uint32_t *code = meta + M_WORDS;                                      // [2][T] result slots
@@ -689,7 +690,7 @@ __global__ void __launch_bounds__(DDM_PERSISTENT_BLOCK, tile_min_blocks<KIND>())
             for (;;) {
                 do {  // the tight loop: one Philox block, three Box-Muller pairs, six predicated steps
                     Normals6Scaled z;
-                    philox_pairs_lg2(blk, trial + a.trial_offset, ds + a.dataset_offset, STREAM_STEP, a.key, z);
+                    philox_pairs_lg2(blk, trial + a.trial_offset, ds + a.dataset_offset, STREAM_STEP, a.key, rk, z);
                     euler6_warp_lb(x, n, alive, lane_bit, c0, h, z, a.max_steps);
                     blk++;
                 } while (__popc(alive) > live_min);  // keep stepping while more lanes than this are alive

@@ -64,7 +64,7 @@ struct RunArgs {
     uint64_t n_items;        // persistent: number of (dataset, tile) work items
     uint32_t n_datasets, n_trials, n_params;
     uint32_t tiles_per_dataset, tile;
-    uint32_t dataset_offset;  // global index of dataset 0 (Philox counter word 2)
+    uint32_t dataset_offset;  // global index of dataset 0 (Philox counter word 3)
     uint32_t trial_offset;
     PhiloxKey key;
     uint32_t max_steps;

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256) normals_histogram_kernel(PhiloxKey key, u
     for (uint32_t b = 0; b < blocks_per_thread; b++) {  // block-uniform trip count: the flush below has barriers
         if (first + b < n_blocks) {
         float z[6];
-        // counters laid out like a trial's: (block, trial, dataset, stream)
+        // counters laid out like a trial's: block b of (trial, dataset) = the low and high words of the thread index
         philox_normals6_f32(b, (uint32_t)tid, (uint32_t)(tid >> 32), STREAM_STEP, key, z);
         float s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
 #pragma unroll

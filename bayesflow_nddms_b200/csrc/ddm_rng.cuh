@@ -3,13 +3,19 @@
 // Philox4x32-10 (Salmon et al., SC'11).  key = (seed_lo, seed_hi) is uniform for
 // a launch, so the ten round keys live in uniform registers / the constant bank
 // and a round costs 2 IMAD.WIDE.U32 + 2 LOP3 per lane.
-// counter = (block, trial, dataset [low 32 bits], stream | dataset [bits 32..55] << 8); one block yields SIX normals:
+// counter = (stream | dataset [bits 32..55] << 8, block, trial, dataset [low 32 bits]); one block yields SIX normals:
 //   stream 0 ("step"):  block b yields the normals of Euler steps 6b..6b+5
 //   stream 1 ("aux"):   normal 0 = the ext-data normal z_ext (drawn after the
 //                       loop in the reference, single_trial_alpha_not_scaled.py:131),
 //                       normal 1+i = i-th candidate of the redraw-until-positive
 //                       boundary / dc loop (:113-116, :932-935)
 // so step normals sit at fixed counters no matter how many pre-draws a trial needs.
+// The word order is chosen for the stepping loop: the block index -- the only word that changes while a trial
+// runs -- sits in word 1, which enters round 0 through an XOR, not through a multiply.  Of the first three rounds'
+// six products, four then depend on (stream, trial, dataset) alone: the compiler's loop-invariant code motion forms
+// them once per entry of the stepping loop (checked in SASS: 16 IMAD.WIDE per block of the tile kernel's loop; with
+// the block index in word 0 -- rounds 1 and 2 -- only two can leave the loop, 18 per block).  Same function, same
+// ten rounds: only which word counts what.
 //
 // 128 bits -> three Box-Muller pairs of 21-bit uniforms (126 bits used, none twice).
 // IMAD.WIDE issues at one per 4 clocks per scheduler on B200 (measured, bench.py
@@ -45,7 +51,7 @@ constexpr uint32_t STREAM_AUX = 1u;
 // an extra uniform-datapath add per round per block.
 struct PhiloxKey {
     uint32_t rk[20];  // rk[2r] = k0 + r*W0, rk[2r+1] = k1 + r*W1
-    // Bits 8..31 of counter word 3 (bits 0..7 = stream): the high part of the 64-bit global dataset
+    // Bits 8..31 of counter word 0 (bits 0..7 = stream): the high part of the 64-bit global dataset
     // index, launch-uniform (a launch never straddles a multiple of 2^32 datasets, ddm_capi.cu:
     // build_args), so long runs roll over into fresh counters instead of running out of them.
     uint32_t c3_hi;
@@ -90,15 +96,17 @@ __device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2
 #endif
 static_assert(DDM_PHILOX_ROUNDS >= 7 && DDM_PHILOX_ROUNDS <= 10, "Philox4x32 rounds: 7 .. 10");
 
-__device__ __forceinline__ void philox4x32_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+// The simulator's counter layout (see the header): block (block, trial, dataset, stream) of a launch's key.
+__device__ __forceinline__ void philox4x32_rk(uint32_t block, uint32_t trial, uint32_t dataset, uint32_t stream,
                                               const PhiloxKey &key, uint32_t (&o)[4]) {
-    c3 |= key.c3_hi;  // uniform: folds into the first round's key operand
+    uint32_t c0 = stream | key.c3_hi, c1 = block, c2 = trial, c3 = dataset;
 #pragma unroll
     for (int r = 0; r < DDM_PHILOX_ROUNDS; r++) {
         const uint64_t p0 = (uint64_t)PHILOX_M0 * c0;
         const uint64_t p1 = (uint64_t)PHILOX_M1 * c2;
-        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ key.rk[2 * r];
-        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ key.rk[2 * r + 1];
+        // (word ^ key) first: where the word is loop-invariant in a caller (see the header) so is this term
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ (c1 ^ key.rk[2 * r]);
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ (c3 ^ key.rk[2 * r + 1]);
         c1 = (uint32_t)p1;
         c3 = (uint32_t)p0;
         c0 = n0;
@@ -161,6 +169,37 @@ __device__ __forceinline__ void box_muller_lg2(uint32_t fu, uint32_t ft, float &
     sn = mufu_sin(a);
 }
 
+// The same map with its two register constants handed in.  LOP3 and FFMA take one immediate each, so the exponent
+// bits and 2 pi sit in registers, and ptxas re-creates them (two IMAD.MOV on the FMA-heavy pipe, the loop's
+// bottleneck) in every block of a stepping loop unless they come out of a volatile asm (pinned_rng_consts).
+struct RngConsts {
+    uint32_t one_bits;
+    float two_pi;
+};
+__device__ __forceinline__ RngConsts pinned_rng_consts() {
+    // ptxas folds a plain mov of an immediate; a value derived from a special register it cannot
+    unsigned eq, id;
+    asm volatile("mov.u32 %0, %%lanemask_eq;" : "=r"(eq));
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(id));
+    const uint32_t one = eq >> id;  // = 1
+    RngConsts k;
+    k.one_bits = 0x3f7fffffu + one;
+    k.two_pi = __uint_as_float(0x40c90fdau + one);
+    return k;
+}
+__device__ __forceinline__ float field_to_unit12(uint32_t x, const RngConsts &k) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(x), "r"(FIELD_MASK), "r"(k.one_bits));  // (a & b) | c
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void box_muller_lg2(uint32_t fu, uint32_t ft, const RngConsts &k, float &s, float &c, float &sn) {
+    const float u = __fadd_rn(field_to_unit12(fu, k), -0.99999976158142089844f);
+    s = mufu_sqrt(fabsf(mufu_lg2(u)));
+    const float a = __fmaf_rn(field_to_unit12(ft, k), k.two_pi, -9.4247779607693797f);
+    c = mufu_cos(a);
+    sn = mufu_sin(a);
+}
+
 constexpr float SQRT_2LN2 = 1.1774100225154747f;         // unit normal = SQRT_2LN2 * s * trig
 constexpr double SQRT_2LN2_D = 1.17741002251547469101;
 
@@ -176,6 +215,15 @@ __device__ __forceinline__ void philox_pairs_lg2(uint32_t block, uint32_t trial,
     box_muller_lg2(w[0], w[1], o.s[0], o.c[0], o.sn[0]);
     box_muller_lg2(w[2], w[3], o.s[1], o.c[1], o.sn[1]);
     box_muller_lg2(leftover_field(w[0], w[1]), leftover_field(w[2], w[3]), o.s[2], o.c[2], o.sn[2]);
+}
+
+__device__ __forceinline__ void philox_pairs_lg2(uint32_t block, uint32_t trial, uint32_t dataset, uint32_t stream,
+                                                 const PhiloxKey &key, const RngConsts &k, Normals6Scaled &o) {
+    uint32_t w[4];
+    philox4x32_rk(block, trial, dataset, stream, key, w);
+    box_muller_lg2(w[0], w[1], k, o.s[0], o.c[0], o.sn[0]);
+    box_muller_lg2(w[2], w[3], k, o.s[1], o.c[1], o.sn[1]);
+    box_muller_lg2(leftover_field(w[0], w[1]), leftover_field(w[2], w[3]), k, o.s[2], o.c[2], o.sn[2]);
 }
 
 // The six unit normals of Philox block (block, trial, dataset, stream), fp32 production map.

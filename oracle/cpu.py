@@ -196,7 +196,7 @@ def philox_normals(seed, dataset, trial, stream, first, count) -> np.ndarray:
     out = np.empty(count, np.float64)
     z = (C.c_double * 6)()
     cached = -1
-    # 64-bit global dataset index: low word = counter word 2, bits 32..55 ride in the stream word (ddm_rng.cuh)
+    # 64-bit global dataset index: low word = counter word 3, bits 32..55 ride in the stream word (word 0) (ddm_rng.cuh)
     dataset = int(dataset)
     stream = int(stream) | ((dataset >> 32) << 8)
     dataset &= 0xFFFFFFFF

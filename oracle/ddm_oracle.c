@@ -124,8 +124,8 @@ ORC_EXPORT void orc_mt_normals(uint32_t seed, double *out, size_t n) {
 
 /* ------------------------------------------------------------------ */
 /* Philox4x32-10 (Salmon et al. 2011), the counter stream of the CUDA   */
-/* kernels.  key = (seed_lo, seed_hi); ctr = (block, trial, dataset,    */
-/* stream).  Pinned by the Random123 known-answer vectors in tests/.    */
+/* kernels.  key = (seed_lo, seed_hi); ctr = (stream, block, trial,     */
+/* dataset).  Pinned by the Random123 known-answer vectors in tests/.   */
 /* ------------------------------------------------------------------ */
 ORC_EXPORT void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
@@ -161,7 +161,7 @@ static inline uint32_t leftover21(uint32_t wa, uint32_t wb) {
 
 ORC_EXPORT void orc_philox_normals6(uint64_t seed, uint32_t block, uint32_t trial,
                                     uint32_t dataset, uint32_t stream, double z[6]) {
-    uint32_t ctr[4] = {block, trial, dataset, stream};
+    uint32_t ctr[4] = {stream, block, trial, dataset}; /* ddm_rng.cuh: the kernels' counter layout */
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     uint32_t w[4];
     orc_philox4x32_10(ctr, key, w);

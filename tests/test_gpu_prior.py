@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _uniforms(oracle, seed, draw, block):
-    w = oracle.philox4x32_10((block, draw & 0xFFFFFFFF, draw >> 32, 2), (seed & 0xFFFFFFFF, seed >> 32))
+    w = oracle.philox4x32_10((2, block, draw & 0xFFFFFFFF, draw >> 32), (seed & 0xFFFFFFFF, seed >> 32))
     ua = ((int(w[0]) >> 5) * 67108864.0 + (int(w[1]) >> 6) + 0.5) / 9007199254740992.0
     ub = ((int(w[2]) >> 5) * 67108864.0 + (int(w[3]) >> 6) + 0.5) / 9007199254740992.0
     return ua, ub
