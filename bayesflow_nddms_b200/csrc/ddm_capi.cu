@@ -167,7 +167,7 @@ struct ddm_ctx {
     Arena<ddm::GenConst> gconst;
     Arena<int32_t> steps, group;
     Arena<double> bound, dbg_z, export_buf, ev_scratch, ev_means, ev_ds_stats, ev_pairs;
-    Arena<float> ev_path, ev_xfinal;
+    Arena<float> ev_path;
     Arena<int64_t> dbg_off;
     Arena<uint32_t> philox_buf;
     Arena<unsigned long long> hist;
@@ -820,7 +820,6 @@ DDM_API int ddm_destroy(ddm_ctx *ctx) {
         ctx->ev_ds_stats.free_();
         ctx->ev_pairs.free_();
         ctx->ev_path.free_();
-        ctx->ev_xfinal.free_();
         ctx->dbg_off.free_();
         ctx->philox_buf.free_();
         ctx->hist.free_();
@@ -1259,18 +1258,14 @@ DDM_API int ddm_simulate_evidence(ddm_ctx *ctx, const double *params, int64_t n_
         if (precision == 32) {
             // (1) step + record with the persistent refill kernel (the basic model's lanes and counters)
             DDM_CUDA(ctx, ctx->dconst.reserve((size_t)n_datasets));
-            DDM_CUDA(ctx, ctx->steps.reserve((size_t)rows));
-            DDM_CUDA(ctx, ctx->ev_pairs.reserve((size_t)rows * 2));
-            DDM_CUDA(ctx, ctx->ev_xfinal.reserve((size_t)rows));
+            DDM_CUDA(ctx, ctx->ev_pairs.reserve((size_t)rows));  // 8 bytes per trial: (steps, choice), final state
             DDM_CUDA(ctx, ctx->ev_path.reserve((size_t)rows * a.n_obs));
             DDM_CUDA(ctx, ddm::launch_prep(ctx->params.p, ctx->dconst.p, (uint32_t)n_datasets, 6u, DDM_MODEL_BASIC, dt, ctx->stream));
             ddm::RunArgs r{};
             r.dconst = ctx->dconst.p;
             r.params = ctx->params.p;
             r.out = ctx->ev_pairs.p;
-            r.steps_out = ctx->steps.p;
             r.rec_path = ctx->ev_path.p;
-            r.rec_xfinal = ctx->ev_xfinal.p;
             r.n_obs = a.n_obs;
             r.work_counter = ctx->counters;
             r.stats = ctx->counters + 1;
@@ -1292,19 +1287,17 @@ DDM_API int ddm_simulate_evidence(ddm_ctx *ctx, const double *params, int64_t n_
             r.n_items = (uint64_t)r.tiles_per_dataset * a.n_datasets;
             if (r.n_items > 0xffffffffULL) return fail(ctx, DDM_ERR_INVALID, "too many trial tiles for one launch");
             r.refill_threshold = ctx->tune_threshold > 0 ? ctx->tune_threshold : default_refill_threshold(dt);
-            const int block = ddm::persistent_block_size();
-            int per_sm = ddm::persistent_record_max_blocks_per_sm(block);
+            const int block = ddm::record_block_size();
+            int per_sm = ddm::record_max_blocks_per_sm(block);
             if (per_sm <= 0) return fail(ctx, DDM_ERR_CUDA, "occupancy query failed for the recording kernel");
             uint64_t grid = (uint64_t)ctx->sm_count * per_sm;
             const uint64_t need = ((uint64_t)rows + block - 1) / block;
             if (grid > need) grid = need;
             if (grid < 1) grid = 1;
-            DDM_CUDA(ctx, ddm::launch_persistent_record(r, (int)grid, block, ctx->stream));
-            // (2) a warp per trial: noise, standardisation, row stores
+            DDM_CUDA(ctx, ddm::launch_record(r, (int)grid, block, ctx->stream));
+            // (2) eight lanes per trial: noise, standardisation, row stores
             a.rec_path = ctx->ev_path.p;
-            a.rec_xfinal = ctx->ev_xfinal.p;
-            a.steps = ctx->steps.p;
-            a.pairs = reinterpret_cast<const double2 *>(ctx->ev_pairs.p);
+            a.rec_meta = reinterpret_cast<const uint2 *>(ctx->ev_pairs.p);
             a.dconst = ctx->dconst.p;
             DDM_CUDA(ctx, ddm::launch_evidence_post(a, out64, (uint64_t)rows, ctx->sm_count, ctx->stream));
             st.kernel_launches += 3;

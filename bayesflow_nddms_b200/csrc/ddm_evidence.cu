@@ -8,14 +8,15 @@
 // params[6] = drift, boundary, beta, tau, dc, sigma1.  path[k] = evidence after Euler step k+1 for
 // k < n, held at the final evidence for k >= n, plus sigma1 * z_noise[k]; then standardised.
 //
-//   production (fp32)         two kernels.  (1) The persistent refill kernel of ddm_kernels.cu in its RECORD form
-//                             steps the trials (same lanes, same Philox counters as DDM_MODEL_BASIC) and stores the
-//                             first n_obs states of each trial, six per block as three 8-byte stores, plus step
-//                             count, final state and the (rt, choice) pair.  (2) evidence_post_kernel: a warp per
-//                             trial turns the recorded states into the observed path -- evidence units, held at the
-//                             final evidence after the crossing, noise normals from the aux Philox stream (six per
-//                             lane), mean / variance by shuffle reduction -- and writes the row with coalesced
-//                             stores.  800 B/trial of output make this the one DDM path where stores matter.
+//   production (fp32)         two kernels.  (1) record_kernel steps the trials (one lane per trial, persistent warps,
+//                             the Philox counters and step arithmetic of DDM_MODEL_BASIC) and stores the first
+//                             n_obs states of each trial one whole 32-byte sector at a time straight from
+//                             registers, plus 8 bytes per trial (steps, choice, final state).
+//                             (2) evidence_post_kernel: eight lanes per trial turn the recorded states into the
+//                             observed path -- evidence units, held at the final evidence after the crossing, noise
+//                             normals from the aux Philox stream (six per lane), mean / variance by shuffle
+//                             reduction -- and write the row with coalesced stores.  800 B/trial of output make
+//                             this the one DDM path where stores matter.
 //   evidence_generic_kernel   validation (fp64): one thread per trial, the reference's operation order and
 //                             left-to-right sums (numba's array_mean / array_var); shared-increment mode.
 //   dataset_stats / finalize  mode 2's second pass, and the dtype conversion of the validation path.
@@ -23,6 +24,179 @@
 
 namespace ddm {
 
+
+// --------------------------------------------------------------------------------------------
+// production, first kernel: step and record
+// --------------------------------------------------------------------------------------------
+// One lane per trial, persistent warps that claim (dataset, tile) work items from a global counter, like the
+// simulator's own kernels -- but time runs in *periods* of four Philox blocks = 24 Euler steps = three 32-byte
+// sectors of a trial's recorded path, and lanes are handed new trials only between periods.  Every lane of a warp
+// is then at the same phase of its trial's 24-step group, so the group's states can stay in registers under
+// static names and leave as whole sectors: block 1 completes sector 0 (states 0..7), block 2 sector 1, block 3
+// sector 2 -- two STG.128 per sector and lane, no staging in shared memory, no per-lane ring position, no
+// partial-sector writes (8-byte stores straight from every block made the kernel L2-bound; a per-lane
+// shared-memory ring, round 1's fix, doubled the instruction count and capped occupancy at 38 %).
+// A lane whose trial ends inside a period goes on "recording" its frozen state to the end of the period: those
+// positions lie past the trial's last step and the post kernel never reads them (at most two surplus sectors per
+// trial, instead of a tail-flush path in every block).  A finished lane waits two blocks on average for the
+// period to end -- 5 % of a 250-step trial, the price of the aligned phases.
+// Philox counters, set-up and step arithmetic are those of DDM_MODEL_BASIC's kernels: a trial's steps, choice and
+// states do not depend on which kernel ran it.
+//   VEC: n_obs is a multiple of 8 (rows are sector-aligned); otherwise guarded scalar stores, six per block.
+constexpr int RECORD_BLOCK = 256;
+#ifndef DDM_RECORD_MIN_BLOCKS
+#define DDM_RECORD_MIN_BLOCKS 5
+#endif
+template <bool VEC>
+__global__ void __launch_bounds__(RECORD_BLOCK, DDM_RECORD_MIN_BLOCKS) record_kernel(const __grid_constant__ RunArgs a) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const RngConsts rk = pinned_rng_consts();
+
+    // warp-uniform tile cursor and the tile's dataset constants (drift*dt/U, start state, half-width)
+    uint32_t cur = 0, end = 0, tile_ds = 0;
+    bool more = true;
+    float t_c0 = 0.f, t_x0 = 0.f, t_h = 0.f;
+
+    // per-lane trial
+    float x = 0.f, h = 0.f, c0 = 0.f;
+    uint32_t n = 0, per = 0, trial = 0, ds = 0;
+    uint32_t p = 0;    // 1 = stepping
+    bool has = false;  // holds a trial (stepping, or finished and waiting to be emitted)
+
+    unsigned long long acc_steps = 0;
+    uint32_t acc_timeouts = 0, acc_upper = 0;
+    uint2 *meta = reinterpret_cast<uint2 *>(a.out);
+    const int thr = a.refill_threshold > 1 ? a.refill_threshold : 1;
+
+    for (;;) {
+        const unsigned live = __ballot_sync(FULL_MASK, has && p != 0u);
+        const bool work_left = more || cur != end;
+        if (__popc(~live) >= (work_left ? thr : 32)) {
+            // ---- finish: 8 bytes per trial ------------------------------------------------------
+            if (has && p == 0u) {
+                int choice = (x >= h) ? 1 : ((x <= -h) ? -1 : 0);
+                // lanes run whole 6-step blocks: a trial still inside the boundaries after max_steps steps is a
+                // timeout whatever it did in the surplus steps of its last block
+                if (n > a.max_steps) { n = a.max_steps; choice = 0; }
+                const uint64_t idx = (uint64_t)ds * a.n_trials + trial;
+                if (DDM_CHECK(a.stats, ds < a.n_datasets && trial < a.n_trials))
+                    meta[idx] = make_uint2((uint32_t)wire_pack(n, choice), __float_as_uint(x));
+                acc_steps += n;
+                acc_timeouts += (choice == 0);
+                acc_upper += (choice > 0);
+                has = false;
+            }
+            // ---- refill: hand out trials of the current tile, claiming tiles as needed ----------
+            for (;;) {
+                const unsigned empty = __ballot_sync(FULL_MASK, !has);
+                if (empty == 0u) break;
+                if (cur == end) {
+                    if (!more) break;
+                    unsigned long long w = 0;
+                    if (lane == 0) w = atomicAdd(a.work_counter, 1ull);
+                    w = __shfl_sync(FULL_MASK, w, 0);
+                    if (w >= a.n_items) { more = false; break; }
+                    uint32_t ti = 0;
+                    if (a.tiles_per_dataset == 1u) {
+                        tile_ds = (uint32_t)w;
+                    } else {
+                        tile_ds = (uint32_t)w / a.tiles_per_dataset;  // host keeps n_items < 2^32
+                        ti = (uint32_t)w - tile_ds * a.tiles_per_dataset;
+                    }
+                    cur = ti * a.tile;
+                    end = min(cur + a.tile, a.n_trials);
+                    const float4 c = __ldg(reinterpret_cast<const float4 *>(a.dconst + tile_ds));
+                    t_c0 = c.x; t_x0 = c.y; t_h = c.z;
+                }
+                const uint32_t rank = __popc(empty & lt_mask);
+                const uint32_t avail = end - cur;
+                if (!has && rank < avail) {
+                    ds = tile_ds;
+                    trial = cur + rank;
+                    x = t_x0; h = t_h; c0 = t_c0;
+                    n = 0;
+                    per = 0;
+                    has = true;
+                    p = ((fabsf(x) < h) && (a.max_steps > 0u)) ? 1u : 0u;
+                }
+                cur += min((uint32_t)__popc(empty), avail);
+            }
+            if (!__any_sync(FULL_MASK, has)) break;
+        }
+
+        // ---- one period: four blocks, three sectors ---------------------------------------------
+        const uint32_t n0 = 24u * per;  // steps a lane that is still stepping has taken
+        const bool rec = has && p != 0u && n0 < a.n_obs;
+        float *dst = a.rec_path + ((uint64_t)ds * a.n_trials + trial) * a.n_obs + n0;
+        const uint32_t tg = trial + a.trial_offset, dg = ds + a.dataset_offset, b0 = 4u * per;
+        Normals6Scaled z;
+        float r[6];
+        if (VEC) {
+            float k0, k1, k2, k3, k4, k5;  // states held over from the previous block
+            philox_pairs_lg2(b0, tg, dg, STREAM_STEP, a.key, rk, z);
+            euler6_rec(x, n, p, c0, h, z, a.max_steps, r);
+            k0 = r[0]; k1 = r[1]; k2 = r[2]; k3 = r[3]; k4 = r[4]; k5 = r[5];
+            philox_pairs_lg2(b0 + 1u, tg, dg, STREAM_STEP, a.key, rk, z);
+            euler6_rec(x, n, p, c0, h, z, a.max_steps, r);
+            if (rec) {  // states 0..7 (n0 < n_obs and both are multiples of 8: the sector lies inside the row)
+                reinterpret_cast<float4 *>(dst)[0] = make_float4(k0, k1, k2, k3);
+                reinterpret_cast<float4 *>(dst)[1] = make_float4(k4, k5, r[0], r[1]);
+            }
+            k0 = r[2]; k1 = r[3]; k2 = r[4]; k3 = r[5];
+            philox_pairs_lg2(b0 + 2u, tg, dg, STREAM_STEP, a.key, rk, z);
+            euler6_rec(x, n, p, c0, h, z, a.max_steps, r);
+            if (rec && n0 + 8u < a.n_obs) {  // states 8..15
+                reinterpret_cast<float4 *>(dst)[2] = make_float4(k0, k1, k2, k3);
+                reinterpret_cast<float4 *>(dst)[3] = make_float4(r[0], r[1], r[2], r[3]);
+            }
+            k0 = r[4]; k1 = r[5];
+            philox_pairs_lg2(b0 + 3u, tg, dg, STREAM_STEP, a.key, rk, z);
+            euler6_rec(x, n, p, c0, h, z, a.max_steps, r);
+            if (rec && n0 + 16u < a.n_obs) {  // states 16..23
+                reinterpret_cast<float4 *>(dst)[4] = make_float4(k0, k1, r[0], r[1]);
+                reinterpret_cast<float4 *>(dst)[5] = make_float4(r[2], r[3], r[4], r[5]);
+            }
+        } else {
+#pragma unroll 1
+            for (uint32_t ph = 0; ph < 4u; ph++) {
+                philox_pairs_lg2(b0 + ph, tg, dg, STREAM_STEP, a.key, rk, z);
+                euler6_rec(x, n, p, c0, h, z, a.max_steps, r);
+#pragma unroll
+                for (uint32_t i = 0; i < 6u; i++)
+                    if (rec && n0 + 6u * ph + i < a.n_obs) dst[6u * ph + i] = r[i];
+            }
+        }
+        per++;
+    }
+
+    // ---- per-warp statistics ----------------------------------------------------------------
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc_steps += __shfl_xor_sync(FULL_MASK, acc_steps, o);
+        acc_timeouts += __shfl_xor_sync(FULL_MASK, acc_timeouts, o);
+        acc_upper += __shfl_xor_sync(FULL_MASK, acc_upper, o);
+    }
+    if (lane == 0) {
+        atomicAdd(a.stats + STAT_STEPS, acc_steps);
+        atomicAdd(a.stats + STAT_TIMEOUTS, (unsigned long long)acc_timeouts);
+        atomicAdd(a.stats + STAT_UPPER, (unsigned long long)acc_upper);
+    }
+}
+
+cudaError_t launch_record(const RunArgs &a, int grid, int block, cudaStream_t s) {
+    if ((a.n_obs & 7u) == 0u) record_kernel<true><<<grid, block, 0, s>>>(a);
+    else record_kernel<false><<<grid, block, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+int record_block_size() { return RECORD_BLOCK; }
+
+int record_max_blocks_per_sm(int block) {
+    int nb = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, record_kernel<true>, block, 0);
+    return (e == cudaSuccess) ? nb : -1;
+}
 
 // --------------------------------------------------------------------------------------------
 // production, second kernel: a warp per trial finishes the recorded path
@@ -56,10 +230,11 @@ __global__ void __launch_bounds__(256) evidence_post_kernel(const EvidenceArgs a
             ds = (uint32_t)(g / a.n_trials);
             trial = (uint32_t)(g - (uint64_t)ds * a.n_trials);
         }
-        const uint32_t nj = (uint32_t)a.steps[g];
+        const uint2 mt = a.rec_meta[g];  // ((steps << 2) | (choice + 1), final state)
+        const uint32_t nj = mt.x >> 2;
         const float h = a.dconst[ds].v[2], u = a.dconst[ds].v[3];
         const float sigma1 = (float)a.params[(size_t)ds * 6 + 5];
-        const float evj = __fmul_rn(__fadd_rn(a.rec_xfinal[g], h), u);
+        const float evj = __fmul_rn(__fadd_rn(__uint_as_float(mt.y), h), u);
         const float *row_in = a.rec_path + g * a.n_obs;
         // 1. recorded states -> evidence units, held at the final evidence after the crossing
         for (uint32_t k = sl; k < a.n_obs; k += G)
@@ -101,15 +276,16 @@ __global__ void __launch_bounds__(256) evidence_post_kernel(const EvidenceArgs a
         // 4. the row
         const uint64_t row = g * cols;
         if (sl == 0 && valid) {
-            const double2 pr = a.pairs[g];  // (rt, choice) from the stepping kernel, reference fp64 arithmetic
+            double rt, ch;  // (rt, choice) in the reference's fp64 arithmetic (basic_ddm_dc_evidence.py:127-135)
+            trial_outputs<true>(0, (int)(mt.x & 3u) - 1, nj, a.dt, a.params[(size_t)ds * 6 + 3], 0.0, rt, ch);
             if (OUT64) {
                 double *o = reinterpret_cast<double *>(a.out) + row;
-                o[0] = pr.x;
-                o[1] = pr.y;
+                o[0] = rt;
+                o[1] = ch;
             } else {
                 float *o = reinterpret_cast<float *>(a.out) + row;
-                o[0] = (float)pr.x;
-                o[1] = (float)pr.y;
+                o[0] = (float)rt;
+                o[1] = (float)ch;
             }
             if (a.mode == 2) a.path_means[g] = (double)mean;
         }

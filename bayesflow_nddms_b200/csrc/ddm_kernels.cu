@@ -137,17 +137,14 @@ __device__ __forceinline__ void store_pair(void *out, uint64_t idx, double o0, d
 // lanes are frozen the warp takes the (divergent, so deliberately batched) finish +
 // refill path.  Philox counters are (step block, trial, dataset): results do not
 // depend on which lane / warp / SM / GPU ran a trial.
-constexpr uint32_t REC_RING = 24;  // floats per lane: three 32-byte sectors, a multiple of the 6-step block
-
 #ifndef DDM_PERSISTENT_BLOCK
 #define DDM_PERSISTENT_BLOCK 256  // threads per block (A/B: 128 and 512 measured equal within 0.5 %)
 #endif
 #ifndef DDM_PERSISTENT_MIN_BLOCKS
 #define DDM_PERSISTENT_MIN_BLOCKS (1536 / DDM_PERSISTENT_BLOCK)
 #endif
-template <int KIND, bool OUT64, bool RECORD = false>
-__global__ void __launch_bounds__(DDM_PERSISTENT_BLOCK, RECORD ? (1024 / DDM_PERSISTENT_BLOCK) : DDM_PERSISTENT_MIN_BLOCKS)
-    persistent_kernel(const RunArgs a) {
+template <int KIND, bool OUT64>
+__global__ void __launch_bounds__(DDM_PERSISTENT_BLOCK, DDM_PERSISTENT_MIN_BLOCKS) persistent_kernel(const RunArgs a) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
 
@@ -168,14 +165,6 @@ __global__ void __launch_bounds__(DDM_PERSISTENT_BLOCK, RECORD ? (1024 / DDM_PER
 
     unsigned long long acc_steps = 0;
     uint32_t acc_timeouts = 0, acc_upper = 0, acc_cap = 0;
-
-    // RECORD (evidence models): each lane stages its recorded states in a 24-float shared-memory ring and
-    // writes them out one full 32-byte sector at a time (two STG.128), so that the path costs its own bytes
-    // of L2/HBM traffic instead of a sector per 8-byte store.  Stride 25 keeps the ring bank-conflict free.
-    extern __shared__ float rec_ring_smem[];
-    float *ring = RECORD ? rec_ring_smem + (size_t)threadIdx.x * (REC_RING + 1) : nullptr;
-    uint32_t flushed = 0, fpos = 0;  // recorded states already in global memory (multiple of 8), its ring position
-    const bool rec_vec = RECORD && (a.n_obs & 3u) == 0u;
 
     const int thr = a.refill_threshold;
     constexpr bool BASIC = (KIND == KIND_FIXED || KIND == KIND_DRIFT);
@@ -212,12 +201,6 @@ __global__ void __launch_bounds__(DDM_PERSISTENT_BLOCK, RECORD ? (1024 / DDM_PER
                 }
             }
             if (a.steps_out) a.steps_out[idx] = (int32_t)n;
-            if (RECORD) {
-                a.rec_xfinal[idx] = x;
-                float *row = a.rec_path + idx * a.n_obs;  // the last, incomplete sector of the recorded path
-                const uint32_t n_rec = min(n, a.n_obs);
-                for (uint32_t k = flushed; k < n_rec; k++) row[k] = ring[k % REC_RING];
-            }
             acc_steps += n;
             acc_timeouts += (choice == 0);
             acc_upper += (choice > 0);
@@ -260,8 +243,6 @@ __global__ void __launch_bounds__(DDM_PERSISTENT_BLOCK, RECORD ? (1024 / DDM_PER
                 x = t.x;
                 n = 0;
                 blk = 0;
-                flushed = 0;
-                fpos = 0;
                 has = true;
                 p = ((fabsf(x) < t.h) && (a.max_steps > 0u)) ? 1u : 0u;
             }
@@ -274,48 +255,12 @@ __global__ void __launch_bounds__(DDM_PERSISTENT_BLOCK, RECORD ? (1024 / DDM_PER
         // ---- step: tight, branch-free inner loop (round keys and constants stay in uniform registers)
         unsigned alive = __ballot_sync(FULL_MASK, p != 0u);
         const int live_min = 32 - thr_now;  // keep stepping while more than this many lanes are alive
-        if (!RECORD) {
-            do {
-                Normals6Scaled z;
-                philox_pairs_lg2(blk, trial + a.trial_offset, ds + a.dataset_offset, STREAM_STEP, a.key, z);
-                euler6_warp(x, n, alive, t.c0, t.h, z, a.max_steps);
-                blk++;
-            } while (__popc(alive) > live_min);
-        } else {
-            // evidence models: the first n_obs states of every trial go to rec_path (values after the crossing
-            // inside a block are the frozen state; the post kernel reads only k < n)
-            float *row = a.rec_path + ((uint64_t)ds * a.n_trials + trial) * a.n_obs;
-            do {
-                Normals6Scaled z;
-                philox_pairs_lg2(blk, trial + a.trial_offset, ds + a.dataset_offset, STREAM_STEP, a.key, z);
-                const uint32_t n0 = n;
-                const bool rec = ((alive >> lane) & 1u) && n0 < a.n_obs;
-                const uint32_t pos = (blk & 3u) * 6u;  // = n0 % 24 for a lane that is stepping
-                float r[6];
-                euler6_warp_rec(x, n, alive, t.c0, t.h, z, a.max_steps, r);
-                if (rec) {
-#pragma unroll
-                    for (int i = 0; i < 6; i++)
-                        if (n0 + i < a.n_obs) ring[pos + i] = r[i];
-                    if (min(n0 + 6u, a.n_obs) - flushed >= 8u) {  // a sector is complete
-                        const float4 v0 = make_float4(ring[fpos], ring[fpos + 1], ring[fpos + 2], ring[fpos + 3]);
-                        const float4 v1 = make_float4(ring[fpos + 4], ring[fpos + 5], ring[fpos + 6], ring[fpos + 7]);
-                        if (rec_vec) {
-                            float4 *dst = reinterpret_cast<float4 *>(row + flushed);
-                            dst[0] = v0;
-                            dst[1] = v1;
-                        } else {
-                            float *d = row + flushed;
-                            d[0] = v0.x; d[1] = v0.y; d[2] = v0.z; d[3] = v0.w;
-                            d[4] = v1.x; d[5] = v1.y; d[6] = v1.z; d[7] = v1.w;
-                        }
-                        flushed += 8u;
-                        fpos = (fpos == 16u) ? 0u : fpos + 8u;
-                    }
-                }
-                blk++;
-            } while (__popc(alive) > live_min);
-        }
+        do {
+            Normals6Scaled z;
+            philox_pairs_lg2(blk, trial + a.trial_offset, ds + a.dataset_offset, STREAM_STEP, a.key, z);
+            euler6_warp(x, n, alive, t.c0, t.h, z, a.max_steps);
+            blk++;
+        } while (__popc(alive) > live_min);
         p = (alive >> lane) & 1u;
     }
 
@@ -1128,20 +1073,6 @@ int tile_kernel_max_blocks_per_sm(int kind, bool out64, int block, size_t smem) 
     else if (kind == KIND_DRIFT) { if (out64) DDM_OCC(KIND_DRIFT, true); else DDM_OCC(KIND_DRIFT, false); }
     else if (kind == KIND_GENERAL) { if (out64) DDM_OCC(KIND_GENERAL, true); else DDM_OCC(KIND_GENERAL, false); }
 #undef DDM_OCC
-    return (e == cudaSuccess) ? nb : -1;
-}
-
-static size_t record_smem_bytes(int block) { return (size_t)block * (REC_RING + 1) * sizeof(float); }
-
-cudaError_t launch_persistent_record(const RunArgs &a, int grid, int block, cudaStream_t s) {
-    persistent_kernel<KIND_FIXED, true, true><<<grid, block, record_smem_bytes(block), s>>>(a);
-    return cudaGetLastError();
-}
-
-int persistent_record_max_blocks_per_sm(int block) {
-    int nb = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, persistent_kernel<KIND_FIXED, true, true>, block,
-                                                                  record_smem_bytes(block));
     return (e == cudaSuccess) ? nb : -1;
 }
 

@@ -56,7 +56,6 @@ struct RunArgs {
     void *out;               // float2 / double2 per trial
     int32_t *steps_out;      // optional
     float *rec_path;         // evidence models: [trial][n_obs] centred, unit-scaled state after each step
-    float *rec_xfinal;       // evidence models: final state per trial
     uint32_t n_obs;
     unsigned long long *work_counter;
     unsigned long long *stats;  // see StatSlot
@@ -288,21 +287,19 @@ __device__ __forceinline__ void euler6_warp_lb(float &x, uint32_t &n, unsigned &
                    "f"(z.s[2]), "f"(z.c[2]), "f"(z.sn[2]), "r"(max_steps), "r"(lane_bit));
 }
 
-// The same block for the evidence-path models: also hands back the state after each of the six
-// steps (r[k] = x after step k+1; frozen at the crossing value once the lane has stopped), which the
-// caller stores as the observed path.
+// The same block for the evidence-path models (record_kernel, ddm_evidence.cu): "still stepping" is the lane's own
+// 0/1 word, and the state after each of the six steps is handed back (r[k] = x after step k+1; frozen at the
+// crossing value once the lane has stopped), which the caller stores as the observed path.
 #define DDM_STEPR(S, T, R) DDM_STEP_G(S, T, "%9", "%10") "mov.f32 " R ", %0;\n\t"
-__device__ __forceinline__ void euler6_warp_rec(float &x, uint32_t &n, unsigned &alive, float c0, float h,
-                                                const Normals6Scaled &z, uint32_t max_steps, float (&r)[6]) {
-    asm volatile("{\n\t.reg .pred q;\n\t.reg .f32 ax, inc;\n\t.reg .b32 t;\n\t"
-                 "mov.u32 t, %%lanemask_eq;\n\t"
-                 "and.b32 t, t, %2;\n\t"
-                 "setp.ne.u32 q, t, 0;\n\t"
+__device__ __forceinline__ void euler6_rec(float &x, uint32_t &n, uint32_t &p, float c0, float h, const Normals6Scaled &z,
+                                           uint32_t max_steps, float (&r)[6]) {
+    asm volatile("{\n\t.reg .pred q;\n\t.reg .f32 ax, inc;\n\t"
+                 "setp.ne.u32 q, %2, 0;\n\t"
                  DDM_STEPR("%11", "%12", "%3") DDM_STEPR("%11", "%13", "%4") DDM_STEPR("%14", "%15", "%5")
                  DDM_STEPR("%14", "%16", "%6") DDM_STEPR("%17", "%18", "%7") DDM_STEPR("%17", "%19", "%8")
                  "setp.lt.and.u32 q, %1, %20, q;\n\t"
-                 "vote.sync.ballot.b32 %2, q, 0xffffffff;\n\t}"
-                 : "+f"(x), "+r"(n), "+r"(alive), "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5])
+                 "selp.u32 %2, 1, 0, q;\n\t}"
+                 : "+f"(x), "+r"(n), "+r"(p), "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5])
                  : "f"(c0), "f"(h), "f"(z.s[0]), "f"(z.c[0]), "f"(z.sn[0]), "f"(z.s[1]), "f"(z.c[1]), "f"(z.sn[1]),
                    "f"(z.s[2]), "f"(z.c[2]), "f"(z.sn[2]), "r"(max_steps));
 }
@@ -342,11 +339,9 @@ struct EvidenceArgs {
     void *out;               // rows of 2 + n_obs values, float64 or float32
     double *scratch;         // validation path: fp64 rows
     double *path_means;      // mode 2: per-trial mean of the noisy path [n_datasets * n_trials]
-    // production path: products of the stepping kernel (persistent_kernel, RECORD form)
+    // production path: products of the stepping kernel (record_kernel)
     const float *rec_path;   // [trial][n_obs] centred, unit-scaled states
-    const float *rec_xfinal; // final state per trial
-    const int32_t *steps;    // Euler steps per trial
-    const double2 *pairs;    // (rt, choice) per trial
+    const uint2 *rec_meta;   // per trial: ((steps << 2) | (choice + 1), final state as fp32 bits)
     const DsConst *dconst;   // per-dataset constants (v[2] = h, v[3] = U)
     unsigned long long *work_counter;
     unsigned long long *stats;
@@ -386,7 +381,9 @@ cudaError_t launch_tile(const RunArgs &a, int kind, bool out64, int grid, int bl
 size_t tile_kernel_smem_bytes(int kind, int block);
 int tile_kernel_max_blocks_per_sm(int kind, bool out64, int block, size_t smem);
 uint32_t tile_kernel_max_tile(int kind);
-cudaError_t launch_persistent_record(const RunArgs &a, int grid, int block, cudaStream_t s);  // KIND_FIXED, float64 pairs
+cudaError_t launch_record(const RunArgs &a, int grid, int block, cudaStream_t s);  // evidence models' stepping kernel (ddm_evidence.cu)
+int record_max_blocks_per_sm(int block);
+int record_block_size();
 cudaError_t launch_prep_general(const double *params, GenConst *gconst, uint32_t n_datasets, double dt, cudaStream_t s);
 cudaError_t launch_generic(const RunArgs &a, int kind, bool f64, bool buffer_src, bool out64,
                            uint64_t total_trials, cudaStream_t s);
@@ -395,7 +392,6 @@ cudaError_t launch_export_normals(PhiloxKey key, uint32_t dataset, uint32_t tria
 cudaError_t launch_philox_blocks(const uint32_t *ctr, const uint32_t *key, uint32_t *out, int64_t n,
                                  cudaStream_t s);
 int persistent_max_blocks_per_sm(int kind, bool out64, int block);
-int persistent_record_max_blocks_per_sm(int block);
 int persistent_block_size();
 
 }  // namespace ddm
