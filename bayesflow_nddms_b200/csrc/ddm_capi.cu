@@ -1259,13 +1259,17 @@ DDM_API int ddm_simulate_evidence(ddm_ctx *ctx, const double *params, int64_t n_
             // (1) step + record with the persistent refill kernel (the basic model's lanes and counters)
             DDM_CUDA(ctx, ctx->dconst.reserve((size_t)n_datasets));
             DDM_CUDA(ctx, ctx->ev_pairs.reserve((size_t)rows));  // 8 bytes per trial: (steps, choice), final state
-            DDM_CUDA(ctx, ctx->ev_path.reserve((size_t)rows * a.n_obs));
+            a.rec_g = ddm::evidence_lanes_per_trial(a.n_obs);
+            a.rec_stride = ddm::evidence_rec_stride(a.n_obs);
+            DDM_CUDA(ctx, ctx->ev_path.reserve((size_t)rows * a.rec_stride));
             DDM_CUDA(ctx, ddm::launch_prep(ctx->params.p, ctx->dconst.p, (uint32_t)n_datasets, 6u, DDM_MODEL_BASIC, dt, ctx->stream));
             ddm::RunArgs r{};
             r.dconst = ctx->dconst.p;
             r.params = ctx->params.p;
             r.out = ctx->ev_pairs.p;
             r.rec_path = ctx->ev_path.p;
+            r.rec_stride = a.rec_stride;
+            r.rec_g = a.rec_g;
             r.n_obs = a.n_obs;
             r.work_counter = ctx->counters;
             r.stats = ctx->counters + 1;

@@ -42,10 +42,22 @@ namespace ddm {
 // period to end -- 5 % of a 250-step trial, the price of the aligned phases.
 // Philox counters, set-up and step arithmetic are those of DDM_MODEL_BASIC's kernels: a trial's steps, choice and
 // states do not depend on which kernel ran it.
-//   VEC: n_obs is a multiple of 8 (rows are sector-aligned); otherwise guarded scalar stores, six per block.
+//   VEC: n_obs is a multiple of 8 (rows are sector-aligned); otherwise guarded scalar stores, six per block, rows in
+//   natural order.
+// Layout of a VEC row (what the post kernel wants to read): the post kernel gives a trial G lanes, lane sl owning the
+// six observations of Philox block b = sl + G it -- 24 bytes at a 24-byte stride across lanes, a third of every sector
+// per load instruction if the row were in time order.  The row is therefore stored in chunks of 6 G observations
+// (= G blocks), each chunk as three planes of G pairs: observation 6 b + 2 j + e of chunk it sits at
+// 6 G it + 2 G j + 2 (b mod G) + e, so that the post kernel's j-th load is 8 contiguous bytes per lane, G lanes
+// contiguous.  For this kernel nothing changes but which register goes where: a period's four blocks are four
+// neighbouring lanes' worth of one chunk, and plane j of the period -- pairs (2j, 2j+1) of the four blocks -- is
+// again one aligned 32-byte sector.  Rows are padded to whole chunks (a.rec_stride floats).
 constexpr int RECORD_BLOCK = 256;
+// four resident blocks (64 registers: a period's 24 states stay in registers until its three sectors are written);
+// at five (48 registers) ptxas interleaves the stores with the next blocks' arithmetic and the kernel waits on the
+// store queue: 1.32 instead of 0.93 ms per 2M trials
 #ifndef DDM_RECORD_MIN_BLOCKS
-#define DDM_RECORD_MIN_BLOCKS 5
+#define DDM_RECORD_MIN_BLOCKS 4
 #endif
 template <bool VEC>
 __global__ void __launch_bounds__(RECORD_BLOCK, DDM_RECORD_MIN_BLOCKS) record_kernel(const __grid_constant__ RunArgs a) {
@@ -128,36 +140,31 @@ __global__ void __launch_bounds__(RECORD_BLOCK, DDM_RECORD_MIN_BLOCKS) record_ke
         // ---- one period: four blocks, three sectors ---------------------------------------------
         const uint32_t n0 = 24u * per;  // steps a lane that is still stepping has taken
         const bool rec = has && p != 0u && n0 < a.n_obs;
-        float *dst = a.rec_path + ((uint64_t)ds * a.n_trials + trial) * a.n_obs + n0;
         const uint32_t tg = trial + a.trial_offset, dg = ds + a.dataset_offset, b0 = 4u * per;
         Normals6Scaled z;
         float r[6];
         if (VEC) {
-            float k0, k1, k2, k3, k4, k5;  // states held over from the previous block
-            philox_pairs_lg2(b0, tg, dg, STREAM_STEP, a.key, rk, z);
-            euler6_rec(x, n, p, c0, h, z, a.max_steps, r);
-            k0 = r[0]; k1 = r[1]; k2 = r[2]; k3 = r[3]; k4 = r[4]; k5 = r[5];
-            philox_pairs_lg2(b0 + 1u, tg, dg, STREAM_STEP, a.key, rk, z);
-            euler6_rec(x, n, p, c0, h, z, a.max_steps, r);
-            if (rec) {  // states 0..7 (n0 < n_obs and both are multiples of 8: the sector lies inside the row)
-                reinterpret_cast<float4 *>(dst)[0] = make_float4(k0, k1, k2, k3);
-                reinterpret_cast<float4 *>(dst)[1] = make_float4(k4, k5, r[0], r[1]);
+            // the period's four blocks in registers, then three sectors: plane j = pairs (2j, 2j+1) of the four blocks
+            float q[4][6];
+#pragma unroll
+            for (int ph = 0; ph < 4; ph++) {
+                philox_pairs_lg2(b0 + (uint32_t)ph, tg, dg, STREAM_STEP, a.key, rk, z);
+                euler6_rec(x, n, p, c0, h, z, a.max_steps, r);
+#pragma unroll
+                for (int i = 0; i < 6; i++) q[ph][i] = r[i];
             }
-            k0 = r[2]; k1 = r[3]; k2 = r[4]; k3 = r[5];
-            philox_pairs_lg2(b0 + 2u, tg, dg, STREAM_STEP, a.key, rk, z);
-            euler6_rec(x, n, p, c0, h, z, a.max_steps, r);
-            if (rec && n0 + 8u < a.n_obs) {  // states 8..15
-                reinterpret_cast<float4 *>(dst)[2] = make_float4(k0, k1, k2, k3);
-                reinterpret_cast<float4 *>(dst)[3] = make_float4(r[0], r[1], r[2], r[3]);
-            }
-            k0 = r[4]; k1 = r[5];
-            philox_pairs_lg2(b0 + 3u, tg, dg, STREAM_STEP, a.key, rk, z);
-            euler6_rec(x, n, p, c0, h, z, a.max_steps, r);
-            if (rec && n0 + 16u < a.n_obs) {  // states 16..23
-                reinterpret_cast<float4 *>(dst)[4] = make_float4(k0, k1, r[0], r[1]);
-                reinterpret_cast<float4 *>(dst)[5] = make_float4(r[2], r[3], r[4], r[5]);
+            if (rec) {
+                const uint32_t g = a.rec_g, it = b0 / g, sl0 = b0 - it * g;  // chunk, first of the four lanes' slots
+                float *dst = a.rec_path + ((uint64_t)ds * a.n_trials + trial) * a.rec_stride + 6u * g * it + 2u * sl0;
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    float4 *d = reinterpret_cast<float4 *>(dst + 2u * g * j);
+                    d[0] = make_float4(q[0][2 * j], q[0][2 * j + 1], q[1][2 * j], q[1][2 * j + 1]);
+                    d[1] = make_float4(q[2][2 * j], q[2][2 * j + 1], q[3][2 * j], q[3][2 * j + 1]);
+                }
             }
         } else {
+            float *dst = a.rec_path + ((uint64_t)ds * a.n_trials + trial) * a.rec_stride + n0;
 #pragma unroll 1
             for (uint32_t ph = 0; ph < 4u; ph++) {
                 philox_pairs_lg2(b0 + ph, tg, dg, STREAM_STEP, a.key, rk, z);
@@ -199,20 +206,33 @@ int record_max_blocks_per_sm(int block) {
 }
 
 // --------------------------------------------------------------------------------------------
-// production, second kernel: a warp per trial finishes the recorded path
+// production, second kernel: G lanes per trial finish the recorded path, the row in registers
 // --------------------------------------------------------------------------------------------
-// G lanes work on one trial, 32 / G trials per warp at a time.  A trial's 200 noise normals are 34 Philox blocks:
-// on 32 lanes that is two passes with the second nearly empty; on 8 lanes it is five passes for four trials
-// (1.25 per trial instead of 2), and the reductions are three shuffle steps instead of five.
-template <bool OUT64, int G>
-__global__ void __launch_bounds__(256) evidence_post_kernel(const EvidenceArgs a, uint64_t total) {
-    // Per-trial staging row: every global access below is contiguous over the G lanes (k = sl, sl + G, ...: whole
-    // 32-byte sectors); the noise normals, which come six per Philox block and per lane, meet the row in shared
-    // memory.
-    extern __shared__ float post_smem[];
+// A trial's n_obs noise normals come six per Philox block of its aux stream, so the natural owner of observations
+// 6b .. 6b+5 is the lane that draws block b.  G lanes share a trial (32 / G trials per warp at a time), lane sl takes
+// blocks sl, sl + G, ... (at most POST_ITER of them) and keeps its <= 6 * POST_ITER observations in registers from the
+// load of the recorded states to the store of the standardised row: 24 contiguous bytes per lane and block in
+// (G lanes: 24 G contiguous bytes, whole sectors) and the same out, mean / variance by shuffle reduction.  Round 1's
+// kernel staged the row in shared memory so that every access ran k = sl, sl + G, ... -- two shared-memory round trips
+// per observation and four loops over the row: 354 warp instructions per trial, instruction-bound at 75 % issue with
+// the memory system half idle.
+// In: the recording kernel's chunked layout (see there) makes a lane's j-th pair of a block 8 contiguous bytes per
+// lane over the G lanes.  Out: rows are in time order, so a chunk's 6 G values take one trip through a per-warp
+// shared-memory buffer (three STS.64, three LDS.64 per lane) and leave as 8 (16 for float64) contiguous bytes per
+// lane -- straight 24-byte-stride stores touched every sector three times (measured: 81 instead of 25 sectors per row).
+//   PAIRS: n_obs is even -- rows are 8-byte aligned, observations move two at a time.
+//   CHUNKED: the recorded rows are in the chunked layout (n_obs a multiple of 8); otherwise in time order.
+constexpr int POST_ITER = 5;
+#ifndef DDM_POST_MIN_BLOCKS
+#define DDM_POST_MIN_BLOCKS 3
+#endif
+
+template <bool OUT64, int G, bool PAIRS, bool CHUNKED>
+__global__ void __launch_bounds__(256, DDM_POST_MIN_BLOCKS) evidence_post_kernel(const EvidenceArgs a, uint64_t total) {
     constexpr unsigned TPW = 32u / G;  // trials per warp
+    __shared__ float tbuf_all[8][192];  // per warp: one chunk of every trial the warp works on, 6 floats per lane
+    float *tbuf = tbuf_all[threadIdx.x >> 5];
     const unsigned lane = threadIdx.x & 31u, sl = lane & (G - 1u), sub = lane / G;
-    float *s = post_smem + ((size_t)(threadIdx.x >> 5) * TPW + sub) * a.n_obs;
     const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const uint32_t cols = 2u + a.n_obs;
@@ -235,45 +255,73 @@ __global__ void __launch_bounds__(256) evidence_post_kernel(const EvidenceArgs a
         const float h = a.dconst[ds].v[2], u = a.dconst[ds].v[3];
         const float sigma1 = (float)a.params[(size_t)ds * 6 + 5];
         const float evj = __fmul_rn(__fadd_rn(__uint_as_float(mt.y), h), u);
-        const float *row_in = a.rec_path + g * a.n_obs;
-        // 1. recorded states -> evidence units, held at the final evidence after the crossing
-        for (uint32_t k = sl; k < a.n_obs; k += G)
-            s[k] = (k < nj) ? __fmul_rn(__fadd_rn(row_in[k], h), u) : evj;
-        __syncwarp();
-        // 2. + sigma1 * z_noise[k]: lane owns Philox blocks sl, sl + G, ... of the trial's aux stream;
-        //    the row sum is taken on the way
+        const float *row_in = a.rec_path + g * a.rec_stride;
+        // 1. recorded states -> evidence units, held at the final evidence after the crossing, + sigma1 * z_noise[k]
+        //    (positions past the trial's last step may never have been written by the recording kernel: selected
+        //    away, never used in arithmetic that survives)
+        float v[POST_ITER][6];
         float sum = 0.f;
-        for (uint32_t b = sl; b < n_blocks; b += G) {
-            float z[6];
-            philox_normals6_f32(b, trial + a.trial_offset, ds + a.dataset_offset, STREAM_AUX, a.key, z);
 #pragma unroll
-            for (int i = 0; i < 6; i++) {
-                const uint32_t k = 6u * b + i;
-                if (k < a.n_obs) {
-                    const float v = __fmaf_rn(sigma1, z[i], s[k]);
-                    s[k] = v;
-                    sum += v;
+        for (int it = 0; it < POST_ITER; it++) {
+            const uint32_t b = sl + (uint32_t)it * G, k0 = 6u * b;
+#pragma unroll
+            for (int i = 0; i < 6; i++) v[it][i] = 0.f;
+            if (b < n_blocks) {
+                float rec[6];
+                if (CHUNKED) {  // padded rows: every block of every chunk lies inside the row's allocation
+#pragma unroll
+                    for (int j = 0; j < 3; j++) {
+                        const float2 t = __ldg(reinterpret_cast<const float2 *>(row_in + 6u * G * it + 2u * G * j + 2u * sl));
+                        rec[2 * j] = t.x;
+                        rec[2 * j + 1] = t.y;
+                    }
+                } else if (PAIRS) {
+#pragma unroll
+                    for (int j = 0; j < 3; j++) {
+                        float2 t = make_float2(0.f, 0.f);
+                        if (k0 + 2u * j < a.n_obs) t = __ldg(reinterpret_cast<const float2 *>(row_in + k0) + j);
+                        rec[2 * j] = t.x;
+                        rec[2 * j + 1] = t.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 6; i++) rec[i] = (k0 + i < a.n_obs) ? __ldg(row_in + k0 + i) : 0.f;
+                }
+                float z[6];
+                philox_normals6_f32(b, trial + a.trial_offset, ds + a.dataset_offset, STREAM_AUX, a.key, z);
+#pragma unroll
+                for (int i = 0; i < 6; i++) {
+                    const uint32_t k = k0 + i;
+                    if (k < a.n_obs) {
+                        const float e = (k < nj) ? __fmul_rn(__fadd_rn(rec[i], h), u) : evj;
+                        v[it][i] = __fmaf_rn(sigma1, z[i], e);
+                        sum += v[it][i];
+                    }
                 }
             }
         }
-        __syncwarp();
-        // 3. mean (and variance) over the row
+        // 2. mean (and variance) over the row
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL_MASK, sum, o);
         const float mean = sum * inv_n;
         float scale = 1.f, shift = 0.f;
         if (a.mode == 1) {
             float ssd = 0.f;
-            for (uint32_t k = sl; k < a.n_obs; k += G) {
-                const float d = s[k] - mean;
-                ssd = __fmaf_rn(d, d, ssd);
+#pragma unroll
+            for (int it = 0; it < POST_ITER; it++) {
+                const uint32_t k0 = 6u * (sl + (uint32_t)it * G);
+#pragma unroll
+                for (int i = 0; i < 6; i++) {
+                    const float d = v[it][i] - mean;
+                    if (k0 + i < a.n_obs) ssd = __fmaf_rn(d, d, ssd);
+                }
             }
 #pragma unroll
             for (int o = G / 2; o > 0; o >>= 1) ssd += __shfl_xor_sync(FULL_MASK, ssd, o);
             scale = 1.f / sqrtf(ssd * inv_n);
             shift = mean;
         }
-        // 4. the row
+        // 3. the row
         const uint64_t row = g * cols;
         if (sl == 0 && valid) {
             double rt, ch;  // (rt, choice) in the reference's fp64 arithmetic (basic_ddm_dc_evidence.py:127-135)
@@ -289,14 +337,46 @@ __global__ void __launch_bounds__(256) evidence_post_kernel(const EvidenceArgs a
             }
             if (a.mode == 2) a.path_means[g] = (double)mean;
         }
-        if (valid) {
-            for (uint32_t k = sl; k < a.n_obs; k += G) {
-                const float v = (s[k] - shift) * scale;
-                if (OUT64) reinterpret_cast<double *>(a.out)[row + 2 + k] = (double)v;
-                else reinterpret_cast<float *>(a.out)[row + 2 + k] = v;
+        if (PAIRS) {
+            // a chunk at a time through the warp's buffer: lane (sub, sl) puts its block at words 6 lane .. 6 lane + 5 and
+            // takes pair sl of each plane m: observations 6 G it + 2 G m + 2 sl (+1)
+#pragma unroll
+            for (int it = 0; it < POST_ITER; it++) {
+                if (6u * G * it >= a.n_obs) break;  // warp-uniform
+#pragma unroll
+                for (int j = 0; j < 3; j++)
+                    reinterpret_cast<float2 *>(tbuf + 6u * lane)[j] =
+                        make_float2((v[it][2 * j] - shift) * scale, (v[it][2 * j + 1] - shift) * scale);
+                __syncwarp();
+#pragma unroll
+                for (int m = 0; m < 3; m++) {
+                    const uint32_t k = 6u * G * it + 2u * G * m + 2u * sl;
+                    const float2 o = *reinterpret_cast<const float2 *>(tbuf + 6u * G * sub + 2u * G * m + 2u * sl);
+                    if (valid && k < a.n_obs) {
+                        const uint64_t at = row + 2u + k;
+                        if (OUT64) *reinterpret_cast<double2 *>(reinterpret_cast<double *>(a.out) + at) = make_double2((double)o.x, (double)o.y);
+                        else *reinterpret_cast<float2 *>(reinterpret_cast<float *>(a.out) + at) = o;
+                    }
+                }
+                __syncwarp();
+            }
+        } else if (valid) {
+#pragma unroll
+            for (int it = 0; it < POST_ITER; it++) {
+                const uint32_t k0 = 6u * (sl + (uint32_t)it * G);
+                const uint64_t at = row + 2u + k0;
+                {
+#pragma unroll
+                    for (int i = 0; i < 6; i++) {
+                        if (k0 + i < a.n_obs) {
+                            const float o0 = (v[it][i] - shift) * scale;
+                            if (OUT64) reinterpret_cast<double *>(a.out)[at + i] = (double)o0;
+                            else reinterpret_cast<float *>(a.out)[at + i] = o0;
+                        }
+                    }
+                }
             }
         }
-        __syncwarp();
     }
 }
 
@@ -427,22 +507,45 @@ template <int G>
 static cudaError_t launch_evidence_post_g(const EvidenceArgs &a, bool out64, uint64_t total, int sm_count, cudaStream_t s) {
     constexpr uint64_t per_block = 8ull * (32 / G);  // 8 warps per block, 32 / G trials per warp per pass
     uint64_t grid = (total + per_block - 1) / per_block;
-    const uint64_t cap = (uint64_t)sm_count * 8 * 4;
+    const uint64_t cap = (uint64_t)sm_count * DDM_POST_MIN_BLOCKS * 8;
     if (grid > cap) grid = cap;
-    const size_t smem = (size_t)per_block * a.n_obs * sizeof(float);
-    if (out64) evidence_post_kernel<true, G><<<(unsigned)grid, 256, smem, s>>>(a, total);
-    else evidence_post_kernel<false, G><<<(unsigned)grid, 256, smem, s>>>(a, total);
+    const bool pairs = (a.n_obs & 1u) == 0u, chunked = (a.n_obs & 7u) == 0u;
+    if (chunked && a.rec_g != (uint32_t)G) return cudaErrorInvalidValue;  // the recording kernel wrote for another split
+    if (out64) {
+        if (chunked) evidence_post_kernel<true, G, true, true><<<(unsigned)grid, 256, 0, s>>>(a, total);
+        else if (pairs) evidence_post_kernel<true, G, true, false><<<(unsigned)grid, 256, 0, s>>>(a, total);
+        else evidence_post_kernel<true, G, false, false><<<(unsigned)grid, 256, 0, s>>>(a, total);
+    } else {
+        if (chunked) evidence_post_kernel<false, G, true, true><<<(unsigned)grid, 256, 0, s>>>(a, total);
+        else if (pairs) evidence_post_kernel<false, G, true, false><<<(unsigned)grid, 256, 0, s>>>(a, total);
+        else evidence_post_kernel<false, G, false, false><<<(unsigned)grid, 256, 0, s>>>(a, total);
+    }
     return cudaGetLastError();
+}
+
+// Lanes per trial in the post kernel, and with it the chunk of the recorded rows' layout (6 G observations): the
+// widest split that keeps a lane's share of the row within POST_ITER Philox blocks.
+uint32_t evidence_lanes_per_trial(uint32_t n_obs) {
+    const uint32_t n_blocks = (n_obs + 5u) / 6u;
+    return n_blocks <= 8u * POST_ITER ? 8u : (n_blocks <= 16u * POST_ITER ? 16u : 32u);
+}
+
+// Floats per recorded row: whole chunks in the chunked layout (n_obs a multiple of 8), n_obs otherwise.
+uint32_t evidence_rec_stride(uint32_t n_obs) {
+    if (n_obs & 7u) return n_obs;
+    const uint32_t g = evidence_lanes_per_trial(n_obs), chunk = 6u * g;
+    return (n_obs + chunk - 1u) / chunk * chunk;
 }
 
 cudaError_t launch_evidence_post(const EvidenceArgs &a, bool out64, uint64_t total, int sm_count, cudaStream_t s) {
     if (total == 0) return cudaSuccess;
-    // the widest split whose staging rows fit the 48 KB a block gets without opting in: 8 lanes per trial up to
-    // 384 observations (the reference uses 200 and 400), then 16, then the whole warp
-    const size_t row = (size_t)a.n_obs * sizeof(float);
-    if (32 * row <= 48 * 1024) return launch_evidence_post_g<8>(a, out64, total, sm_count, s);
-    if (16 * row <= 48 * 1024) return launch_evidence_post_g<16>(a, out64, total, sm_count, s);
-    return launch_evidence_post_g<32>(a, out64, total, sm_count, s);
+    // the widest split that keeps a lane's share of the row within POST_ITER Philox blocks: 8 lanes per trial up to
+    // 240 observations (the reference's 200), 16 up to 480 (its 400), the whole warp up to 960
+    const uint32_t n_blocks = (a.n_obs + 5u) / 6u;
+    if (n_blocks <= 8u * POST_ITER) return launch_evidence_post_g<8>(a, out64, total, sm_count, s);
+    if (n_blocks <= 16u * POST_ITER) return launch_evidence_post_g<16>(a, out64, total, sm_count, s);
+    if (n_blocks <= 32u * POST_ITER) return launch_evidence_post_g<32>(a, out64, total, sm_count, s);
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_evidence_generic(const EvidenceArgs &a, bool buffer_src, uint64_t total, cudaStream_t s) {

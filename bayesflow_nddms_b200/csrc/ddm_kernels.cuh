@@ -55,7 +55,9 @@ struct RunArgs {
     // outputs
     void *out;               // float2 / double2 per trial
     int32_t *steps_out;      // optional
-    float *rec_path;         // evidence models: [trial][n_obs] centred, unit-scaled state after each step
+    float *rec_path;         // evidence models: [trial][rec_stride] centred, unit-scaled state after each step
+    uint32_t rec_stride;     // floats per recorded row; rec_g: lanes per trial of the post kernel (chunk = 6 rec_g
+    uint32_t rec_g;          // observations, see record_kernel)
     uint32_t n_obs;
     unsigned long long *work_counter;
     unsigned long long *stats;  // see StatSlot
@@ -340,7 +342,8 @@ struct EvidenceArgs {
     double *scratch;         // validation path: fp64 rows
     double *path_means;      // mode 2: per-trial mean of the noisy path [n_datasets * n_trials]
     // production path: products of the stepping kernel (record_kernel)
-    const float *rec_path;   // [trial][n_obs] centred, unit-scaled states
+    const float *rec_path;   // [trial][rec_stride] centred, unit-scaled states (layout: record_kernel)
+    uint32_t rec_stride, rec_g;
     const uint2 *rec_meta;   // per trial: ((steps << 2) | (choice + 1), final state as fp32 bits)
     const DsConst *dconst;   // per-dataset constants (v[2] = h, v[3] = U)
     unsigned long long *work_counter;
@@ -362,6 +365,8 @@ cudaError_t launch_rt_histogram(const void *rows, bool rows64, uint64_t n_rows, 
 cudaError_t launch_normals_histogram(const PhiloxKey &key, uint64_t n_blocks, uint32_t nb_abs, double z_max, uint32_t nb_ang,
                                      unsigned long long *hist, double *moments, int sm_count, cudaStream_t s);
 cudaError_t launch_evidence_post(const EvidenceArgs &a, bool out64, uint64_t total, int sm_count, cudaStream_t s);
+uint32_t evidence_lanes_per_trial(uint32_t n_obs);
+uint32_t evidence_rec_stride(uint32_t n_obs);
 cudaError_t launch_evidence_generic(const EvidenceArgs &a, bool buffer_src, uint64_t total, cudaStream_t s);
 cudaError_t launch_evidence_dataset_stats(const double *path_means, double *ds_stats, uint32_t n_datasets,
                                           uint32_t n_trials, cudaStream_t s);
