@@ -343,6 +343,22 @@ def other_configs(sim, issue_peak, want_cpu=True) -> dict:
             orc.simulate_mt(5, pp[idx[i]], 1, seed=i, bound_in=[alphas[i]])
         out["C4"]["cpu_port_1thread_ms"] = (time.perf_counter() - t0) * 97 * 1e3
 
+    # ---- evidence-path variant: 200 observed states per trial, per-trial z-score, device-resident float32 rows
+    from bayesflow_nddms_b200 import basic_ddm_dc_evidence as mev
+    Pe = mev.batch_draw_prior(2048)
+    best = None
+    for _ in range(4):
+        b = sim.simulate_evidence(Pe, 1000, 200, 1, flags=capi.FLAG_OUT_F32, device=True)
+        del b
+        ste = sim.last_stats()
+        best = ste if best is None or ste["kernel_ms"] < best["kernel_ms"] else best
+    out["evidence_path"] = {
+        "workload": "retired_models/basic_ddm_dc_evidence: 2048 datasets x 1000 trials, dt=.001, 200 observed evidence states + noise "
+                    "per trial, z-scored, (rt, choice, path[200]) float32 rows device-resident (808 B per trial)",
+        "kernel_ms": best["kernel_ms"], "kernels": "record_kernel (step + record) + evidence_post_kernel (noise, z-score, rows)",
+        "trials_per_s": best["n_trials"] / (best["kernel_ms"] * 1e-3), "steps_per_s": best["total_steps"] / (best["kernel_ms"] * 1e-3),
+        "output_gb_per_s": best["n_trials"] * 808 / (best["kernel_ms"] * 1e-3) / 1e9}
+
     # ---- C5 in the fp64 validation mode (the reference's own precision): bounded sample
     Ps = sweep_params(2000, seed=99)
     best = None

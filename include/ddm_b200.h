@@ -157,7 +157,7 @@ int ddm_set_host_decode(ddm_ctx *ctx, int n_threads);
  * out_host (B, n_trials, 2) f64 (or f32 with DDM_FLAG_OUT_F32); (B, n_trials, 3) for DDM_MODEL_GENERAL.  out_host may be
  * NULL: results stay on the device (ddm_last_output_dlpack / ddm_download).
  * dt, max_steps: the reference's default kwargs (.01, 400).  Philox key = seed;
- * counters = (step block, trial, dataset_offset + b, stream), so the result of
+ * counter words = (stream, step block, trial, dataset_offset + b), so the result of
  * dataset b does not depend on how datasets are sharded over GPUs.  dataset_offset is a
  * 64-bit global index below 2^56: its low 32 bits are a counter word, the rest rides in the
  * stream word, so a long run rolls over into fresh counters; one call must not straddle a
