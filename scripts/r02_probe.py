@@ -10,7 +10,8 @@ from bayesflow_nddms_b200 import priors
 case, variant, thr, tile = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 2
 CASES = {"sweep": (0, "sweep", 100_000, 1000, 1e-3, 4000), "c3": (1, "alpha", 20_000, 1000, 0.01, 400),
-         "basic01": (0, "basic", 40_000, 1000, 0.01, 400), "sweep20k": (0, "sweep", 20_000, 1000, 1e-3, 4000)}
+         "basic01": (0, "basic", 40_000, 1000, 0.01, 400), "sweep20k": (0, "sweep", 20_000, 1000, 1e-3, 4000),
+         "c3small": (1, "alpha", 1024, 1000, 0.01, 400)}
 model, prior, B, n, dt, ms = CASES[case]
 sim = pkg.DDMSimulator(device=0, seed=2023)
 sim.set_kernel_variant(variant)
