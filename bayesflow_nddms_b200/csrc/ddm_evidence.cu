@@ -153,7 +153,8 @@ __global__ void __launch_bounds__(RECORD_BLOCK, DDM_RECORD_MIN_BLOCKS) record_ke
 #pragma unroll
                 for (int i = 0; i < 6; i++) q[ph][i] = r[i];
             }
-            if (rec) {
+            if (rec && DDM_CHECK(a.stats, ds < a.n_datasets && trial < a.n_trials &&
+                                              6u * a.rec_g * (b0 / a.rec_g) + 4u * a.rec_g + 2u * (b0 % a.rec_g) + 8u <= a.rec_stride)) {
                 const uint32_t g = a.rec_g, it = b0 / g, sl0 = b0 - it * g;  // chunk, first of the four lanes' slots
                 float *dst = a.rec_path + ((uint64_t)ds * a.n_trials + trial) * a.rec_stride + 6u * g * it + 2u * sl0;
 #pragma unroll
