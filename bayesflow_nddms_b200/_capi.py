@@ -97,6 +97,7 @@ SIGNATURES = {
     "ddm_set_pipeline": (C.c_int, [_vp, C.c_int64, C.c_int64]),
     "ddm_set_host_decode": (C.c_int, [_vp, C.c_int]),
     "ddm_pipeline_chunks": (C.c_int64, [C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int64]),
+    "ddm_histogram_chunks": (C.c_int64, [C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int64]),
     "ddm_wire_decode_host": (C.c_int, [C.c_void_p, C.c_void_p, _dp, C.c_int, C.c_int64, C.c_int64, C.c_double, C.c_int,
                                        C.c_int, C.c_int]),
     "ddm_simulate": (C.c_int, [_vp, C.c_int, _dp, C.c_int64, C.c_int, C.c_int64, C.c_double, C.c_int, C.c_uint64,

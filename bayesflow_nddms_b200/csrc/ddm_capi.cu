@@ -211,6 +211,7 @@ struct ddm_ctx {
     size_t wire_cap[3] = {0, 0, 0};
     ddm::HostWorkers *workers = nullptr;
     int tune_host_decode = 0;  // 0 automatic thread count, > 0 that many threads, < 0 plain 16-byte rows over PCIe
+    cudaStream_t hist_stream = nullptr;  // streamed ddm_simulate_histogram: each chunk's reduction runs beside the next chunk's kernel
 
     // tuning (0 = automatic)
     int tune_threshold = 0, tune_blocks_per_sm = 0, tune_tile = 0;
@@ -560,6 +561,19 @@ std::vector<std::pair<int64_t, int64_t>> pipeline_chunks(int64_t n_datasets, int
     return chunks;
 }
 
+// Streams, events and the second work counter of the chunked paths (created on first use).
+int ensure_pipe_streams(ddm_ctx *ctx) {
+    if (ctx->copy_stream) return DDM_OK;
+    DDM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    DDM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->pipe_stream2, cudaStreamNonBlocking));
+    DDM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->hist_stream, cudaStreamNonBlocking));
+    DDM_CUDA(ctx, cudaMalloc(&ctx->work_counter2, sizeof(unsigned long long)));
+    DDM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_ready, cudaEventDisableTiming));
+    for (int b = 0; b < 2; b++) DDM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_kernel_done[b], cudaEventDisableTiming));
+    for (int b = 0; b < 3; b++) DDM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_copy_done[b], cudaEventDisableTiming));
+    return DDM_OK;
+}
+
 int run_pipelined(ddm_ctx *ctx, const double *params_host, int64_t n_trials, double dt, int max_steps, uint64_t seed,
                   uint64_t dataset_offset, int precision, int flags, void *out_host, bool want_compact) {
     const int model = ctx->model;
@@ -613,14 +627,8 @@ int run_pipelined(ddm_ctx *ctx, const double *params_host, int64_t n_trials, dou
         rc = ensure_workers(ctx);
         if (rc) return rc;
     }
-    if (!ctx->copy_stream) {
-        DDM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-        DDM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->pipe_stream2, cudaStreamNonBlocking));
-        DDM_CUDA(ctx, cudaMalloc(&ctx->work_counter2, sizeof(unsigned long long)));
-        DDM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_ready, cudaEventDisableTiming));
-        for (int b = 0; b < 2; b++) DDM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_kernel_done[b], cudaEventDisableTiming));
-        for (int b = 0; b < 3; b++) DDM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_copy_done[b], cudaEventDisableTiming));
-    }
+    rc = ensure_pipe_streams(ctx);
+    if (rc) return rc;
     ddm_stats st{};
     st.n_trials = (uint64_t)(n_datasets * n_trials);
     DDM_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long) * (1 + ddm::STAT_COUNT), ctx->stream));
@@ -739,6 +747,135 @@ int run_pipelined(ddm_ctx *ctx, const double *params_host, int64_t n_trials, dou
     return DDM_OK;
 }
 
+// ddm_simulate_histogram for large batches (C5 as SURVEY.md section 8d specifies it, end to end): the batch stays
+// resident as one buffer, exactly as after ddm_run, but it is produced in a few chunks of datasets so that nothing but
+// the first chunk's parameters has to cross PCIe before the GPU starts and nothing but the last chunk's reduction is
+// left when it stops.  Chunk i: parameters H2D on the copy stream -> prep + simulator kernel on the ctx stream (even i)
+// or the second kernel stream (odd i; own work counter, so its blocks move in as the previous chunk's retire) ->
+// rt_histogram_kernel over the chunk's rows on the histogram stream, accumulating into one device histogram (it runs
+// in the SM time the next kernel's start and the previous kernel's tail leave).  Schedule: a sixteenth of the batch
+// first (12 ms of kernel at 1e9 trials: time to upload the next chunk's 19 MB from pageable memory), then half of what
+// is left each time down to 32 Mi trials (six chunks at 1e9 trials; the last reduction covers 6 % of the rows, 0.1 ms).
+// Measured at 1e6 x 1000 (scripts/r02_hist_stream_ab.py): 199.0-199.8 ms per call with one upload, one launch and one
+// reduction, 197.4 ms chunked.  Results do not depend on the chunking: a trial's Philox counters are its global
+// (dataset, trial) indices and the histogram is additive.
+constexpr int64_t kHistStreamMinRows = 64ll << 20;
+constexpr int64_t kHistStreamMinChunkRows = 32ll << 20;  // a chunk boundary costs ~0.2 ms (profiles/r02_hist_stream_ab.txt)
+
+std::vector<std::pair<int64_t, int64_t>> histogram_chunks(int64_t n_datasets, int64_t n_trials, int64_t min_chunk_rows) {
+    std::vector<std::pair<int64_t, int64_t>> chunks;
+    const int64_t per_ds = n_trials > 0 ? n_trials : 1;
+    if (min_chunk_rows <= 0) min_chunk_rows = kHistStreamMinChunkRows;
+    const int64_t min_cnt = std::max<int64_t>(1, (min_chunk_rows + per_ds - 1) / per_ds);
+    for (int64_t lo = 0; lo < n_datasets;) {
+        const int64_t left = n_datasets - lo;
+        int64_t cnt = chunks.empty() ? n_datasets / 16 : left / 2;
+        if (cnt < min_cnt) cnt = min_cnt;
+        if (left - cnt < min_cnt) cnt = left;  // no crumbs
+        chunks.emplace_back(lo, cnt);
+        lo += cnt;
+    }
+    return chunks;
+}
+
+int run_histogram_streamed(ddm_ctx *ctx, const double *params_host, int64_t n_trials, double dt, int max_steps, uint64_t seed,
+                           uint64_t dataset_offset, int precision, int flags, int n_bins, double rt_max, uint64_t *hist_host) {
+    const int model = ctx->model;
+    const int64_t n_datasets = ctx->n_datasets;
+    ddm::RunArgs base;
+    int rc = build_args(ctx, model, n_datasets, n_trials, dt, max_steps, seed, dataset_offset, 0, precision, flags, base);
+    if (rc) return rc;
+    const bool out64 = !(flags & DDM_FLAG_OUT_F32);
+    const int cols = n_cols_of(model);
+    const size_t row_bytes = (size_t)cols * (out64 ? 8 : 4);
+    const int64_t rows = n_datasets * n_trials;
+    rc = ensure_output(ctx, (size_t)rows * row_bytes);
+    if (rc) return rc;
+    rc = ensure_pipe_streams(ctx);
+    if (rc) return rc;
+    const size_t n_cells = 2 * (size_t)n_bins + 2;
+    DDM_CUDA(ctx, ctx->hist.reserve(n_cells));
+    const bool dconst = uses_dconst(ctx, model, precision);
+    if (dconst) DDM_CUDA(ctx, ctx->dconst.reserve((size_t)n_datasets));
+    const bool basic = model == DDM_MODEL_BASIC || model == DDM_MODEL_ETA;
+    const std::vector<std::pair<int64_t, int64_t>> chunks = histogram_chunks(n_datasets, n_trials, ctx->tune_pipeline_chunk_rows);
+    const int64_t n_chunks = (int64_t)chunks.size();
+    // one event per chunk and stage; they live for this call only
+    struct Events {
+        std::vector<cudaEvent_t> v;
+        ~Events() { for (cudaEvent_t e : v) cudaEventDestroy(e); }
+    } up, kd;
+    for (int64_t i = 0; i < n_chunks; i++) {
+        cudaEvent_t e = nullptr;
+        DDM_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        up.v.push_back(e);
+        DDM_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        kd.v.push_back(e);
+    }
+    ddm_stats st{};
+    st.n_trials = (uint64_t)rows;
+    DDM_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long) * (1 + ddm::STAT_COUNT), ctx->stream));
+    DDM_CUDA(ctx, cudaMemsetAsync(ctx->hist.p, 0, n_cells * sizeof(unsigned long long), ctx->stream));
+    DDM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    // the side streams start behind whatever the caller's stream still holds (earlier runs read the same arenas)
+    DDM_CUDA(ctx, cudaEventRecord(ctx->pipe_ready, ctx->stream));
+    DDM_CUDA(ctx, cudaStreamWaitEvent(ctx->pipe_stream2, ctx->pipe_ready, 0));
+    DDM_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->pipe_ready, 0));
+    DDM_CUDA(ctx, cudaStreamWaitEvent(ctx->hist_stream, ctx->pipe_ready, 0));
+    for (int64_t i = 0; i < n_chunks; i++) {
+        const int b = (int)(i & 1);
+        cudaStream_t ks = b ? ctx->pipe_stream2 : ctx->stream;
+        const int64_t lo = chunks[i].first, cnt = chunks[i].second;
+        const size_t p_lo = (size_t)lo * ctx->n_params;
+        DDM_CUDA(ctx, cudaMemcpyAsync(ctx->params.p + p_lo, params_host + p_lo, (size_t)cnt * ctx->n_params * sizeof(double),
+                                      cudaMemcpyHostToDevice, ctx->copy_stream));
+        DDM_CUDA(ctx, cudaEventRecord(up.v[i], ctx->copy_stream));
+        DDM_CUDA(ctx, cudaStreamWaitEvent(ks, up.v[i], 0));
+        if (dconst) {
+            DDM_CUDA(ctx, ddm::launch_prep(ctx->params.p + p_lo, ctx->dconst.p + lo, (uint32_t)cnt, (uint32_t)ctx->n_params, model, dt, ks));
+            st.kernel_launches++;
+        }
+        ddm::RunArgs a = base;
+        if (b) a.work_counter = ctx->work_counter2;
+        a.params = ctx->params.p + p_lo;
+        a.dconst = dconst ? ctx->dconst.p + lo : nullptr;
+        a.n_datasets = (uint32_t)cnt;
+        a.dataset_offset = (uint32_t)(dataset_offset + (uint64_t)lo);
+        char *chunk_out = static_cast<char *>(ctx->out) + (size_t)lo * (size_t)n_trials * row_bytes;
+        a.out = chunk_out;
+        a.steps_out = nullptr;
+        rc = launch_sim(ctx, a, precision, st, ks);
+        if (rc) return rc;
+        DDM_CUDA(ctx, cudaEventRecord(kd.v[i], ks));
+        DDM_CUDA(ctx, cudaStreamWaitEvent(ctx->hist_stream, kd.v[i], 0));
+        DDM_CUDA(ctx, ddm::launch_rt_histogram(chunk_out, out64, (uint64_t)cnt * (uint64_t)n_trials, (uint32_t)cols, basic, (uint32_t)n_bins,
+                                               rt_max, ctx->hist.p, ctx->sm_count, ctx->hist_stream));
+        st.kernel_launches++;
+    }
+    // the histogram stream has waited for every kernel: join it back into the caller's stream
+    DDM_CUDA(ctx, cudaEventRecord(ctx->pipe_kernel_done[0], ctx->hist_stream));
+    DDM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pipe_kernel_done[0], 0));
+    DDM_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    DDM_CUDA(ctx, cudaMemcpyAsync(hist_host, ctx->hist.p, n_cells * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    DDM_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, ctx->counters, sizeof(unsigned long long) * (1 + ddm::STAT_COUNT),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    DDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stats = st;
+    ctx->stats_pending = true;
+    ctx->have_run = true;
+    ctx->out64 = out64;
+    ctx->out_bytes = (size_t)rows * row_bytes;
+    ctx->have_steps = false;
+    ctx->run_rows = rows;
+    ctx->run_datasets = n_datasets;
+    ctx->run_trials = n_trials;
+    ctx->run_trialwise = false;
+    ctx->run_cols = cols;
+    ctx->run_model = model;
+    ctx->out_resident = true;
+    return DDM_OK;
+}
+
 int finish_stats(ddm_ctx *ctx) {
     if (!ctx->stats_pending) return DDM_OK;
     DDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -834,6 +971,7 @@ DDM_API int ddm_destroy(ddm_ctx *ctx) {
         if (ctx->workers) ddm::host_workers_destroy(ctx->workers);
         if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
         if (ctx->pipe_stream2) cudaStreamDestroy(ctx->pipe_stream2);
+        if (ctx->hist_stream) cudaStreamDestroy(ctx->hist_stream);
         if (ctx->work_counter2) cudaFree(ctx->work_counter2);
         if (ctx->pipe_ready) cudaEventDestroy(ctx->pipe_ready);
         if (ctx->counters) cudaFree(ctx->counters);
@@ -1400,9 +1538,22 @@ DDM_API int ddm_simulate_histogram(ddm_ctx *ctx, int model, const double *params
     if (n_bins < 1 || n_bins > 8192 || !(rt_max > 0.0)) return fail(ctx, DDM_ERR_INVALID, "need 1 <= n_bins <= 8192 and rt_max > 0");
     if (model == DDM_MODEL_GENERAL || model == DDM_MODEL_TRIALWISE)
         return fail(ctx, DDM_ERR_INVALID, "ddm_simulate_histogram takes the two-column dataset-wise models");
+    const int run_flags = (flags | DDM_FLAG_OUT_F32) & ~DDM_FLAG_KEEP_STEPS;
+    // ddm_set_pipeline governs this path as it does ddm_simulate's: min_rows >= 0 replaces the threshold (a huge one
+    // switches the chunking off, 0 forces it), chunk_rows > 0 the smallest chunk
+    const int64_t stream_from = ctx->tune_pipeline_min_rows >= 0 ? ctx->tune_pipeline_min_rows : kHistStreamMinRows;
+    if (n_datasets > 0 && n_trials > 0 && n_datasets * n_trials >= stream_from && !ctx->dbg_on) {
+        int rc = upload_params_impl(ctx, model, params, n_datasets, n_params, false);
+        if (rc) return rc;
+        if (takes_persistent_kernel(ctx, model, precision, run_flags) && max_steps >= 0 && (uint32_t)max_steps <= ddm::TILE_MAX_STEPS) {
+            DeviceGuard g(ctx->device);
+            return run_histogram_streamed(ctx, params, n_trials, dt, max_steps, seed, dataset_offset, precision, run_flags, n_bins, rt_max,
+                                          hist_host);
+        }
+    }
     int rc = ddm_upload_params(ctx, model, params, n_datasets, n_params);
     if (rc) return rc;
-    rc = ddm_run(ctx, n_trials, dt, max_steps, seed, dataset_offset, precision, (flags | DDM_FLAG_OUT_F32) & ~DDM_FLAG_KEEP_STEPS);
+    rc = ddm_run(ctx, n_trials, dt, max_steps, seed, dataset_offset, precision, run_flags);
     if (rc) return rc;
     if (n_datasets * n_trials == 0) {
         std::memset(hist_host, 0, (2 * (size_t)n_bins + 2) * sizeof(uint64_t));
@@ -1524,6 +1675,17 @@ DDM_API int64_t ddm_pipeline_chunks(int64_t n_datasets, int64_t n_trials, int64_
     if (n_datasets < 0 || n_trials < 0) return DDM_ERR_INVALID;
     const auto chunks = pipeline_chunks(n_datasets, n_trials, chunk_rows);
     for (size_t i = 0; i < chunks.size() && (int64_t)i < capacity; i++) {
+        if (first) first[i] = chunks[i].first;
+        if (count) count[i] = chunks[i].second;
+    }
+    return (int64_t)chunks.size();
+}
+
+DDM_API int64_t ddm_histogram_chunks(int64_t n_datasets, int64_t n_trials, int64_t min_chunk_rows, int64_t *first, int64_t *count,
+                                     int64_t capacity) {
+    if (n_datasets < 0 || n_trials < 0) return -1;
+    const auto chunks = histogram_chunks(n_datasets, n_trials, min_chunk_rows);
+    for (int64_t i = 0; i < (int64_t)chunks.size() && i < capacity; i++) {
         if (first) first[i] = chunks[i].first;
         if (count) count[i] = chunks[i].second;
     }

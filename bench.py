@@ -335,6 +335,17 @@ def other_configs(sim, issue_peak, want_cpu=True) -> dict:
                  "call_ms": g_host, "call": "impute_dataset(subj_idx, pre_Pe, participant params) -> (19374, 2) float64 host array",
                  "device_resident_ms": g_dev, "device_call": "impute_dataset(..., device=True) -> torch tensor over the DLPack capsule",
                  "trials_per_s_device": 19374 / (g_dev * 1e-3), **kernel_fields(st)}
+    # where the call's time goes: the reference's own NumPy preprocessing (np.unique over the subject column, the Pe
+    # standardisation; imputation_from_stahl_not_scaled.py:59-105) against the library call that replaces its per-row loop
+    _, alphas4 = stahl.boundaries_from_pe(pe)
+    _, idx4 = np.unique(subj, return_inverse=True)
+    out["C4"]["simulate_call_ms"] = _median_ms(lambda: sim.simulate_trialwise(idx4, alphas4, pp), sim, 50)
+    out["C4"]["simulate_call"] = "ddm_simulate_trialwise(group (n,) i32, bound (n,) f64, params (89,4)) -> (n, 2) float64 host array"
+    t0 = time.perf_counter()
+    for _ in range(50):
+        stahl.boundaries_from_pe(pe)
+        np.unique(subj, return_inverse=True)
+    out["C4"]["host_numpy_preprocessing_ms"] = (time.perf_counter() - t0) / 50 * 1e3
     if orc is not None:
         _, alphas = stahl.boundaries_from_pe(pe)
         _, idx = np.unique(subj, return_inverse=True)
@@ -667,8 +678,13 @@ def main():
                "api": "basic_ddm_dc.batch_simulate_histogram(params (B,5) f64 host, n_trials) -> RT histogram by boundary (401 bins "
                       "of 10 ms x 2 + missing + overflow) as host arrays; one ddm_simulate_histogram call: H2D of the parameters, "
                       "prep + stepping kernel (float32 rows stay in HBM), histogram kernel, D2H of 804 counters -- C5 as SURVEY.md "
-                      "section 8d specifies it (outputs reduced on device)"}
-        launches += (st_h["kernel_launches"] + 1) * ke
+                      "section 8d specifies it (outputs reduced on device).  From 64 Mi trials on the call works through a few "
+                      "chunks of datasets (ddm_histogram_chunks: six at 1e9 trials) so that uploads and reductions run beside "
+                      "the neighbouring chunks' kernels; same resident rows, same histogram"}
+        # the chunked call counts its histogram launches itself; the single-launch form adds one
+        hist_call_launches = st_h["kernel_launches"] + (1 if st_h["kernel_launches"] <= 2 else 0)
+        e2e["launches_per_call"] = hist_call_launches
+        launches += hist_call_launches * ke
 
         # (2) the same batch delivered as host rows: float64 (what simulate_trials returns) and float32 (what the
         # reference's configurator turns it into at once, basic_ddm_dc.py:146), against the host's streaming-store rate

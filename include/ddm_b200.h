@@ -226,7 +226,11 @@ int ddm_last_output_histogram(ddm_ctx *ctx, int n_bins, double rt_max, uint64_t 
  * call takes host parameters, simulates the batch into resident float32 rows, reduces them on the device and
  * returns only the histogram of ddm_last_output_histogram (2 n_bins + 2 counters).  Replaces
  * [simulate_trials(p, n_trials) for p in params] followed by a histogram of the stacked rows; two-column
- * dataset-wise models only.  The rows stay resident afterwards (ddm_last_output_dlpack / ddm_download). */
+ * dataset-wise models only.  The rows stay resident afterwards (ddm_last_output_dlpack / ddm_download).  From 64 Mi
+ * trials on the batch is produced in a few chunks of datasets (ddm_histogram_chunks) -- each chunk's parameters cross
+ * PCIe while the previous chunk is simulated and its rows are reduced beside the next chunk's kernel -- into the same
+ * resident buffer and with the same results (ddm_set_pipeline's min_rows / chunk_rows govern the threshold and the
+ * smallest chunk here, too). */
 int ddm_simulate_histogram(ddm_ctx *ctx, int model, const double *params, int64_t n_datasets, int n_params,
                            int64_t n_trials, double dt, int max_steps, uint64_t seed, uint64_t dataset_offset,
                            int precision, int flags, int n_bins, double rt_max, uint64_t *hist_host);
@@ -261,6 +265,10 @@ int ddm_philox4x32(ddm_ctx *ctx, const uint32_t *ctr4, const uint32_t *key2, uin
  * (first dataset, datasets) pairs and returns the number of chunks.  chunk_rows as in ddm_set_pipeline. */
 int64_t ddm_pipeline_chunks(int64_t n_datasets, int64_t n_trials, int64_t chunk_rows, int64_t *first, int64_t *count,
                             int64_t capacity);
+/* The chunk schedule ddm_simulate_histogram uses from 64 Mi trials on (no GPU needed): a sixteenth of the batch, then
+ * half of what is left each time, no chunk below min_chunk_rows trials (<= 0: the default, 32 Mi). */
+int64_t ddm_histogram_chunks(int64_t n_datasets, int64_t n_trials, int64_t min_chunk_rows, int64_t *first, int64_t *count,
+                             int64_t capacity);
 /* The host half of ddm_set_host_decode on its own (no GPU needed): expands n_datasets * n_trials wire
  * records -- int32 (steps << 2 | choice + 1) when basic_columns, else {that, fp32 bits} pairs -- into
  * (rows, 2) float64 / float32 with n_threads threads.  tau = params[d * n_params + 3]. */

@@ -1019,6 +1019,40 @@ def test_simulate_histogram_is_the_histogram_of_the_rows(sim):
         sim.simulate_histogram(7, np.zeros((2, 24)), 10)
 
 
+@pytest.mark.parametrize("prior,basic", [("sweep", True), ("alpha", False)])
+def test_streamed_histogram_equals_one_launch(sim, prior, basic):
+    """From 64 Mi trials on ddm_simulate_histogram produces the batch in chunks of datasets (parameters of chunk i+1
+    uploaded, and rows of chunk i-1 reduced, beside chunk i's kernel).  Forced at a small size with small chunks, it
+    returns the histogram, the counters and the resident rows of the single-launch path, bit for bit."""
+    import torch
+
+    from bayesflow_nddms_b200 import basic_ddm_dc as m0
+    from bayesflow_nddms_b200 import priors
+    from bayesflow_nddms_b200 import single_trial_alpha_not_scaled as m1
+
+    mod = m0 if basic else m1
+    P = priors.draw_prior_batch(prior, 3000, np.random.default_rng(11))
+    kw = dict(dt=1e-3, max_steps=4000) if basic else dict(dt=0.01, max_steps=400)
+    try:
+        sim.set_pipeline(1 << 62, -1)                       # chunking off
+        h1 = mod.batch_simulate_histogram(P, 500, sim, seed=8, dataset_offset=77, n_bins=120, rt_max=3.0, **kw)
+        st1 = sim.last_stats()
+        rows1 = torch.from_dlpack(sim.last_output_dlpack()).cpu().numpy().copy()
+        sim.set_pipeline(0, 40_000)                         # forced, chunks of >= 80 datasets: 188, 1406, 703, ...
+        h2 = mod.batch_simulate_histogram(P, 500, sim, seed=8, dataset_offset=77, n_bins=120, rt_max=3.0, **kw)
+        st2 = sim.last_stats()
+        rows2 = torch.from_dlpack(sim.last_output_dlpack()).cpu().numpy().copy()
+    finally:
+        sim.set_pipeline(-1, -1)
+    assert st2["kernel_launches"] > st1["kernel_launches"] + 4     # it did run in chunks
+    for key in ("upper", "lower"):
+        assert np.array_equal(h1[key], h2[key]), key
+    assert h1["missing"] == h2["missing"] and h1["overflow"] == h2["overflow"]
+    for key in ("total_steps", "n_timeouts", "n_upper", "n_trials"):
+        assert st1[key] == st2[key], key
+    assert rows1.shape == rows2.shape and np.array_equal(rows1, rows2)
+
+
 @pytest.mark.parametrize("model,prior", [(0, "basic"), (1, "alpha")])
 def test_default_transfer_plan_at_a_million_trials(sim, model, prior):
     """Round 2 lowered the streaming thresholds to 1e6 trials (compact records for (rt, choice) rows, two plain chunks

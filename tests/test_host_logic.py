@@ -350,6 +350,37 @@ def test_simulator_counters_roll_over_multiples_of_2_32():
     assert seen == [1 << 32, (1 << 32) + 8]
 
 
+@pytest.mark.parametrize("n_datasets,n_trials", [(1_000_000, 1000), (70_000, 1000), (4_200, 1000), (7, 30_000_000), (3, 5), (0, 10),
+                                                 (100_003, 777)])
+@pytest.mark.parametrize("min_chunk_rows", [-1, 1, 50_000, 4 << 20])
+def test_streamed_histogram_chunk_schedule(n_datasets, n_trials, min_chunk_rows):
+    """include/ddm_b200.h: ddm_histogram_chunks -- every dataset exactly once, in order; a sixteenth of the batch first
+    (the GPU starts after a small upload), then half of what is left each time, no chunk below the minimum."""
+    import ctypes as C
+
+    from bayesflow_nddms_b200 import _capi
+
+    lib = _capi.load()
+    cap = 4096
+    first = (C.c_int64 * cap)()
+    count = (C.c_int64 * cap)()
+    n = lib.ddm_histogram_chunks(n_datasets, n_trials, min_chunk_rows, first, count, cap)
+    if n_datasets == 0:
+        assert n == 0
+        return
+    assert 1 <= n <= 64                                    # geometric: a handful of launches whatever the size
+    f, c = np.array(first[:n]), np.array(count[:n])
+    assert f[0] == 0 and np.all(c >= 1) and np.array_equal(f[1:], np.cumsum(c)[:-1]) and f[-1] + c[-1] == n_datasets
+    floor_rows = (32 << 20) if min_chunk_rows <= 0 else min_chunk_rows
+    floor = max(1, -(-floor_rows // n_trials))             # in datasets
+    assert np.all(c >= min(floor, n_datasets))
+    if n > 1:
+        assert c[0] == max(n_datasets // 16, floor)
+        left = n_datasets - f[1:]
+        assert np.all((c[1:] == np.maximum(left // 2, floor)) | (c[1:] == left))   # half of what is left, or the rest
+    assert lib.ddm_histogram_chunks(-1, 5, 0, None, None, 0) == -1
+
+
 @pytest.mark.parametrize("n_datasets,n_trials", [(1_000_000, 1000), (16_384, 1000), (4_200, 1000), (7, 3_000_000), (3, 5), (0, 10),
                                                  (100_003, 33)])
 @pytest.mark.parametrize("chunk_rows", [-1, -2, -3, 1, 257 * 7, 32 << 20])
