@@ -118,6 +118,8 @@ SIGNATURES = {
     "ddm_host_stream_peak": (C.c_int, [C.c_int, C.c_size_t, _dp]),
     "ddm_last_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
     "ddm_last_output_dlpack": (C.c_int, [_vp, C.POINTER(C.POINTER(DLManagedTensor))]),
+    "ddm_training_batch": (C.c_int, [_vp, C.c_int, C.c_int64, C.c_int64, C.c_double, C.c_int, C.c_uint64, C.c_uint64, C.c_int, _dp,
+                                     C.POINTER(C.POINTER(DLManagedTensor))]),
     "ddm_last_output_device_ptr": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_size_t)]),
     "ddm_set_normals_debug": (C.c_int, [_vp, _dp, C.c_size_t, C.POINTER(C.c_int64), C.c_int64]),
     "ddm_export_normals": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,

@@ -91,6 +91,10 @@ class ModelAPI:
         ``device_prior=True`` draws the parameters on the GPU too (``ddm_draw_prior``): prior and
         simulation are two launches and the parameters never cross PCIe on their way in."""
         n = int(prior_N())
+        if device_prior and device:  # the whole batch in one call: one FFI crossing, one stream synchronisation
+            prior_draws, data = self.sim(simulator).training_batch(self.prior_name, batch_size, n, self.dt, int(self.max_steps),
+                                                                   flags=self.flags | _capi.FLAG_OUT_F32)
+            return {'prior_draws': prior_draws, 'sim_data': data, 'sim_non_batchable_context': n}
         if device_prior:
             sim = self.sim(simulator)
             prior_draws = sim.draw_prior(self.prior_name, batch_size)

@@ -211,6 +211,8 @@ struct ddm_ctx {
     size_t wire_cap[3] = {0, 0, 0};
     ddm::HostWorkers *workers = nullptr;
     int tune_host_decode = 0;  // 0 automatic thread count, > 0 that many threads, < 0 plain 16-byte rows over PCIe
+    double *train_stage = nullptr;  // pinned: ddm_training_batch's prior draws on their way to the caller's array
+    size_t train_stage_cap = 0;
     cudaStream_t hist_stream = nullptr;  // streamed ddm_simulate_histogram: each chunk's reduction runs beside the next chunk's kernel
 
     // tuning (0 = automatic)
@@ -972,6 +974,7 @@ DDM_API int ddm_destroy(ddm_ctx *ctx) {
         if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
         if (ctx->pipe_stream2) cudaStreamDestroy(ctx->pipe_stream2);
         if (ctx->hist_stream) cudaStreamDestroy(ctx->hist_stream);
+        if (ctx->train_stage) cudaFreeHost(ctx->train_stage);
         if (ctx->work_counter2) cudaFree(ctx->work_counter2);
         if (ctx->pipe_ready) cudaEventDestroy(ctx->pipe_ready);
         if (ctx->counters) cudaFree(ctx->counters);
@@ -1607,6 +1610,38 @@ DDM_API int ddm_last_output_dlpack(ddm_ctx *ctx, struct DLManagedTensor **out) {
     ctx->out = nullptr;  // ownership moved to the consumer
     ctx->out_cap = 0;
     *out = &h->t;
+    return DDM_OK;
+}
+
+// One online-training batch in one call: what bf.simulation.GenerativeModel(prior, simulator)(batch_size) produces
+// (basic_ddm_dc.py:129-133, single_trial_alpha_not_scaled.py:270-274) -- prior draws on the device, simulated where they
+// are, the draws copied out for the trainer's targets, the batch handed over as DLPack -- with everything enqueued
+// before the one stream synchronisation (the three-call sequence ddm_draw_prior / ddm_run / ddm_last_output_dlpack
+// waits for the GPU twice and crosses the FFI three times; at 64 x 500 trials that is a third of the batch's latency).
+DDM_API int ddm_training_batch(ddm_ctx *ctx, int prior, int64_t n_draws, int64_t n_trials, double dt, int max_steps, uint64_t seed,
+                               uint64_t draw_offset, int flags, double *params_host, struct DLManagedTensor **out) {
+    if (!ctx || !out) return DDM_ERR_INVALID;
+    if (prior == DDM_PRIOR_EVIDENCE) return fail(ctx, DDM_ERR_INVALID, "ddm_training_batch takes the dataset-wise models' priors");
+    if (n_draws <= 0 || n_trials <= 0) return fail(ctx, DDM_ERR_INVALID, "ddm_training_batch needs n_draws >= 1 and n_trials >= 1");
+    int rc = ddm_draw_prior(ctx, prior, n_draws, seed, draw_offset, nullptr);
+    if (rc) return rc;
+    rc = ddm_run(ctx, n_trials, dt, max_steps, seed, draw_offset, 32, flags);
+    if (rc) return rc;
+    const size_t n = (size_t)n_draws * (size_t)ctx->n_params;
+    if (params_host) {
+        DeviceGuard g(ctx->device);
+        if (ctx->train_stage_cap < n) {
+            if (ctx->train_stage) cudaFreeHost(ctx->train_stage);
+            ctx->train_stage = nullptr;
+            ctx->train_stage_cap = 0;
+            DDM_CUDA(ctx, cudaHostAlloc(&ctx->train_stage, n * sizeof(double), cudaHostAllocDefault));
+            ctx->train_stage_cap = n;
+        }
+        DDM_CUDA(ctx, cudaMemcpyAsync(ctx->train_stage, ctx->params.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    rc = ddm_last_output_dlpack(ctx, out);  // synchronises the stream
+    if (rc) return rc;
+    if (params_host) std::memcpy(params_host, ctx->train_stage, n * sizeof(double));
     return DDM_OK;
 }
 

@@ -238,6 +238,23 @@ class DDMSimulator:
                                       self.seed if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF, off,
                                       int(precision), int(flags)))
 
+    def training_batch(self, prior: str, n_draws: int, n_trials: int, dt: float = 0.01, max_steps: int = 400, *, seed=None,
+                       draw_offset=None, flags: int = _capi.FLAG_OUT_F32, to_host: bool = True):
+        """One online-training batch in one call (``ddm_training_batch``): device prior -> simulation on the resident
+        draws -> DLPack hand-off, with the (n_draws, P) draws copied out for the trainer's targets.  Returns
+        ``(prior_draws, DeviceBatch)``; the same bits as ``draw_prior`` + ``run_uploaded`` + ``last_output_dlpack``."""
+        pid, cols = _capi.PRIORS[prior]
+        off = self._next_offset(n_draws, draw_offset)
+        draws = np.empty((int(n_draws), cols), dtype=np.float64) if to_host else None
+        m = C.POINTER(_capi.DLManagedTensor)()
+        self._check(self._lib.ddm_training_batch(
+            self._ctx, pid, int(n_draws), int(n_trials), float(dt), int(max_steps),
+            self.seed if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF, off, int(flags),
+            draws.ctypes.data_as(_capi._dp) if to_host else None, C.byref(m)))
+        self._prior_offset = off
+        t = m.contents.dl_tensor
+        return draws, DeviceBatch(m, [t.shape[i] for i in range(t.ndim)], t.dtype.bits, t.device.device_id)
+
     def run(self, model: int, params, n_trials: int, dt: float = 0.01, max_steps: int = 400, *, seed=None,
             dataset_offset=None, precision: int = 32, flags: int = 0):
         """Upload (B, P) parameters and launch; results stay on the device."""

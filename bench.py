@@ -793,15 +793,24 @@ def main():
             for _ in range(5):                                                    # five blocks of 40 batches: the median block
                 t0 = time.perf_counter()
                 for _ in range(reps // 5):
+                    pd, batch = sim.training_batch("basic", B2, N2, 0.01, 400)    # device prior, simulate, (64,5) draws out, hand-off
+                    del batch
+                blocks.append((time.perf_counter() - t0) / (reps // 5))
+            lat = float(np.median(blocks))
+            blocks3 = []
+            for _ in range(5):                                                    # the same batch through the three separate calls
+                t0 = time.perf_counter()
+                for _ in range(reps // 5):
                     pd = sim.draw_prior("basic", B2)                              # device prior + (64,5) copy out
                     sim.run_uploaded(N2, 0.01, 400, flags=capi.FLAG_OUT_F32)      # simulate on the resident draws
                     batch = sim.last_output_dlpack()                              # hand-off (syncs the stream)
                     del batch
-                blocks.append((time.perf_counter() - t0) / (reps // 5))
-            lat = float(np.median(blocks))
+                blocks3.append((time.perf_counter() - t0) / (reps // 5))
             training_batch = {"workload": "C2 basic_ddm_dc online-training batch: 64 datasets x 500 trials, dt=.01, max_steps=400",
-                              "path": "ddm_draw_prior -> ddm_run -> ddm_last_output_dlpack (device-resident f32 batch)",
+                              "path": "ddm_training_batch: device prior -> simulate -> draws to the host + DLPack hand-off of the "
+                                      "device-resident f32 batch, one call and one stream synchronisation",
                               "ms_per_batch": lat * 1e3, "ms_per_batch_blocks_of_40": [b * 1e3 for b in blocks],
+                              "ms_per_batch_three_calls": float(np.median(blocks3)) * 1e3,
                               "trials_per_s": B2 * N2 / lat, "launches_per_batch": 3}
             if not args.no_cpu_baseline and world == 1:
                 from oracle import cpu as orc

@@ -215,6 +215,14 @@ int ddm_simulate_exact(ddm_ctx *ctx, const double *params, int64_t n_datasets, i
 /* Per-trial Euler-step counts of the last run (needs DDM_FLAG_KEEP_STEPS). */
 int ddm_last_steps(ddm_ctx *ctx, int32_t *steps_host);
 int ddm_last_stats(ddm_ctx *ctx, ddm_stats *out);
+/* One online-training batch in one call -- replaces bf.simulation.GenerativeModel(prior, simulator)(batch_size)
+ * (basic_ddm_dc.py:129-133; single_trial_alpha_not_scaled.py:270-274): ddm_draw_prior on the device (draws keyed by
+ * draw_offset ..), ddm_run on the resident draws (datasets keyed by the same indices; precision 32, `flags` as in
+ * ddm_run), the (n_draws, P) draws copied to params_host (may be NULL), the batch handed over like
+ * ddm_last_output_dlpack.  Same bits as the three calls; one stream synchronisation instead of two. */
+int ddm_training_batch(ddm_ctx *ctx, int prior, int64_t n_draws, int64_t n_trials, double dt, int max_steps, uint64_t seed,
+                       uint64_t draw_offset, int flags, double *params_host, struct DLManagedTensor **out);
+
 /* Response-time histogram of the last run's resident output, reduced on the device (no row leaves HBM):
  * hist_host[0 .. n_bins) counts upper-boundary responses with |rt| in [k, k+1) * rt_max / n_bins,
  * hist_host[n_bins .. 2 n_bins) the lower-boundary ones, hist_host[2 n_bins] trials without a response

@@ -91,3 +91,32 @@ def test_generative_model_with_device_prior(sim):
     t = torch.from_dlpack(dd['sim_data'])
     assert t.is_cuda and tuple(t.shape) == (16, dd['sim_non_batchable_context'], 2) and dd['prior_draws'].shape == (16, 7)
     assert torch.isfinite(t).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prior,cols", [("basic", 5), ("alpha", 7), ("eta", 6)])
+def test_training_batch_is_the_three_calls(sim, prior, cols):
+    """ddm_training_batch (one FFI crossing, one stream synchronisation) returns the draws and the batch of
+    ddm_draw_prior + ddm_run + ddm_last_output_dlpack, bit for bit, and advances the dataset counter like them."""
+    import torch
+
+    from bayesflow_nddms_b200 import _capi
+
+    sim.dataset_counter = 9000
+    draws, batch = sim.training_batch(prior, 48, 333, 0.01, 400)
+    t = torch.from_dlpack(batch).cpu().numpy()
+    assert draws.shape == (48, cols) and t.shape == (48, 333, 2) and t.dtype == np.float32 and sim.dataset_counter == 9048
+    sim.dataset_counter = 9000
+    draws3 = sim.draw_prior(prior, 48)
+    sim.run_uploaded(333, 0.01, 400, flags=_capi.FLAG_OUT_F32)
+    t3 = torch.from_dlpack(sim.last_output_dlpack()).cpu().numpy()
+    assert np.array_equal(draws, draws3) and np.array_equal(t, t3)
+    # the batch is the simulation of exactly these draws
+    again = sim.simulate(_capi.PRIORS[prior][0] if prior != "basic" else 0, draws, 333, dataset_offset=9000, flags=_capi.FLAG_OUT_F32)
+    assert np.array_equal(again, t)
+    # no host copy of the draws
+    sim.dataset_counter = 9000
+    none, batch = sim.training_batch(prior, 48, 333, 0.01, 400, to_host=False)
+    assert none is None and np.array_equal(torch.from_dlpack(batch).cpu().numpy(), t)
+    with pytest.raises(ValueError):
+        sim.training_batch("evidence", 4, 10)
