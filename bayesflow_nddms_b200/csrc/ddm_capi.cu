@@ -217,7 +217,9 @@ struct ddm_ctx {
 
     // tuning (0 = automatic)
     int tune_threshold = 0, tune_blocks_per_sm = 0, tune_tile = 0;
-    int tune_kernel_variant = -1;  // -1 / 0 = tile kernel (production), 1 = round-1 persistent kernel (A/B measurements)
+    // -1 = automatic (tile kernel; latency kernel for launches of at most kLatencyMaxRows trials), 0 = tile kernel,
+    // 1 = round-1 persistent kernel (A/B measurements), 2 = latency kernel at any size
+    int tune_kernel_variant = -1;
     bool trialwise_degenerate = false;  // last trialwise call: some group has dc == 0 (no noise unit)
     int64_t tune_pipeline_min_rows = -1, tune_pipeline_chunk_rows = -1;  // < 0: default
 };
@@ -368,6 +370,7 @@ bool uses_dconst(const ddm_ctx *ctx, int model, int precision) {
 
 // Enqueue the simulator kernel for the datasets described by `a` (pointers already offset to the
 // range) on the ctx stream.  The stats counters accumulate; only the work counter is reset.
+constexpr int64_t kLatencyMaxRows = 256 << 10;  // it leads up to here for every model, scripts/r02_latency_probe.py
 int launch_sim(ddm_ctx *ctx, ddm::RunArgs &a, int precision, ddm_stats &st, cudaStream_t stream = nullptr) {
     if (!stream) stream = ctx->stream;
     const int model = a.model, flags = a.flags;
@@ -382,6 +385,20 @@ int launch_sim(ddm_ctx *ctx, ddm::RunArgs &a, int precision, ddm_stats &st, cuda
     if (degenerate) a.flags |= ddm::FLAG_REFERENCE_ARITHMETIC;
     const bool persistent = precision == 32 && !ctx->dbg_on && !degenerate &&
                             !(flags & (DDM_FLAG_FORCE_GENERIC | DDM_FLAG_OUT_STATE)) && (uint32_t)a.max_steps <= ddm::TILE_MAX_STEPS;
+    // Small launches -- one trial per lane or fewer, nothing to refill: the reference's own batch sizes -- last as long as
+    // their longest trial's dependent chain; the latency kernel (speculative six-step blocks, one thread per trial) is
+    // built for that (scripts/r02_latency_probe.py).  Same bits as the persistent kernels.
+    const bool latency = persistent && kind != ddm::KIND_GENERAL && !(a.flags & ddm::FLAG_WIRE_COMPACT) &&
+                         (ctx->tune_kernel_variant == 2 || (ctx->tune_kernel_variant == -1 && rows <= kLatencyMaxRows));
+    if (latency) {
+        DDM_CUDA(ctx, ddm::launch_latency(a, kind, out64, (uint64_t)rows, stream));
+        st.used_persistent = 1;  // a production kernel, not the validation twin
+        st.scheduler = 3;
+        st.grid = (int)(((uint64_t)rows + 127) / 128);
+        st.block = 128;
+        st.kernel_launches++;
+        return DDM_OK;
+    }
     DDM_CUDA(ctx, cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), stream));
     if (persistent) {
         const int block = ddm::persistent_block_size();
@@ -1016,8 +1033,9 @@ DDM_API int ddm_set_tuning(ddm_ctx *ctx, int refill_threshold, int blocks_per_sm
 
 DDM_API int ddm_set_kernel_variant(ddm_ctx *ctx, int variant) {
     if (!ctx) return DDM_ERR_INVALID;
-    if (variant < -1 || variant > 1)
-        return fail(ctx, DDM_ERR_INVALID, "kernel variant must be -1 (automatic), 0 (tile kernel) or 1 (round-1 persistent kernel)");
+    if (variant < -1 || variant > 2)
+        return fail(ctx, DDM_ERR_INVALID,
+                    "kernel variant must be -1 (automatic), 0 (tile kernel), 1 (round-1 persistent kernel) or 2 (latency kernel)");
     ctx->tune_kernel_variant = variant;
     return DDM_OK;
 }

@@ -839,6 +839,109 @@ __global__ void __launch_bounds__(128) generic_kernel(const RunArgs a, uint64_t 
 }
 
 // --------------------------------------------------------------------------------
+// latency kernel: small launches (one trial per lane or fewer -- the reference's own batch sizes: 1 x 300, 64 x 500,
+// 19 374 Stahl trials).  With nothing to refill, a launch lasts as long as its longest trial's chain of dependent
+// instructions, so this kernel is written for the chain and not for the issue slots: one thread per trial, and a
+// six-step block is SPECULATIVE -- the six states x1..x6 are a bare chain of six FADDs, the six boundary tests are
+// independent of one another, and the step at which the trial stops (and its state there) is selected afterwards --
+// instead of the production loop's predicated chain  FADD -> FSETP -> @p FADD -> ...  whose every step waits for the
+// previous step's predicate.  The next block's Philox rounds and Box-Muller pairs do not depend on the state at all and
+// run under the current block's steps (two blocks per iteration).  Same Philox counters, same set-up, same fp32
+// operations on the states that are kept: results are bit-identical to the tile kernel's (tests).  Lanes run whole
+// blocks and the count is clamped at the end, exactly like the tile kernel.
+// --------------------------------------------------------------------------------
+__device__ __forceinline__ void spec_block(float &x, uint32_t &n, bool &alive, float c0, float h, const Normals6Scaled &z) {
+    const float x1 = __fadd_rn(x, __fmaf_rn(z.s[0], z.c[0], c0));
+    const float x2 = __fadd_rn(x1, __fmaf_rn(z.s[0], z.sn[0], c0));
+    const float x3 = __fadd_rn(x2, __fmaf_rn(z.s[1], z.c[1], c0));
+    const float x4 = __fadd_rn(x3, __fmaf_rn(z.s[1], z.sn[1], c0));
+    const float x5 = __fadd_rn(x4, __fmaf_rn(z.s[2], z.c[2], c0));
+    const float x6 = __fadd_rn(x5, __fmaf_rn(z.s[2], z.sn[2], c0));
+    const bool i1 = fabsf(x1) < h, i2 = fabsf(x2) < h, i3 = fabsf(x3) < h, i4 = fabsf(x4) < h, i5 = fabsf(x5) < h,
+               i6 = fabsf(x6) < h;
+    // steps taken = 1 + the number of leading "still inside" tests among the first five; the state is the one after the last step taken
+    const bool a2 = i1 && i2, a3 = a2 && i3, a4 = a3 && i4, a5 = a4 && i5;
+    const uint32_t k = 1u + (i1 ? 1u : 0u) + (a2 ? 1u : 0u) + (a3 ? 1u : 0u) + (a4 ? 1u : 0u) + (a5 ? 1u : 0u);
+    const float xs = a5 ? x6 : (a4 ? x5 : (a3 ? x4 : (a2 ? x3 : (i1 ? x2 : x1))));
+    if (alive) {
+        x = xs;
+        n += k;
+        alive = a5 && i6;
+    }
+}
+
+template <int KIND, bool OUT64>
+__global__ void __launch_bounds__(128) latency_kernel(const RunArgs a, uint64_t total) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long acc_steps = 0;
+    uint32_t tout = 0, upper = 0, cap = 0;
+    if (g < total) {
+        uint32_t ds, trial;
+        if (KIND == KIND_TRIALWISE) {
+            ds = 0;
+            trial = (uint32_t)g;
+        } else {
+            ds = (uint32_t)(g / a.n_trials);
+            trial = (uint32_t)(g - (uint64_t)ds * a.n_trials);
+        }
+        const uint32_t ds_g = ds + a.dataset_offset, trial_g = trial + a.trial_offset;
+        const double *prm = (KIND == KIND_TRIALWISE) ? a.params + (size_t)a.group[g] * 4 : a.params + (size_t)ds * a.n_params;
+        const double tau = (KIND == KIND_TRIALWISE) ? prm[2] : prm[3];
+        TrialF32 t;
+        if (KIND == KIND_TRIALWISE) {
+            trial_setup_trialwise(a.dconst[a.group[g]], (float)a.bound_in[g], t);
+        } else {
+            const DsConst dc = a.dconst[ds];
+            trial_setup_f32<(KIND == KIND_TRIALWISE ? KIND_FIXED : KIND)>(dc, trial_g, ds_g, a.key, t, cap);
+        }
+        float x = t.x;
+        uint32_t n = 0;
+        bool alive = (fabsf(x) < t.h) && (a.max_steps > 0u);
+        // software-pipelined: the normals of blocks b+2, b+3 are drawn while blocks b, b+1 step (they depend on the
+        // block index alone), so an iteration lasts max(generator chain, step chain) instead of their sum
+        Normals6Scaled z0, z1;
+        if (alive) {
+            philox_pairs_lg2(0u, trial_g, ds_g, STREAM_STEP, a.key, z0);
+            philox_pairs_lg2(1u, trial_g, ds_g, STREAM_STEP, a.key, z1);
+        }
+        for (uint32_t blk = 2u; alive; blk += 2u) {
+            Normals6Scaled y0, y1;
+            philox_pairs_lg2(blk, trial_g, ds_g, STREAM_STEP, a.key, y0);
+            philox_pairs_lg2(blk + 1u, trial_g, ds_g, STREAM_STEP, a.key, y1);
+            spec_block(x, n, alive, t.c0, t.h, z0);
+            alive = alive && (n < a.max_steps);
+            spec_block(x, n, alive, t.c0, t.h, z1);
+            alive = alive && (n < a.max_steps);
+            z0 = y0;
+            z1 = y1;
+        }
+        int choice = (x >= t.h) ? 1 : ((x <= -t.h) ? -1 : 0);
+        if (n > a.max_steps) { n = a.max_steps; choice = 0; }  // whole blocks: a trial inside the boundaries after max_steps steps timed out
+        const double ext = (KIND == KIND_TRIALWISE) ? a.bound_in[g] : (double)t.ext;
+        double o0, o1;
+        trial_outputs<(KIND == KIND_FIXED || KIND == KIND_DRIFT)>(a.flags, choice, n, a.dt, tau, ext, o0, o1);
+        store_pair<OUT64>(a.out, g, o0, o1);
+        if (a.steps_out) a.steps_out[g] = (int32_t)n;
+        acc_steps = n;
+        tout = (choice == 0);
+        upper = (choice > 0);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc_steps += __shfl_xor_sync(FULL_MASK, acc_steps, o);
+        tout += __shfl_xor_sync(FULL_MASK, tout, o);
+        upper += __shfl_xor_sync(FULL_MASK, upper, o);
+        cap += __shfl_xor_sync(FULL_MASK, cap, o);
+    }
+    if ((threadIdx.x & 31u) == 0u) {
+        atomicAdd(a.stats + STAT_STEPS, acc_steps);
+        if (tout) atomicAdd(a.stats + STAT_TIMEOUTS, (unsigned long long)tout);
+        if (upper) atomicAdd(a.stats + STAT_UPPER, (unsigned long long)upper);
+        if (cap) atomicAdd(a.stats + STAT_REJECT_CAP, (unsigned long long)cap);
+    }
+}
+
+// --------------------------------------------------------------------------------
 // general (two-latent, two-channel) model, one thread per trial: validation twin of
 // persistent_kernel<KIND_GENERAL>
 // --------------------------------------------------------------------------------
@@ -1116,6 +1219,26 @@ static cudaError_t launch_generic_1(const RunArgs &a, int kind, bool buffer_src,
     case KIND_DC: return launch_generic_2<Real, KIND_DC>(a, buffer_src, out64, total, s);
     case KIND_TRIALWISE: return launch_generic_2<Real, KIND_TRIALWISE>(a, buffer_src, out64, total, s);
     case KIND_DRIFT: return launch_generic_2<Real, KIND_DRIFT>(a, buffer_src, out64, total, s);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+template <int KIND>
+static cudaError_t launch_latency_kind(const RunArgs &a, bool out64, uint64_t total, cudaStream_t s) {
+    const unsigned grid = (unsigned)((total + 127) / 128);
+    if (grid == 0) return cudaSuccess;
+    if (out64) latency_kernel<KIND, true><<<grid, 128, 0, s>>>(a, total);
+    else latency_kernel<KIND, false><<<grid, 128, 0, s>>>(a, total);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_latency(const RunArgs &a, int kind, bool out64, uint64_t total_trials, cudaStream_t s) {
+    switch (kind) {
+    case KIND_FIXED: return launch_latency_kind<KIND_FIXED>(a, out64, total_trials, s);
+    case KIND_BOUND: return launch_latency_kind<KIND_BOUND>(a, out64, total_trials, s);
+    case KIND_DC: return launch_latency_kind<KIND_DC>(a, out64, total_trials, s);
+    case KIND_TRIALWISE: return launch_latency_kind<KIND_TRIALWISE>(a, out64, total_trials, s);
+    case KIND_DRIFT: return launch_latency_kind<KIND_DRIFT>(a, out64, total_trials, s);
     default: return cudaErrorInvalidValue;
     }
 }

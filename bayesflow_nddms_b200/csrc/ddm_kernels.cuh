@@ -390,6 +390,8 @@ cudaError_t launch_record(const RunArgs &a, int grid, int block, cudaStream_t s)
 int record_max_blocks_per_sm(int block);
 int record_block_size();
 cudaError_t launch_prep_general(const double *params, GenConst *gconst, uint32_t n_datasets, double dt, cudaStream_t s);
+// small launches (every kind but KIND_GENERAL): one thread per trial, speculative six-step blocks
+cudaError_t launch_latency(const RunArgs &a, int kind, bool out64, uint64_t total_trials, cudaStream_t s);
 cudaError_t launch_generic(const RunArgs &a, int kind, bool f64, bool buffer_src, bool out64,
                            uint64_t total_trials, cudaStream_t s);
 cudaError_t launch_export_normals(PhiloxKey key, uint32_t dataset, uint32_t trial, uint32_t stream,

@@ -159,8 +159,9 @@ class DDMSimulator:
         self._check(self._lib.ddm_set_tuning(self._ctx, refill_threshold, blocks_per_sm, tile))
 
     def set_kernel_variant(self, variant: int = -1):
-        """-1 / 0 (default): the tile-staged persistent kernel; 1: the round-1 persistent kernel.  Bit-identical
-        results (A/B measurements, tests)."""
+        """-1 (default): the tile-staged persistent kernel, and the latency kernel (one thread per trial, speculative
+        six-step blocks) for launches of at most 256 Ki trials; 0: the tile kernel at any size; 1: the round-1
+        persistent kernel; 2: the latency kernel at any size.  Bit-identical results (A/B measurements, tests)."""
         self._check(self._lib.ddm_set_kernel_variant(self._ctx, int(variant)))
 
     def set_stream(self, cuda_stream_ptr: int | None):

@@ -68,7 +68,7 @@ def parse_args():
     ap.add_argument("--microbench", action="store_true", help="also measure per-pipe issue rates")
     ap.add_argument("--no-configs", action="store_true", help="skip the C1/C3/C4/fp64 legs")
     ap.add_argument("--no-host-rows", action="store_true", help="skip the host-row legs of the end-to-end section")
-    ap.add_argument("--kernel-variant", type=int, default=-1, help="-1 automatic (default), 0 tile kernel, 1 the round-1 persistent kernel")
+    ap.add_argument("--kernel-variant", type=int, default=-1, help="-1 automatic (default: latency kernel up to 256 Ki trials, tile kernel above), 0 tile kernel, 1 the round-1 persistent kernel, 2 latency kernel")
     return ap.parse_args()
 
 
@@ -263,7 +263,7 @@ def other_configs(sim, issue_peak, want_cpu=True) -> dict:
     def kernel_fields(st):
         k_s = st["kernel_ms"] * 1e-3
         d = {"kernel_ms": st["kernel_ms"], "euler_steps": st["total_steps"],
-             "scheduler": {1: "round-1 persistent kernel", 2: "tile kernel"}.get(st["scheduler"], "generic")}
+             "scheduler": {1: "round-1 persistent kernel", 2: "tile kernel", 3: "latency kernel"}.get(st["scheduler"], "generic")}
         if k_s > 0:
             d["kernel_steps_per_s"] = st["total_steps"] / k_s
             d["kernel_roofline_frac"] = st["total_steps"] * I_STEP / 32.0 / k_s / issue_peak
@@ -833,7 +833,7 @@ def main():
         "mean_steps_per_trial": steps_per_step / trials_per_step,
         "timeout_frac": sum_over_ranks(float(st["n_timeouts"])) / trials_per_step,
         "kernel": {"grid": st["grid"], "block": st["block"], "refill_threshold": st["refill_threshold"], "tile": st["tile"],
-                   "persistent": bool(st["used_persistent"]), "scheduler": {1: "round-1 persistent kernel", 2: "tile kernel"}.get(st["scheduler"], "generic")},
+                   "persistent": bool(st["used_persistent"]), "scheduler": {1: "round-1 persistent kernel", 2: "tile kernel", 3: "latency kernel"}.get(st["scheduler"], "generic")},
         "clocks": clk, "roofline": roofline, "gpu_launches": launches,
     }
     line["device_reduction"] = reduction

@@ -109,12 +109,13 @@ typedef struct ddm_stats {
     uint64_t reject_cap_hits;/* per-trial redraw loops that hit the iteration cap */
     double kernel_ms;        /* CUDA-event time of the simulator kernel(s), launching stream */
     int32_t kernel_launches; /* kernels of this library launched by the last run */
-    int32_t used_persistent; /* 1 if the persistent refill kernel ran, 0 if generic */
+    int32_t used_persistent; /* 1 if a production fp32 kernel ran (scheduler 1-3), 0 if the generic / validation kernel */
     int32_t grid, block, refill_threshold, tile;
     uint64_t debug_overruns; /* shared-increment mode: trials that ran past the normals buffer */
     uint64_t d2h_bytes;      /* output bytes the run copied device -> host itself (0: batch left resident) */
     int32_t host_decode_threads; /* > 0: compact wire records were expanded by that many host threads */
-    int32_t scheduler;       /* 0 one thread per trial (generic / validation), 1 round-1 persistent kernel, 2 tile kernel */
+    int32_t scheduler;       /* 0 one thread per trial (generic / validation), 1 round-1 persistent kernel, 2 tile kernel,
+                              * 3 latency kernel (small launches) */
 } ddm_stats;
 
 /* ---- lifecycle -------------------------------------------------------- */
@@ -129,10 +130,12 @@ int ddm_set_stream(ddm_ctx *ctx, void *cuda_stream); /* NULL restores the ctx-ow
 int ddm_synchronize(ddm_ctx *ctx);
 /* tuning knobs; 0 = automatic */
 int ddm_set_tuning(ddm_ctx *ctx, int refill_threshold, int blocks_per_sm, int tile);
-/* Scheduler of the production (precision 32) path: 0 (and -1, the default) the tile-staged persistent kernel (set-up and
- * emission a tile at a time through shared memory, finished lanes refilled inside the stepping loop), 1 the round-1
- * persistent kernel (per-lane set-up and emission inside a refill pass), kept for A/B measurements.  Results are
- * bit-identical. */
+/* Scheduler of the production (precision 32) path: 0 the tile-staged persistent kernel (set-up and emission a tile at a
+ * time through shared memory, finished lanes refilled inside the stepping loop); 1 the round-1 persistent kernel
+ * (per-lane set-up and emission inside a refill pass), kept for A/B measurements; 2 the latency kernel (one thread per
+ * trial, speculative six-step blocks with the next blocks' normals drawn under them: a launch with nothing to refill
+ * lasts as long as its longest trial's dependent chain); -1, the default: the latency kernel for launches of at most
+ * 256 Ki trials -- the reference's own batch sizes -- and the tile kernel above that.  Results are bit-identical. */
 int ddm_set_kernel_variant(ddm_ctx *ctx, int variant);
 /* ddm_simulate with a host destination streams batches of at least min_rows trials to the host in
  * chunks of about chunk_rows trials, overlapping kernel and PCIe copy (defaults: min_rows 8 Mi trials, 10^6 into a

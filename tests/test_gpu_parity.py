@@ -890,9 +890,67 @@ def test_tile_kernel_equals_round1_persistent_kernel(sim, model):
             sim.set_tuning(2, 1, 16)   # few warps, small tiles: most tiles are recycled with trials still running
             f32 = sim.simulate(model, params, 307, seed=9, dataset_offset=3, flags=F_F32, **kw)
             assert np.array_equal(f32, ref.astype(np.float32))
+            # the latency kernel (small launches' default: one thread per trial, speculative six-step blocks)
+            for variant in (2, -1):
+                sim.set_kernel_variant(variant)
+                sim.set_tuning(0, 0, 0)
+                out = sim.simulate(model, params, 307, seed=9, dataset_offset=3, flags=F_STEPS, **kw)
+                steps, st = sim.last_steps(53 * 307), sim.last_stats()
+                assert st["used_persistent"] == 1 and st["scheduler"] == 3, variant
+                assert np.array_equal(out.view(np.uint64), ref.view(np.uint64)), (kw, variant)
+                assert np.array_equal(steps, ref_steps)
+                for k in ("total_steps", "n_timeouts", "n_upper", "reject_cap_hits", "n_trials"):
+                    assert st[k] == ref_st[k], (k, variant)
+                f32 = sim.simulate(model, params, 307, seed=9, dataset_offset=3, flags=F_F32, **kw)
+                assert np.array_equal(f32, ref.astype(np.float32))
     finally:
         sim.set_kernel_variant(-1)
         sim.set_tuning(0, 0, 0)
+
+
+def test_latency_kernel_edges_and_routing(sim):
+    """The latency kernel against the tile kernel where the block structure shows: max_steps that is not a multiple of
+    six (and of twelve: two blocks per iteration), 0, 1 and 5; trials that start on a boundary; the trialwise (Stahl)
+    model; and the automatic choice -- launches of at most 256 Ki trials take it, larger ones the tile kernel."""
+    from bayesflow_nddms_b200 import priors
+    from bayesflow_nddms_b200.imputation_from_stahl_not_scaled import synthetic_stahl_like, boundaries_from_pe, draw_participant_params
+
+    P = priors.draw_prior_batch("sweep", 40, np.random.default_rng(77))
+    P[0, 2] = 0.0            # starts on the lower boundary: no step
+    P[1, 2] = 1.0            # ... on the upper one
+    P[2, 1] = 1e-3           # a tiny boundary: crosses at the first step
+    try:
+        for ms in (0, 1, 5, 6, 7, 11, 12, 13, 400, 401, 407):
+            res = {}
+            for variant in (0, 2):
+                sim.set_kernel_variant(variant)
+                out = sim.simulate(0, P, 211, dt=0.01, max_steps=ms, seed=3, dataset_offset=5, flags=F_STEPS)
+                res[variant] = (out.copy(), sim.last_steps(40 * 211).copy(), sim.last_stats())
+            assert res[0][2]["scheduler"] == 2 and res[2][2]["scheduler"] == 3
+            assert np.array_equal(res[0][0].view(np.uint64), res[2][0].view(np.uint64)), ms
+            assert np.array_equal(res[0][1], res[2][1]) and res[2][1].max() <= ms
+            for k in ("total_steps", "n_timeouts", "n_upper"):
+                assert res[0][2][k] == res[2][2][k], (k, ms)
+        # trialwise model
+        subj, pe = synthetic_stahl_like(np.random.default_rng(3), nsubs=12, ntrials_total=2500)
+        _, alphas = boundaries_from_pe(pe)
+        alphas[:3] = 0.0
+        _, idx = np.unique(subj, return_inverse=True)
+        pp = draw_participant_params(12, np.random.default_rng(4))
+        tw = {}
+        for variant in (0, 2, -1):
+            sim.set_kernel_variant(variant)
+            tw[variant] = sim.simulate_trialwise(idx, alphas, pp, trial_offset=123).copy()
+            assert sim.last_stats()["scheduler"] == (2 if variant == 0 else 3)
+        assert np.array_equal(tw[0].view(np.uint64), tw[2].view(np.uint64)) and np.array_equal(tw[0].view(np.uint64), tw[-1].view(np.uint64))
+        # automatic choice by size
+        sim.set_kernel_variant(-1)
+        sim.run(0, P, 6553, 0.01, 400)                       # 262 120 trials <= 256 Ki
+        assert sim.last_stats()["scheduler"] == 3
+        sim.run(0, P, 6554, 0.01, 400)
+        assert sim.last_stats()["scheduler"] == 2
+    finally:
+        sim.set_kernel_variant(-1)
 
 
 def test_tile_kernel_general_model_and_wire(sim):
@@ -938,9 +996,16 @@ def test_trialwise_persistent_equals_generic_bitwise(sim):
     group = rng.integers(0, G, n).astype(np.int32)
     bounds = _stahl_like_bounds(rng, n)
     for kw in (dict(dt=0.01, max_steps=400), dict(dt=0.001, max_steps=777)):
-        a = sim.simulate_trialwise(group, bounds, pp, seed=3, trial_offset=11, flags=F_STEPS, **kw)
+        sim.set_kernel_variant(0)
+        try:
+            a = sim.simulate_trialwise(group, bounds, pp, seed=3, trial_offset=11, flags=F_STEPS, **kw)
+        finally:
+            sim.set_kernel_variant(-1)
         sa, st = sim.last_steps(n), sim.last_stats()
         assert st["used_persistent"] == 1 and st["scheduler"] == 2
+        c = sim.simulate_trialwise(group, bounds, pp, seed=3, trial_offset=11, flags=F_STEPS, **kw)   # default at this size: latency kernel
+        assert sim.last_stats()["scheduler"] == 3 and np.array_equal(a.view(np.uint64), c.view(np.uint64))
+        assert np.array_equal(sa, sim.last_steps(n))
         b = sim.simulate_trialwise(group, bounds, pp, seed=3, trial_offset=11, flags=F_STEPS | F_GENERIC, **kw)
         sb, st2 = sim.last_steps(n), sim.last_stats()
         assert st2["used_persistent"] == 0
