@@ -870,6 +870,9 @@ __device__ __forceinline__ void spec_block(float &x, uint32_t &n, bool &alive, f
     }
 }
 
+#ifndef DDM_LATENCY_BLOCKS
+#define DDM_LATENCY_BLOCKS 2  // blocks per iteration
+#endif
 template <int KIND, bool OUT64>
 __global__ void __launch_bounds__(128) latency_kernel(const RunArgs a, uint64_t total) {
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -897,23 +900,25 @@ __global__ void __launch_bounds__(128) latency_kernel(const RunArgs a, uint64_t 
         float x = t.x;
         uint32_t n = 0;
         bool alive = (fabsf(x) < t.h) && (a.max_steps > 0u);
-        // software-pipelined: the normals of blocks b+2, b+3 are drawn while blocks b, b+1 step (they depend on the
-        // block index alone), so an iteration lasts max(generator chain, step chain) instead of their sum
-        Normals6Scaled z0, z1;
+        // software-pipelined: the normals of the next DDM_LATENCY_BLOCKS blocks are drawn while the current ones step (they
+        // depend on the block index alone), so an iteration lasts max(generator chain, step chain) instead of their sum
+        constexpr uint32_t NB = DDM_LATENCY_BLOCKS;
+        Normals6Scaled z[NB];
         if (alive) {
-            philox_pairs_lg2(0u, trial_g, ds_g, STREAM_STEP, a.key, z0);
-            philox_pairs_lg2(1u, trial_g, ds_g, STREAM_STEP, a.key, z1);
+#pragma unroll
+            for (uint32_t j = 0; j < NB; j++) philox_pairs_lg2(j, trial_g, ds_g, STREAM_STEP, a.key, z[j]);
         }
-        for (uint32_t blk = 2u; alive; blk += 2u) {
-            Normals6Scaled y0, y1;
-            philox_pairs_lg2(blk, trial_g, ds_g, STREAM_STEP, a.key, y0);
-            philox_pairs_lg2(blk + 1u, trial_g, ds_g, STREAM_STEP, a.key, y1);
-            spec_block(x, n, alive, t.c0, t.h, z0);
-            alive = alive && (n < a.max_steps);
-            spec_block(x, n, alive, t.c0, t.h, z1);
-            alive = alive && (n < a.max_steps);
-            z0 = y0;
-            z1 = y1;
+        for (uint32_t blk = NB; alive; blk += NB) {
+            Normals6Scaled y[NB];
+#pragma unroll
+            for (uint32_t j = 0; j < NB; j++) philox_pairs_lg2(blk + j, trial_g, ds_g, STREAM_STEP, a.key, y[j]);
+#pragma unroll
+            for (uint32_t j = 0; j < NB; j++) {
+                spec_block(x, n, alive, t.c0, t.h, z[j]);
+                alive = alive && (n < a.max_steps);
+            }
+#pragma unroll
+            for (uint32_t j = 0; j < NB; j++) z[j] = y[j];
         }
         int choice = (x >= t.h) ? 1 : ((x <= -t.h) ? -1 : 0);
         if (n > a.max_steps) { n = a.max_steps; choice = 0; }  // whole blocks: a trial inside the boundaries after max_steps steps timed out
