@@ -50,7 +50,7 @@ for variant in (0, 1):
             b = sim.simulate(7, canon, 211, seed=4, dataset_offset=0, flags=8)
             clean()
             assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
-sim.set_kernel_variant(-1)
+sim.set_kernel_variant(0)   # the tile kernel at these sizes, too (the default would take the latency kernel, which has no slots to check)
 for thr, bps, tile in ((0, 0, 0), (2, 1, 5), (4, 0, 96)):
     sim.set_tuning(thr, bps, tile)
     n = 20_011
@@ -63,6 +63,7 @@ for thr, bps, tile in ((0, 0, 0), (2, 1, 5), (4, 0, 96)):
     clean()
     assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
 sim.set_tuning(0, 0, 0)
+sim.set_kernel_variant(-1)
 # large launches: many tiles per warp, stragglers, the chunked host path with the compact wire, the histogram call
 P = priors.draw_prior_batch("sweep", 6000, rng)
 out = sim.simulate(0, P, 1000, 1e-3, 4000, seed=1, dataset_offset=0, flags=2)
@@ -70,6 +71,11 @@ clean()
 h = sim.simulate_histogram(0, P, 1000, 1e-3, 4000, seed=1, dataset_offset=0, n_bins=100, rt_max=4.0)
 st = clean()
 assert int(h["upper"].sum() + h["lower"].sum()) + h["missing"] + h["overflow"] == 6000 * 1000
+sim.set_pipeline(0, 300_000)   # the same call in chunks (forced; by default from 64 Mi trials on)
+h2 = sim.simulate_histogram(0, P, 1000, 1e-3, 4000, seed=1, dataset_offset=0, n_bins=100, rt_max=4.0)
+clean()
+sim.set_pipeline(-1, -1)
+assert np.array_equal(h["upper"], h2["upper"]) and np.array_equal(h["lower"], h2["lower"]) and h["missing"] == h2["missing"]
 Pa = priors.draw_prior_batch("alpha", 5000, rng)
 sim.simulate(1, Pa, 1000, 0.01, 400, seed=1, dataset_offset=0)
 clean()
