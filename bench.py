@@ -335,16 +335,16 @@ def other_configs(sim, issue_peak, want_cpu=True) -> dict:
                  "call_ms": g_host, "call": "impute_dataset(subj_idx, pre_Pe, participant params) -> (19374, 2) float64 host array",
                  "device_resident_ms": g_dev, "device_call": "impute_dataset(..., device=True) -> torch tensor over the DLPack capsule",
                  "trials_per_s_device": 19374 / (g_dev * 1e-3), **kernel_fields(st)}
-    # where the call's time goes: the reference's own NumPy preprocessing (np.unique over the subject column, the Pe
+    # where the call's time goes: the reference's own NumPy preprocessing (the participant index of the subject column, the Pe
     # standardisation; imputation_from_stahl_not_scaled.py:59-105) against the library call that replaces its per-row loop
     _, alphas4 = stahl.boundaries_from_pe(pe)
-    _, idx4 = np.unique(subj, return_inverse=True)
+    _, idx4 = stahl.unique_inverse(subj)
     out["C4"]["simulate_call_ms"] = _median_ms(lambda: sim.simulate_trialwise(idx4, alphas4, pp), sim, 50)
     out["C4"]["simulate_call"] = "ddm_simulate_trialwise(group (n,) i32, bound (n,) f64, params (89,4)) -> (n, 2) float64 host array"
     t0 = time.perf_counter()
     for _ in range(50):
         stahl.boundaries_from_pe(pe)
-        np.unique(subj, return_inverse=True)
+        stahl.unique_inverse(subj)
     out["C4"]["host_numpy_preprocessing_ms"] = (time.perf_counter() - t0) / 50 * 1e3
     if orc is not None:
         _, alphas = stahl.boundaries_from_pe(pe)

@@ -417,3 +417,19 @@ def test_streamed_path_chunk_schedule(n_datasets, n_trials, chunk_rows):
             assert rows[-1] <= 4 << 20 < rows[0]                        # large batches end with small chunks
     elif chunk_rows > 0:
         assert np.all(c[:-1] == max(1, chunk_rows // n_trials))
+
+
+def test_unique_inverse_is_np_unique():
+    """imputation_from_stahl_not_scaled.unique_inverse: the participant index without a sort, same arrays as
+    np.unique(..., return_inverse=True) for every kind of id column."""
+    from bayesflow_nddms_b200.imputation_from_stahl_not_scaled import synthetic_stahl_like, unique_inverse
+
+    rng = np.random.default_rng(5)
+    subj, _ = synthetic_stahl_like()
+    cases = [subj, subj.astype(np.int32), rng.integers(-50, 50, 1000), rng.integers(0, 3, 10).astype(np.uint8),
+             np.array([7]), np.array([], dtype=np.int64), rng.integers(0, 10**12, 500),      # sparse: falls back to the sort
+             rng.normal(size=100), np.array(["b", "a", "b"])]
+    for a in cases:
+        u1, i1 = np.unique(a, return_inverse=True)
+        u2, i2 = unique_inverse(a)
+        assert u1.dtype == u2.dtype and np.array_equal(u1, u2) and np.array_equal(i1, i2), a[:5]
