@@ -37,9 +37,14 @@ def unique_inverse(ids):
 def boundaries_from_pe(all_Pe):
     """:82-105 -> (alpha_like_Pe, single_trial_alphas), both (n,) float64."""
     all_Pe = np.asarray(all_Pe, dtype=np.float64)
-    all_standard_Pe = (all_Pe - np.mean(all_Pe)) / np.std(all_Pe)
-    alpha_like_Pe = (all_standard_Pe + 3) / 3
-    single_trial_alphas = (all_standard_Pe + 3) / 3
+    # (all_Pe - mean) / std, (. + 3) / 3 twice, clip -- the reference's operations in its order, but the centred column
+    # is formed once (np.std forms it again: same sums, same bits -- tests) and the two identical columns are one
+    alpha_like_Pe = all_Pe - np.mean(all_Pe)
+    sd = np.sqrt(np.add.reduce(alpha_like_Pe * alpha_like_Pe) / all_Pe.size) if all_Pe.size else np.float64(np.nan)
+    alpha_like_Pe /= sd
+    alpha_like_Pe += 3
+    alpha_like_Pe /= 3
+    single_trial_alphas = alpha_like_Pe.copy()
     single_trial_alphas[single_trial_alphas < 0] = 0
     return alpha_like_Pe, single_trial_alphas
 

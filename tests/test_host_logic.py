@@ -433,3 +433,21 @@ def test_unique_inverse_is_np_unique():
         u1, i1 = np.unique(a, return_inverse=True)
         u2, i2 = unique_inverse(a)
         assert u1.dtype == u2.dtype and np.array_equal(u1, u2) and np.array_equal(i1, i2), a[:5]
+
+
+def test_boundaries_from_pe_is_the_reference_arithmetic():
+    """imputation_from_stahl_not_scaled.py:82-105 written out literally gives the bits boundaries_from_pe returns
+    (which forms the centred column once and copies the two identical columns)."""
+    from bayesflow_nddms_b200.imputation_from_stahl_not_scaled import boundaries_from_pe
+
+    rng = np.random.default_rng(9)
+    for n in (2, 3, 13, 337, 19374, 100_003):
+        for scale in (1.0, 1e-3, 1e3):
+            all_Pe = np.clip(rng.normal(0.0, 5.8, n), -35, 35) * scale
+            all_standard_Pe = (all_Pe - np.mean(all_Pe)) / np.std(all_Pe)
+            alpha_like_Pe = (all_standard_Pe + 3) / 3
+            single_trial_alphas = (all_standard_Pe + 3) / 3
+            single_trial_alphas[single_trial_alphas < 0] = 0
+            a, b = boundaries_from_pe(all_Pe)
+            assert np.array_equal(a, alpha_like_Pe) and np.array_equal(b, single_trial_alphas) and b.min() >= 0
+            assert a is not b and not np.shares_memory(a, b)
