@@ -949,6 +949,9 @@ def test_latency_kernel_edges_and_routing(sim):
         assert sim.last_stats()["scheduler"] == 3
         sim.run(0, P, 6554, 0.01, 400)
         assert sim.last_stats()["scheduler"] == 2
+        for bad in (3, -2):
+            with pytest.raises(ValueError):
+                sim.set_kernel_variant(bad)
     finally:
         sim.set_kernel_variant(-1)
 
