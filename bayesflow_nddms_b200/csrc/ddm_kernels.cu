@@ -873,8 +873,11 @@ __device__ __forceinline__ void spec_block(float &x, uint32_t &n, bool &alive, f
 #ifndef DDM_LATENCY_BLOCKS
 #define DDM_LATENCY_BLOCKS 2  // blocks per iteration
 #endif
+#ifndef DDM_LATENCY_THREADS
+#define DDM_LATENCY_THREADS 128  // threads per block
+#endif
 template <int KIND, bool OUT64>
-__global__ void __launch_bounds__(128) latency_kernel(const RunArgs a, uint64_t total) {
+__global__ void __launch_bounds__(DDM_LATENCY_THREADS) latency_kernel(const RunArgs a, uint64_t total) {
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long acc_steps = 0;
     uint32_t tout = 0, upper = 0, cap = 0;
@@ -1230,10 +1233,10 @@ static cudaError_t launch_generic_1(const RunArgs &a, int kind, bool buffer_src,
 
 template <int KIND>
 static cudaError_t launch_latency_kind(const RunArgs &a, bool out64, uint64_t total, cudaStream_t s) {
-    const unsigned grid = (unsigned)((total + 127) / 128);
+    const unsigned grid = (unsigned)((total + DDM_LATENCY_THREADS - 1) / DDM_LATENCY_THREADS);
     if (grid == 0) return cudaSuccess;
-    if (out64) latency_kernel<KIND, true><<<grid, 128, 0, s>>>(a, total);
-    else latency_kernel<KIND, false><<<grid, 128, 0, s>>>(a, total);
+    if (out64) latency_kernel<KIND, true><<<grid, DDM_LATENCY_THREADS, 0, s>>>(a, total);
+    else latency_kernel<KIND, false><<<grid, DDM_LATENCY_THREADS, 0, s>>>(a, total);
     return cudaGetLastError();
 }
 
