@@ -371,6 +371,15 @@ bool uses_dconst(const ddm_ctx *ctx, int model, int precision) {
 // Enqueue the simulator kernel for the datasets described by `a` (pointers already offset to the
 // range) on the ctx stream.  The stats counters accumulate; only the work counter is reset.
 constexpr int64_t kLatencyMaxRows = 256 << 10;  // it leads up to here for every model, scripts/r02_latency_probe.py
+// (flags: the ddm_flags of the call plus the internal ones already set in RunArgs)
+bool takes_latency_kernel(const ddm_ctx *ctx, int model, int64_t rows, int precision, int flags, uint32_t max_steps) {
+    const bool trialwise = (model == DDM_MODEL_TRIALWISE);
+    const bool degenerate = trialwise ? ctx->trialwise_degenerate : ctx->degenerate_noise;
+    const bool persistent = precision == 32 && !ctx->dbg_on && !degenerate && !(flags & (DDM_FLAG_FORCE_GENERIC | DDM_FLAG_OUT_STATE)) &&
+                            max_steps <= ddm::TILE_MAX_STEPS;
+    return persistent && kind_of(model) != ddm::KIND_GENERAL && !(flags & ddm::FLAG_WIRE_COMPACT) && rows > 0 &&
+           (ctx->tune_kernel_variant == 2 || (ctx->tune_kernel_variant == -1 && rows <= kLatencyMaxRows));
+}
 int launch_sim(ddm_ctx *ctx, ddm::RunArgs &a, int precision, ddm_stats &st, cudaStream_t stream = nullptr) {
     if (!stream) stream = ctx->stream;
     const int model = a.model, flags = a.flags;
@@ -388,8 +397,7 @@ int launch_sim(ddm_ctx *ctx, ddm::RunArgs &a, int precision, ddm_stats &st, cuda
     // Small launches -- one trial per lane or fewer, nothing to refill: the reference's own batch sizes -- last as long as
     // their longest trial's dependent chain; the latency kernel (speculative six-step blocks, one thread per trial) is
     // built for that (scripts/r02_latency_probe.py).  Same bits as the persistent kernels.
-    const bool latency = persistent && kind != ddm::KIND_GENERAL && !(a.flags & ddm::FLAG_WIRE_COMPACT) &&
-                         (ctx->tune_kernel_variant == 2 || (ctx->tune_kernel_variant == -1 && rows <= kLatencyMaxRows));
+    const bool latency = takes_latency_kernel(ctx, model, rows, precision, a.flags, a.max_steps);
     if (latency) {
         DDM_CUDA(ctx, ddm::launch_latency(a, kind, out64, (uint64_t)rows, stream));
         st.used_persistent = 1;  // a production kernel, not the validation twin
@@ -399,6 +407,8 @@ int launch_sim(ddm_ctx *ctx, ddm::RunArgs &a, int precision, ddm_stats &st, cuda
         st.kernel_launches++;
         return DDM_OK;
     }
+    if (persistent && kind != ddm::KIND_GENERAL && !a.dconst)
+        return fail(ctx, DDM_ERR_STATE, "internal: per-dataset constants missing for a persistent launch");
     DDM_CUDA(ctx, cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), stream));
     if (persistent) {
         const int block = ddm::persistent_block_size();
@@ -483,7 +493,9 @@ int run_common(ddm_ctx *ctx, int model, int64_t n_datasets, int64_t n_trials, do
     st.n_trials = (uint64_t)rows;
     DDM_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long) * (1 + ddm::STAT_COUNT), ctx->stream));
     if (rows > 0) {
-        if (uses_dconst(ctx, model, precision)) {
+        if (takes_latency_kernel(ctx, model, rows, precision, flags, (uint32_t)max_steps)) {
+            a.dconst = nullptr;  // a launch this small forms its constants itself: no prep_kernel in front of it (-4 us of ~40)
+        } else if (uses_dconst(ctx, model, precision)) {
             if (trialwise) {  // per-participant constants; the boundary comes per trial
                 DDM_CUDA(ctx, ctx->dconst.reserve((size_t)(n_groups > 0 ? n_groups : 1)));
                 a.dconst = ctx->dconst.p;

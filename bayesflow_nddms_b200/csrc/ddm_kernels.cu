@@ -18,11 +18,10 @@ namespace ddm {
 // --------------------------------------------------------------------------------
 // prep: one thread per dataset
 // --------------------------------------------------------------------------------
-__global__ void prep_kernel(const double *__restrict__ params, DsConst *__restrict__ dconst,
-                            uint32_t n_datasets, uint32_t n_params, int model, double dt) {
-    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= n_datasets) return;
-    const double *p = params + (size_t)d * n_params;
+// The per-dataset (per-participant, model 5) constants of the production kernels from one row of parameters: fp64
+// arithmetic, rounded once.  prep_kernel runs it once per dataset; the latency kernel, whose launches are too small to
+// be worth a kernel of their own in front of them, runs it per trial (same code, same bits).
+__device__ __forceinline__ DsConst prep_constants(const double *__restrict__ p, int model, double dt) {
     DsConst c;
 #pragma unroll
     for (int i = 0; i < 8; i++) c.v[i] = 0.f;
@@ -65,7 +64,14 @@ __global__ void prep_kernel(const double *__restrict__ params, DsConst *__restri
         c.v[6] = (model == 3) ? (float)p[7] : (model == 4 ? 2.f : 1.f);
         c.v[7] = (float)U;
     }
-    dconst[d] = c;
+    return c;
+}
+
+__global__ void prep_kernel(const double *__restrict__ params, DsConst *__restrict__ dconst,
+                            uint32_t n_datasets, uint32_t n_params, int model, double dt) {
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n_datasets) return;
+    dconst[d] = prep_constants(params + (size_t)d * n_params, model, dt);
 }
 
 __global__ void prep_general_kernel(const double *__restrict__ params, GenConst *__restrict__ gconst, uint32_t n_datasets,
@@ -894,12 +900,10 @@ __global__ void __launch_bounds__(DDM_LATENCY_THREADS) latency_kernel(const RunA
         const double *prm = (KIND == KIND_TRIALWISE) ? a.params + (size_t)a.group[g] * 4 : a.params + (size_t)ds * a.n_params;
         const double tau = (KIND == KIND_TRIALWISE) ? prm[2] : prm[3];
         TrialF32 t;
-        if (KIND == KIND_TRIALWISE) {
-            trial_setup_trialwise(a.dconst[a.group[g]], (float)a.bound_in[g], t);
-        } else {
-            const DsConst dc = a.dconst[ds];
-            trial_setup_f32<(KIND == KIND_TRIALWISE ? KIND_FIXED : KIND)>(dc, trial_g, ds_g, a.key, t, cap);
-        }
+        // a.dconst == nullptr: no prep_kernel ran in front of this launch, the constants are formed here
+        const DsConst dc = a.dconst ? ((KIND == KIND_TRIALWISE) ? a.dconst[a.group[g]] : a.dconst[ds]) : prep_constants(prm, a.model, a.dt);
+        if (KIND == KIND_TRIALWISE) trial_setup_trialwise(dc, (float)a.bound_in[g], t);
+        else trial_setup_f32<(KIND == KIND_TRIALWISE ? KIND_FIXED : KIND)>(dc, trial_g, ds_g, a.key, t, cap);
         float x = t.x;
         uint32_t n = 0;
         bool alive = (fabsf(x) < t.h) && (a.max_steps > 0u);

@@ -811,7 +811,7 @@ def main():
                                       "device-resident f32 batch, one call and one stream synchronisation",
                               "ms_per_batch": lat * 1e3, "ms_per_batch_blocks_of_40": [b * 1e3 for b in blocks],
                               "ms_per_batch_three_calls": float(np.median(blocks3)) * 1e3,
-                              "trials_per_s": B2 * N2 / lat, "launches_per_batch": 3}
+                              "trials_per_s": B2 * N2 / lat, "launches_per_batch": 2}
             if not args.no_cpu_baseline and world == 1:
                 from oracle import cpu as orc
 
